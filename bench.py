@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — prefill KV-compress throughput on B200 (BASELINE.json metric).
+
+A step = one pass of the hot path (K1 prompt_mass -> K2 score_select -> K3
+quant_gather) over every decoder layer of one prefill.  Default workload is
+BASELINE.json configs[1]: Llama-2-7B random-init, 32 layers x 4096 tokens, batch 1,
+fp32 K/V (the reference runs the model in fp32), bits 8/4/2, theta 0.7/0.3.
+N>1 (torchrun): every rank compresses its own sequence (batch sharding, no
+collective on the data path) -> weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c4]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "realtime-kv-cache-compression_b200"))
+
+WORKLOADS = {
+    "tiny": ("tiny self-test workload (not a BASELINE config)", 3, 256, 4, 512, 320, 1, (2, 4, 8)),
+    # name: (description, layers, hidden, heads, intermediate, S, B, bits(low,mid,high))
+    "c1": ("single layer K/V [1,32,2048,128] fp32 (configs[0])", 1, 4096, 32, 11008, 2048, 1, (2, 4, 8)),
+    "c2": ("Llama-2-7B random-init, 32-layer prefill of 4096 tokens, batch 1 (configs[1])", 32, 4096, 32, 11008, 4096, 1, (2, 4, 8)),
+    "c4": ("Llama-2-13B random-init, 40-layer prefill of 16384 tokens, batch 1 (configs[3], mixed 8/4/2)", 40, 5120, 40, 13824, 16384, 1, (2, 4, 8)),
+}
+PEAKS_FALLBACK_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return PEAKS_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- synthetic prefill
+def rope_tables(S, D, device):
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=device, dtype=torch.float32) / D))
+    ang = torch.arange(S, device=device, dtype=torch.float32)[:, None] * inv[None, :]
+    ang = torch.cat([ang, ang], dim=-1)
+    return ang.cos(), ang.sin()
+
+
+def rope(x, cos, sin):
+    h = x.shape[-1] // 2
+    rot = torch.cat([-x[..., h:], x[..., :h]], dim=-1)
+    return x * cos + rot * sin
+
+
+def rmsnorm(x):
+    return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)
+
+
+@torch.no_grad()
+def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, keep_layers=None):
+    """Random-init Llama-2 stack (N(0,0.02) weights, RoPE, causal softmax attention, SwiGLU MLP)
+    run in plain torch fp32 as SETUP: yields per layer the K/V the compressor sees
+    ([B,S,H*D] after RoPE, as modified_llama.py:105-108) and the first P key columns of the
+    softmaxed attention ([B,H,S,P]; the reference never reads any other column)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    D = hidden // heads
+    ids = torch.randint(0, 32000, (B, S), generator=g, device=device)
+    emb = torch.randn(32000, hidden, generator=g, device=device) * 0.02
+    x = emb[ids]
+    del emb
+    cos, sin = rope_tables(S, D, device)
+    out = []
+    rows = max(128, min(S, (1 << 28) // (heads * S)))       # query rows per softmax block (<= 1 GiB logits)
+    for l in range(n_layers):
+        def w(o, i):
+            return torch.randn(o, i, generator=g, device=device) * 0.02
+        h = rmsnorm(x)
+        q = (h @ w(hidden, hidden).T).view(B, S, heads, D).transpose(1, 2)
+        k = (h @ w(hidden, hidden).T).view(B, S, heads, D).transpose(1, 2)
+        v = (h @ w(hidden, hidden).T).view(B, S, heads, D).transpose(1, 2)
+        q, k = rope(q, cos, sin), rope(k, cos, sin)
+        A = torch.empty(B, heads, S, P, device=device)
+        ctx = torch.empty(B, heads, S, D, device=device)
+        for r0 in range(0, S, rows):
+            r1 = min(S, r0 + rows)
+            logits = q[:, :, r0:r1] @ k.transpose(-1, -2) / math.sqrt(D)
+            causal = torch.arange(S, device=device)[None, :] > torch.arange(r0, r1, device=device)[:, None]
+            logits.masked_fill_(causal, float("-inf"))
+            probs = torch.softmax(logits, dim=-1)
+            A[:, :, r0:r1] = probs[..., :P]
+            ctx[:, :, r0:r1] = probs @ v
+            del logits, probs
+        if keep_layers is None or l in keep_layers:
+            out.append((l, k.transpose(1, 2).reshape(B, S, hidden).contiguous(),
+                        v.transpose(1, 2).reshape(B, S, hidden).contiguous(), A))
+        x = x + ctx.transpose(1, 2).reshape(B, S, hidden) @ w(hidden, hidden).T
+        h = rmsnorm(x)
+        gate, up = h @ w(inter, hidden).T, h @ w(inter, hidden).T
+        x = x + (torch.nn.functional.silu(gate) * up) @ w(hidden, inter).T
+        del q, k, v, ctx, gate, up, h
+    return out
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(layers_host, cfg, bits, S, n_layers_total, B, reps=1):
+    """Oracle port of the reference's CPU path (quantise every token, then select and gather, as
+    the reference does) timed on the host cores over a bounded sample of layers."""
+    import oracle
+    from rtkv.selective_propagation import SelectiveTokenPropagator
+    prop = SelectiveTokenPropagator(cfg)
+    P = max(1, min(S // 5, 128))
+    l0, K0, V0, A0 = layers_host[0]
+    oracle.compress_layer(K0[:, :256], V0[:, :256], oracle.F32, A0[:, :, :256], oracle.F32, min(P, 51),
+                          cfg.alpha, cfg.beta, cfg.gamma, 1.0, cfg.theta_h, cfg.theta_m, bits, 0.8)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for (l, K, V, A) in layers_host:
+            oracle.compress_layer(K, V, oracle.F32, A, oracle.F32, P, cfg.alpha, cfg.beta, cfg.gamma,
+                                  cfg.layer_weights[l], cfg.theta_h, cfg.theta_m, bits,
+                                  prop.get_layer_propagation_ratio(l))
+    dt = (time.perf_counter() - t0) / reps
+    per_layer = dt / len(layers_host)
+    return B * S / (per_layer * n_layers_total), per_layer, oracle.num_threads()
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="rtkv", choices=["rtkv", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "rtkv" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, L, hidden, heads, inter, S, B, bits = WORKLOADS[args.workload]
+    P = max(1, min(S // 5, 128))
+    sample_layers = sorted({0, L // 3, (2 * L) // 3, L - 1})
+
+    import rtkv
+    cfg = rtkv.CompressionConfig(num_hidden_layers=max(L, 2), num_attention_heads=heads, hidden_size=hidden,
+                                 high_precision_bits=bits[2], medium_precision_bits=bits[1],
+                                 low_precision_bits=bits[0])
+    config = {"workload": desc, "layers": L, "seq_len": S, "batch_per_gpu": B, "kv_width": hidden, "heads": heads,
+              "prompt_len": P, "bits_low_mid_high": list(bits), "theta_h": cfg.theta_h, "theta_m": cfg.theta_m,
+              "ratios": [cfg.early_layer_ratio, cfg.middle_layer_ratio, cfg.later_layer_ratio],
+              "kv_dtype": "float32", "attention_input": f"[B,H,S,P={P}] probability slice, float32",
+              "sharding": "batch (one sequence per GPU, no collective)" if world > 1 else "single GPU",
+              "l2": "per-step working set (inputs+outputs, all layers) far exceeds the 126 MB L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
+        if dev.type == "cuda":
+            torch.cuda.set_device(dev)
+        layers = llama_prefill_inputs(L, hidden, heads, inter, S, B, P, 1234, dev, keep_layers=set(sample_layers))
+        host = [(l, K.cpu().numpy(), V.cpu().numpy(), A.cpu().numpy()) for (l, K, V, A) in layers]
+        del layers
+        vals = []
+        for it in range(args.warmup + args.steps):
+            v, per_layer, cores = cpu_baseline(host, cfg, bits, S, L, B)
+            if it >= args.warmup:
+                vals.append((v, per_layer))
+        value = float(np.mean([v for v, _ in vals]))
+        per_layer = float(np.mean([p for _, p in vals]))
+        line = {"impl": "reference", "metric": "prefill_kv_compress_tokens_per_s", "value": value, "unit": "tokens/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": per_layer * len(sample_layers) * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                 "sample": f"layers {sample_layers} of {L} per step, C/OpenMP port of the reference's "
+                                           f"CPU path (oracle/), per-layer time x {L} layers"},
+                "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ rtkv arm (GPU)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    layers = llama_prefill_inputs(L, hidden, heads, inter, S, B, P, 1234 + rank, dev)
+    torch.cuda.synchronize()
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    outs = [(torch.empty_like(K), torch.empty_like(V)) for (_, K, V, _) in layers]
+    ev_k3 = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in layers]
+             for _ in range(args.steps)]
+    from rtkv import ops
+
+    def step(events=None):
+        sels = []
+        for j, (l, K, V, A) in enumerate(layers):
+            params, _ = comp.layer_params(l, S, ops.F32)
+            mass = ops.prompt_mass(A, prompt_len=P)
+            sel = ops.score_select(params, B, S, dev, mass=mass)
+            if events is not None:
+                events[j][0].record()
+            ops.quant_gather(K, V, sel, sel.labels, bits, S, zero_pad=False, out0=outs[j][0], out1=outs[j][1])
+            if events is not None:
+                events[j][1].record()
+            sels.append(sel)
+        return sels
+
+    for _ in range(args.warmup):
+        sels = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for it in range(args.steps):
+        sels = step(ev_k3[it])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B * S / (ms_per_step * 1e-3)
+
+    # measured retained rows -> algorithmic bytes (SURVEY.md §8d formula, measured rho)
+    kept = [int(s.read_stats()[1]["n_selected"].sum()) for s in sels]
+    e = 4
+    k3_bytes = [n * 2 * hidden * (e + e) for n in kept]
+    k1_bytes = B * S * heads * P * e + B * S * 4
+    k2_bytes = B * S * 12
+    path_bytes = sum(k3_bytes) + L * (k1_bytes + k2_bytes)
+    k3_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in evs) for evs in ev_k3]))
+    peak, peak_src = measured_hbm_peak()
+    achieved = sum(k3_bytes) / (k3_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "quant_gather_vec_kernel (K3)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "launch_ms_avg": k3_ms / L, "bytes_per_launch_avg": sum(k3_bytes) / L,
+                "k3_share_of_step": k3_ms / ms_per_step,
+                "retained_fraction": sum(kept) / (L * B * S),
+                "whole_path": {"achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "frac_of_8TBs_nominal": path_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0,
+                               "bytes_per_step": path_bytes}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic"] = json.load(f).get("quant_gather_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {"metric": "prefill_kv_compress_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": 3 * L * args.steps, "roofline": roofline,
+            "reference_recorded": {"tokens_per_s": 173, "note": "BASELINE.md: derived from the reference's recorded "
+                                   "runs (23.7 s per 4096-token prefill, bits 16/8/4, unnamed GPU); not a published number"}}
+
+    # ------------------------------------------------------------------ e2e: public API, host buffers
+    if not args.no_e2e:
+        host_in = [(l, K.cpu().pin_memory(), V.cpu().pin_memory(), A.cpu().pin_memory()) for (l, K, V, A) in layers]
+        ids = torch.zeros(B, S, dtype=torch.long)
+        ko = [torch.empty(B * S * hidden, dtype=torch.float32).pin_memory() for _ in range(2)]
+        vo = [torch.empty(B * S * hidden, dtype=torch.float32).pin_memory() for _ in range(2)]
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            d2h = 0
+            for j, (l, K, V, A) in enumerate(host_in):
+                k_sel, v_sel, info = comp.compress_layer_kv_cache(K, V, A, ids, l, out_keys=ko[j & 1], out_values=vo[j & 1])
+                d2h += 2 * k_sel.numel() * 4 + B * S * 6 + 16 + 72 * B
+            return d2h
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d2h = e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        h2d = sum(K.numel() * 4 + V.numel() * 4 + A.numel() * 4 for (_, K, V, A) in host_in)
+        line["e2e"] = {"value": world * B * S / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+                       "steps": e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "api": "RealTimePrefillCompressor.compress_layer_kv_cache on pinned host tensors "
+                              "(rtkv_compress_layer_host), synchronous per layer"}
+        del host_in, ko, vo
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        host = [(l, K.cpu().numpy(), V.cpu().numpy(), A.cpu().numpy()) for (l, K, V, A) in layers if l in sample_layers]
+        v, per_layer, cores = cpu_baseline(host, cfg, bits, S, L, B)
+        line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                "sample": f"layers {sample_layers} of {L}, once each, C/OpenMP port of the reference's "
+                                          f"CPU path (oracle/): {per_layer * 1e3:.1f} ms per layer x {L} layers"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

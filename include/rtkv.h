@@ -1,0 +1,199 @@
+/*
+ * rtkv.h — C ABI of librtkv.so: the B200 (sm_100a) implementation of the
+ * reference's per-layer prefill KV-compression hot path.
+ *
+ * Every entry point replaces one reference interface (paths relative to the
+ * reference repository, EvelynHung-79/RealTime-KV-cache-Compression):
+ *
+ *   rtkv_prompt_mass            src/compression/token_importance.py:21-47
+ *   rtkv_prompt_mass_qk         (no reference code: fused Q*K_prompt^T entry)
+ *   rtkv_position_bias          src/compression/token_importance.py:87-110
+ *   rtkv_normalize_mass         src/compression/token_importance.py:49-85
+ *   rtkv_score_select           src/compression/token_importance.py:134-176
+ *                               + dynamic_quantization.py:21-60
+ *                               + selective_propagation.py:40-161,203-211
+ *   rtkv_quant_gather           src/compression/dynamic_quantization.py:62-196
+ *                               + selective_propagation.py:213-232
+ *   rtkv_quant_params / rtkv_quantize_with_params
+ *                               src/compression/dynamic_quantization.py:62-126
+ *   rtkv_gather_scalars         src/compression/selective_propagation.py:231-232
+ *   rtkv_quant_pack / rtkv_unpack_dequant
+ *                               (no reference code: packed-code layout)
+ *   rtkv_compress_layer_host    src/compression/unified_compressor.py:95-172 (host buffers)
+ *
+ * Conventions
+ *   - Plain C types only.  Unless a parameter is marked [host], every pointer
+ *     is a DEVICE pointer valid on the current CUDA device.
+ *   - All work is enqueued on the caller's stream (cudaStream_t passed as
+ *     void*); no entry point except rtkv_compress_layer_host synchronises.
+ *   - Return value: 0 ok; <0 rtkv error (bad argument / unsupported); >0 a
+ *     cudaError_t.  rtkv_last_error() gives a thread-local message.  The
+ *     library never aborts the process and has no CPU fallback.
+ *   - Inputs are borrowed and never written; outputs are caller-owned.
+ */
+#ifndef RTKV_H
+#define RTKV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTKV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RTKV_API __attribute__((visibility("default")))
+#else
+#define RTKV_API
+#endif
+
+enum { RTKV_F32 = 0, RTKV_F16 = 1, RTKV_BF16 = 2 };
+
+enum {
+    RTKV_OK = 0,
+    RTKV_EINVAL = -1,       /* bad argument */
+    RTKV_EUNSUPPORTED = -2, /* shape / dtype / bit width outside the supported set */
+    RTKV_ENOMEM = -3,
+    RTKV_ENODEVICE = -4     /* no usable sm_100 device */
+};
+
+/* flags of rtkv_score_select */
+enum {
+    RTKV_FROM_MASS = 1,    /* scores are computed from `mass` (else `scores` is an input) */
+    RTKV_MAKE_LABELS = 2,  /* labels are computed from the scores (else `labels` is an input) */
+    RTKV_SELECT = 4,       /* run the budgeted selection */
+    RTKV_FALLBACK = 8      /* apply the top-10% emergency fallback when no row selected anything */
+};
+
+/* Per-layer scalars (reference: configs/base_config.py:4-57).  bits = {low, medium, high}. */
+typedef struct rtkv_layer_params {
+    double alpha, beta, gamma; /* CompressionConfig.alpha/beta/gamma                        */
+    double layer_weight;       /* config.layer_weights[layer_idx]                            */
+    double theta_h, theta_m;   /* precision thresholds                                       */
+    double budget;             /* seq_len * propagation_ratio (selective_propagation.py:96)  */
+    int32_t bits[3];           /* low/medium/high_precision_bits                             */
+    int32_t prompt_len;        /* P (unified_compressor.py:55)                               */
+    int32_t score_dtype;       /* dtype of the attention tensor the mass came from: half
+                                  dtypes round the attention term like torch does            */
+    int32_t fallback_topk;     /* max(1, int(0.1*S)) (selective_propagation.py:207)          */
+} rtkv_layer_params;
+
+/* Written by rtkv_score_select, one per batch row. */
+typedef struct rtkv_row_stats {
+    int32_t n_selected;       /* tokens kept in this row (after fallback, if it fired)       */
+    int32_t n_selected_greedy;/* tokens kept by the budgeted selection proper                */
+    int32_t sel_class[3];     /* kept tokens per label (low, medium, high), greedy selection */
+    int32_t label_count[3];   /* tokens per label in the row                                 */
+    int64_t cost_bits;        /* 8 * sum of selected token costs                             */
+    double sel_score_sum;     /* sum of the selected tokens' scores                          */
+    double score_sum;         /* sum of all scores of the row                                */
+    double score_sumsq;
+    float score_min, score_max;
+} rtkv_row_stats;
+
+/* Written by rtkv_score_select, one per call. */
+typedef struct rtkv_layer_stats {
+    int32_t max_selected;     /* max over rows of n_selected = S' of the output tensors      */
+    int32_t used_fallback;    /* 1 if the emergency top-k fallback replaced the selection    */
+    int32_t reserved[2];
+} rtkv_layer_stats;
+
+RTKV_API int rtkv_abi_version(void);
+RTKV_API const char *rtkv_last_error(void);
+/* [host] out: name, SM count, compute capability of the current device. */
+RTKV_API int rtkv_device_info(char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* Scratch needed by rtkv_score_select for a [B,S] problem.  The scratch must be
+ * zero-filled once after allocation; calls leave it zeroed again. */
+RTKV_API int rtkv_scratch_bytes(int B, int S, size_t *bytes);
+
+/* mass[b,i] = sum_p mean_h A[b,h,i,idx[p]]   (idx == NULL: idx[p] = p).
+ * A: [B,H,S,*] with element strides sb, sh, si and unit stride in the last dim. */
+RTKV_API int rtkv_prompt_mass(const void *A, int dtype, int B, int H, int S,
+                     int64_t sb, int64_t sh, int64_t si,
+                     const int64_t *idx, int P, float *mass, void *stream);
+
+/* Same quantity without a materialised attention matrix:
+ * mass[b,i] = (1/H) sum_h sum_{j<P, j<=i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i]).
+ * Q: [B,H,S,D], Kp: [B,H,P,D] (bf16 or f16, D == 128), lse: [B,H,S] natural-log row
+ * log-sum-exp of the layer's causal attention logits.  Uses tcgen05 tensor cores. */
+RTKV_API int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype,
+                        int B, int H, int S, int D, int P, float scale, int causal,
+                        float *mass, void *stream);
+
+RTKV_API int rtkv_position_bias(int S, float *pb, void *stream);
+RTKV_API int rtkv_normalize_mass(const float *mass, int dtype, int B, int S, float *out, void *stream);
+
+/* Scores -> labels -> budgeted selection for every row of a [B,S] layer (one launch).
+ *   mass    [B,S] f32 in  (RTKV_FROM_MASS)            scores [B,S] f32 in/out
+ *   labels  [B,S] u8 in/out (0 low, 1 medium, 2 high) mask   [B,S] u8 out (1 = kept)
+ *   sel_idx [B,S] i32 out: kept token indices, ascending, first n_selected valid
+ *   row_stats [B], layer_stats [1], scratch: rtkv_scratch_bytes. */
+RTKV_API int rtkv_score_select(const float *mass, float *scores, uint8_t *labels, uint8_t *mask,
+                      int32_t *sel_idx, rtkv_row_stats *row_stats, rtkv_layer_stats *layer_stats,
+                      void *scratch, int B, int S, const rtkv_layer_params *params /*[host]*/,
+                      int flags, void *stream);
+
+/* Per-token asymmetric min/max fake-quantisation of the kept rows, written compacted.
+ *   X0, X1   [B,S,n] inputs (X1 may be NULL); Y0, Y1 [B,out_rows,n] outputs.
+ *   sel_idx  [B,S] or NULL (identity: row r is token r, every token kept)
+ *   row_stats: n_selected per row is read from it (NULL with sel_idx == NULL)
+ *   labels   [B,S] u8 or NULL (NULL or bits == NULL: rows are copied unquantised)
+ *   Output rows r >= n_selected are zero-filled when zero_pad != 0. */
+RTKV_API int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                      const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                      const uint8_t *labels, const int32_t *bits /*[host] [3] or NULL*/,
+                      int out_rows, int zero_pad, void *Y0, void *Y1, void *stream);
+
+/* Whole-tensor scale / zero-point (qparams[0] = scale, [1] = zero_point, in `dtype`,
+ * stored as f32) and quantise-dequantise with given parameters. */
+RTKV_API int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bits, float *qparams,
+                      void *scratch, void *stream);
+RTKV_API int rtkv_quantize_with_params(const void *x, int dtype, int64_t numel, int bits,
+                              const float *qparams, void *y, void *stream);
+
+/* selected_scores [B,out_rows] f32 and selected_labels [B,out_rows] i64, zero padded. */
+RTKV_API int rtkv_gather_scalars(const float *scores, const uint8_t *labels, const int32_t *sel_idx,
+                        const rtkv_row_stats *row_stats, int B, int S, int out_rows,
+                        float *sel_scores, int64_t *sel_labels, void *stream);
+
+/* labels u8 -> i64 (the dtype the reference returns), and bool mask -> selection
+ * lists, for callers that hand in their own mask. */
+RTKV_API int rtkv_labels_to_i64(const uint8_t *labels, int64_t n, int64_t *out, void *stream);
+
+/* Packed rows (layout: DESIGN.md "packed rows").  row_bytes = rtkv_packed_row_bytes(n, max bits).
+ * codes [B,out_rows,row_bytes] u8, qparams [B,out_rows,2] f32 (scale, zero_point). */
+RTKV_API int64_t rtkv_packed_row_bytes(int n, int bits);
+RTKV_API int rtkv_quant_pack(const void *X, int dtype, int B, int S, int n,
+                    const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                    const uint8_t *labels, const int32_t *bits /*[host]*/,
+                    int out_rows, int64_t row_bytes, uint8_t *codes, float *qparams,
+                    void *stream);
+RTKV_API int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int dtype, int B, int S, int n,
+                        const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                        const uint8_t *labels, const int32_t *bits /*[host]*/,
+                        int out_rows, int64_t row_bytes, void *Y, void *stream);
+
+/* One layer with HOST buffers (pinned or pageable): copies K, V and the first P
+ * key columns of A to the device, runs the path, copies the results back and
+ * synchronises.  K_out/V_out must hold B*S*n elements; they are filled as a
+ * contiguous [B, *max_selected, n].  scores [B,S] f32, labels/mask [B,S] u8,
+ * row_stats [B] may be NULL.  ctx: rtkv_ctx_create. */
+typedef struct rtkv_ctx rtkv_ctx;
+RTKV_API int rtkv_ctx_create(rtkv_ctx **ctx);
+RTKV_API int rtkv_ctx_destroy(rtkv_ctx *ctx);
+RTKV_API int rtkv_compress_layer_host(rtkv_ctx *ctx,
+                             const void *K, const void *V, int dtype, int B, int S, int n,
+                             const void *A, int a_dtype, int H,
+                             int64_t sb, int64_t sh, int64_t si,
+                             const rtkv_layer_params *params,
+                             void *K_out, void *V_out, int32_t *max_selected,
+                             float *scores, uint8_t *labels, uint8_t *mask,
+                             rtkv_row_stats *row_stats, rtkv_layer_stats *layer_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTKV_H */

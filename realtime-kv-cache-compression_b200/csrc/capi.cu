@@ -1,0 +1,216 @@
+// capi.cu — error plumbing, device query and the host-buffer entry point of librtkv.
+//
+// rtkv_compress_layer_host is the whole reference call
+//   RealTimePrefillCompressor.compress_layer_kv_cache (src/compression/unified_compressor.py:95-172)
+// for callers that hold HOST tensors: it stages K, V and the prompt columns of
+// the attention matrix to the device, runs K1a -> K2 -> K3 and copies the
+// compacted result back.  K/V uploads ride a second stream so they overlap the
+// scoring kernels, which only need the attention slice.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rtkv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+extern "C" int rtkv_abi_version(void) { return RTKV_ABI_VERSION; }
+extern "C" const char *rtkv_last_error(void) { return g_err; }
+
+extern "C" int rtkv_device_info(char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor)
+{
+    int dev = 0, n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("rtkv_device_info: no CUDA device (%s)", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return RTKV_ENODEVICE;
+    }
+    RTKV_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    RTKV_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return RTKV_OK;
+}
+
+// ---- host-buffer context -----------------------------------------------------------
+struct rtkv_ctx {
+    cudaStream_t s_main = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_kv = nullptr;
+    void *dK = nullptr, *dV = nullptr, *dKo = nullptr, *dVo = nullptr, *dA = nullptr;
+    size_t cap_kv = 0, cap_a = 0, cap_bs = 0;
+    int cap_b = 0;
+    float *mass = nullptr, *scores = nullptr;
+    uint8_t *labels = nullptr, *mask = nullptr;
+    int32_t *sel_idx = nullptr;
+    rtkv_row_stats *rs = nullptr, *h_rs = nullptr;
+    rtkv_layer_stats *ls = nullptr, *h_ls = nullptr;
+    void *scratch = nullptr;
+};
+
+static void ctx_free_buffers(rtkv_ctx *c)
+{
+    void *dev[] = {c->dK, c->dV, c->dKo, c->dVo, c->dA, c->mass, c->scores, c->labels, c->mask,
+                   c->sel_idx, c->rs, c->ls, c->scratch};
+    for (void *p : dev) if (p) cudaFree(p);
+    if (c->h_rs) cudaFreeHost(c->h_rs);
+    if (c->h_ls) cudaFreeHost(c->h_ls);
+}
+
+extern "C" int rtkv_ctx_create(rtkv_ctx **out)
+{
+    RTKV_CHECK_ARG(out, "rtkv_ctx_create: null pointer");
+    int rc = rtkv_device_info(nullptr, 0, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    rtkv_ctx *c = new rtkv_ctx();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_kv, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 256);
+    if (e == cudaSuccess) e = cudaMemset(c->scratch, 0, 256);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->ls, sizeof(rtkv_layer_stats));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_ls, sizeof(rtkv_layer_stats));
+    if (e != cudaSuccess) { rtkv_ctx_destroy(c); return cuda_fail(e, "rtkv_ctx_create"); }
+    *out = c;
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_ctx_destroy(rtkv_ctx *c)
+{
+    if (!c) return RTKV_OK;
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    ctx_free_buffers(c);
+    if (c->ev_kv) cudaEventDestroy(c->ev_kv);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    delete c;
+    return RTKV_OK;
+}
+
+template <class T> static cudaError_t regrow(T **p, size_t bytes)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, bytes);
+}
+
+static int ctx_reserve(rtkv_ctx *c, size_t kv_bytes, size_t a_bytes, int B, int S)
+{
+    if (kv_bytes > c->cap_kv) {
+        c->cap_kv = 0;
+        RTKV_CUDA(regrow(&c->dK, kv_bytes)); RTKV_CUDA(regrow(&c->dV, kv_bytes));
+        RTKV_CUDA(regrow(&c->dKo, kv_bytes)); RTKV_CUDA(regrow(&c->dVo, kv_bytes));
+        c->cap_kv = kv_bytes;
+    }
+    if (a_bytes > c->cap_a) {
+        c->cap_a = 0;
+        RTKV_CUDA(regrow(&c->dA, a_bytes));
+        c->cap_a = a_bytes;
+    }
+    const size_t bs = (size_t)B * S;
+    if (bs > c->cap_bs) {
+        c->cap_bs = 0;
+        RTKV_CUDA(regrow(&c->mass, bs * 4)); RTKV_CUDA(regrow(&c->scores, bs * 4));
+        RTKV_CUDA(regrow(&c->labels, bs)); RTKV_CUDA(regrow(&c->mask, bs));
+        RTKV_CUDA(regrow(&c->sel_idx, bs * 4));
+        c->cap_bs = bs;
+    }
+    if (B > c->cap_b) {
+        c->cap_b = 0;
+        RTKV_CUDA(regrow(&c->rs, (size_t)B * sizeof(rtkv_row_stats)));
+        if (c->h_rs) cudaFreeHost(c->h_rs);
+        c->h_rs = nullptr;
+        RTKV_CUDA(cudaMallocHost((void **)&c->h_rs, (size_t)B * sizeof(rtkv_row_stats)));
+        c->cap_b = B;
+    }
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *V, int dtype, int B, int S, int n,
+                                        const void *A, int a_dtype, int H, int64_t sb, int64_t sh, int64_t si,
+                                        const rtkv_layer_params *prm, void *K_out, void *V_out,
+                                        int32_t *max_selected, float *scores, uint8_t *labels, uint8_t *mask,
+                                        rtkv_row_stats *row_stats, rtkv_layer_stats *layer_stats)
+{
+    RTKV_CHECK_ARG(c && K && V && A && prm && K_out && V_out && max_selected, "rtkv_compress_layer_host: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype) && dtype_ok(a_dtype), "rtkv_compress_layer_host: bad dtype");
+    RTKV_CHECK_ARG(B > 0 && S > 0 && n > 0 && H > 0, "rtkv_compress_layer_host: bad shape");
+    const int P = prm->prompt_len;
+    RTKV_CHECK_ARG(P > 0, "rtkv_compress_layer_host: prompt_len must be positive");
+    const size_t es = dtype_bytes(dtype), ea = dtype_bytes(a_dtype);
+    const size_t kv_bytes = (size_t)B * S * n * es;
+    const size_t a_bytes = (size_t)B * H * S * P * ea;
+    int rc = ctx_reserve(c, kv_bytes, a_bytes, B, S);
+    if (rc) return rc;
+
+    // K, V on the copy stream; prompt columns of A (a strided 2-D copy) on the main stream
+    RTKV_CUDA(cudaMemcpyAsync(c->dK, K, kv_bytes, cudaMemcpyHostToDevice, c->s_copy));
+    RTKV_CUDA(cudaMemcpyAsync(c->dV, V, kv_bytes, cudaMemcpyHostToDevice, c->s_copy));
+    RTKV_CUDA(cudaEventRecord(c->ev_kv, c->s_copy));
+    if (sh == (int64_t)S * si && sb == (int64_t)H * sh) {
+        RTKV_CUDA(cudaMemcpy2DAsync(c->dA, P * ea, A, (size_t)si * ea, P * ea, (size_t)B * H * S,
+                                    cudaMemcpyHostToDevice, c->s_main));
+    } else {
+        for (int b = 0; b < B; ++b)
+            for (int h = 0; h < H; ++h)
+                RTKV_CUDA(cudaMemcpy2DAsync((char *)c->dA + ((size_t)b * H + h) * S * P * ea, P * ea,
+                                            (const char *)A + ((size_t)b * sb + (size_t)h * sh) * ea,
+                                            (size_t)si * ea, P * ea, (size_t)S, cudaMemcpyHostToDevice, c->s_main));
+    }
+    rc = rtkv_prompt_mass(c->dA, a_dtype, B, H, S, (int64_t)H * S * P, (int64_t)S * P, P, nullptr, P, c->mass, c->s_main);
+    if (rc) return rc;
+    rtkv_layer_params lp = *prm;
+    lp.score_dtype = a_dtype;
+    rc = rtkv_score_select(c->mass, c->scores, c->labels, c->mask, c->sel_idx, c->rs, c->ls, c->scratch, B, S, &lp,
+                           RTKV_FROM_MASS | RTKV_MAKE_LABELS | RTKV_SELECT | RTKV_FALLBACK, c->s_main);
+    if (rc) return rc;
+    RTKV_CUDA(cudaMemcpyAsync(c->h_ls, c->ls, sizeof(rtkv_layer_stats), cudaMemcpyDeviceToHost, c->s_main));
+    RTKV_CUDA(cudaMemcpyAsync(c->h_rs, c->rs, (size_t)B * sizeof(rtkv_row_stats), cudaMemcpyDeviceToHost, c->s_main));
+    RTKV_CUDA(cudaStreamSynchronize(c->s_main));          // the one data-dependent shape: S' = max_selected
+    const int ms = c->h_ls->max_selected;
+    *max_selected = ms;
+    if (layer_stats) *layer_stats = *c->h_ls;
+    if (row_stats) memcpy(row_stats, c->h_rs, (size_t)B * sizeof(rtkv_row_stats));
+
+    RTKV_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_kv, 0));
+    rc = rtkv_quant_gather(c->dK, c->dV, dtype, B, S, n, c->sel_idx, c->rs, c->labels, lp.bits, ms, 1,
+                           c->dKo, c->dVo, c->s_main);
+    if (rc) return rc;
+    const size_t out_bytes = (size_t)B * ms * n * es;
+    if (out_bytes) {
+        RTKV_CUDA(cudaMemcpyAsync(K_out, c->dKo, out_bytes, cudaMemcpyDeviceToHost, c->s_main));
+        RTKV_CUDA(cudaMemcpyAsync(V_out, c->dVo, out_bytes, cudaMemcpyDeviceToHost, c->s_main));
+    }
+    const size_t bs = (size_t)B * S;
+    if (scores) RTKV_CUDA(cudaMemcpyAsync(scores, c->scores, bs * 4, cudaMemcpyDeviceToHost, c->s_main));
+    if (labels) RTKV_CUDA(cudaMemcpyAsync(labels, c->labels, bs, cudaMemcpyDeviceToHost, c->s_main));
+    if (mask) RTKV_CUDA(cudaMemcpyAsync(mask, c->mask, bs, cudaMemcpyDeviceToHost, c->s_main));
+    RTKV_CUDA(cudaStreamSynchronize(c->s_main));
+    return RTKV_OK;
+}
+
+// Fused Q*K_prompt^T scoring (tcgen05): implemented in prompt_mass_qk.cu.

@@ -1,0 +1,204 @@
+// common.cuh — shared device helpers for librtkv (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtkv.h"
+
+namespace rtkv {
+
+// ---- error plumbing (host) -------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+#define RTKV_CHECK_ARG(cond, ...)                                   \
+    do {                                                            \
+        if (!(cond)) { rtkv::set_error(__VA_ARGS__); return RTKV_EINVAL; } \
+    } while (0)
+#define RTKV_CUDA(call)                                             \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return rtkv::cuda_fail(e__, #call); \
+    } while (0)
+#define RTKV_LAUNCH_CHECK(name)                                     \
+    do {                                                            \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return rtkv::cuda_fail(e__, name);  \
+    } while (0)
+
+// ---- element types: every arithmetic op rounds to the tensor dtype ---------
+// (the reference runs torch ops on the tensor dtype; torch computes half ops in
+//  fp32 and rounds the result, which is what rnd<> reproduces)
+template <int DT> struct Elem;
+template <> struct Elem<RTKV_F32> {
+    using T = float;
+    static constexpr int kBytes = 4;
+    __device__ __forceinline__ static float rnd(float x) { return x; }
+};
+template <> struct Elem<RTKV_F16> {
+    using T = __half;
+    static constexpr int kBytes = 2;
+    __device__ __forceinline__ static float rnd(float x) { return __half2float(__float2half_rn(x)); }
+};
+template <> struct Elem<RTKV_BF16> {
+    using T = __nv_bfloat16;
+    static constexpr int kBytes = 2;
+    __device__ __forceinline__ static float rnd(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+};
+
+__device__ __forceinline__ float rnd_dt(float x, int dt)
+{
+    if (dt == RTKV_F16) return Elem<RTKV_F16>::rnd(x);
+    if (dt == RTKV_BF16) return Elem<RTKV_BF16>::rnd(x);
+    return x;
+}
+
+__device__ __forceinline__ float half_bits_to_float(uint16_t b, int dt)
+{
+    if (dt == RTKV_BF16) return __uint_as_float((uint32_t)b << 16);
+    return __half2float(__ushort_as_half(b));
+}
+
+template <int DT> __device__ __forceinline__ float load_elem(const void *p, int64_t i)
+{
+    if constexpr (DT == RTKV_F32) return ((const float *)p)[i];
+    else if constexpr (DT == RTKV_F16) return __half2float(((const __half *)p)[i]);
+    else return __bfloat162float(((const __nv_bfloat16 *)p)[i]);
+}
+template <int DT> __device__ __forceinline__ void store_elem(void *p, int64_t i, float v)
+{
+    if constexpr (DT == RTKV_F32) ((float *)p)[i] = v;
+    else if constexpr (DT == RTKV_F16) ((__half *)p)[i] = __float2half_rn(v);
+    else ((__nv_bfloat16 *)p)[i] = __float2bfloat16_rn(v);
+}
+
+// 128-bit streaming accesses: the K/V rows and attention slices are touched once.
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// unpack a 16-byte vector into floats (4 for f32, 8 for half types) and back
+template <int DT> struct Vec16 {
+    static constexpr int kElems = 16 / Elem<DT>::kBytes;
+    __device__ __forceinline__ static void unpack(uint4 v, float *f)
+    {
+        if constexpr (DT == RTKV_F32) {
+            f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+            f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+        } else {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if constexpr (DT == RTKV_BF16) {
+                    f[2 * k] = __uint_as_float(w[k] << 16);
+                    f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+                } else {
+                    __half2 h = *reinterpret_cast<const __half2 *>(&w[k]);
+                    float2 t = __half22float2(h);
+                    f[2 * k] = t.x; f[2 * k + 1] = t.y;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ static uint4 pack(const float *f)
+    {
+        uint4 v;
+        if constexpr (DT == RTKV_F32) {
+            v.x = __float_as_uint(f[0]); v.y = __float_as_uint(f[1]);
+            v.z = __float_as_uint(f[2]); v.w = __float_as_uint(f[3]);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if constexpr (DT == RTKV_BF16) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                    w[k] = *reinterpret_cast<uint32_t *>(&h);
+                } else {
+                    __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+                    w[k] = *reinterpret_cast<uint32_t *>(&h);
+                }
+            }
+            v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+        }
+        return v;
+    }
+};
+
+// ---- warp / block reductions -------------------------------------------------
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- quantisation of one element (dynamic_quantization.py:116-126) ---------------
+// All operations are single IEEE roundings in the tensor dtype; the __f*_rn
+// intrinsics are never contracted into FMAs.
+template <int DT>
+__device__ __forceinline__ float quant_code(float x, float scale, float zp, float qmax_r)
+{
+    float t = Elem<DT>::rnd(__fdiv_rn(x, scale));
+    t = Elem<DT>::rnd(__fadd_rn(t, zp));
+    float q = rintf(t);                      // round half to even, like torch.round
+    if (q == q) q = fminf(fmaxf(q, 0.0f), qmax_r); // torch.clamp keeps NaN
+    return q;
+}
+template <int DT>
+__device__ __forceinline__ float dequant_code(float q, float scale, float zp)
+{
+    return Elem<DT>::rnd(__fmul_rn(Elem<DT>::rnd(__fsub_rn(q, zp)), scale));
+}
+// scale / zero-point from a row's min and max (dynamic_quantization.py:79-93)
+template <int DT>
+__device__ __forceinline__ void quant_params(float mn, float mx, int bits, float &scale, float &zp)
+{
+    if (mx == mn) { scale = 1.0f; zp = 0.0f; return; }
+    float qmax = (float)((1ll << bits) - 1);
+    scale = Elem<DT>::rnd(__fdiv_rn(Elem<DT>::rnd(__fsub_rn(mx, mn)), qmax));
+    zp = Elem<DT>::rnd(__fsub_rn(0.0f, Elem<DT>::rnd(__fdiv_rn(mn, scale))));
+}
+template <int DT> __device__ __forceinline__ float qmax_rounded(int bits)
+{
+    return Elem<DT>::rnd((float)((1ll << bits) - 1));
+}
+
+inline int dtype_bytes(int dt) { return dt == RTKV_F32 ? 4 : 2; }
+inline bool dtype_ok(int dt) { return dt == RTKV_F32 || dt == RTKV_F16 || dt == RTKV_BF16; }
+
+} // namespace rtkv

@@ -1,0 +1,456 @@
+// quant_gather.cu — K3: per-token asymmetric min/max fake-quantisation fused
+// with the compacting gather of the kept K/V rows.
+//
+// Reference semantics (paths relative to the reference repo):
+//   src/compression/dynamic_quantization.py:62-126   scale/zero-point, round, clamp, dequantise
+//   src/compression/dynamic_quantization.py:128-196  bits picked per token by its label
+//   src/compression/selective_propagation.py:213-232 kept rows, ascending index, zero padded
+// The reference quantises every token and then drops the unselected ones; here
+// only the kept rows are read (each exactly once) and written (exactly once).
+//
+// HBM-bound streaming kernel: 2 * rho * B*S * n elements in, the same out.
+// Fast path: one CTA of 256 threads per (output row, tensor); the row lives in
+// registers (up to kMaxVec 16-byte vectors per thread), so the min/max pass and
+// the quantise pass cost no extra memory traffic.  Loads/stores are 128-bit,
+// coalesced, streaming (L1::no_allocate).
+#include "common.cuh"
+
+namespace rtkv {
+
+constexpr int kQT = 256;     // threads per row CTA
+constexpr int kMaxVec = 8;   // 16-byte vectors per thread held in registers
+
+struct QGParams {
+    const void *x[2];
+    void *y[2];
+    const int32_t *sel_idx;
+    const rtkv_row_stats *row_stats;
+    const uint8_t *labels;
+    int B, S, n, out_rows, zero_pad, quantize;
+    int bits[3];
+};
+
+// no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
+__device__ __forceinline__ int pick_bits(const QGParams &p, int label)
+{
+    return label == 0 ? p.bits[0] : (label == 1 ? p.bits[1] : p.bits[2]);
+}
+__device__ __forceinline__ const void *pick_x(const QGParams &p, int t) { return t ? p.x[1] : p.x[0]; }
+__device__ __forceinline__ void *pick_y(const QGParams &p, int t) { return t ? p.y[1] : p.y[0]; }
+
+// block-wide min / max / any-NaN over kQT threads
+__device__ __forceinline__ void block_minmax(float &mn, float &mx, int nan, float *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { red[warp] = mn; red[8 + warp] = mx; }
+    const int any_nan = __syncthreads_or(nan);
+    float a = red[lane & 7], z = red[8 + (lane & 7)];
+#pragma unroll
+    for (int o = 4; o; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        z = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, o));
+    }
+    mn = a; mx = z;
+    if (any_nan) mn = mx = __int_as_float(0x7fc00000); // torch.min/max propagate NaN
+}
+
+// NV = 16-byte vectors per thread (n <= NV * kQT * elems_per_vec, n % elems_per_vec == 0)
+template <int DT, int NV>
+__global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
+    if (r >= cnt) {
+        if (p.zero_pad)
+            for (int v = threadIdx.x; v < nvec; v += kQT) stg_stream(dst + v, make_uint4(0, 0, 0, 0));
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint4 *src = (const uint4 *)((const char *)pick_x(p, t) + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+
+    uint4 raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+    if (!p.quantize) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            if (v < nvec) stg_stream(dst + v, raw[k]);
+        }
+        return;
+    }
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (threadIdx.x + k * kQT < nvec) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+        }
+    }
+    block_minmax(mn, mx, nan, red);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    float scale, zp;
+    quant_params<DT>(mn, mx, bits, scale, zp);
+    const float qmax_r = qmax_rounded<DT>(bits);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        if (v < nvec) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+            stg_stream(dst + v, Vec16<DT>::pack(f));
+        }
+    }
+}
+
+// Any n / alignment: scalar accesses, the row is read twice (second read hits L1/L2).
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
+{
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int64_t dst = ((int64_t)b * p.out_rows + r) * p.n;
+    if (r >= cnt) {
+        if (p.zero_pad)
+            for (int c = threadIdx.x; c < p.n; c += kQT) store_elem<DT>(pick_y(p, t), dst + c, 0.0f);
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int64_t src = ((int64_t)b * p.S + tok) * p.n;
+    if (!p.quantize) {
+        for (int c = threadIdx.x; c < p.n; c += kQT) store_elem<DT>(pick_y(p, t), dst + c, load_elem<DT>(pick_x(p, t), src + c));
+        return;
+    }
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        float v = load_elem<DT>(pick_x(p, t), src + c);
+        nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    block_minmax(mn, mx, nan, red);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    float scale, zp;
+    quant_params<DT>(mn, mx, bits, scale, zp);
+    const float qmax_r = qmax_rounded<DT>(bits);
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        float v = load_elem<DT>(pick_x(p, t), src + c);
+        store_elem<DT>(pick_y(p, t), dst + c, dequant_code<DT>(quant_code<DT>(v, scale, zp, qmax_r), scale, zp));
+    }
+}
+
+template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    dim3 grid(p.out_rows, p.B, ntensors);
+    bool vec = p.n % EPV == 0 && p.n <= kMaxVec * kQT * EPV;
+    for (int t = 0; t < ntensors; ++t)
+        vec = vec && ((uintptr_t)p.x[t] % 16 == 0) && ((uintptr_t)p.y[t] % 16 == 0);
+    if (vec) {
+        const int nv = (p.n / EPV + kQT - 1) / kQT;
+        if (nv <= 1) quant_gather_vec_kernel<DT, 1><<<grid, kQT, 0, st>>>(p);
+        else if (nv <= 2) quant_gather_vec_kernel<DT, 2><<<grid, kQT, 0, st>>>(p);
+        else if (nv <= 4) quant_gather_vec_kernel<DT, 4><<<grid, kQT, 0, st>>>(p);
+        else quant_gather_vec_kernel<DT, kMaxVec><<<grid, kQT, 0, st>>>(p);
+    } else {
+        quant_gather_generic_kernel<DT><<<grid, kQT, 0, st>>>(p);
+    }
+    RTKV_LAUNCH_CHECK("quant_gather_kernel");
+    return RTKV_OK;
+}
+
+// ---- whole-tensor parameters (component API: get_quantization_params / quantize_tensor) ----
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// scratch: [0] min (ordered uint), [1] max, [2] nan flag, [3] ticket
+template <int DT>
+__global__ void __launch_bounds__(kQT) tensor_minmax_kernel(const void *x, int64_t numel, int bits,
+                                                            unsigned *scratch, float *qparams)
+{
+    __shared__ float red[16];
+    __shared__ int last;
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kQT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * kQT) {
+        float v = load_elem<DT>(x, i);
+        nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    block_minmax(mn, mx, nan, red);
+    if (threadIdx.x == 0) {
+        if (mn != mn) atomicOr(&scratch[2], 1u);
+        else { atomicMin(&scratch[0], f2ord(mn)); atomicMax(&scratch[1], f2ord(mx)); }
+        __threadfence();
+        last = atomicAdd(&scratch[3], 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            float a = ord2f(((volatile unsigned *)scratch)[0]), z = ord2f(((volatile unsigned *)scratch)[1]);
+            if (((volatile unsigned *)scratch)[2]) a = z = __int_as_float(0x7fc00000);
+            float scale, zp;
+            quant_params<DT>(a, z, bits, scale, zp);
+            qparams[0] = scale; qparams[1] = zp;
+            scratch[0] = 0xffffffffu; scratch[1] = 0u; scratch[2] = 0u; scratch[3] = 0u;
+        }
+    }
+}
+__global__ void minmax_init_kernel(unsigned *scratch)
+{
+    scratch[0] = 0xffffffffu; scratch[1] = 0u; scratch[2] = 0u; scratch[3] = 0u;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kQT) quantize_with_params_kernel(const void *x, int64_t numel, int bits,
+                                                                   const float *qparams, void *y)
+{
+    const float scale = qparams[0], zp = qparams[1];
+    const float qmax_r = qmax_rounded<DT>(bits);
+    for (int64_t i = (int64_t)blockIdx.x * kQT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * kQT)
+        store_elem<DT>(y, i, dequant_code<DT>(quant_code<DT>(load_elem<DT>(x, i), scale, zp, qmax_r), scale, zp));
+}
+
+// ---- packed rows (project-defined layout, DESIGN.md "packed rows") ---------------------
+// One CTA per (row, batch).  bits in {1,2,4,8}: 8/bits codes per byte, first code in
+// the least significant bits; bits in 9..16: one little-endian uint16 per code.
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_pack_kernel(QGParams p, int64_t row_bytes, uint8_t *codes, float *qparams)
+{
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    uint8_t *dst = codes + ((size_t)b * p.out_rows + r) * (size_t)row_bytes;
+    float *qp = qparams + ((size_t)b * p.out_rows + r) * 2;
+    if (r >= cnt) {
+        if (p.zero_pad) {
+            for (int64_t c = threadIdx.x; c < row_bytes; c += kQT) dst[c] = 0;
+            if (threadIdx.x == 0) { qp[0] = 0.0f; qp[1] = 0.0f; }
+        }
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int64_t src = ((int64_t)b * p.S + tok) * p.n;
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        float v = load_elem<DT>(p.x[0], src + c);
+        nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    block_minmax(mn, mx, nan, red);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    float scale, zp;
+    quant_params<DT>(mn, mx, bits, scale, zp);
+    const float qmax_r = qmax_rounded<DT>(bits);
+    if (threadIdx.x == 0) { qp[0] = scale; qp[1] = zp; }
+    if (bits > 8) {
+        for (int c = threadIdx.x; c < p.n; c += kQT) {
+            float q = quant_code<DT>(load_elem<DT>(p.x[0], src + c), scale, zp, qmax_r);
+            ((uint16_t *)dst)[c] = (uint16_t)(q == q ? (unsigned)q : 0u);
+        }
+        for (int64_t c = 2 * (int64_t)p.n + threadIdx.x; c < row_bytes; c += kQT) dst[c] = 0;
+    } else {
+        const int per = 8 / bits;
+        const int nbytes = (p.n + per - 1) / per;
+        for (int by = threadIdx.x; by < nbytes; by += kQT) {
+            unsigned acc = 0;
+            for (int e = 0; e < per; ++e) {
+                const int c = by * per + e;
+                if (c < p.n) {
+                    float q = quant_code<DT>(load_elem<DT>(p.x[0], src + c), scale, zp, qmax_r);
+                    acc |= (q == q ? (unsigned)q : 0u) << (e * bits);
+                }
+            }
+            dst[by] = (uint8_t)acc;
+        }
+        for (int64_t c = nbytes + threadIdx.x; c < row_bytes; c += kQT) dst[c] = 0;
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kQT) unpack_dequant_kernel(QGParams p, int64_t row_bytes, const uint8_t *codes,
+                                                             const float *qparams)
+{
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int64_t dst = ((int64_t)b * p.out_rows + r) * p.n;
+    if (r >= cnt) {
+        if (p.zero_pad) for (int c = threadIdx.x; c < p.n; c += kQT) store_elem<DT>(p.y[0], dst + c, 0.0f);
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint8_t *src = codes + ((size_t)b * p.out_rows + r) * (size_t)row_bytes;
+    const float scale = qparams[((size_t)b * p.out_rows + r) * 2], zp = qparams[((size_t)b * p.out_rows + r) * 2 + 1];
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        unsigned q;
+        if (bits > 8) q = ((const uint16_t *)src)[c];
+        else { const int per = 8 / bits; q = (src[c / per] >> ((c % per) * bits)) & ((1u << bits) - 1u); }
+        store_elem<DT>(p.y[0], dst + c, dequant_code<DT>((float)q, scale, zp));
+    }
+}
+
+static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S, int n,
+                       const int32_t *sel_idx, const rtkv_row_stats *row_stats, const uint8_t *labels,
+                       const int32_t *bits, int out_rows, int zero_pad, void *Y0, void *Y1)
+{
+    p.x[0] = X0; p.x[1] = X1; p.y[0] = Y0; p.y[1] = Y1;
+    p.sel_idx = sel_idx; p.row_stats = row_stats; p.labels = labels;
+    p.B = B; p.S = S; p.n = n; p.out_rows = out_rows; p.zero_pad = zero_pad;
+    p.quantize = (labels != nullptr && bits != nullptr);
+    for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
+    return RTKV_OK;
+}
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+#define RTKV_DISPATCH(dt, CALL)                                 \
+    switch (dt) {                                               \
+    case RTKV_F32: { constexpr int DT = RTKV_F32; CALL; } break; \
+    case RTKV_F16: { constexpr int DT = RTKV_F16; CALL; } break; \
+    default: { constexpr int DT = RTKV_BF16; CALL; } break;      \
+    }
+
+static int check_bits(const int32_t *bits, int dtype, const char *who)
+{
+    if (!bits) return RTKV_OK;
+    for (int c = 0; c < 3; ++c) {
+        if (bits[c] < 1 || bits[c] > 24) { set_error("%s: bits[%d]=%d outside 1..24", who, c, bits[c]); return RTKV_EINVAL; }
+        // the reference raises here: torch.clamp(x, 0, 2^bits-1) overflows fp16 (dynamic_quantization.py:121)
+        if (dtype == RTKV_F16 && bits[c] >= 16) {
+            set_error("%s: value cannot be converted to type c10::Half without overflow (bits=%d)", who, bits[c]);
+            return RTKV_EUNSUPPORTED;
+        }
+    }
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                 const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                 const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                 void *Y0, void *Y1, void *stream)
+{
+    RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1), "rtkv_quant_gather: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather: bad dtype %d", dtype);
+    RTKV_CHECK_ARG(B > 0 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather: bad shape");
+    RTKV_CHECK_ARG(B <= 65535, "rtkv_quant_gather: B > 65535");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather: out_rows > S without sel_idx");
+    int rc = check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather");
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream));
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bits, float *qparams,
+                                 void *scratch, void *stream)
+{
+    RTKV_CHECK_ARG(x && qparams && scratch && numel > 0 && dtype_ok(dtype), "rtkv_quant_params: bad argument");
+    int32_t b3[3] = {bits, bits, bits};
+    int rc = check_bits(b3, dtype, "rtkv_quant_params");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned *sc = (unsigned *)scratch + 16; // past the score_select ticket
+    minmax_init_kernel<<<1, 1, 0, st>>>(sc);
+    int64_t ctas = (numel + kQT * 8 - 1) / (kQT * 8);
+    int grid = (int)(ctas < 148 * 8 ? ctas : 148 * 8);
+    RTKV_DISPATCH(dtype, (tensor_minmax_kernel<DT><<<grid, kQT, 0, st>>>(x, numel, bits, sc, qparams)));
+    RTKV_LAUNCH_CHECK("tensor_minmax_kernel");
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quantize_with_params(const void *x, int dtype, int64_t numel, int bits,
+                                         const float *qparams, void *y, void *stream)
+{
+    RTKV_CHECK_ARG(x && y && qparams && numel > 0 && dtype_ok(dtype), "rtkv_quantize_with_params: bad argument");
+    int32_t b3[3] = {bits, bits, bits};
+    int rc = check_bits(b3, dtype, "rtkv_quantize_with_params");
+    if (rc) return rc;
+    int64_t ctas = (numel + kQT * 4 - 1) / (kQT * 4);
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    RTKV_DISPATCH(dtype, (quantize_with_params_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(x, numel, bits, qparams, y)));
+    RTKV_LAUNCH_CHECK("quantize_with_params_kernel");
+    return RTKV_OK;
+}
+
+extern "C" int64_t rtkv_packed_row_bytes(int n, int bits)
+{
+    if (n <= 0 || bits < 1 || bits > 16) return -1;
+    int64_t raw = bits > 8 ? 2 * (int64_t)n : ((int64_t)n + (8 / bits) - 1) / (8 / bits);
+    return (raw + 15) / 16 * 16;
+}
+
+static int check_pack_bits(const int32_t *bits, const char *who)
+{
+    for (int c = 0; c < 3; ++c) {
+        int b = bits[c];
+        if (!(b == 1 || b == 2 || b == 4 || b == 8 || (b > 8 && b <= 16))) {
+            set_error("%s: packed rows need bits in {1,2,4,8,9..16}, got %d", who, b);
+            return RTKV_EUNSUPPORTED;
+        }
+    }
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_pack(const void *X, int dtype, int B, int S, int n,
+                               const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                               const uint8_t *labels, const int32_t *bits, int out_rows, int64_t row_bytes,
+                               uint8_t *codes, float *qparams, void *stream)
+{
+    RTKV_CHECK_ARG(X && labels && bits && codes && qparams, "rtkv_quant_pack: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_pack: bad shape");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_pack: sel_idx needs row_stats");
+    int rc = check_bits(bits, dtype, "rtkv_quant_pack");
+    if (!rc) rc = check_pack_bits(bits, "rtkv_quant_pack");
+    if (rc) return rc;
+    int mb = bits[0] > bits[1] ? bits[0] : bits[1]; mb = mb > bits[2] ? mb : bits[2];
+    RTKV_CHECK_ARG(row_bytes >= rtkv_packed_row_bytes(n, mb), "rtkv_quant_pack: row_bytes too small");
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X, nullptr, B, S, n, sel_idx, row_stats, labels, bits, out_rows, 1, nullptr, nullptr);
+    dim3 grid(out_rows, B);
+    RTKV_DISPATCH(dtype, (quant_pack_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, row_bytes, codes, qparams)));
+    RTKV_LAUNCH_CHECK("quant_pack_kernel");
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int dtype, int B, int S, int n,
+                                   const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                   const uint8_t *labels, const int32_t *bits, int out_rows, int64_t row_bytes,
+                                   void *Y, void *stream)
+{
+    RTKV_CHECK_ARG(codes && qparams && labels && bits && Y, "rtkv_unpack_dequant: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_unpack_dequant: bad shape");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_unpack_dequant: sel_idx needs row_stats");
+    int rc = check_pack_bits(bits, "rtkv_unpack_dequant");
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, nullptr, nullptr, B, S, n, sel_idx, row_stats, labels, bits, out_rows, 1, Y, nullptr);
+    dim3 grid(out_rows, B);
+    RTKV_DISPATCH(dtype, (unpack_dequant_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, row_bytes, codes, qparams)));
+    RTKV_LAUNCH_CHECK("unpack_dequant_kernel");
+    return RTKV_OK;
+}

@@ -1,0 +1,320 @@
+"""Tensor-level wrappers over the C ABI (include/rtkv.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every
+computation is a librtkv kernel.  All functions take CUDA tensors, enqueue on
+torch's current stream and do not synchronise unless their docstring says so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F16, BF16, FROM_MASS, MAKE_LABELS, SELECT, FALLBACK, LayerParams, check, lib
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+LAYER_STATS_BYTES = _lib.LAYER_STATS.itemsize
+ROW_STATS_BYTES = _lib.ROW_STATS.itemsize
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("rtkv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def dtype_code(t):
+    try:
+        return _DT[t.dtype if isinstance(t, torch.Tensor) else t]
+    except KeyError:
+        raise TypeError(f"rtkv supports float32/float16/bfloat16, got {t.dtype if isinstance(t, torch.Tensor) else t}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_scratch = {}
+
+
+def scratch(device):
+    """Zero-filled per-device scratch required by rtkv_score_select / rtkv_quant_params."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None:
+        n = ctypes.c_size_t()
+        check(lib.rtkv_scratch_bytes(1, 1, ctypes.byref(n)))
+        buf = torch.zeros(n.value, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def make_params(config, layer_idx, seq_len, prompt_len, ratio, score_dtype=F32):
+    """rtkv_layer_params from a CompressionConfig (configs/base_config.py)."""
+    p = LayerParams()
+    p.alpha, p.beta, p.gamma = float(config.alpha), float(config.beta), float(config.gamma)
+    p.layer_weight = float(config.layer_weights[layer_idx])
+    p.theta_h, p.theta_m = float(config.theta_h), float(config.theta_m)
+    p.budget = seq_len * ratio                      # selective_propagation.py:96
+    p.bits[0], p.bits[1], p.bits[2] = (int(config.low_precision_bits), int(config.medium_precision_bits),
+                                       int(config.high_precision_bits))
+    p.prompt_len = int(prompt_len)
+    p.score_dtype = int(score_dtype)
+    p.fallback_topk = max(1, int(seq_len * 0.1))    # selective_propagation.py:207
+    return p
+
+
+def prompt_mass(attn, prompt_len=None, prompt_indices=None):
+    """mass[b,i] = sum_p mean_h attn[b,h,i,idx[p]] -> float32 [B,S] (token_importance.py:41-45)."""
+    require_cuda()
+    assert attn.is_cuda and attn.dim() == 4
+    if attn.stride(-1) != 1:
+        attn = attn.contiguous()
+    B, H, S, W = attn.shape
+    idx = None
+    if prompt_indices is not None:
+        P = int(prompt_indices.numel())
+        ar = torch.arange(P, device=prompt_indices.device, dtype=prompt_indices.dtype)
+        if not (P <= W and bool(torch.equal(prompt_indices.reshape(-1), ar))):
+            idx = prompt_indices.reshape(-1).to(device=attn.device, dtype=torch.int64).contiguous()
+            if P and (int(idx.min()) < -W or int(idx.max()) >= W):
+                raise IndexError("prompt index out of range")
+            idx = torch.where(idx < 0, idx + W, idx)
+    else:
+        P = int(prompt_len)
+        if P > W:
+            raise IndexError(f"prompt_len {P} exceeds attention width {W}")
+    mass = torch.empty(B, S, dtype=torch.float32, device=attn.device)
+    if P == 0:
+        return mass.zero_()
+    check(lib.rtkv_prompt_mass(_ptr(attn), dtype_code(attn), B, H, S, attn.stride(0), attn.stride(1),
+                               attn.stride(2), _ptr(idx), P, _ptr(mass), _stream()))
+    return mass
+
+
+def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
+    """Fused Q.K_prompt^T scoring: q [B,H,S,D], k_prompt [B,H,P,D], lse [B,H,S] -> mass [B,S]."""
+    require_cuda()
+    q, k_prompt, lse = q.contiguous(), k_prompt.contiguous(), lse.contiguous().float()
+    B, H, S, D = q.shape
+    P = k_prompt.shape[2]
+    mass = torch.empty(B, S, dtype=torch.float32, device=q.device)
+    check(lib.rtkv_prompt_mass_qk(_ptr(q), _ptr(k_prompt), _ptr(lse), dtype_code(q), B, H, S, D, P,
+                                  float(scale), int(bool(causal)), _ptr(mass), _stream()))
+    return mass
+
+
+def position_bias(seq_len, device):
+    require_cuda()
+    pb = torch.empty(seq_len, dtype=torch.float32, device=device)
+    check(lib.rtkv_position_bias(int(seq_len), _ptr(pb), _stream()))
+    return pb
+
+
+def normalize_mass(mass, dt=F32):
+    require_cuda()
+    mass = mass.contiguous()
+    out = torch.empty_like(mass)
+    B, S = mass.shape
+    check(lib.rtkv_normalize_mass(_ptr(mass), int(dt), B, S, _ptr(out), _stream()))
+    return out
+
+
+class Selection:
+    """Device-side result of rtkv_score_select."""
+    __slots__ = ("scores", "labels", "mask", "sel_idx", "stats", "B", "S")
+
+    def __init__(self, scores, labels, mask, sel_idx, stats, B, S):
+        self.scores, self.labels, self.mask, self.sel_idx, self.stats = scores, labels, mask, sel_idx, stats
+        self.B, self.S = B, S
+
+    @property
+    def row_stats_ptr(self):
+        return ctypes.c_void_p(self.stats.data_ptr() + LAYER_STATS_BYTES)
+
+    def read_stats(self, pinned=None):
+        """D2H of the statistics block + synchronise.  Returns (layer record, row records)."""
+        host = pinned if pinned is not None else torch.empty(self.stats.numel(), dtype=torch.uint8, pin_memory=True)
+        host = host[: self.stats.numel()]
+        host.copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = host.numpy()
+        layer = raw[:LAYER_STATS_BYTES].view(_lib.LAYER_STATS)[0]
+        rows = raw[LAYER_STATS_BYTES:].view(_lib.ROW_STATS)
+        return layer.copy(), rows.copy()
+
+
+def score_select(params, B, S, device, mass=None, scores=None, labels=None, select=True, fallback=True):
+    """Scores -> labels -> budgeted selection (one launch).
+
+    mass given: scores are computed (token_importance.py:134-176); else `scores` is used.
+    labels None: labels are computed from the scores (dynamic_quantization.py:38-45)."""
+    require_cuda()
+    flags = 0
+    if mass is not None:
+        flags |= FROM_MASS
+        mass = mass.contiguous()
+        scores = torch.empty(B, S, dtype=torch.float32, device=device)
+    else:
+        scores = scores.to(torch.float32).contiguous()
+    if labels is None:
+        flags |= MAKE_LABELS
+        labels = torch.empty(B, S, dtype=torch.uint8, device=device)
+    else:
+        labels = labels.to(torch.uint8).contiguous()
+    mask = sel_idx = None
+    if select:
+        flags |= SELECT
+        if fallback:
+            flags |= FALLBACK
+        mask = torch.empty(B, S, dtype=torch.uint8, device=device)
+        sel_idx = torch.empty(B, S, dtype=torch.int32, device=device)
+    stats = torch.empty(LAYER_STATS_BYTES + ROW_STATS_BYTES * B, dtype=torch.uint8, device=device)
+    check(lib.rtkv_score_select(_ptr(mass), _ptr(scores), _ptr(labels), _ptr(mask), _ptr(sel_idx),
+                                ctypes.c_void_p(stats.data_ptr() + LAYER_STATS_BYTES), _ptr(stats),
+                                _ptr(scratch(device)), B, S, ctypes.byref(params), flags, _stream()))
+    return Selection(scores, labels, mask, sel_idx, stats, B, S)
+
+
+def quant_gather(x0, x1, sel, labels, bits, out_rows, zero_pad=True, out0=None, out1=None):
+    """Fake-quantise (bits given) or copy (bits None) the kept rows of x0/x1 [B,S,n] into
+    [B,out_rows,n].  sel: Selection or None (identity: all rows, out_rows <= S)."""
+    require_cuda()
+    x0 = x0.contiguous()
+    B, S, n = x0.shape
+    if x1 is not None:
+        x1 = x1.contiguous()
+        assert x1.shape == x0.shape and x1.dtype == x0.dtype
+    y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = None
+    if x1 is not None:
+        y1 = out1 if out1 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    lab = labels.to(torch.uint8).contiguous() if (labels is not None and bits is not None) else None
+    check(lib.rtkv_quant_gather(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,
+                                _ptr(sel.sel_idx) if sel is not None else None,
+                                sel.row_stats_ptr if sel is not None else None,
+                                _ptr(lab), _lib.bits3(bits) if lab is not None else None,
+                                int(out_rows), int(bool(zero_pad)), _ptr(y0), _ptr(y1), _stream()))
+    return y0, y1
+
+
+def quant_params(x, bits):
+    """Whole-tensor (scale, zero_point) as a float32 [2] device tensor (dynamic_quantization.py:62-95)."""
+    require_cuda()
+    x = x.contiguous()
+    qp = torch.empty(2, dtype=torch.float32, device=x.device)
+    check(lib.rtkv_quant_params(_ptr(x), dtype_code(x), x.numel(), int(bits), _ptr(qp), _ptr(scratch(x.device)), _stream()))
+    return qp
+
+
+def quantize_with_params(x, bits, qp):
+    require_cuda()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.rtkv_quantize_with_params(_ptr(x), dtype_code(x), x.numel(), int(bits), _ptr(qp), _ptr(y), _stream()))
+    return y
+
+
+def gather_scalars(sel, out_rows):
+    """selected_scores [B,out_rows] f32, selected_labels [B,out_rows] i64 (zero padded)."""
+    require_cuda()
+    dev = sel.scores.device
+    ss = torch.empty(sel.B, out_rows, dtype=torch.float32, device=dev)
+    sl = torch.empty(sel.B, out_rows, dtype=torch.int64, device=dev)
+    check(lib.rtkv_gather_scalars(_ptr(sel.scores), _ptr(sel.labels), _ptr(sel.sel_idx), sel.row_stats_ptr,
+                                  sel.B, sel.S, int(out_rows), _ptr(ss), _ptr(sl), _stream()))
+    return ss, sl
+
+
+def labels_to_i64(labels):
+    require_cuda()
+    labels = labels.contiguous()
+    out = torch.empty(labels.shape, dtype=torch.int64, device=labels.device)
+    check(lib.rtkv_labels_to_i64(_ptr(labels), labels.numel(), _ptr(out), _stream()))
+    return out
+
+
+def packed_row_bytes(n, bits):
+    v = lib.rtkv_packed_row_bytes(int(n), int(bits))
+    if v < 0:
+        raise ValueError(f"packed rows need n > 0 and bits in 1..16 (n={n}, bits={bits})")
+    return int(v)
+
+
+def quant_pack(x, sel, labels, bits, out_rows):
+    """Packed integer codes [B,out_rows,row_bytes] u8 + (scale, zero_point) [B,out_rows,2] f32."""
+    require_cuda()
+    x = x.contiguous()
+    B, S, n = x.shape
+    rb = packed_row_bytes(n, max(bits))
+    codes = torch.empty(B, out_rows, rb, dtype=torch.uint8, device=x.device)
+    qp = torch.empty(B, out_rows, 2, dtype=torch.float32, device=x.device)
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_quant_pack(_ptr(x), dtype_code(x), B, S, n, _ptr(sel.sel_idx) if sel is not None else None,
+                              sel.row_stats_ptr if sel is not None else None, _ptr(lab), _lib.bits3(bits),
+                              int(out_rows), rb, _ptr(codes), _ptr(qp), _stream()))
+    return codes, qp
+
+
+def unpack_dequant(codes, qp, dtype, S, n, sel, labels, bits):
+    require_cuda()
+    B, out_rows, rb = codes.shape
+    y = torch.empty(B, out_rows, n, dtype=dtype, device=codes.device)
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_unpack_dequant(_ptr(codes), _ptr(qp), dtype_code(dtype), B, S, n,
+                                  _ptr(sel.sel_idx) if sel is not None else None,
+                                  sel.row_stats_ptr if sel is not None else None, _ptr(lab), _lib.bits3(bits),
+                                  int(out_rows), rb, _ptr(y), _stream()))
+    return y
+
+
+class HostContext:
+    """rtkv_ctx: device staging buffers for the host-buffer entry point."""
+
+    def __init__(self):
+        require_cuda()
+        self._h = ctypes.c_void_p()
+        check(lib.rtkv_ctx_create(ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.rtkv_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress_layer(self, K, V, attn, params, k_out=None, v_out=None, want_aux=True):
+        """One layer on HOST tensors (synchronous).  Returns dict with k, v ([B,S',n] views of the
+        output buffers), max_selected, scores/labels/mask (host) and the statistics records."""
+        assert not K.is_cuda and not V.is_cuda and not attn.is_cuda
+        K, V = K.contiguous(), V.contiguous()
+        if attn.stride(-1) != 1:
+            attn = attn.contiguous()
+        B, S, n = K.shape
+        H = attn.shape[1]
+        if k_out is None:
+            k_out = torch.empty(B * S * n, dtype=K.dtype)
+        if v_out is None:
+            v_out = torch.empty(B * S * n, dtype=K.dtype)
+        scores = torch.empty(B, S, dtype=torch.float32) if want_aux else None
+        labels = torch.empty(B, S, dtype=torch.uint8) if want_aux else None
+        mask = torch.empty(B, S, dtype=torch.uint8) if want_aux else None
+        rows = np.zeros(B, dtype=_lib.ROW_STATS)
+        layer = _lib.LayerStats()
+        ms = ctypes.c_int32(0)
+        check(lib.rtkv_compress_layer_host(
+            self._h, _ptr(K), _ptr(V), dtype_code(K), B, S, n, _ptr(attn), dtype_code(attn), H,
+            attn.stride(0), attn.stride(1), attn.stride(2), ctypes.byref(params), _ptr(k_out), _ptr(v_out),
+            ctypes.byref(ms), _ptr(scores), _ptr(labels), _ptr(mask),
+            ctypes.c_void_p(rows.ctypes.data), ctypes.byref(layer)))
+        m = int(ms.value)
+        return dict(k=k_out.view(-1)[: B * m * n].view(B, m, n), v=v_out.view(-1)[: B * m * n].view(B, m, n),
+                    max_selected=m, scores=scores, labels=labels, mask=mask, rows=rows,
+                    used_fallback=int(layer.used_fallback))

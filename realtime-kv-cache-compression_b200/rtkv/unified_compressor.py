@@ -1,0 +1,266 @@
+"""RealTimePrefillCompressor — drop-in for src/compression/unified_compressor.py.
+
+compress_layer_kv_cache(K, V, attention, input_ids, layer_idx) runs three kernels on
+the caller's CUDA stream:
+    K1  prompt_mass      attention -> per-token prompt mass
+    K2  score_select     mass -> scores, labels, budgeted selection, statistics
+    K3  quant_gather     kept K/V rows -> fake-quantised, compacted [B,S',HD]
+with ONE host synchronisation in between (S' = max_selected is a tensor shape).
+Host tensors go through the C-ABI host entry (rtkv_compress_layer_host) and
+come back as host tensors.  There is no CPU path.
+"""
+import math
+import os
+import time
+
+import numpy as np
+import psutil
+import torch
+
+from . import ops
+from .dynamic_quantization import DynamicPrecisionQuantizer
+from .selective_propagation import SelectiveTokenPropagator, selection_info_from_rows
+from .token_importance import LayerWiseImportanceTracker
+
+
+def _importance_stats(rows, n_tokens):
+    """mean / unbiased std / min / max over all B*S scores (unified_compressor.py:158-163)."""
+    s = float(rows["score_sum"].sum())
+    ss = float(rows["score_sumsq"].sum())
+    mean = s / n_tokens
+    if n_tokens > 1:
+        var = max(0.0, (ss - s * s / n_tokens) / (n_tokens - 1))
+        std = math.sqrt(var)
+    else:
+        std = float("nan")
+    mins, maxs = rows["score_min"], rows["score_max"]
+    mn = float("nan") if np.isnan(mins).any() else float(mins.min())
+    mx = float("nan") if np.isnan(maxs).any() else float(maxs.max())
+    return {"mean_score": mean, "std_score": std, "min_score": mn, "max_score": mx}
+
+
+def _precision_stats(rows, n_tokens):
+    cnt = rows["label_count"].sum(axis=0)
+    high, medium = int(cnt[2]), int(cnt[1])
+    low = n_tokens - high - medium
+    return {"high_count": high, "medium_count": medium, "low_count": low,
+            "high_ratio": high / n_tokens, "medium_ratio": medium / n_tokens, "low_ratio": low / n_tokens}
+
+
+class RealTimePrefillCompressor:
+    """reference: unified_compressor.py:12-247"""
+
+    def __init__(self, config, model_config=None):
+        self.config = config
+        self.model_config = model_config
+        self.importance_tracker = LayerWiseImportanceTracker(config)
+        self.quantizer = DynamicPrecisionQuantizer(config)
+        self.propagator = SelectiveTokenPropagator(config)
+        self.compression_stats = {}
+        self.layer_states = {}
+        self._host_ctx = None
+        self._pinned = None
+
+    # -- prompt span ---------------------------------------------------------------
+    def identify_prompt_tokens(self, input_ids, special_tokens=None):
+        """first max(1, min(S//5, 128)) positions (:35-58)."""
+        seq_len = input_ids.shape[1]
+        return torch.arange(self.prompt_length(seq_len), device=input_ids.device)
+
+    @staticmethod
+    def prompt_length(seq_len):
+        return max(1, min(seq_len // 5, 128))
+
+    def extract_attention_weights(self, attention_output, layer_idx):
+        """The reference's placeholder fabricates random attention when none is attached
+        (:60-93, and its fallback line is broken); here the caller must provide it."""
+        if hasattr(attention_output, "attentions"):
+            return attention_output.attentions
+        raise ValueError("attention weights are not available on this output; run the model with "
+                         "output_attentions=True or pass them to compress_layer_kv_cache")
+
+    # -- parameters ------------------------------------------------------------------
+    def layer_params(self, layer_idx, seq_len, score_dtype=ops.F32):
+        ratio = self.propagator.get_layer_propagation_ratio(layer_idx)
+        return ops.make_params(self.config, layer_idx, seq_len, self.prompt_length(seq_len), ratio,
+                               score_dtype), ratio
+
+    def _bits(self):
+        c = self.config
+        return (c.low_precision_bits, c.medium_precision_bits, c.high_precision_bits)
+
+    def _stats_buffer(self, nbytes):
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            self._pinned = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, pin_memory=True)
+        return self._pinned
+
+    # -- the hot path ------------------------------------------------------------------
+    def compress_layer_kv_cache(self, key_states, value_states, attention_weights, input_ids, layer_idx,
+                                out_keys=None, out_values=None):
+        """(:95-172)  key/value [B,S,HD]; attention [B,H,S,>=P]; returns (K', V', info).
+        out_keys/out_values (extension, host tensors only): flat buffers of B*S*HD elements the
+        result is written into (e.g. pinned memory); the returned tensors are views of them."""
+        start_time = time.time()
+        B, S, HD = key_states.shape
+        if value_states.shape != key_states.shape or value_states.dtype != key_states.dtype:
+            raise ValueError("key_states and value_states must have the same shape and dtype")
+        if attention_weights.dim() != 4 or attention_weights.shape[0] != B or attention_weights.shape[2] != S:
+            raise ValueError("attention_weights must be [batch, heads, seq_len, keys]")
+        P = self.prompt_length(input_ids.shape[1])
+        if P > attention_weights.shape[-1]:
+            raise IndexError(f"prompt length {P} exceeds the attention width {attention_weights.shape[-1]}")
+        params, ratio = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
+        params.prompt_len = P
+        n_tokens = B * S
+
+        if key_states.is_cuda:
+            if not (value_states.is_cuda and attention_weights.is_cuda):
+                raise ValueError("key, value and attention tensors must live on the same device")
+            dev = key_states.device
+            mass = ops.prompt_mass(attention_weights, prompt_len=P)
+            sel = ops.score_select(params, B, S, dev, mass=mass)
+            # one readback (statistics + scores + labels) and one synchronisation: S' is a shape
+            nstat = sel.stats.numel()
+            off = (nstat + 3) // 4 * 4
+            host = self._stats_buffer(off + 5 * n_tokens)
+            h_stat = host[:nstat]
+            h_scores = host[off: off + 4 * n_tokens].view(torch.float32).view(B, S)
+            h_labels = host[off + 4 * n_tokens: off + 5 * n_tokens].view(B, S)
+            h_stat.copy_(sel.stats, non_blocking=True)
+            h_scores.copy_(sel.scores, non_blocking=True)
+            h_labels.copy_(sel.labels, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            raw = h_stat.numpy()
+            layer = raw[: ops.LAYER_STATS_BYTES].view(ops._lib.LAYER_STATS)[0]
+            rows = raw[ops.LAYER_STATS_BYTES:].view(ops._lib.ROW_STATS).copy()
+            max_selected = int(layer["max_selected"])
+            selected_keys, selected_values = ops.quant_gather(
+                key_states, value_states, sel, sel.labels, self._bits(), max_selected)
+            scores_cpu = h_scores.clone()
+            labels_np = h_labels.numpy().astype(np.int64)
+            selection_mask = sel.mask.view(torch.bool)
+        else:
+            if self._host_ctx is None:
+                self._host_ctx = ops.HostContext()
+            out = self._host_ctx.compress_layer(key_states, value_states, attention_weights, params,
+                                                k_out=out_keys, v_out=out_values)
+            rows = out["rows"]
+            max_selected = out["max_selected"]
+            selected_keys, selected_values = out["k"], out["v"]
+            scores_cpu = out["scores"]
+            labels_np = out["labels"].numpy().astype(np.int64)
+            selection_mask = out["mask"].view(torch.bool)
+
+        self.importance_tracker.layer_scores[layer_idx] = scores_cpu       # token_importance.py:198
+        precision_stats = _precision_stats(rows, n_tokens)
+        quant_info = {"scales": {}, "zero_points": {}, "bit_assignments": labels_np}
+        propagation_info = {
+            "layer_idx": layer_idx, "propagation_ratio": ratio, "original_length": S,
+            "max_selected_length": max_selected, "selection_mask": selection_mask,
+            "selection_stats": selection_info_from_rows(rows, S * ratio)}
+
+        original_memory = key_states.numel() + value_states.numel()
+        compressed_memory = selected_keys.numel() + selected_values.numel()
+        compression_ratio = compressed_memory / original_memory if original_memory > 0 else 0
+        processing_time = time.time() - start_time
+        compression_info = {
+            "layer_idx": layer_idx,
+            "processing_time": processing_time,
+            "original_shape": key_states.shape,
+            "compressed_shape": selected_keys.shape,
+            "compression_ratio": compression_ratio,
+            "memory_savings": 1.0 - compression_ratio,
+            "importance_stats": _importance_stats(rows, n_tokens),
+            "precision_stats": precision_stats,
+            "quantization_info": quant_info,
+            "propagation_info": propagation_info,
+        }
+        self.layer_states[layer_idx] = compression_info
+        return selected_keys, selected_values, compression_info
+
+    # BASELINE.json wording
+    compress = compress_layer_kv_cache
+
+    def compress_layer_kv_cache_async(self, key_states, value_states, attention_weights, layer_idx,
+                                      out_keys, out_values, zero_pad=False):
+        """Fixed-capacity, synchronisation-free variant for pipelined prefill and CUDA graphs.
+
+        out_keys/out_values: preallocated [B,S,HD]; rows [0, n_selected[b]) of batch row b hold the
+        kept tokens, the rest is untouched (or zeroed with zero_pad).  Returns the device-side
+        Selection (scores, labels, mask, sel_idx, statistics); nothing is read back."""
+        B, S, HD = key_states.shape
+        P = self.prompt_length(S)
+        params, _ = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
+        mass = ops.prompt_mass(attention_weights, prompt_len=P)
+        sel = ops.score_select(params, B, S, key_states.device, mass=mass)
+        ops.quant_gather(key_states, value_states, sel, sel.labels, self._bits(), S, zero_pad=zero_pad,
+                         out0=out_keys, out1=out_values)
+        return sel
+
+    # -- aggregation (:174-230) ----------------------------------------------------------
+    def get_overall_compression_stats(self):
+        if not self.layer_states:
+            return {}
+        states = list(self.layer_states.values())
+        n = len(states)
+        total_time = sum(s["processing_time"] for s in states)
+        high = sum(s["precision_stats"]["high_count"] for s in states)
+        medium = sum(s["precision_stats"]["medium_count"] for s in states)
+        low = sum(s["precision_stats"]["low_count"] for s in states)
+        tokens = high + medium + low
+        ordered = sorted(states, key=lambda s: s["layer_idx"])
+        cumulative = 1.0
+        first_len = ordered[0]["original_shape"][1]
+        if first_len > 0:
+            cumulative = ordered[-1]["compressed_shape"][1] / first_len
+        return {
+            "total_layers_processed": n,
+            "total_processing_time": total_time,
+            "avg_processing_time_per_layer": total_time / n,
+            "avg_compression_ratio": sum(s["compression_ratio"] for s in states) / n,
+            "avg_memory_savings": sum(s["memory_savings"] for s in states) / n,
+            "cumulative_compression": cumulative,
+            "overall_memory_savings": 1.0 - cumulative,
+            "precision_distribution": {
+                "high_ratio": high / tokens if tokens > 0 else 0,
+                "medium_ratio": medium / tokens if tokens > 0 else 0,
+                "low_ratio": low / tokens if tokens > 0 else 0},
+        }
+
+    def reset_compression_state(self):
+        """(:232-235)"""
+        self.layer_states = {}
+        self.importance_tracker.layer_scores = {}
+
+    def estimate_memory_usage(self):
+        """(:237-247)"""
+        mem = psutil.Process(os.getpid()).memory_info()
+        cuda = torch.cuda.is_available()
+        return {"rss_mb": mem.rss / (1024 * 1024), "vms_mb": mem.vms / (1024 * 1024),
+                "gpu_memory_mb": torch.cuda.memory_allocated() / (1024 * 1024) if cuda else 0,
+                "gpu_memory_cached_mb": torch.cuda.memory_reserved() / (1024 * 1024) if cuda else 0}
+
+
+UnifiedCompressor = RealTimePrefillCompressor
+
+
+class CompressionHook:
+    """Forward-hook registrar kept for API compatibility (reference :250-286 is a print-only
+    stub).  The real integration is rtkv.llama_hooks.set_compressor."""
+
+    def __init__(self, compressor):
+        self.compressor = compressor
+        self.hooks = []
+
+    def register_hooks(self, model):
+        for layer_idx, layer in enumerate(model.model.layers):
+            self.hooks.append(layer.register_forward_hook(
+                lambda module, inputs, output, l=layer_idx: self._compression_hook(module, inputs, output, l)))
+
+    def _compression_hook(self, module, inputs, output, layer_idx):
+        return output
+
+    def remove_hooks(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []

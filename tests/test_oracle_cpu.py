@@ -1,0 +1,102 @@
+"""CPU: the oracle (oracle/rtkv_oracle.c) against the golden fixtures that the real
+reference produced (oracle/pin_against_reference.py)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import LAYER_CASES, STAGE_CASES, load_golden
+
+
+def ulp(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_matches_reference(name):
+    g = load_golden(name)
+    m = g["meta"]
+    o = oracle.compress_layer(g["K"], g["V"], m["dt"], g["A"], m["dt"], m["P"], m["alpha"], m["beta"],
+                              m["gamma"], m["layer_weight"], m["theta_h"], m["theta_m"], m["bits"], m["ratio"])
+    # prompt-mass reduction order is ATen's in the reference: a few ulp
+    assert ulp(o["scores"], g["scores"]).max() <= 8
+    np.testing.assert_array_equal(o["labels"], g["labels"])
+    np.testing.assert_array_equal(o["mask"], g["mask"])          # bit-exact retained index set
+    assert o["max_sel"] == m["compressed_shape"][1]
+    np.testing.assert_array_equal(o["k_sel"], g["k_sel"])        # bit-exact fake-quant values
+    np.testing.assert_array_equal(o["v_sel"], g["v_sel"])
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_stages_exact_given_reference_scores(name):
+    g = load_golden(name)
+    m = g["meta"]
+    labels, counts = oracle.assign_precision(g["scores"], m["theta_h"], m["theta_m"])
+    np.testing.assert_array_equal(labels, g["labels"])
+    ps = m["precision_stats"]
+    assert [int(counts[0]), int(counts[1]), int(counts[2])] == [ps["low_count"], ps["medium_count"], ps["high_count"]]
+    mask, cnt, cost, ssum, cc = oracle.select_tokens(g["scores"], labels, m["bits"], m["S"] * m["ratio"])
+    if m["name"].endswith("fallback"):
+        assert cnt.max() == 0
+        k = max(1, int(m["S"] * 0.1))
+        np.testing.assert_array_equal(oracle.topk_mask(g["scores"], k), g["mask"])
+    else:
+        np.testing.assert_array_equal(mask, g["mask"])
+        assert list(cnt[cnt > 0]) == m["selected_counts"]
+        np.testing.assert_allclose(cost[cnt > 0] / (m["S"] * m["ratio"]), m["budget_utilization"], rtol=1e-12)
+        np.testing.assert_allclose(ssum[cnt > 0] / cnt[cnt > 0], m["avg_importance"], rtol=1e-5)
+        cd = m["cost_distribution"]
+        assert [int(cc[:, 0].sum()), int(cc[:, 1].sum()), int(cc[:, 2].sum())] == [cd["low"], cd["medium"], cd["high"]]
+
+
+@pytest.mark.parametrize("name", STAGE_CASES)
+def test_stage_fixtures(name):
+    g = load_golden(name)
+    m = g["meta"]
+    labels, _ = oracle.assign_precision(g["scores"], m["theta_h"], m["theta_m"])
+    np.testing.assert_array_equal(labels, g["labels"])
+    kq, _, _ = oracle.fake_quant_rows(g["K"], m["dt"], labels, m["bits"])
+    vq, _, _ = oracle.fake_quant_rows(g["V"], m["dt"], labels, m["bits"])
+    np.testing.assert_array_equal(kq, g["k_quant"])
+    np.testing.assert_array_equal(vq, g["v_quant"])
+    budget = m["S"] * m["ratio"]
+    for lab, want in ((labels, g["mask_mono"]), (g["rand_labels"], g["mask_rand"])):
+        mask, cnt, _, _, _ = oracle.select_tokens(g["scores"], lab, m["bits"], budget)
+        np.testing.assert_array_equal(mask, want)
+    mask, cnt, _, _, _ = oracle.select_tokens(g["scores"], g["rand_labels"], m["bits"], budget)
+    ms = int(cnt.max())
+    np.testing.assert_array_equal(oracle.gather_rows(g["K"], m["dt"], mask, ms), g["k_sel"])
+    np.testing.assert_array_equal(oracle.gather_rows(g["V"], m["dt"], mask, ms), g["v_sel"])
+
+
+def test_constant_row_quirk():
+    """scale=1, zp=0 when max==min: a row of -2.0 dequantises to 0.0 (dynamic_quantization.py:83-86)."""
+    x = np.full((1, 1, 16), -2.0, np.float32)
+    out, codes, qp = oracle.fake_quant_rows(x, oracle.F32, np.zeros((1, 1), np.uint8), (2, 4, 8), True, True)
+    assert (out == 0).all() and qp[0, 0] == 1.0 and qp[0, 1] == 0.0
+    x[:] = 2.5   # rint half-to-even: 2.5 -> 2
+    out, _, _ = oracle.fake_quant_rows(x, oracle.F32, np.full((1, 1), 2, np.uint8), (2, 4, 8))
+    assert (out == 2.0).all()
+
+
+def test_budget_is_double_arithmetic():
+    """4096*0.8 = 3276.8: all-MID 4-bit tokens (cost 0.5) -> 6553 fit; 8-bit (1.0) -> 3276 (+ cheaper ones)."""
+    S = 4096
+    scores = np.linspace(1, 0, S, dtype=np.float32)[None]
+    lab = np.ones((1, S), np.uint8)
+    lab[0, -10:] = 0
+    mask, cnt, cost, _, cc = oracle.select_tokens(scores, lab, (2, 8, 8), S * 0.8)
+    assert cc[0, 1] == 3276 and cc[0, 0] == 3 and cost[0] == 3276.75   # 3 LOW tokens (0.25 each) still fit
+
+
+def test_ties_lowest_index_first():
+    scores = np.zeros((1, 40), np.float32)
+    lab = np.full((1, 40), 2, np.uint8)
+    mask, cnt, _, _, _ = oracle.select_tokens(scores, lab, (8, 8, 8), 10.0)
+    assert cnt[0] == 10 and mask[0, :10].all() and not mask[0, 10:].any()
+
+
+def test_position_bias_properties():
+    pb = oracle.position_bias(50)        # tests/test_importance_scoring.py:80-102
+    assert pb[0] == 0 and abs(pb[-1] - 1) < 1e-6 and (np.diff(pb) >= 0).all()
+    assert (oracle.position_bias(1) == 0).all()
+    assert oracle.context_relevance(20, 4) == np.float32(0.2)
