@@ -425,6 +425,11 @@ extern "C" int rtkv_quant_pack(const void *X, int dtype, int B, int S, int n,
     int rc = check_bits(bits, dtype, "rtkv_quant_pack");
     if (!rc) rc = check_pack_bits(bits, "rtkv_quant_pack");
     if (rc) return rc;
+    for (int c = 0; c < 3; ++c)
+        if (dtype == RTKV_BF16 && bits[c] == 16) {  // clamp bound rnd(65535) = 65536 has no 16-bit code
+            set_error("rtkv_quant_pack: 16-bit codes are not representable for bf16 rows");
+            return RTKV_EUNSUPPORTED;
+        }
     int mb = bits[0] > bits[1] ? bits[0] : bits[1]; mb = mb > bits[2] ? mb : bits[2];
     RTKV_CHECK_ARG(row_bytes >= rtkv_packed_row_bytes(n, mb), "rtkv_quant_pack: row_bytes too small");
     if (out_rows == 0) return RTKV_OK;

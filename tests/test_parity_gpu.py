@@ -254,7 +254,7 @@ def test_select_fallback_topk(rt):
         assert int(layer["used_fallback"]) == 0
         mask, cnt, _, _, _ = oracle.select_tokens(scores, labels, (4, 8, 16), 1.5)
         np.testing.assert_array_equal(host(sel.mask), mask)
-        assert rows["n_selected"].tolist() == cnt.tolist() and cnt[0] == 0 and cnt[1] == 3
+        assert rows["n_selected"].tolist() == cnt.tolist() and cnt[0] == 0 and cnt[1] == min(3, S)
 
 
 def test_scratch_is_left_zeroed(rt):
@@ -321,7 +321,7 @@ def test_quant_gather_selected_rows_zero_padded(rt, dt):
     scores[1] *= 0.2                                   # fewer HIGH tokens -> different counts per row
     labels, _ = oracle.assign_precision(scores, 0.7, 0.3)
     bits = (2, 4, 8)
-    sel, layer, rows = run_select(ops, scores, labels, bits, S * 0.6)
+    sel, layer, rows = run_select(ops, scores, labels, bits, S * 0.25)
     ms = int(layer["max_selected"])
     K = torch.from_numpy(rng.standard_normal((B, S, n)).astype(np.float32)).to(TDT[dt])
     V = torch.from_numpy(rng.standard_normal((B, S, n)).astype(np.float32)).to(TDT[dt])
@@ -361,8 +361,16 @@ def test_whole_tensor_params_and_quantize(rt):
 
 
 # ---------------------------------------------------------------- packed rows
-@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16])
-@pytest.mark.parametrize("bits", [(2, 4, 8), (4, 8, 16), (1, 2, 4)])
+def test_packed_bf16_sixteen_bits_unsupported(rt):
+    """bf16 rounds the clamp bound 65535 to 65536, which has no 16-bit code."""
+    _, ops = rt
+    x = torch.randn(1, 4, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="bf16"):
+        ops.quant_pack(x, None, torch.zeros(1, 4, dtype=torch.uint8, device="cuda"), (4, 8, 16), 4)
+
+
+@pytest.mark.parametrize("dt,bits", [(oracle.F32, (2, 4, 8)), (oracle.F32, (4, 8, 16)), (oracle.F32, (1, 2, 4)),
+                                     (oracle.BF16, (2, 4, 8)), (oracle.BF16, (4, 8, 12)), (oracle.F16, (1, 8, 15))])
 def test_packed_codes_bit_exact_and_roundtrip(rt, dt, bits):
     _, ops = rt
     rng = np.random.default_rng(bits[0] + 100)
