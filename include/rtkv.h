@@ -105,15 +105,28 @@ RTKV_API const char *rtkv_last_error(void);
 /* [host] out: name, SM count, compute capability of the current device. */
 RTKV_API int rtkv_device_info(char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor);
 
-/* Scratch needed by rtkv_score_select for a [B,S] problem.  The scratch must be
- * zero-filled once after allocation; calls leave it zeroed again. */
+/* Per-device scratch: a 256-byte header (whole-tensor min/max words) followed by the table
+ * (float)log((double)(i+1)) of the position bias, shared by all layers and sequence lengths
+ * up to S.  rtkv_scratch_init fills it once (enqueued on `stream`); a scratch sized for a
+ * smaller S than a later call still works (entries past the table are computed in place). */
 RTKV_API int rtkv_scratch_bytes(int B, int S, size_t *bytes);
+RTKV_API int rtkv_scratch_init(void *scratch, size_t bytes, void *stream);
 
 /* mass[b,i] = sum_p mean_h A[b,h,i,idx[p]]   (idx == NULL: idx[p] = p).
  * A: [B,H,S,*] with element strides sb, sh, si and unit stride in the last dim. */
 RTKV_API int rtkv_prompt_mass(const void *A, int dtype, int B, int H, int S,
                      int64_t sb, int64_t sh, int64_t si,
                      const int64_t *idx, int P, float *mass, void *stream);
+
+/* Head sharding (one rank holds H_local = n_groups*group_size consecutive heads; float32 only):
+ * partials[b,i,g] = sum_p sum_{h in local group g} A[b,h,i,idx[p]],  [B,S,H_local/group_size].
+ * After the ranks' partials are gathered into [B*S, 8] (group_size = H/8 of the full model),
+ * rtkv_mass_from_partials gives mass = (p0 + ... + p7) / H — bit-identical to rtkv_prompt_mass
+ * on the unsharded tensor. */
+RTKV_API int rtkv_prompt_mass_partials(const void *A, int dtype, int B, int H_local, int S,
+                     int64_t sb, int64_t sh, int64_t si, const int64_t *idx, int P,
+                     int group_size, float *partials, void *stream);
+RTKV_API int rtkv_mass_from_partials(const float *partials, int64_t n, int H, float *mass, void *stream);
 
 /* Same quantity without a materialised attention matrix:
  * mass[b,i] = (1/H) sum_h sum_{j<P, j<=i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i]).
@@ -130,11 +143,12 @@ RTKV_API int rtkv_normalize_mass(const float *mass, int dtype, int B, int S, flo
  *   mass    [B,S] f32 in  (RTKV_FROM_MASS)            scores [B,S] f32 in/out
  *   labels  [B,S] u8 in/out (0 low, 1 medium, 2 high) mask   [B,S] u8 out (1 = kept)
  *   sel_idx [B,S] i32 out: kept token indices, ascending, first n_selected valid
- *   row_stats [B], layer_stats [1], scratch: rtkv_scratch_bytes. */
+ *   row_stats [B], layer_stats [1] (when B > 1, layer_stats->reserved must be zero on entry;
+ *   it is left zero), scratch/scratch_bytes: an initialised scratch or NULL/0. */
 RTKV_API int rtkv_score_select(const float *mass, float *scores, uint8_t *labels, uint8_t *mask,
                       int32_t *sel_idx, rtkv_row_stats *row_stats, rtkv_layer_stats *layer_stats,
-                      void *scratch, int B, int S, const rtkv_layer_params *params /*[host]*/,
-                      int flags, void *stream);
+                      const void *scratch, size_t scratch_bytes, int B, int S,
+                      const rtkv_layer_params *params /*[host]*/, int flags, void *stream);
 
 /* Per-token asymmetric min/max fake-quantisation of the kept rows, written compacted.
  *   X0, X1   [B,S,n] inputs (X1 may be NULL); Y0, Y1 [B,out_rows,n] outputs.

@@ -102,6 +102,28 @@ def prompt_mass(A, adt, P, idx=None):
     return mass
 
 
+def prompt_mass_groups(A, adt, P, idx=None):
+    """fp32 only: (mass [B,S], per-head-group partial sums [B,S,8])."""
+    assert A.ndim == 4 and A.strides[-1] == A.itemsize
+    B, H, S, _ = A.shape
+    sb, sh, si = (s // A.itemsize for s in A.strides[:3])
+    mass = np.empty((B, S), np.float32)
+    parts = np.zeros((B, S, 8), np.float32)
+    if idx is not None:
+        idx = _c(idx, np.int64)
+        P = len(idx)
+    lib().orc_prompt_mass_groups(_p(A), adt, B, H, S, ctypes.c_int64(sb), ctypes.c_int64(sh),
+                                 ctypes.c_int64(si), _p(idx), int(P), _p(mass), _p(parts))
+    return mass, parts
+
+
+def mass_from_partials(partials, H):
+    partials = _c(partials, np.float32)
+    mass = np.empty(partials.shape[:-1], np.float32)
+    lib().orc_mass_from_partials(_p(partials), ctypes.c_int64(mass.size), int(H), _p(mass))
+    return mass
+
+
 def position_bias(S):
     pb = np.empty((S,), np.float32)
     lib().orc_position_bias(int(S), _p(pb))

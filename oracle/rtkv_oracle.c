@@ -23,7 +23,7 @@
  * build container by oracle/pin_against_reference.py, which also writes the
  * fixtures under tests/golden/.  Two things the reference leaves to ATen are
  * *defined* here (and implemented identically by the kernels):
- *   (1) the order of the H*P-term prompt-mass reduction (see orc_prompt_mass),
+ *   (1) the order of the H*P-term prompt-mass reduction (see orc_prompt_mass_groups),
  *   (2) logf of the position bias = (float)log((double)x) (correctly rounded),
  *   (3) ties in the descending score sort break towards the lowest index.
  * Against the reference those two stages agree to a few ulp; every later
@@ -74,39 +74,95 @@ static inline void st(void *p, int64_t i, float v, int dt) {
 
 /* ---------- a5: prompt-attention mass  (token_importance.py:41-45) ----------
  * mass[b,i] = sum_p ( mean_h A[b,h,i,idx[p]] ).
- * Defined reduction order (the kernels implement exactly this):
- *   per prompt position p : s = A[h=0] + A[h=1] + ... sequentially in fp32,
- *                           m_p = rnd(s / (float)H)
- *   position p belongs to "lane" (p mod 128) / 4; each of the 32 lanes adds its
- *   m_p in increasing p;  the 32 lane sums are combined by an xor butterfly
- *   (offsets 16, 8, 4, 2, 1).  For half dtypes the result is rounded once more.
+ * The reference leaves the order of this H*P-term reduction to ATen; here it is
+ * DEFINED (the kernels implement exactly this, bit for bit):
+ *   heads are split into 8 groups of gs = ceil(H/8) consecutive heads (groups past
+ *   H are empty and contribute +0.0).  Prompt position p belongs to "lane"
+ *   (p mod 128) / 4.
+ *   fp32:  per group g: per position the group's heads are added sequentially;
+ *          each lane adds its positions in increasing p; the 32 lane sums are
+ *          combined by an xor butterfly (16,8,4,2,1) -> partial[g].
+ *          mass = (partial[0] + partial[1] + ... + partial[7]) / (float)H.
+ *          (scalar per-group partials are what head-sharded ranks exchange, so
+ *           1/2/4/8-GPU runs are bit-identical to the single-GPU result)
+ *   half:  torch rounds the per-position head mean to the tensor dtype, so per
+ *          position s = group sums added in group order (fp32), m = rnd(s/H);
+ *          lanes add their m in increasing p; butterfly; final rnd.
  * idx == NULL means idx[p] = p.
  */
-void orc_prompt_mass(const void *A, int adt, int B, int H, int S,
-                     int64_t sb, int64_t sh, int64_t si,
-                     const int64_t *idx, int P, float *mass)
+static float butterfly32(float *lane)
 {
+    for (int off = 16; off >= 1; off >>= 1) {
+        float nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
+        memcpy(lane, nxt, sizeof(float) * 32);
+    }
+    return lane[0];
+}
+
+/* partials: optional [B,S,8] output of the fp32 per-group partial sums */
+void orc_prompt_mass_groups(const void *A, int adt, int B, int H, int S,
+                            int64_t sb, int64_t sh, int64_t si,
+                            const int64_t *idx, int P, float *mass, float *partials)
+{
+    const int gs = (H + 7) / 8;
     for (int b = 0; b < B; ++b) {
 #pragma omp parallel for schedule(static)
         for (int i = 0; i < S; ++i) {
             float lane[32];
-            for (int l = 0; l < 32; ++l) lane[l] = 0.0f;
-            for (int p = 0; p < P; ++p) {
-                int64_t col = idx ? idx[p] : p;
-                float s = 0.0f;
-                for (int h = 0; h < H; ++h)
-                    s = s + ld(A, b * sb + h * sh + (int64_t)i * si + col, adt);
-                float m = rnd(s / (float)H, adt);
-                int l = (p & 127) >> 2;
-                lane[l] = lane[l] + m;
+            const int64_t row = b * sb + (int64_t)i * si;
+            if (adt == ORC_F32) {
+                float tot = 0.0f;
+                for (int g = 0; g < 8; ++g) {
+                    for (int l = 0; l < 32; ++l) lane[l] = 0.0f;
+                    const int h0 = g * gs, h1 = (h0 + gs < H) ? h0 + gs : H;
+                    for (int p = 0; p < P; ++p) {
+                        int64_t col = idx ? idx[p] : p;
+                        float s = 0.0f;
+                        for (int h = h0; h < h1; ++h) s = s + ld(A, row + h * sh + col, adt);
+                        int l = (p & 127) >> 2;
+                        lane[l] = lane[l] + s;
+                    }
+                    float part = butterfly32(lane);
+                    if (partials) partials[((int64_t)b * S + i) * 8 + g] = part;
+                    tot = g == 0 ? part : tot + part;
+                }
+                mass[(int64_t)b * S + i] = tot / (float)H;
+            } else {
+                for (int l = 0; l < 32; ++l) lane[l] = 0.0f;
+                for (int p = 0; p < P; ++p) {
+                    int64_t col = idx ? idx[p] : p;
+                    float s = 0.0f;
+                    for (int g = 0; g < 8; ++g) {
+                        const int h0 = g * gs, h1 = (h0 + gs < H) ? h0 + gs : H;
+                        float gsum = 0.0f;
+                        for (int h = h0; h < h1; ++h) gsum = gsum + ld(A, row + h * sh + col, adt);
+                        s = g == 0 ? gsum : s + gsum;
+                    }
+                    float m = rnd(s / (float)H, adt);
+                    int l = (p & 127) >> 2;
+                    lane[l] = lane[l] + m;
+                }
+                mass[(int64_t)b * S + i] = rnd(butterfly32(lane), adt);
             }
-            for (int off = 16; off >= 1; off >>= 1) {
-                float nxt[32];
-                for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
-                memcpy(lane, nxt, sizeof lane);
-            }
-            mass[(int64_t)b * S + i] = rnd(lane[0], adt);
         }
+    }
+}
+
+void orc_prompt_mass(const void *A, int adt, int B, int H, int S,
+                     int64_t sb, int64_t sh, int64_t si,
+                     const int64_t *idx, int P, float *mass)
+{
+    orc_prompt_mass_groups(A, adt, B, H, S, sb, sh, si, idx, P, mass, NULL);
+}
+
+/* head-sharded combine: partials [B,S,8] (all groups, gathered) -> mass */
+void orc_mass_from_partials(const float *partials, int64_t n, int H, float *mass)
+{
+    for (int64_t t = 0; t < n; ++t) {
+        float tot = partials[t * 8];
+        for (int g = 1; g < 8; ++g) tot = tot + partials[t * 8 + g];
+        mass[t] = tot / (float)H;
     }
 }
 

@@ -69,6 +69,7 @@ struct rtkv_ctx {
     rtkv_row_stats *rs = nullptr, *h_rs = nullptr;
     rtkv_layer_stats *ls = nullptr, *h_ls = nullptr;
     void *scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 static void ctx_free_buffers(rtkv_ctx *c)
@@ -89,9 +90,8 @@ extern "C" int rtkv_ctx_create(rtkv_ctx **out)
     cudaError_t e = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_kv, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 256);
-    if (e == cudaSuccess) e = cudaMemset(c->scratch, 0, 256);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ls, sizeof(rtkv_layer_stats));
+    if (e == cudaSuccess) e = cudaMemset(c->ls, 0, sizeof(rtkv_layer_stats));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_ls, sizeof(rtkv_layer_stats));
     if (e != cudaSuccess) { rtkv_ctx_destroy(c); return cuda_fail(e, "rtkv_ctx_create"); }
     *out = c;
@@ -139,6 +139,16 @@ static int ctx_reserve(rtkv_ctx *c, size_t kv_bytes, size_t a_bytes, int B, int 
         RTKV_CUDA(regrow(&c->sel_idx, bs * 4));
         c->cap_bs = bs;
     }
+    size_t need = 0;
+    int rc = rtkv_scratch_bytes(B, S, &need);
+    if (rc) return rc;
+    if (need > c->scratch_bytes) {
+        c->scratch_bytes = 0;
+        RTKV_CUDA(regrow(&c->scratch, need));
+        rc = rtkv_scratch_init(c->scratch, need, c->s_main);
+        if (rc) return rc;
+        c->scratch_bytes = need;
+    }
     if (B > c->cap_b) {
         c->cap_b = 0;
         RTKV_CUDA(regrow(&c->rs, (size_t)B * sizeof(rtkv_row_stats)));
@@ -185,7 +195,7 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     if (rc) return rc;
     rtkv_layer_params lp = *prm;
     lp.score_dtype = a_dtype;
-    rc = rtkv_score_select(c->mass, c->scores, c->labels, c->mask, c->sel_idx, c->rs, c->ls, c->scratch, B, S, &lp,
+    rc = rtkv_score_select(c->mass, c->scores, c->labels, c->mask, c->sel_idx, c->rs, c->ls, c->scratch, c->scratch_bytes, B, S, &lp,
                            RTKV_FROM_MASS | RTKV_MAKE_LABELS | RTKV_SELECT | RTKV_FALLBACK, c->s_main);
     if (rc) return rc;
     RTKV_CUDA(cudaMemcpyAsync(c->h_ls, c->ls, sizeof(rtkv_layer_stats), cudaMemcpyDeviceToHost, c->s_main));

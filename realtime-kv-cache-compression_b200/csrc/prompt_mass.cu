@@ -4,19 +4,26 @@
 //
 // HBM-bound streaming reduction: B*H*S*P elements are read exactly once
 // (64 MiB per Llama-2-7B layer at S=4096, P=128, fp32) and B*S floats written.
-// One warp owns one query row (b,i).  For every head it reads the row's P
-// contiguous probabilities as one 512-byte (fp32) / 256-byte (half) coalesced
-// request, lane l holding columns 4l..4l+3, with eight heads' loads in flight
-// before the first add.  The reduction order is the one oracle/rtkv_oracle.c
-// (orc_prompt_mass) defines, so the result is bit-identical to the oracle:
-//   per column: heads summed sequentially in fp32, then / H;
-//   per lane  : its columns added in increasing order;
-//   lanes     : xor butterfly 16,8,4,2,1.
+//
+// One CTA of 8 warps owns one query row (b,i); warp g owns head group g
+// (gs = ceil(H/8) consecutive heads).  For every head of its group a warp reads
+// the row's P contiguous probabilities as one 512-byte (fp32) / 256-byte (half)
+// coalesced request, lane l holding columns 4l..4l+3, with all heads of the
+// group in flight before the first add.  Thousands of small CTAs keep
+// ~128 KB of loads in flight per SM and leave no tail wave.
+//
+// The reduction order is the one oracle/rtkv_oracle.c (orc_prompt_mass_groups)
+// defines, so results are bit-identical to the oracle, and the fp32 per-group
+// scalar partials are exactly what head-sharded ranks exchange:
+//   fp32: per group: per column heads added sequentially; per lane columns in
+//         increasing order; xor butterfly -> partial[g]; mass = (sum_g partial[g]) / H
+//   half: per column the group sums are added in group order, m = rnd(s/H) (torch
+//         rounds the head mean to the tensor dtype); lanes add m; butterfly; rnd.
 #include "common.cuh"
 
 namespace rtkv {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kGroups = 8;          // head groups == warps per CTA
 constexpr int kHeadUnroll = 8;
 
 template <int DT> struct Quad { // 4 consecutive elements
@@ -40,109 +47,199 @@ template <int DT> struct Quad { // 4 consecutive elements
     }
 };
 
-// VEC: rows are 16B(f32)/8B(half)-aligned and idx == NULL -> vector loads.
+// Sum of this warp's head group for the lane's 4 columns of one 128-column chunk.
 template <int DT, bool VEC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S,
-                   int64_t sb, int64_t sh, int64_t si,
-                   const int64_t *__restrict__ idx, int P, float *__restrict__ mass)
+__device__ __forceinline__ void group_column_sums(const typename Elem<DT>::T *rowp, int64_t sh, int h0, int h1,
+                                                  int p0, int P, const int64_t *idx, float s[4])
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int64_t rows = (int64_t)B * S;
-    const float fH = (float)H;
     using E = typename Elem<DT>::T;
-    const E *base = (const E *)A;
-
-    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < rows;
-         row += (int64_t)gridDim.x * kWarpsPerCta) {
-        const int b = (int)(row / S);
-        const int i = (int)(row - (int64_t)b * S);
-        const E *rowp = base + b * sb + (int64_t)i * si;
-        float lane_acc = 0.0f;
-        for (int c0 = 0; c0 < P; c0 += 128) {          // chunks of 128 prompt positions
-            const int p0 = c0 + 4 * lane;               // this lane's 4 positions
-            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (p0 < P) {
-                const bool full = (p0 + 4 <= P);
-                int64_t col[4];
+    s[0] = s[1] = s[2] = s[3] = 0.0f;
+    if (p0 >= P) return;
+    const bool full = (p0 + 4 <= P);
+    int64_t col[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int p = p0 + k;
-                    col[k] = (p < P) ? (VEC ? (int64_t)p : (idx ? idx[p] : (int64_t)p)) : -1;
+    for (int k = 0; k < 4; ++k) {
+        const int p = p0 + k;
+        col[k] = (p < P) ? ((!VEC && idx) ? idx[p] : (int64_t)p) : -1;
+    }
+    for (int hb = h0; hb < h1; hb += kHeadUnroll) {
+        float v[kHeadUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kHeadUnroll; ++u) {             // issue every load of the batch first
+            const int h = hb + u;
+            if (h < h1) {
+                const E *hp = rowp + (int64_t)h * sh;
+                if (VEC && full) {
+                    Quad<DT>::load_vec(hp + p0, v[u]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[u][k] = col[k] >= 0 ? load_elem<DT>(hp, col[k]) : 0.0f;
                 }
-                for (int h0 = 0; h0 < H; h0 += kHeadUnroll) {
-                    float v[kHeadUnroll][4];
+            } else {
 #pragma unroll
-                    for (int u = 0; u < kHeadUnroll; ++u) {     // issue all loads first
-                        const int h = h0 + u;
-                        if (h < H) {
-                            const E *hp = rowp + (int64_t)h * sh;
-                            if (VEC && full) {
-                                Quad<DT>::load_vec(hp + p0, v[u]);
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    v[u][k] = col[k] >= 0 ? load_elem<DT>(hp, col[k]) : 0.0f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) v[u][k] = 0.0f;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kHeadUnroll; ++u)       // then add in head order
-                        if (h0 + u < H) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) s[k] = __fadd_rn(s[k], v[u][k]);
-                        }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (p0 + k < P)
-                        lane_acc = __fadd_rn(lane_acc, Elem<DT>::rnd(__fdiv_rn(s[k], fH)));
+                for (int k = 0; k < 4; ++k) v[u][k] = 0.0f;
             }
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1)
-            lane_acc = __fadd_rn(lane_acc, __shfl_xor_sync(0xffffffffu, lane_acc, o));
-        if (lane == 0) mass[row] = Elem<DT>::rnd(lane_acc);
+        for (int u = 0; u < kHeadUnroll; ++u)               // then add in head order
+            if (hb + u < h1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s[k] = __fadd_rn(s[k], v[u][k]);
+            }
     }
+}
+
+__device__ __forceinline__ float butterfly(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// mass != NULL: full result for H heads.  partials != NULL (fp32 only): per-group
+// scalar partial sums [B,S,n_groups] of the local heads (head sharding).
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(kGroups * 32)
+prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, int64_t sh, int64_t si,
+                   const int64_t *__restrict__ idx, int P, int gs, int n_groups,
+                   float *__restrict__ mass, float *__restrict__ partials)
+{
+    using E = typename Elem<DT>::T;
+    __shared__ float part[kGroups][129];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t rows = (int64_t)B * S;
+    const int h0 = g * gs, h1 = min(H, h0 + gs);
+    const float fH = (float)H;
+
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int b = (int)(row / S);
+        const int i = (int)(row - (int64_t)b * S);
+        const E *rowp = (const E *)A + b * sb + (int64_t)i * si;
+        if constexpr (DT == RTKV_F32) {
+            float lane_acc = 0.0f;
+            for (int c0 = 0; c0 < P; c0 += 128) {
+                float s[4];
+                group_column_sums<DT, VEC>(rowp, sh, h0, h1, c0 + 4 * lane, P, idx, s);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + 4 * lane + k < P) lane_acc = __fadd_rn(lane_acc, s[k]);
+            }
+            const float pg = butterfly(lane_acc);
+            if (partials) {
+                if (lane == 0 && g < n_groups) partials[row * n_groups + g] = pg;
+            }
+            if (mass) {
+                if (lane == 0) part[g][0] = pg;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    float tot = part[0][0];
+#pragma unroll
+                    for (int k = 1; k < kGroups; ++k) tot = __fadd_rn(tot, part[k][0]);
+                    mass[row] = __fdiv_rn(tot, fH);
+                }
+                __syncthreads();
+            }
+        } else {
+            float lane_acc = 0.0f;
+            for (int c0 = 0; c0 < P; c0 += 128) {
+                float s[4];
+                group_column_sums<DT, VEC>(rowp, sh, h0, h1, c0 + 4 * lane, P, idx, s);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) part[g][4 * lane + k] = s[k];
+                __syncthreads();
+                if (g == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (c0 + 4 * lane + k < P) {
+                            float tot = part[0][4 * lane + k];
+#pragma unroll
+                            for (int q = 1; q < kGroups; ++q) tot = __fadd_rn(tot, part[q][4 * lane + k]);
+                            lane_acc = __fadd_rn(lane_acc, Elem<DT>::rnd(__fdiv_rn(tot, fH)));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (g == 0) {
+                const float tot = butterfly(lane_acc);
+                if (lane == 0) mass[row] = Elem<DT>::rnd(tot);
+            }
+        }
+    }
+}
+
+// head-sharded combine: partials [n,8] -> mass [n] = (p0 + p1 + ... + p7) / H
+__global__ void mass_from_partials_kernel(const float *__restrict__ partials, int64_t n, float fH, float *mass)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float4 a = reinterpret_cast<const float4 *>(partials)[2 * t];
+    const float4 c = reinterpret_cast<const float4 *>(partials)[2 * t + 1];
+    float tot = a.x;
+    tot = __fadd_rn(tot, a.y); tot = __fadd_rn(tot, a.z); tot = __fadd_rn(tot, a.w);
+    tot = __fadd_rn(tot, c.x); tot = __fadd_rn(tot, c.y); tot = __fadd_rn(tot, c.z); tot = __fadd_rn(tot, c.w);
+    mass[t] = __fdiv_rn(tot, fH);
 }
 
 template <int DT>
 static int launch_mass(const void *A, int B, int H, int S, int64_t sb, int64_t sh, int64_t si,
-                       const int64_t *idx, int P, float *mass, cudaStream_t st)
+                       const int64_t *idx, int P, int gs, int n_groups, float *mass, float *partials,
+                       cudaStream_t st)
 {
     const int eb = Elem<DT>::kBytes;
     const int64_t quad = 4 * eb; // bytes of one lane's vector load
-    bool vec = idx == nullptr && ((uintptr_t)A % quad == 0) && (sb * eb) % quad == 0 &&
-               (sh * eb) % quad == 0 && (si * eb) % quad == 0;
+    const bool vec = idx == nullptr && ((uintptr_t)A % quad == 0) && (sb * eb) % quad == 0 &&
+                     (sh * eb) % quad == 0 && (si * eb) % quad == 0;
     const int64_t rows = (int64_t)B * S;
-    int64_t ctas = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    int grid = (int)(ctas < 148 * 64 ? ctas : 148 * 64);
+    const int grid = (int)(rows < (1 << 20) ? rows : (1 << 20));
     if (vec)
-        prompt_mass_kernel<DT, true><<<grid, kWarpsPerCta * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, mass);
+        prompt_mass_kernel<DT, true><<<grid, kGroups * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, gs, n_groups, mass, partials);
     else
-        prompt_mass_kernel<DT, false><<<grid, kWarpsPerCta * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, mass);
+        prompt_mass_kernel<DT, false><<<grid, kGroups * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, gs, n_groups, mass, partials);
     RTKV_LAUNCH_CHECK("prompt_mass_kernel");
     return RTKV_OK;
 }
 
 } // namespace rtkv
 
+using namespace rtkv;
+
 extern "C" int rtkv_prompt_mass(const void *A, int dtype, int B, int H, int S,
                                 int64_t sb, int64_t sh, int64_t si,
                                 const int64_t *idx, int P, float *mass, void *stream)
 {
-    using namespace rtkv;
     RTKV_CHECK_ARG(A && mass, "rtkv_prompt_mass: null pointer");
     RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_prompt_mass: bad dtype %d", dtype);
     RTKV_CHECK_ARG(B > 0 && H > 0 && S > 0 && P > 0, "rtkv_prompt_mass: bad shape B=%d H=%d S=%d P=%d", B, H, S, P);
     cudaStream_t st = (cudaStream_t)stream;
+    const int gs = (H + kGroups - 1) / kGroups;
     switch (dtype) {
-    case RTKV_F32: return launch_mass<RTKV_F32>(A, B, H, S, sb, sh, si, idx, P, mass, st);
-    case RTKV_F16: return launch_mass<RTKV_F16>(A, B, H, S, sb, sh, si, idx, P, mass, st);
-    default: return launch_mass<RTKV_BF16>(A, B, H, S, sb, sh, si, idx, P, mass, st);
+    case RTKV_F32: return launch_mass<RTKV_F32>(A, B, H, S, sb, sh, si, idx, P, gs, kGroups, mass, nullptr, st);
+    case RTKV_F16: return launch_mass<RTKV_F16>(A, B, H, S, sb, sh, si, idx, P, gs, kGroups, mass, nullptr, st);
+    default: return launch_mass<RTKV_BF16>(A, B, H, S, sb, sh, si, idx, P, gs, kGroups, mass, nullptr, st);
     }
+}
+
+extern "C" int rtkv_prompt_mass_partials(const void *A, int dtype, int B, int H_local, int S,
+                                         int64_t sb, int64_t sh, int64_t si, const int64_t *idx, int P,
+                                         int group_size, float *partials, void *stream)
+{
+    RTKV_CHECK_ARG(A && partials, "rtkv_prompt_mass_partials: null pointer");
+    RTKV_CHECK_ARG(dtype == RTKV_F32, "rtkv_prompt_mass_partials: head sharding needs float32 probabilities "
+                   "(half dtypes round the per-column head mean, which does not decompose over ranks)");
+    RTKV_CHECK_ARG(B > 0 && H_local > 0 && S > 0 && P > 0 && group_size > 0, "rtkv_prompt_mass_partials: bad shape");
+    RTKV_CHECK_ARG(H_local % group_size == 0 && H_local / group_size <= kGroups,
+                   "rtkv_prompt_mass_partials: H_local=%d must be a multiple of group_size=%d with at most 8 groups",
+                   H_local, group_size);
+    return launch_mass<RTKV_F32>(A, B, H_local, S, sb, sh, si, idx, P, group_size, H_local / group_size, nullptr,
+                                 partials, (cudaStream_t)stream);
+}
+
+extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int H, float *mass, void *stream)
+{
+    RTKV_CHECK_ARG(partials && mass && n > 0 && H > 0, "rtkv_mass_from_partials: bad argument");
+    RTKV_CHECK_ARG((uintptr_t)partials % 16 == 0, "rtkv_mass_from_partials: partials must be 16-byte aligned");
+    mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, (float)H, mass);
+    RTKV_LAUNCH_CHECK("mass_from_partials_kernel");
+    return RTKV_OK;
 }

@@ -372,7 +372,7 @@ extern "C" int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bi
     int rc = check_bits(b3, dtype, "rtkv_quant_params");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned *sc = (unsigned *)scratch + 16; // past the score_select ticket
+    unsigned *sc = (unsigned *)scratch + 16; // inside the 256-byte scratch header
     minmax_init_kernel<<<1, 1, 0, st>>>(sc);
     int64_t ctas = (numel + kQT * 8 - 1) / (kQT * 8);
     int grid = (int)(ctas < 148 * 8 ? ctas : 148 * 8);

@@ -37,13 +37,15 @@ constexpr int kMaxDepth = 8;
 
 struct K2Params {
     const float *mass;
+    const float *log_tab;   // (float)log((double)(i+1)), i < log_tab_len; NULL: compute in place
+    int log_tab_len;
+    int staged;             // scores/labels of the row are staged in shared memory
     float *scores;
     uint8_t *labels;
     uint8_t *mask;
     int32_t *sel_idx;
     rtkv_row_stats *row_stats;
     rtkv_layer_stats *layer_stats;
-    unsigned int *ticket;
     int B, S, flags, score_dt;
     float alpha, beta, gamma, w_l, theta_h, theta_m, rel, log_S;
     int bits[3];
@@ -62,6 +64,10 @@ struct Smem {
     float red_f[32];
     int red_i[32];
     unsigned red_u[32];
+    double agg_d[32][2];
+    float agg_f[32][2];
+    unsigned agg_u[32][2];
+    int agg_i[32][4];
     unsigned long long thr[3];
     unsigned long long lvl_lo[kMaxDepth];
     int lvl_shift[kMaxDepth], lvl_nb[kMaxDepth], lvl_resume[kMaxDepth];
@@ -91,6 +97,60 @@ struct OpMinF { __device__ float operator()(float a, float b) const { return fmi
 struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 struct OpMinU { __device__ unsigned operator()(unsigned a, unsigned b) const { return a < b ? a : b; } };
 struct OpMaxU { __device__ unsigned operator()(unsigned a, unsigned b) const { return a > b ? a : b; } };
+
+// One fused block reduction for a whole record of row statistics (2 barriers in total).
+struct RowAgg {
+    double sum, sumsq;
+    float fmin, fmax;
+    unsigned kmin, kmax;
+    int n0, n1, n2, nan;
+};
+__device__ __forceinline__ RowAgg agg_combine(RowAgg a, int o)
+{
+    RowAgg r;
+    r.sum = a.sum + __shfl_xor_sync(0xffffffffu, a.sum, o);
+    r.sumsq = a.sumsq + __shfl_xor_sync(0xffffffffu, a.sumsq, o);
+    r.fmin = fminf(a.fmin, __shfl_xor_sync(0xffffffffu, a.fmin, o));
+    r.fmax = fmaxf(a.fmax, __shfl_xor_sync(0xffffffffu, a.fmax, o));
+    unsigned k = __shfl_xor_sync(0xffffffffu, a.kmin, o); r.kmin = k < a.kmin ? k : a.kmin;
+    k = __shfl_xor_sync(0xffffffffu, a.kmax, o); r.kmax = k > a.kmax ? k : a.kmax;
+    r.n0 = a.n0 + __shfl_xor_sync(0xffffffffu, a.n0, o);
+    r.n1 = a.n1 + __shfl_xor_sync(0xffffffffu, a.n1, o);
+    r.n2 = a.n2 + __shfl_xor_sync(0xffffffffu, a.n2, o);
+    r.nan = a.nan | __shfl_xor_sync(0xffffffffu, a.nan, o);
+    return r;
+}
+__device__ __forceinline__ RowAgg agg_identity()
+{
+    RowAgg a;
+    a.sum = a.sumsq = 0.0; a.fmin = INFINITY; a.fmax = -INFINITY; a.kmin = 0xffffffffu; a.kmax = 0u;
+    a.n0 = a.n1 = a.n2 = a.nan = 0;
+    return a;
+}
+__device__ RowAgg block_reduce_agg(RowAgg a, Smem &sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a = agg_combine(a, o);
+    if (lane == 0) {
+        sm.agg_d[warp][0] = a.sum; sm.agg_d[warp][1] = a.sumsq;
+        sm.agg_f[warp][0] = a.fmin; sm.agg_f[warp][1] = a.fmax;
+        sm.agg_u[warp][0] = a.kmin; sm.agg_u[warp][1] = a.kmax;
+        sm.agg_i[warp][0] = a.n0; sm.agg_i[warp][1] = a.n1; sm.agg_i[warp][2] = a.n2; sm.agg_i[warp][3] = a.nan;
+    }
+    __syncthreads();
+    RowAgg r = agg_identity();
+    if (lane < (int)(blockDim.x >> 5)) {
+        r.sum = sm.agg_d[lane][0]; r.sumsq = sm.agg_d[lane][1];
+        r.fmin = sm.agg_f[lane][0]; r.fmax = sm.agg_f[lane][1];
+        r.kmin = sm.agg_u[lane][0]; r.kmax = sm.agg_u[lane][1];
+        r.n0 = sm.agg_i[lane][0]; r.n1 = sm.agg_i[lane][1]; r.n2 = sm.agg_i[lane][2]; r.nan = sm.agg_i[lane][3];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) r = agg_combine(r, o);
+    __syncthreads();
+    return r;
+}
 
 // ---- walk-order key ------------------------------------------------------------------
 // torch.argsort(descending=True): NaN first, then +inf ... -inf, -0 == +0.
@@ -318,77 +378,83 @@ __device__ void emit_selection(const float *sc, const uint8_t *lb, int S, uint8_
         __syncthreads();
     }
     count = base;
-    sel_sum = block_reduce(ssum, OpAddD(), 0.0, sm.red_d);
-    sel_class[0] = block_reduce(c0, OpAddI(), 0, sm.red_i);
-    sel_class[1] = block_reduce(c1, OpAddI(), 0, sm.red_i);
-    sel_class[2] = block_reduce(c2, OpAddI(), 0, sm.red_i);
+    RowAgg a = agg_identity();
+    a.sum = ssum; a.n0 = c0; a.n1 = c1; a.n2 = c2;
+    a = block_reduce_agg(a, sm);
+    sel_sum = a.sum;
+    sel_class[0] = a.n0; sel_class[1] = a.n1; sel_class[2] = a.n2;
+}
+
+__device__ __forceinline__ float position_bias_at(int i, int S, const float *tab, int tab_len, float log_S)
+{
+    if (S <= 1) return 0.0f;
+    const float lg = (i < tab_len) ? tab[i] : (float)log((double)(float)(i + 1));
+    return __fdiv_rn(lg, log_S);
 }
 
 __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
 {
-    __shared__ Smem sm;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    Smem &sm = *reinterpret_cast<Smem *>(dyn_smem);
     const int b = blockIdx.x, S = p.S;
     float *sc = p.scores + (int64_t)b * S;
     uint8_t *lb = p.labels + (int64_t)b * S;
+    // staged copies of the row (scores + labels) in shared memory: every later pass reads these
+    float *s_sc = reinterpret_cast<float *>(dyn_smem + ((sizeof(Smem) + 15) / 16) * 16);
+    uint8_t *s_lb = reinterpret_cast<uint8_t *>(s_sc + ((S + 3) / 4) * 4);
+    const float *rsc = p.staged ? s_sc : sc;
+    const uint8_t *rlb = p.staged ? s_lb : lb;
 
     // ---- scores (token_importance.py:134-176) ----
+    float mn = 0.0f, den = 0.0f;
     if (p.flags & RTKV_FROM_MASS) {
         const float *ms = p.mass + (int64_t)b * S;
-        float mn = INFINITY, mx = -INFINITY;
-        int nan = 0;
+        RowAgg a = agg_identity();
         for (int i = threadIdx.x; i < S; i += kT) {
-            float v = ms[i];
-            nan |= (v != v);
-            mn = fminf(mn, v); mx = fmaxf(mx, v);
+            const float v = ms[i];
+            a.nan |= (v != v);
+            a.fmin = fminf(a.fmin, v); a.fmax = fmaxf(a.fmax, v);
         }
-        mn = block_reduce(mn, OpMinF(), INFINITY, sm.red_f);
-        mx = block_reduce(mx, OpMaxF(), -INFINITY, sm.red_f);
-        nan = block_reduce(nan, OpAddI(), 0, sm.red_i);
-        if (nan) mn = mx = __int_as_float(0x7fc00000);
-        const int dt = p.score_dt;
-        const float den = rnd_dt(__fsub_rn(mx, mn), dt);
-        const bool ok = den > 1e-8f;
-        const float t3 = __fmul_rn(p.gamma, p.rel);
-        for (int i = threadIdx.x; i < S; i += kT) {
-            float n = 0.0f;
-            if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(ms[i], mn), dt), den), dt);
-            const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
-            float pb = 0.0f;
-            if (S > 1) pb = __fdiv_rn((float)log((double)(float)(i + 1)), p.log_S);
-            const float t2 = __fmul_rn(p.beta, pb);
-            sc[i] = __fadd_rn(__fadd_rn(t1, t2), t3);
-        }
-        __syncthreads();
+        a = block_reduce_agg(a, sm);
+        mn = a.fmin;
+        float mx = a.fmax;
+        if (a.nan) mn = mx = __int_as_float(0x7fc00000);
+        den = rnd_dt(__fsub_rn(mx, mn), p.score_dt);
     }
 
-    // ---- labels + row statistics ----
-    double sum = 0.0, sumsq = 0.0;
-    float smin = INFINITY, smax = -INFINITY;
-    int n0 = 0, n1 = 0, n2 = 0, snan = 0;
-    unsigned kmin = 0xffffffffu, kmax = 0u;
-    for (int i = threadIdx.x; i < S; i += kT) {
-        const float s = sc[i];
-        int l;
-        if (p.flags & RTKV_MAKE_LABELS) { l = label_of(s, p.theta_h, p.theta_m); lb[i] = (uint8_t)l; }
-        else l = lab_at(lb, i);
-        n0 += (l == 0); n1 += (l == 1); n2 += (l == 2);
-        sum += (double)s; sumsq += (double)s * (double)s;
-        snan |= (s != s);
-        smin = fminf(smin, s); smax = fmaxf(smax, s);
-        const unsigned k = score_key_desc(s);
-        kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax;
+    // ---- one pass: score, label, row statistics ----
+    RowAgg st = agg_identity();
+    {
+        const int dt = p.score_dt;
+        const bool ok = den > 1e-8f;
+        const float t3 = __fmul_rn(p.gamma, p.rel);
+        const float *ms = p.mass + (int64_t)b * S;
+        for (int i = threadIdx.x; i < S; i += kT) {
+            float s;
+            if (p.flags & RTKV_FROM_MASS) {
+                float n = 0.0f;
+                if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(ms[i], mn), dt), den), dt);
+                const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                const float t2 = __fmul_rn(p.beta, position_bias_at(i, S, p.log_tab, p.log_tab_len, p.log_S));
+                s = __fadd_rn(__fadd_rn(t1, t2), t3);
+                sc[i] = s;
+            } else {
+                s = sc[i];
+            }
+            int l;
+            if (p.flags & RTKV_MAKE_LABELS) { l = label_of(s, p.theta_h, p.theta_m); lb[i] = (uint8_t)l; }
+            else l = lab_at(lb, i);
+            if (p.staged) { s_sc[i] = s; s_lb[i] = (uint8_t)l; }
+            st.n0 += (l == 0); st.n1 += (l == 1); st.n2 += (l == 2);
+            st.sum += (double)s; st.sumsq += (double)s * (double)s;
+            st.nan |= (s != s);
+            st.fmin = fminf(st.fmin, s); st.fmax = fmaxf(st.fmax, s);
+            const unsigned k = score_key_desc(s);
+            st.kmin = k < st.kmin ? k : st.kmin; st.kmax = k > st.kmax ? k : st.kmax;
+        }
     }
-    sum = block_reduce(sum, OpAddD(), 0.0, sm.red_d);
-    sumsq = block_reduce(sumsq, OpAddD(), 0.0, sm.red_d);
-    smin = block_reduce(smin, OpMinF(), INFINITY, sm.red_f);
-    smax = block_reduce(smax, OpMaxF(), -INFINITY, sm.red_f);
-    snan = block_reduce(snan, OpAddI(), 0, sm.red_i);
-    n0 = block_reduce(n0, OpAddI(), 0, sm.red_i);
-    n1 = block_reduce(n1, OpAddI(), 0, sm.red_i);
-    n2 = block_reduce(n2, OpAddI(), 0, sm.red_i);
-    kmin = block_reduce(kmin, OpMinU(), 0xffffffffu, sm.red_u);
-    kmax = block_reduce(kmax, OpMaxU(), 0u, sm.red_u);
-    if (snan) smin = smax = __int_as_float(0x7fc00000);
+    st = block_reduce_agg(st, sm);          // (also orders the staged writes before the reads below)
+    if (st.nan) st.fmin = st.fmax = __int_as_float(0x7fc00000);
 
     // ---- budgeted selection ----
     int count = 0, sel_class[3] = {0, 0, 0};
@@ -398,46 +464,53 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         SelCfg cfg;
         cfg.bits[0] = p.bits[0]; cfg.bits[1] = p.bits[1]; cfg.bits[2] = p.bits[2];
         cfg.budget_bits = p.budget_bits;
-        select_thresholds(sc, lb, S, kmin, kmax, cfg, sm);
+        select_thresholds(rsc, rlb, S, st.kmin, st.kmax, cfg, sm);
         cost_bits = sm.cur;
-        emit_selection(sc, lb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
+        emit_selection(rsc, rlb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
                        sel_class, sel_sum);
     }
     if (threadIdx.x == 0) {
         rtkv_row_stats &r = p.row_stats[b];
         r.n_selected = count; r.n_selected_greedy = count;
         r.sel_class[0] = sel_class[0]; r.sel_class[1] = sel_class[1]; r.sel_class[2] = sel_class[2];
-        r.label_count[0] = n0; r.label_count[1] = n1; r.label_count[2] = n2;
+        r.label_count[0] = st.n0; r.label_count[1] = st.n1; r.label_count[2] = st.n2;
         r.cost_bits = cost_bits; r.sel_score_sum = sel_sum;
-        r.score_sum = sum; r.score_sumsq = sumsq; r.score_min = smin; r.score_max = smax;
+        r.score_sum = st.sum; r.score_sumsq = st.sumsq; r.score_min = st.fmin; r.score_max = st.fmax;
     }
 
     // ---- last CTA: layer statistics and the emergency fallback (selective_propagation.py:203-211)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) sm.bc_i = (atomicAdd(p.ticket, 1u) == (unsigned)(p.B - 1));
-    __syncthreads();
-    if (!sm.bc_i) return;
-    __threadfence();
-    int mx = 0;
-    for (int r = 0; r < p.B; ++r) { int c = ((volatile rtkv_row_stats *)p.row_stats)[r].n_selected; mx = c > mx ? c : mx; }
+    // The ticket lives in layer_stats.reserved[1]; it must be 0 on entry and is left 0.
+    int mx = count;
+    if (p.B > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0)
+            sm.bc_i = (atomicAdd((unsigned int *)&p.layer_stats->reserved[1], 1u) == (unsigned)(p.B - 1));
+        __syncthreads();
+        if (!sm.bc_i) return;
+        __threadfence();
+        mx = 0;
+        for (int r = 0; r < p.B; ++r) {
+            const int c = ((volatile rtkv_row_stats *)p.row_stats)[r].n_selected;
+            mx = c > mx ? c : mx;
+        }
+    }
     int used_fb = 0;
     if ((p.flags & RTKV_SELECT) && (p.flags & RTKV_FALLBACK) && mx == 0 && p.fallback_topk > 0) {
         used_fb = 1;
         SelCfg cfg;
         cfg.bits[0] = cfg.bits[1] = cfg.bits[2] = 1;
         cfg.budget_bits = p.fallback_topk;
-        for (int r = 0; r < p.B; ++r) {
+        for (int r = 0; r < p.B; ++r) {      // rare path: rows read from global memory
             const float *rs = p.scores + (int64_t)r * S;
             const uint8_t *rl = p.labels + (int64_t)r * S;
-            unsigned a = 0xffffffffu, z = 0u;
+            RowAgg a = agg_identity();
             for (int i = threadIdx.x; i < S; i += kT) {
                 const unsigned k = score_key_desc(rs[i]);
-                a = k < a ? k : a; z = k > z ? k : z;
+                a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
             }
-            a = block_reduce(a, OpMinU(), 0xffffffffu, sm.red_u);
-            z = block_reduce(z, OpMaxU(), 0u, sm.red_u);
-            select_thresholds(rs, rl, S, a, z, cfg, sm);
+            a = block_reduce_agg(a, sm);
+            select_thresholds(rs, rl, S, a.kmin, a.kmax, cfg, sm);
             int cnt, cls[3]; double ss;
             emit_selection(rs, rl, S, p.mask + (int64_t)r * S, p.sel_idx + (int64_t)r * S, sm, cnt, cls, ss);
             if (threadIdx.x == 0) p.row_stats[r].n_selected = cnt;
@@ -447,9 +520,16 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
     if (threadIdx.x == 0) {
         p.layer_stats->max_selected = mx;
         p.layer_stats->used_fallback = used_fb;
-        p.layer_stats->reserved[0] = p.layer_stats->reserved[1] = 0;
-        *p.ticket = 0u; // leave the scratch zeroed for the next call
+        p.layer_stats->reserved[0] = 0;
+        p.layer_stats->reserved[1] = 0;   // ticket back to zero for the next call
     }
+}
+
+// (float)log((double)(i+1)) table shared by every layer and every sequence length
+__global__ void log_table_kernel(float *tab, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = (float)log((double)(float)(i + 1));
 }
 
 // ---- small stand-alone kernels (component API) -----------------------------------
@@ -504,22 +584,41 @@ __global__ void gather_scalars_kernel(const float *scores, const uint8_t *labels
 
 using namespace rtkv;
 
+// scratch layout: [0,256) reserved words (whole-tensor min/max of rtkv_quant_params),
+//                 [256, 256 + 4*n) log table of n = (bytes - 256) / 4 entries.
+constexpr size_t kScratchHeader = 256;
+
 extern "C" int rtkv_scratch_bytes(int B, int S, size_t *bytes)
 {
     RTKV_CHECK_ARG(bytes && B > 0 && S > 0, "rtkv_scratch_bytes: bad argument");
-    *bytes = 256;
+    *bytes = kScratchHeader + 4 * (size_t)S;
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_scratch_init(void *scratch, size_t bytes, void *stream)
+{
+    RTKV_CHECK_ARG(scratch && bytes >= kScratchHeader, "rtkv_scratch_init: scratch too small");
+    RTKV_CHECK_ARG((uintptr_t)scratch % 16 == 0, "rtkv_scratch_init: scratch must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap = (bytes - kScratchHeader) / 4;
+    const int n = (int)(cap < (size_t)1 << 30 ? cap : (size_t)1 << 30);
+    RTKV_CUDA(cudaMemsetAsync(scratch, 0, kScratchHeader, st));
+    if (n > 0) {
+        log_table_kernel<<<(n + 255) / 256, 256, 0, st>>>((float *)((char *)scratch + kScratchHeader), n);
+        RTKV_LAUNCH_CHECK("log_table_kernel");
+    }
     return RTKV_OK;
 }
 
 extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labels, uint8_t *mask,
                                  int32_t *sel_idx, rtkv_row_stats *row_stats,
-                                 rtkv_layer_stats *layer_stats, void *scratch, int B, int S,
-                                 const rtkv_layer_params *prm, int flags, void *stream)
+                                 rtkv_layer_stats *layer_stats, const void *scratch, size_t scratch_bytes,
+                                 int B, int S, const rtkv_layer_params *prm, int flags, void *stream)
 {
     RTKV_CHECK_ARG(prm, "rtkv_score_select: params is null");
     RTKV_CHECK_ARG(B > 0 && S > 0, "rtkv_score_select: bad shape B=%d S=%d", B, S);
     RTKV_CHECK_ARG(S < (1 << 30), "rtkv_score_select: S too large");
-    RTKV_CHECK_ARG(scores && labels && row_stats && layer_stats && scratch, "rtkv_score_select: null pointer");
+    RTKV_CHECK_ARG(scores && labels && row_stats && layer_stats, "rtkv_score_select: null pointer");
     RTKV_CHECK_ARG(!(flags & RTKV_FROM_MASS) || mass, "rtkv_score_select: mass is null");
     RTKV_CHECK_ARG(!(flags & RTKV_SELECT) || (mask && sel_idx), "rtkv_score_select: mask/sel_idx is null");
     RTKV_CHECK_ARG(dtype_ok(prm->score_dtype), "rtkv_score_select: bad score_dtype");
@@ -528,7 +627,12 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
             RTKV_CHECK_ARG(prm->bits[c] >= 1 && prm->bits[c] <= 24, "rtkv_score_select: bits[%d]=%d outside 1..24", c, prm->bits[c]);
     K2Params p;
     p.mass = mass; p.scores = scores; p.labels = labels; p.mask = mask; p.sel_idx = sel_idx;
-    p.row_stats = row_stats; p.layer_stats = layer_stats; p.ticket = (unsigned int *)scratch;
+    p.row_stats = row_stats; p.layer_stats = layer_stats;
+    p.log_tab = nullptr; p.log_tab_len = 0;
+    if (scratch && scratch_bytes > kScratchHeader) {   // table length is implied by the size rtkv_scratch_init saw
+        p.log_tab = (const float *)((const char *)scratch + kScratchHeader);
+        p.log_tab_len = (int)((scratch_bytes - kScratchHeader) / 4);
+    }
     p.B = B; p.S = S; p.flags = flags; p.score_dt = prm->score_dtype;
     p.alpha = (float)prm->alpha; p.beta = (float)prm->beta; p.gamma = (float)prm->gamma;
     p.w_l = (float)prm->layer_weight; p.theta_h = (float)prm->theta_h; p.theta_m = (float)prm->theta_m;
@@ -541,7 +645,19 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
     else if (b8 >= 9.0e18) p.budget_bits = LLONG_MAX / 2;
     else p.budget_bits = (long long)floor(b8);
     p.fallback_topk = prm->fallback_topk < S ? prm->fallback_topk : S;
-    score_select_kernel<<<B, kT, 0, (cudaStream_t)stream>>>(p);
+    // shared memory: control block + (when it fits) the row's scores and labels
+    const size_t base = ((sizeof(Smem) + 15) / 16) * 16;
+    const size_t staged = base + 4 * (size_t)((S + 3) / 4 * 4) + (size_t)S;
+    p.staged = staged <= 200 * 1024;
+    const size_t smem = p.staged ? staged : base;
+    static size_t attr_bytes[64] = {0};
+    int dev = 0;
+    RTKV_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && attr_bytes[dev] < smem) {
+        RTKV_CUDA(cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_bytes[dev] = 200 * 1024;
+    }
+    score_select_kernel<<<B, kT, smem, (cudaStream_t)stream>>>(p);
     RTKV_LAUNCH_CHECK("score_select_kernel");
     return RTKV_OK;
 }

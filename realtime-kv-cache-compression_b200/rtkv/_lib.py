@@ -48,13 +48,18 @@ PROTOTYPES = {
     "rtkv_scratch_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "rtkv_prompt_mass": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_i64, c_i64, c_i64, c_vp, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_prompt_mass_partials": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 c_i64, c_i64, c_i64, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_mass_from_partials": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_scratch_init": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp]),
     "rtkv_prompt_mass_qk": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int,
                                            c_vp, c_vp]),
     "rtkv_position_bias": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp]),
     "rtkv_normalize_mass": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
-    "rtkv_score_select": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
-                                         ctypes.c_int, ctypes.POINTER(LayerParams), ctypes.c_int, c_vp]),
+    "rtkv_score_select": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t,
+                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(LayerParams), ctypes.c_int,
+                                         c_vp]),
     "rtkv_quant_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
                                          c_vp, c_vp, c_vp]),

@@ -40,14 +40,17 @@ def _stream():
 _scratch = {}
 
 
-def scratch(device):
-    """Zero-filled per-device scratch required by rtkv_score_select / rtkv_quant_params."""
+def scratch(device, seq_len=1):
+    """Per-device scratch (rtkv_scratch_init): header + position-bias log table for seq_len
+    entries.  Grown (and re-initialised on the current stream) when a longer sequence shows up."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     buf = _scratch.get(key)
-    if buf is None:
+    want = max(int(seq_len), 4096)
+    if buf is None or (buf.numel() - 256) // 4 < want:
         n = ctypes.c_size_t()
-        check(lib.rtkv_scratch_bytes(1, 1, ctypes.byref(n)))
-        buf = torch.zeros(n.value, dtype=torch.uint8, device=device)
+        check(lib.rtkv_scratch_bytes(1, 1 << (want - 1).bit_length(), ctypes.byref(n)))
+        buf = torch.empty(n.value, dtype=torch.uint8, device=device)
+        check(lib.rtkv_scratch_init(_ptr(buf), buf.numel(), _stream()))
         _scratch[key] = buf
     return buf
 
@@ -92,6 +95,31 @@ def prompt_mass(attn, prompt_len=None, prompt_indices=None):
         return mass.zero_()
     check(lib.rtkv_prompt_mass(_ptr(attn), dtype_code(attn), B, H, S, attn.stride(0), attn.stride(1),
                                attn.stride(2), _ptr(idx), P, _ptr(mass), _stream()))
+    return mass
+
+
+def prompt_mass_partials(attn_local, prompt_len, group_size):
+    """Head-sharded K1a: per-head-group scalar partial sums [B,S,H_local/group_size] (float32 only)."""
+    require_cuda()
+    if attn_local.stride(-1) != 1:
+        attn_local = attn_local.contiguous()
+    B, Hl, S, W = attn_local.shape
+    if prompt_len > W:
+        raise IndexError(f"prompt_len {prompt_len} exceeds attention width {W}")
+    parts = torch.empty(B, S, Hl // max(1, group_size), dtype=torch.float32, device=attn_local.device)
+    check(lib.rtkv_prompt_mass_partials(_ptr(attn_local), dtype_code(attn_local), B, Hl, S, attn_local.stride(0),
+                                        attn_local.stride(1), attn_local.stride(2), None, int(prompt_len),
+                                        int(group_size), _ptr(parts), _stream()))
+    return parts
+
+
+def mass_from_partials(partials, num_heads):
+    """partials [B,S,8] (all head groups, in group order) -> mass [B,S] = (p0+...+p7)/H."""
+    require_cuda()
+    partials = partials.contiguous()
+    assert partials.shape[-1] == 8 and partials.dtype == torch.float32
+    mass = torch.empty(partials.shape[:-1], dtype=torch.float32, device=partials.device)
+    check(lib.rtkv_mass_from_partials(_ptr(partials), mass.numel(), int(num_heads), _ptr(mass), _stream()))
     return mass
 
 
@@ -172,10 +200,13 @@ def score_select(params, B, S, device, mass=None, scores=None, labels=None, sele
             flags |= FALLBACK
         mask = torch.empty(B, S, dtype=torch.uint8, device=device)
         sel_idx = torch.empty(B, S, dtype=torch.int32, device=device)
-    stats = torch.empty(LAYER_STATS_BYTES + ROW_STATS_BYTES * B, dtype=torch.uint8, device=device)
+    # the cross-row ticket lives in the layer record and must start at zero when B > 1
+    alloc = torch.zeros if B > 1 else torch.empty
+    stats = alloc(LAYER_STATS_BYTES + ROW_STATS_BYTES * B, dtype=torch.uint8, device=device)
+    scr = scratch(device, S)
     check(lib.rtkv_score_select(_ptr(mass), _ptr(scores), _ptr(labels), _ptr(mask), _ptr(sel_idx),
                                 ctypes.c_void_p(stats.data_ptr() + LAYER_STATS_BYTES), _ptr(stats),
-                                _ptr(scratch(device)), B, S, ctypes.byref(params), flags, _stream()))
+                                _ptr(scr), scr.numel(), B, S, ctypes.byref(params), flags, _stream()))
     return Selection(scores, labels, mask, sel_idx, stats, B, S)
 
 

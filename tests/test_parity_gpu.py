@@ -257,13 +257,33 @@ def test_select_fallback_topk(rt):
         assert rows["n_selected"].tolist() == cnt.tolist() and cnt[0] == 0 and cnt[1] == min(3, S)
 
 
-def test_scratch_is_left_zeroed(rt):
+def test_cross_row_ticket_is_left_zeroed(rt):
     _, ops = rt
     scores = np.random.default_rng(1).random((5, 300), dtype=np.float32)
     labels = np.ones((5, 300), np.uint8)
     for _ in range(3):
-        check_select(ops, scores, labels, (2, 4, 8), 200.0)
-    assert int(ops.scratch(torch.device("cuda")).sum()) == 0
+        sel, layer, rows = run_select(ops, scores, labels, (2, 4, 8), 200.0)
+        assert layer["reserved"].tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("H,S,P", [(32, 300, 60), (40, 200, 40), (8, 1000, 128), (16, 77, 15)])
+def test_head_sharded_partials_are_bit_identical(rt, H, S, P):
+    """ranks holding H/R consecutive heads exchange scalar per-group partials; the combined mass
+    equals the unsharded kernel (and the oracle) bit for bit for R = 1, 2, 4, 8."""
+    _, ops = rt
+    gen = torch.Generator().manual_seed(H * S)
+    A = causal_probs(2, H, S, gen)
+    want, wparts = oracle.prompt_mass_groups(A.numpy(), oracle.F32, P)
+    full = ops.prompt_mass(A.cuda(), prompt_len=P)
+    np.testing.assert_array_equal(host(full), want)
+    gs = H // 8
+    for R in (1, 2, 4, 8):
+        hl = H // R
+        parts = [ops.prompt_mass_partials(A[:, r * hl:(r + 1) * hl].contiguous().cuda(), P, gs) for r in range(R)]
+        gathered = torch.cat(parts, dim=-1)                       # what the all-gather produces
+        np.testing.assert_array_equal(host(gathered), wparts)
+        np.testing.assert_array_equal(host(ops.mass_from_partials(gathered, H)), want)
+    np.testing.assert_array_equal(oracle.mass_from_partials(wparts, H), want)
 
 
 # ---------------------------------------------------------------- K3 quant + gather
