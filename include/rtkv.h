@@ -190,6 +190,10 @@ RTKV_API int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int
                         const uint8_t *labels, const int32_t *bits /*[host]*/,
                         int out_rows, int64_t row_bytes, void *Y, void *stream);
 
+/* Profiling aid: when set to a device buffer of 64 int64, every rtkv_score_select launch writes
+ * buf[0] = number of ticks and buf[1..] = clock64() at its phase boundaries (row 0).  NULL: off. */
+RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);
+
 /* One layer with HOST buffers (pinned or pageable): copies K, V and the first P
  * key columns of A to the device, runs the path, copies the results back and
  * synchronises.  K_out/V_out must hold B*S*n elements; they are filled as a

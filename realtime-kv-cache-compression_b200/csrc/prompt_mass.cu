@@ -24,7 +24,7 @@
 namespace rtkv {
 
 constexpr int kGroups = 8;          // head groups == warps per CTA
-constexpr int kHeadUnroll = 8;
+constexpr int kHeadUnroll = 4;
 
 template <int DT> struct Quad { // 4 consecutive elements
     __device__ __forceinline__ static void load_vec(const void *p, float f[4])
@@ -99,7 +99,7 @@ __device__ __forceinline__ float butterfly(float v)
 // mass != NULL: full result for H heads.  partials != NULL (fp32 only): per-group
 // scalar partial sums [B,S,n_groups] of the local heads (head sharding).
 template <int DT, bool VEC>
-__global__ void __launch_bounds__(kGroups * 32)
+__global__ void __launch_bounds__(kGroups * 32, 6)
 prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, int64_t sh, int64_t si,
                    const int64_t *__restrict__ idx, int P, int gs, int n_groups,
                    float *__restrict__ mass, float *__restrict__ partials)

@@ -37,6 +37,7 @@ constexpr int kMaxDepth = 8;
 
 struct K2Params {
     const float *mass;
+    long long *dbg;
     const float *log_tab;   // (float)log((double)(i+1)), i < log_tab_len; NULL: compute in place
     int log_tab_len;
     int staged;             // scores/labels of the row are staged in shared memory
@@ -54,6 +55,8 @@ struct K2Params {
 };
 
 struct Smem {
+    long long *dbg;          // optional phase timestamps (rtkv_debug_k2_timing)
+    int dbg_n;
     int hist[3][kNB];
     unsigned long long cand_key[kMaxCand];
     unsigned long long sort_key[kMaxCand];
@@ -64,10 +67,11 @@ struct Smem {
     float red_f[32];
     int red_i[32];
     unsigned red_u[32];
-    double agg_d[32][2];
-    float agg_f[32][2];
-    unsigned agg_u[32][2];
-    int agg_i[32][4];
+    double agg_d[33][2];
+    unsigned agg_u[33][2];
+    int agg_i[33][4];
+    int scan_pre[32];
+    int scan_total;
     unsigned long long thr[3];
     unsigned long long lvl_lo[kMaxDepth];
     int lvl_shift[kMaxDepth], lvl_nb[kMaxDepth], lvl_resume[kMaxDepth];
@@ -75,6 +79,12 @@ struct Smem {
     int alive[3];
     int depth, found, ncand, run_base, bc_i;
 };
+
+// phase timestamps for profiling: dbg[0] = count, dbg[1..] = clock64() at each tick
+__device__ __forceinline__ void tick(Smem &sm)
+{
+    if (sm.dbg && threadIdx.x == 0 && blockIdx.x == 0 && sm.dbg_n < 62) sm.dbg[1 + sm.dbg_n++] = clock64();
+}
 
 // ---- block reductions (all 1024 threads; result broadcast; fixed order) ----------
 template <class T, class Op>
@@ -98,58 +108,94 @@ struct OpMaxF { __device__ float operator()(float a, float b) const { return fma
 struct OpMinU { __device__ unsigned operator()(unsigned a, unsigned b) const { return a < b ? a : b; } };
 struct OpMaxU { __device__ unsigned operator()(unsigned a, unsigned b) const { return a > b ? a : b; } };
 
-// One fused block reduction for a whole record of row statistics (2 barriers in total).
+// One fused block reduction for a whole record of row statistics: integer fields go
+// through the single-instruction warp reductions (REDUX), the two double sums through
+// shuffles; only warp 0 combines the 32 per-warp records (2 barriers in total).
+// Score min/max are carried as walk keys: kmin <-> largest score, kmax <-> smallest.
 struct RowAgg {
     double sum, sumsq;
-    float fmin, fmax;
     unsigned kmin, kmax;
     int n0, n1, n2, nan;
 };
-__device__ __forceinline__ RowAgg agg_combine(RowAgg a, int o)
-{
-    RowAgg r;
-    r.sum = a.sum + __shfl_xor_sync(0xffffffffu, a.sum, o);
-    r.sumsq = a.sumsq + __shfl_xor_sync(0xffffffffu, a.sumsq, o);
-    r.fmin = fminf(a.fmin, __shfl_xor_sync(0xffffffffu, a.fmin, o));
-    r.fmax = fmaxf(a.fmax, __shfl_xor_sync(0xffffffffu, a.fmax, o));
-    unsigned k = __shfl_xor_sync(0xffffffffu, a.kmin, o); r.kmin = k < a.kmin ? k : a.kmin;
-    k = __shfl_xor_sync(0xffffffffu, a.kmax, o); r.kmax = k > a.kmax ? k : a.kmax;
-    r.n0 = a.n0 + __shfl_xor_sync(0xffffffffu, a.n0, o);
-    r.n1 = a.n1 + __shfl_xor_sync(0xffffffffu, a.n1, o);
-    r.n2 = a.n2 + __shfl_xor_sync(0xffffffffu, a.n2, o);
-    r.nan = a.nan | __shfl_xor_sync(0xffffffffu, a.nan, o);
-    return r;
-}
 __device__ __forceinline__ RowAgg agg_identity()
 {
     RowAgg a;
-    a.sum = a.sumsq = 0.0; a.fmin = INFINITY; a.fmax = -INFINITY; a.kmin = 0xffffffffu; a.kmax = 0u;
+    a.sum = a.sumsq = 0.0; a.kmin = 0xffffffffu; a.kmax = 0u;
     a.n0 = a.n1 = a.n2 = a.nan = 0;
     return a;
 }
-__device__ RowAgg block_reduce_agg(RowAgg a, Smem &sm)
+__device__ __forceinline__ RowAgg agg_warp(RowAgg a, bool with_sums)
+{
+    a.kmin = __reduce_min_sync(0xffffffffu, a.kmin);
+    a.kmax = __reduce_max_sync(0xffffffffu, a.kmax);
+    a.n0 = __reduce_add_sync(0xffffffffu, a.n0);
+    a.n1 = __reduce_add_sync(0xffffffffu, a.n1);
+    a.n2 = __reduce_add_sync(0xffffffffu, a.n2);
+    a.nan = __reduce_or_sync(0xffffffffu, (unsigned)a.nan);
+    if (with_sums) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            a.sum += __shfl_xor_sync(0xffffffffu, a.sum, o);
+            a.sumsq += __shfl_xor_sync(0xffffffffu, a.sumsq, o);
+        }
+    }
+    return a;
+}
+__device__ RowAgg block_reduce_agg(RowAgg a, Smem &sm, bool with_sums = true)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) a = agg_combine(a, o);
+    a = agg_warp(a, with_sums);
     if (lane == 0) {
         sm.agg_d[warp][0] = a.sum; sm.agg_d[warp][1] = a.sumsq;
-        sm.agg_f[warp][0] = a.fmin; sm.agg_f[warp][1] = a.fmax;
         sm.agg_u[warp][0] = a.kmin; sm.agg_u[warp][1] = a.kmax;
         sm.agg_i[warp][0] = a.n0; sm.agg_i[warp][1] = a.n1; sm.agg_i[warp][2] = a.n2; sm.agg_i[warp][3] = a.nan;
     }
     __syncthreads();
-    RowAgg r = agg_identity();
-    if (lane < (int)(blockDim.x >> 5)) {
+    if (warp == 0) {
+        RowAgg r;
         r.sum = sm.agg_d[lane][0]; r.sumsq = sm.agg_d[lane][1];
-        r.fmin = sm.agg_f[lane][0]; r.fmax = sm.agg_f[lane][1];
         r.kmin = sm.agg_u[lane][0]; r.kmax = sm.agg_u[lane][1];
         r.n0 = sm.agg_i[lane][0]; r.n1 = sm.agg_i[lane][1]; r.n2 = sm.agg_i[lane][2]; r.nan = sm.agg_i[lane][3];
+        r = agg_warp(r, with_sums);
+        if (lane == 0) {
+            sm.agg_d[32][0] = r.sum; sm.agg_d[32][1] = r.sumsq;
+            sm.agg_u[32][0] = r.kmin; sm.agg_u[32][1] = r.kmax;
+            sm.agg_i[32][0] = r.n0; sm.agg_i[32][1] = r.n1; sm.agg_i[32][2] = r.n2; sm.agg_i[32][3] = r.nan;
+        }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) r = agg_combine(r, o);
     __syncthreads();
+    RowAgg r;
+    r.sum = sm.agg_d[32][0]; r.sumsq = sm.agg_d[32][1];
+    r.kmin = sm.agg_u[32][0]; r.kmax = sm.agg_u[32][1];
+    r.n0 = sm.agg_i[32][0]; r.n1 = sm.agg_i[32][1]; r.n2 = sm.agg_i[32][2]; r.nan = sm.agg_i[32][3];
     return r;
+}
+
+// block-wide exclusive scan of one int per thread (+ total); only warp 0 scans the warp totals
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ int block_excl_scan(int v, int &total, Smem &sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int incl = warp_incl_scan(v, lane);
+    if (lane == 31) sm.red_i[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int t = sm.red_i[lane];
+        const int ti = warp_incl_scan(t, lane);
+        sm.scan_pre[lane] = ti - t;
+        if (lane == 31) sm.scan_total = ti;
+    }
+    __syncthreads();
+    total = sm.scan_total;
+    return sm.scan_pre[warp] + incl - v;
 }
 
 // ---- walk-order key ------------------------------------------------------------------
@@ -161,6 +207,12 @@ __device__ __forceinline__ unsigned score_key_desc(float s)
     if (u == 0x80000000u) u = 0u;
     unsigned asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     return ~asc;
+}
+// inverse of score_key_desc (NaN is reported through the nan flag, -0 comes back as +0)
+__device__ __forceinline__ float score_of_key(unsigned k)
+{
+    const unsigned asc = ~k;
+    return __uint_as_float((asc & 0x80000000u) ? (asc & 0x7fffffffu) : ~asc);
 }
 __device__ __forceinline__ unsigned long long walk_key(float s, int i)
 {
@@ -198,37 +250,24 @@ __device__ void build_hist(const float *sc, const uint8_t *lb, int S, Smem &sm)
 
 // First bucket x >= b0 where the live tokens up to and including x no longer fit.
 // Leaves sm.found (INT_MAX if everything fits), sm.sum_before, sm.total.
+// (weights fit in 32 bits: S <= 2^24 tokens x <= 24 bits)
 __device__ void scan_find(int b0, const SelCfg &cfg, Smem &sm)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = sm.lvl_nb[sm.depth];
-    const long long w0c = sm.alive[0] ? cfg.bits[0] : 0, w1c = sm.alive[1] ? cfg.bits[1] : 0,
-                    w2c = sm.alive[2] ? cfg.bits[2] : 0;
-    const long long room = cfg.budget_bits - sm.cur;
-    long long w[2];
+    const int w0c = sm.alive[0] ? cfg.bits[0] : 0, w1c = sm.alive[1] ? cfg.bits[1] : 0,
+              w2c = sm.alive[2] ? cfg.bits[2] : 0;
+    const long long room_ll = cfg.budget_bits - sm.cur;
+    const int room = room_ll > 0x7fffffffLL ? 0x7fffffff : (room_ll < -1 ? -1 : (int)room_ll);
+    int w[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        int x = 2 * threadIdx.x + k;
-        w[k] = (x >= b0 && x < nb)
-                   ? w0c * sm.hist[0][x] + w1c * sm.hist[1][x] + w2c * sm.hist[2][x] : 0;
+        const int x = 2 * threadIdx.x + k;
+        w[k] = (x >= b0 && x < nb) ? w0c * sm.hist[0][x] + w1c * sm.hist[1][x] + w2c * sm.hist[2][x] : 0;
     }
-    long long incl = w[0] + w[1];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) sm.red_ll[warp] = incl;
     if (threadIdx.x == 0) sm.found = INT_MAX;
-    __syncthreads();
-    long long woff = 0, tot = 0;
-    for (int k = 0; k < 32; ++k) {
-        long long t = sm.red_ll[k];
-        if (k < warp) woff += t;
-        tot += t;
-    }
-    const long long excl = woff + incl - (w[0] + w[1]);
-    const long long p0 = excl + w[0], p1 = p0 + w[1];
+    int tot;
+    const int excl = block_excl_scan(w[0] + w[1], tot, sm);   // (barriers also order the sm.found reset)
+    const int p0 = excl + w[0], p1 = p0 + w[1];
     int mine = INT_MAX;
     if (w[0] > 0 && p0 > room) mine = 2 * threadIdx.x;
     else if (w[1] > 0 && p1 > room) mine = 2 * threadIdx.x + 1;
@@ -306,11 +345,12 @@ __device__ void select_thresholds(const float *sc, const uint8_t *lb, int S, uns
     __syncthreads();
     bool need_hist = true;
     for (;;) {
-        if (need_hist) build_hist(sc, lb, S, sm);
+        if (need_hist) { build_hist(sc, lb, S, sm); tick(sm); }
         need_hist = false;
         if (!(sm.alive[0] | sm.alive[1] | sm.alive[2])) break;
         const int d = sm.depth;
         scan_find(sm.lvl_resume[d], cfg, sm);
+        tick(sm);
         const int f = sm.found;
         if (f == INT_MAX) {                 // every live token of this level fits
             __syncthreads();
@@ -328,6 +368,7 @@ __device__ void select_thresholds(const float *sc, const uint8_t *lb, int S, uns
         __syncthreads();
         if (m_alive <= kMaxCand || shift == 0 || d + 1 >= kMaxDepth) {
             walk_bucket(sc, lb, S, f, cfg, sm);
+            tick(sm);
         } else {                            // refine the boundary bucket
             if (threadIdx.x == 0) {
                 const int ns = shift > 11 ? shift - 11 : 0;
@@ -344,42 +385,50 @@ __device__ void select_thresholds(const float *sc, const uint8_t *lb, int S, uns
     __syncthreads();
 }
 
-// mask, compacted ascending index list and the per-row selection statistics
+// mask, compacted ascending index list and the per-row selection statistics.
+// Warp w owns the contiguous token range [w*chunk, (w+1)*chunk): it counts its kept tokens,
+// one block-wide scan turns the 32 counts into output offsets, then it writes its part.
 __device__ void emit_selection(const float *sc, const uint8_t *lb, int S, uint8_t *mask,
                                int32_t *sel_idx, Smem &sm, int &count, int sel_class[3],
                                double &sel_sum)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long t0 = sm.thr[0], t1 = sm.thr[1], t2 = sm.thr[2];
-    int base = 0, c0 = 0, c1 = 0, c2 = 0;
-    double ssum = 0.0;
-    for (int tile = 0; tile < S; tile += kT) {
-        const int i = tile + threadIdx.x;
+    const int chunk = ((S + 31) / 32 + 31) / 32 * 32;           // multiple of 32 tokens per warp
+    const int beg = warp * chunk, end = min(S, beg + chunk);
+    int mine = 0;
+    for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        bool keep = false;
+        if (i < end) {
+            const int l = lab_at(lb, i);
+            keep = walk_key(sc[i], i) < (l == 0 ? t0 : (l == 1 ? t1 : t2));
+        }
+        mine += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    int total;
+    int off = block_excl_scan(lane == 0 ? mine : 0, total, sm);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    RowAgg a = agg_identity();
+    for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
         bool keep = false;
         float s = 0.0f;
         int l = 0;
-        if (i < S) {
+        if (i < end) {
             s = sc[i]; l = lab_at(lb, i);
-            const unsigned long long k = walk_key(s, i);
-            keep = k < (l == 0 ? t0 : (l == 1 ? t1 : t2));
+            keep = walk_key(s, i) < (l == 0 ? t0 : (l == 1 ? t1 : t2));
             mask[i] = keep ? 1 : 0;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) sm.red_i[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int k = 0; k < 32; ++k) { int t = sm.red_i[k]; if (k < warp) woff += t; tot += t; }
         if (keep) {
-            sel_idx[base + woff + __popc(bal & ((1u << lane) - 1u))] = i;
-            ssum += (double)s;
-            c0 += (l == 0); c1 += (l == 1); c2 += (l == 2);
+            sel_idx[off + __popc(bal & ((1u << lane) - 1u))] = i;
+            a.sum += (double)s;
+            a.n0 += (l == 0); a.n1 += (l == 1); a.n2 += (l == 2);
         }
-        base += tot;
-        __syncthreads();
+        off += __popc(bal);
     }
-    count = base;
-    RowAgg a = agg_identity();
-    a.sum = ssum; a.n0 = c0; a.n1 = c1; a.n2 = c2;
+    count = total;
     a = block_reduce_agg(a, sm);
     sel_sum = a.sum;
     sel_class[0] = a.n0; sel_class[1] = a.n1; sel_class[2] = a.n2;
@@ -404,23 +453,26 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
     uint8_t *s_lb = reinterpret_cast<uint8_t *>(s_sc + ((S + 3) / 4) * 4);
     const float *rsc = p.staged ? s_sc : sc;
     const uint8_t *rlb = p.staged ? s_lb : lb;
+    if (threadIdx.x == 0) { sm.dbg = p.dbg; sm.dbg_n = 0; tick(sm); }
 
     // ---- scores (token_importance.py:134-176) ----
     float mn = 0.0f, den = 0.0f;
     if (p.flags & RTKV_FROM_MASS) {
         const float *ms = p.mass + (int64_t)b * S;
-        RowAgg a = agg_identity();
+        RowAgg a = agg_identity();                      // kmin/kmax hold the mass range as walk keys
         for (int i = threadIdx.x; i < S; i += kT) {
             const float v = ms[i];
             a.nan |= (v != v);
-            a.fmin = fminf(a.fmin, v); a.fmax = fmaxf(a.fmax, v);
+            const unsigned k = score_key_desc(v);
+            a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
         }
-        a = block_reduce_agg(a, sm);
-        mn = a.fmin;
-        float mx = a.fmax;
+        a = block_reduce_agg(a, sm, false);
+        mn = score_of_key(a.kmax);                      // largest key = smallest value
+        float mx = score_of_key(a.kmin);
         if (a.nan) mn = mx = __int_as_float(0x7fc00000);
         den = rnd_dt(__fsub_rn(mx, mn), p.score_dt);
     }
+    tick(sm);   // 1: mass min/max done
 
     // ---- one pass: score, label, row statistics ----
     RowAgg st = agg_identity();
@@ -448,13 +500,14 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
             st.n0 += (l == 0); st.n1 += (l == 1); st.n2 += (l == 2);
             st.sum += (double)s; st.sumsq += (double)s * (double)s;
             st.nan |= (s != s);
-            st.fmin = fminf(st.fmin, s); st.fmax = fmaxf(st.fmax, s);
             const unsigned k = score_key_desc(s);
             st.kmin = k < st.kmin ? k : st.kmin; st.kmax = k > st.kmax ? k : st.kmax;
         }
     }
     st = block_reduce_agg(st, sm);          // (also orders the staged writes before the reads below)
-    if (st.nan) st.fmin = st.fmax = __int_as_float(0x7fc00000);
+    float smin = score_of_key(st.kmax), smax = score_of_key(st.kmin);
+    if (st.nan) smin = smax = __int_as_float(0x7fc00000);
+    tick(sm);   // 2: scores, labels, statistics done
 
     // ---- budgeted selection ----
     int count = 0, sel_class[3] = {0, 0, 0};
@@ -466,8 +519,10 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         cfg.budget_bits = p.budget_bits;
         select_thresholds(rsc, rlb, S, st.kmin, st.kmax, cfg, sm);
         cost_bits = sm.cur;
+        tick(sm);   // thresholds done
         emit_selection(rsc, rlb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
                        sel_class, sel_sum);
+        tick(sm);   // emit done
     }
     if (threadIdx.x == 0) {
         rtkv_row_stats &r = p.row_stats[b];
@@ -475,7 +530,7 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         r.sel_class[0] = sel_class[0]; r.sel_class[1] = sel_class[1]; r.sel_class[2] = sel_class[2];
         r.label_count[0] = st.n0; r.label_count[1] = st.n1; r.label_count[2] = st.n2;
         r.cost_bits = cost_bits; r.sel_score_sum = sel_sum;
-        r.score_sum = st.sum; r.score_sumsq = st.sumsq; r.score_min = st.fmin; r.score_max = st.fmax;
+        r.score_sum = st.sum; r.score_sumsq = st.sumsq; r.score_min = smin; r.score_max = smax;
     }
 
     // ---- last CTA: layer statistics and the emergency fallback (selective_propagation.py:203-211)
@@ -509,7 +564,7 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
                 const unsigned k = score_key_desc(rs[i]);
                 a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
             }
-            a = block_reduce_agg(a, sm);
+            a = block_reduce_agg(a, sm, false);
             select_thresholds(rs, rl, S, a.kmin, a.kmax, cfg, sm);
             int cnt, cls[3]; double ss;
             emit_selection(rs, rl, S, p.mask + (int64_t)r * S, p.sel_idx + (int64_t)r * S, sm, cnt, cls, ss);
@@ -518,6 +573,8 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         }
     }
     if (threadIdx.x == 0) {
+        tick(sm);
+        if (sm.dbg && blockIdx.x == 0) sm.dbg[0] = sm.dbg_n;
         p.layer_stats->max_selected = mx;
         p.layer_stats->used_fallback = used_fb;
         p.layer_stats->reserved[0] = 0;
@@ -584,6 +641,13 @@ __global__ void gather_scalars_kernel(const float *scores, const uint8_t *labels
 
 using namespace rtkv;
 
+static long long *g_k2_dbg = nullptr;
+extern "C" int rtkv_debug_k2_timing(void *device_buffer_64_i64)
+{
+    g_k2_dbg = (long long *)device_buffer_64_i64;
+    return RTKV_OK;
+}
+
 // scratch layout: [0,256) reserved words (whole-tensor min/max of rtkv_quant_params),
 //                 [256, 256 + 4*n) log table of n = (bytes - 256) / 4 entries.
 constexpr size_t kScratchHeader = 256;
@@ -617,7 +681,7 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
 {
     RTKV_CHECK_ARG(prm, "rtkv_score_select: params is null");
     RTKV_CHECK_ARG(B > 0 && S > 0, "rtkv_score_select: bad shape B=%d S=%d", B, S);
-    RTKV_CHECK_ARG(S < (1 << 30), "rtkv_score_select: S too large");
+    RTKV_CHECK_ARG(S <= (1 << 24), "rtkv_score_select: S > 2^24 is not supported");
     RTKV_CHECK_ARG(scores && labels && row_stats && layer_stats, "rtkv_score_select: null pointer");
     RTKV_CHECK_ARG(!(flags & RTKV_FROM_MASS) || mass, "rtkv_score_select: mass is null");
     RTKV_CHECK_ARG(!(flags & RTKV_SELECT) || (mask && sel_idx), "rtkv_score_select: mask/sel_idx is null");
@@ -628,6 +692,7 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
     K2Params p;
     p.mass = mass; p.scores = scores; p.labels = labels; p.mask = mask; p.sel_idx = sel_idx;
     p.row_stats = row_stats; p.layer_stats = layer_stats;
+    p.dbg = g_k2_dbg;
     p.log_tab = nullptr; p.log_tab_len = 0;
     if (scratch && scratch_bytes > kScratchHeader) {   // table length is implied by the size rtkv_scratch_init saw
         p.log_tab = (const float *)((const char *)scratch + kScratchHeader);
