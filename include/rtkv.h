@@ -161,6 +161,14 @@ RTKV_API int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int B,
                       const uint8_t *labels, const int32_t *bits /*[host] [3] or NULL*/,
                       int out_rows, int zero_pad, void *Y0, void *Y1, void *stream);
 
+/* Same, restricted to batch rows [b_begin, b_begin+b_count) and output rows
+ * [row_begin, row_begin+row_count): lets a caller pipeline the gather with its copies. */
+RTKV_API int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                      const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                      const uint8_t *labels, const int32_t *bits /*[host] [3] or NULL*/,
+                      int out_rows, int zero_pad, void *Y0, void *Y1,
+                      int b_begin, int b_count, int row_begin, int row_count, void *stream);
+
 /* Whole-tensor scale / zero-point (qparams[0] = scale, [1] = zero_point, in `dtype`,
  * stored as f32) and quantise-dequantise with given parameters. */
 RTKV_API int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bits, float *qparams,

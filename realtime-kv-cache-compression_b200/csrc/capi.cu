@@ -57,15 +57,18 @@ extern "C" int rtkv_device_info(char *name, size_t name_len, int *sm_count, int 
 }
 
 // ---- host-buffer context -----------------------------------------------------------
+constexpr int kMaxPieces = 64;   // K/V upload pieces per call (per-piece events)
+
 struct rtkv_ctx {
-    cudaStream_t s_main = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_kv = nullptr;
+    cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_sel = nullptr;
+    cudaEvent_t ev_up[kMaxPieces] = {}, ev_k3[kMaxPieces] = {};
     void *dK = nullptr, *dV = nullptr, *dKo = nullptr, *dVo = nullptr, *dA = nullptr;
     size_t cap_kv = 0, cap_a = 0, cap_bs = 0;
     int cap_b = 0;
     float *mass = nullptr, *scores = nullptr;
     uint8_t *labels = nullptr, *mask = nullptr;
-    int32_t *sel_idx = nullptr;
+    int32_t *sel_idx = nullptr, *h_sel = nullptr;
     rtkv_row_stats *rs = nullptr, *h_rs = nullptr;
     rtkv_layer_stats *ls = nullptr, *h_ls = nullptr;
     void *scratch = nullptr;
@@ -79,6 +82,7 @@ static void ctx_free_buffers(rtkv_ctx *c)
     for (void *p : dev) if (p) cudaFree(p);
     if (c->h_rs) cudaFreeHost(c->h_rs);
     if (c->h_ls) cudaFreeHost(c->h_ls);
+    if (c->h_sel) cudaFreeHost(c->h_sel);
 }
 
 extern "C" int rtkv_ctx_create(rtkv_ctx **out)
@@ -88,8 +92,14 @@ extern "C" int rtkv_ctx_create(rtkv_ctx **out)
     if (rc) return rc;
     rtkv_ctx *c = new rtkv_ctx();
     cudaError_t e = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_kv, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sel, cudaEventDisableTiming);
+    for (int i = 0; i < kMaxPieces && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_k3[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ls, sizeof(rtkv_layer_stats));
     if (e == cudaSuccess) e = cudaMemset(c->ls, 0, sizeof(rtkv_layer_stats));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_ls, sizeof(rtkv_layer_stats));
@@ -101,12 +111,16 @@ extern "C" int rtkv_ctx_create(rtkv_ctx **out)
 extern "C" int rtkv_ctx_destroy(rtkv_ctx *c)
 {
     if (!c) return RTKV_OK;
-    if (c->s_main) cudaStreamSynchronize(c->s_main);
-    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    cudaStream_t st[] = {c->s_main, c->s_h2d, c->s_d2h};
+    for (cudaStream_t q : st) if (q) cudaStreamSynchronize(q);
     ctx_free_buffers(c);
-    if (c->ev_kv) cudaEventDestroy(c->ev_kv);
-    if (c->s_main) cudaStreamDestroy(c->s_main);
-    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_sel) cudaEventDestroy(c->ev_sel);
+    for (int i = 0; i < kMaxPieces; ++i) {
+        if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+        if (c->ev_k3[i]) cudaEventDestroy(c->ev_k3[i]);
+    }
+    for (cudaStream_t q : st) if (q) cudaStreamDestroy(q);
     delete c;
     return RTKV_OK;
 }
@@ -137,6 +151,9 @@ static int ctx_reserve(rtkv_ctx *c, size_t kv_bytes, size_t a_bytes, int B, int 
         RTKV_CUDA(regrow(&c->mass, bs * 4)); RTKV_CUDA(regrow(&c->scores, bs * 4));
         RTKV_CUDA(regrow(&c->labels, bs)); RTKV_CUDA(regrow(&c->mask, bs));
         RTKV_CUDA(regrow(&c->sel_idx, bs * 4));
+        if (c->h_sel) cudaFreeHost(c->h_sel);
+        c->h_sel = nullptr;
+        RTKV_CUDA(cudaMallocHost((void **)&c->h_sel, bs * 4));
         c->cap_bs = bs;
     }
     size_t need = 0;
@@ -160,6 +177,18 @@ static int ctx_reserve(rtkv_ctx *c, size_t kv_bytes, size_t a_bytes, int B, int 
     return RTKV_OK;
 }
 
+// first output row of batch row b whose token index is >= t (sel is ascending)
+static int first_row_at(const int32_t *sel, int n, int t)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sel[mid] < t) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// Three streams: uploads (attention slice first, then K/V in token-range pieces), compute,
+// downloads.  Scores and the selection only need the attention slice, so they run while K/V are
+// still arriving; each K/V piece is quantised and its output rows start downloading as soon as it
+// lands, which keeps both PCIe directions busy at once.
 extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *V, int dtype, int B, int S, int n,
                                         const void *A, int a_dtype, int H, int64_t sb, int64_t sh, int64_t si,
                                         const rtkv_layer_params *prm, void *K_out, void *V_out,
@@ -174,52 +203,107 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     const size_t es = dtype_bytes(dtype), ea = dtype_bytes(a_dtype);
     const size_t kv_bytes = (size_t)B * S * n * es;
     const size_t a_bytes = (size_t)B * H * S * P * ea;
+    const size_t row_bytes = (size_t)n * es;
     int rc = ctx_reserve(c, kv_bytes, a_bytes, B, S);
     if (rc) return rc;
 
-    // K, V on the copy stream; prompt columns of A (a strided 2-D copy) on the main stream
-    RTKV_CUDA(cudaMemcpyAsync(c->dK, K, kv_bytes, cudaMemcpyHostToDevice, c->s_copy));
-    RTKV_CUDA(cudaMemcpyAsync(c->dV, V, kv_bytes, cudaMemcpyHostToDevice, c->s_copy));
-    RTKV_CUDA(cudaEventRecord(c->ev_kv, c->s_copy));
+    // ---- uploads: prompt columns of A (a strided 2-D copy), then K/V pieces
     if (sh == (int64_t)S * si && sb == (int64_t)H * sh) {
         RTKV_CUDA(cudaMemcpy2DAsync(c->dA, P * ea, A, (size_t)si * ea, P * ea, (size_t)B * H * S,
-                                    cudaMemcpyHostToDevice, c->s_main));
+                                    cudaMemcpyHostToDevice, c->s_h2d));
     } else {
         for (int b = 0; b < B; ++b)
             for (int h = 0; h < H; ++h)
                 RTKV_CUDA(cudaMemcpy2DAsync((char *)c->dA + ((size_t)b * H + h) * S * P * ea, P * ea,
                                             (const char *)A + ((size_t)b * sb + (size_t)h * sh) * ea,
-                                            (size_t)si * ea, P * ea, (size_t)S, cudaMemcpyHostToDevice, c->s_main));
+                                            (size_t)si * ea, P * ea, (size_t)S, cudaMemcpyHostToDevice, c->s_h2d));
     }
+    RTKV_CUDA(cudaEventRecord(c->ev_a, c->s_h2d));
+    int per_row = kMaxPieces / B;                      // pieces per batch row
+    if (per_row < 1) per_row = 1;
+    if (per_row > 8) per_row = 8;
+    const int tok_per_piece = (S + per_row - 1) / per_row;
+    const bool piecewise = (B * per_row <= kMaxPieces);
+    int n_pieces = 0;
+    if (piecewise) {
+        for (int b = 0; b < B; ++b)
+            for (int t0 = 0; t0 < S; t0 += tok_per_piece) {
+                const int t1 = t0 + tok_per_piece < S ? t0 + tok_per_piece : S;
+                const size_t off = ((size_t)b * S + t0) * row_bytes, len = (size_t)(t1 - t0) * row_bytes;
+                RTKV_CUDA(cudaMemcpyAsync((char *)c->dK + off, (const char *)K + off, len, cudaMemcpyHostToDevice, c->s_h2d));
+                RTKV_CUDA(cudaMemcpyAsync((char *)c->dV + off, (const char *)V + off, len, cudaMemcpyHostToDevice, c->s_h2d));
+                RTKV_CUDA(cudaEventRecord(c->ev_up[n_pieces++], c->s_h2d));
+            }
+    } else {
+        RTKV_CUDA(cudaMemcpyAsync(c->dK, K, kv_bytes, cudaMemcpyHostToDevice, c->s_h2d));
+        RTKV_CUDA(cudaMemcpyAsync(c->dV, V, kv_bytes, cudaMemcpyHostToDevice, c->s_h2d));
+        RTKV_CUDA(cudaEventRecord(c->ev_up[0], c->s_h2d));
+    }
+
+    // ---- scores + selection as soon as the attention slice is on the device
+    RTKV_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_a, 0));
     rc = rtkv_prompt_mass(c->dA, a_dtype, B, H, S, (int64_t)H * S * P, (int64_t)S * P, P, nullptr, P, c->mass, c->s_main);
     if (rc) return rc;
     rtkv_layer_params lp = *prm;
     lp.score_dtype = a_dtype;
-    rc = rtkv_score_select(c->mass, c->scores, c->labels, c->mask, c->sel_idx, c->rs, c->ls, c->scratch, c->scratch_bytes, B, S, &lp,
+    rc = rtkv_score_select(c->mass, c->scores, c->labels, c->mask, c->sel_idx, c->rs, c->ls, c->scratch,
+                           c->scratch_bytes, B, S, &lp,
                            RTKV_FROM_MASS | RTKV_MAKE_LABELS | RTKV_SELECT | RTKV_FALLBACK, c->s_main);
     if (rc) return rc;
-    RTKV_CUDA(cudaMemcpyAsync(c->h_ls, c->ls, sizeof(rtkv_layer_stats), cudaMemcpyDeviceToHost, c->s_main));
-    RTKV_CUDA(cudaMemcpyAsync(c->h_rs, c->rs, (size_t)B * sizeof(rtkv_row_stats), cudaMemcpyDeviceToHost, c->s_main));
-    RTKV_CUDA(cudaStreamSynchronize(c->s_main));          // the one data-dependent shape: S' = max_selected
+    RTKV_CUDA(cudaEventRecord(c->ev_sel, c->s_main));
+    RTKV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_sel, 0));
+    RTKV_CUDA(cudaMemcpyAsync(c->h_ls, c->ls, sizeof(rtkv_layer_stats), cudaMemcpyDeviceToHost, c->s_d2h));
+    RTKV_CUDA(cudaMemcpyAsync(c->h_rs, c->rs, (size_t)B * sizeof(rtkv_row_stats), cudaMemcpyDeviceToHost, c->s_d2h));
+    if (piecewise)
+        RTKV_CUDA(cudaMemcpyAsync(c->h_sel, c->sel_idx, (size_t)B * S * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    RTKV_CUDA(cudaStreamSynchronize(c->s_d2h));           // the one data-dependent shape: S' = max_selected
     const int ms = c->h_ls->max_selected;
     *max_selected = ms;
     if (layer_stats) *layer_stats = *c->h_ls;
     if (row_stats) memcpy(row_stats, c->h_rs, (size_t)B * sizeof(rtkv_row_stats));
 
-    RTKV_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_kv, 0));
-    rc = rtkv_quant_gather(c->dK, c->dV, dtype, B, S, n, c->sel_idx, c->rs, c->labels, lp.bits, ms, 1,
-                           c->dKo, c->dVo, c->s_main);
-    if (rc) return rc;
-    const size_t out_bytes = (size_t)B * ms * n * es;
-    if (out_bytes) {
-        RTKV_CUDA(cudaMemcpyAsync(K_out, c->dKo, out_bytes, cudaMemcpyDeviceToHost, c->s_main));
-        RTKV_CUDA(cudaMemcpyAsync(V_out, c->dVo, out_bytes, cudaMemcpyDeviceToHost, c->s_main));
+    // ---- quantise + download piece by piece
+    if (piecewise) {
+        int piece = 0;
+        for (int b = 0; b < B; ++b) {
+            const int cnt = c->h_rs[b].n_selected;
+            const int32_t *sel = c->h_sel + (size_t)b * S;
+            for (int t0 = 0; t0 < S; t0 += tok_per_piece, ++piece) {
+                const int t1 = t0 + tok_per_piece < S ? t0 + tok_per_piece : S;
+                const int r0 = first_row_at(sel, cnt, t0);
+                const int r1 = (t1 == S) ? ms : first_row_at(sel, cnt, t1);   // the last piece carries the zero padding
+                RTKV_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_up[piece], 0));
+                if (r1 <= r0) continue;
+                rc = rtkv_quant_gather_range(c->dK, c->dV, dtype, B, S, n, c->sel_idx, c->rs, c->labels, lp.bits, ms, 1,
+                                             c->dKo, c->dVo, b, 1, r0, r1 - r0, c->s_main);
+                if (rc) return rc;
+                RTKV_CUDA(cudaEventRecord(c->ev_k3[piece], c->s_main));
+                RTKV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k3[piece], 0));
+                const size_t off = ((size_t)b * ms + r0) * row_bytes, len = (size_t)(r1 - r0) * row_bytes;
+                RTKV_CUDA(cudaMemcpyAsync((char *)K_out + off, (char *)c->dKo + off, len, cudaMemcpyDeviceToHost, c->s_d2h));
+                RTKV_CUDA(cudaMemcpyAsync((char *)V_out + off, (char *)c->dVo + off, len, cudaMemcpyDeviceToHost, c->s_d2h));
+            }
+        }
+    } else {
+        RTKV_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_up[0], 0));
+        rc = rtkv_quant_gather(c->dK, c->dV, dtype, B, S, n, c->sel_idx, c->rs, c->labels, lp.bits, ms, 1,
+                               c->dKo, c->dVo, c->s_main);
+        if (rc) return rc;
+        RTKV_CUDA(cudaEventRecord(c->ev_k3[0], c->s_main));
+        RTKV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k3[0], 0));
+        const size_t out_bytes = (size_t)B * ms * row_bytes;
+        if (out_bytes) {
+            RTKV_CUDA(cudaMemcpyAsync(K_out, c->dKo, out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+            RTKV_CUDA(cudaMemcpyAsync(V_out, c->dVo, out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
     }
     const size_t bs = (size_t)B * S;
-    if (scores) RTKV_CUDA(cudaMemcpyAsync(scores, c->scores, bs * 4, cudaMemcpyDeviceToHost, c->s_main));
-    if (labels) RTKV_CUDA(cudaMemcpyAsync(labels, c->labels, bs, cudaMemcpyDeviceToHost, c->s_main));
-    if (mask) RTKV_CUDA(cudaMemcpyAsync(mask, c->mask, bs, cudaMemcpyDeviceToHost, c->s_main));
+    if (scores) RTKV_CUDA(cudaMemcpyAsync(scores, c->scores, bs * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (labels) RTKV_CUDA(cudaMemcpyAsync(labels, c->labels, bs, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (mask) RTKV_CUDA(cudaMemcpyAsync(mask, c->mask, bs, cudaMemcpyDeviceToHost, c->s_d2h));
     RTKV_CUDA(cudaStreamSynchronize(c->s_main));
+    RTKV_CUDA(cudaStreamSynchronize(c->s_d2h));
+    RTKV_CUDA(cudaStreamSynchronize(c->s_h2d));
     return RTKV_OK;
 }
 

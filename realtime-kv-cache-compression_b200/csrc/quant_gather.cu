@@ -28,6 +28,7 @@ struct QGParams {
     const uint8_t *labels;
     int B, S, n, out_rows, zero_pad, quantize;
     int bits[3];
+    int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
 };
 
 // no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
 {
     constexpr int EPV = Vec16<DT>::kElems;
     __shared__ float red[16];
-    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int r = blockIdx.x + p.row_begin, b = blockIdx.y + p.b_begin, t = blockIdx.z;
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
     const int nvec = p.n / EPV;
     uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
@@ -121,7 +122,7 @@ template <int DT>
 __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
 {
     __shared__ float red[16];
-    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int r = blockIdx.x + p.row_begin, b = blockIdx.y + p.b_begin, t = blockIdx.z;
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
     const int64_t dst = ((int64_t)b * p.out_rows + r) * p.n;
     if (r >= cnt) {
@@ -152,10 +153,10 @@ __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
     }
 }
 
-template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st)
+template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st, int nrows, int nb)
 {
     constexpr int EPV = Vec16<DT>::kElems;
-    dim3 grid(p.out_rows, p.B, ntensors);
+    dim3 grid(nrows, nb, ntensors);
     bool vec = p.n % EPV == 0 && p.n <= kMaxVec * kQT * EPV;
     for (int t = 0; t < ntensors; ++t)
         vec = vec && ((uintptr_t)p.x[t] % 16 == 0) && ((uintptr_t)p.y[t] % 16 == 0);
@@ -316,6 +317,7 @@ static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S
     p.B = B; p.S = S; p.n = n; p.out_rows = out_rows; p.zero_pad = zero_pad;
     p.quantize = (labels != nullptr && bits != nullptr);
     for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
+    p.row_begin = 0; p.b_begin = 0;
     return RTKV_OK;
 }
 
@@ -360,7 +362,30 @@ extern "C" int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int 
     if (out_rows == 0) return RTKV_OK;
     QGParams p;
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
-    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream));
+    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, out_rows, B));
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                       const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                       const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                       void *Y0, void *Y1, int b_begin, int b_count, int row_begin, int row_count,
+                                       void *stream)
+{
+    RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1), "rtkv_quant_gather_range: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather_range: bad dtype %d", dtype);
+    RTKV_CHECK_ARG(B > 0 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather_range: bad shape");
+    RTKV_CHECK_ARG(b_begin >= 0 && b_count >= 0 && b_begin + b_count <= B && b_count <= 65535 && row_begin >= 0 &&
+                   row_count >= 0 && row_begin + row_count <= out_rows, "rtkv_quant_gather_range: bad range");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_range: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_range: out_rows > S without sel_idx");
+    int rc = check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather_range");
+    if (rc) return rc;
+    if (row_count == 0 || b_count == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    p.row_begin = row_begin; p.b_begin = b_begin;
+    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, row_count, b_count));
     return RTKV_OK;
 }
 

@@ -517,7 +517,14 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         SelCfg cfg;
         cfg.bits[0] = p.bits[0]; cfg.bits[1] = p.bits[1]; cfg.bits[2] = p.bits[2];
         cfg.budget_bits = p.budget_bits;
-        select_thresholds(rsc, rlb, S, st.kmin, st.kmax, cfg, sm);
+        const long long all_bits = (long long)cfg.bits[0] * st.n0 + (long long)cfg.bits[1] * st.n1 +
+                                   (long long)cfg.bits[2] * st.n2;
+        if (all_bits <= cfg.budget_bits) {            // the whole row fits: no walk needed
+            if (threadIdx.x == 0) { sm.thr[0] = sm.thr[1] = sm.thr[2] = ~0ull; sm.cur = all_bits; }
+            __syncthreads();
+        } else {
+            select_thresholds(rsc, rlb, S, st.kmin, st.kmax, cfg, sm);
+        }
         cost_bits = sm.cur;
         tick(sm);   // thresholds done
         emit_selection(rsc, rlb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
