@@ -117,6 +117,17 @@ def prompt_mass_groups(A, adt, P, idx=None):
     return mass, parts
 
 
+def prompt_mass_partials(A_local, P, group_size):
+    """fp32 local head slice [B,H_local,S,>=P] -> per-group partial sums [B,S,H_local/group_size]."""
+    assert A_local.ndim == 4 and A_local.dtype == np.float32 and A_local.strides[-1] == 4
+    B, Hl, S, _ = A_local.shape
+    sb, sh, si = (s // 4 for s in A_local.strides[:3])
+    parts = np.zeros((B, S, Hl // group_size), np.float32)
+    lib().orc_prompt_mass_partials(_p(A_local), B, Hl, S, ctypes.c_int64(sb), ctypes.c_int64(sh),
+                                   ctypes.c_int64(si), int(P), int(group_size), _p(parts))
+    return parts
+
+
 def mass_from_partials(partials, H):
     partials = _c(partials, np.float32)
     mass = np.empty(partials.shape[:-1], np.float32)

@@ -156,6 +156,28 @@ void orc_prompt_mass(const void *A, int adt, int B, int H, int S,
     orc_prompt_mass_groups(A, adt, B, H, S, sb, sh, si, idx, P, mass, NULL);
 }
 
+/* head-sharded rank: per-group scalar partial sums of a local head slice (fp32),
+ * partials [B,S,H_local/group_size]; same per-group order as orc_prompt_mass_groups */
+void orc_prompt_mass_partials(const float *A, int B, int H_local, int S,
+                              int64_t sb, int64_t sh, int64_t si, int P, int group_size, float *partials)
+{
+    const int ng = H_local / group_size;
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < S; ++i)
+            for (int g = 0; g < ng; ++g) {
+                float lane[32];
+                for (int l = 0; l < 32; ++l) lane[l] = 0.0f;
+                for (int p = 0; p < P; ++p) {
+                    float s = 0.0f;
+                    for (int h = g * group_size; h < (g + 1) * group_size; ++h)
+                        s = s + A[b * sb + h * sh + (int64_t)i * si + p];
+                    int l = (p & 127) >> 2;
+                    lane[l] = lane[l] + s;
+                }
+                partials[((int64_t)b * S + i) * ng + g] = butterfly32(lane);
+            }
+}
+
 /* head-sharded combine: partials [B,S,8] (all groups, gathered) -> mass */
 void orc_mass_from_partials(const float *partials, int64_t n, int H, float *mass)
 {

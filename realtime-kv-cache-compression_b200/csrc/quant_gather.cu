@@ -29,6 +29,7 @@ struct QGParams {
     int B, S, n, out_rows, zero_pad, quantize;
     int bits[3];
     int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
+    const float *ext_minmax;  // [B,out_rows,4] = (min0, max0, min1, max1) of the WHOLE row (head sharding) or NULL
 };
 
 // no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
@@ -99,7 +100,12 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
             for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
         }
     }
-    block_minmax(mn, mx, nan, red);
+    if (p.ext_minmax) {         // row min/max reduced over all ranks' head shards
+        const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
+        mn = mm[0]; mx = mm[1];
+    } else {
+        block_minmax(mn, mx, nan, red);
+    }
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
     float scale, zp;
     quant_params<DT>(mn, mx, bits, scale, zp);
@@ -142,7 +148,12 @@ __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
         float v = load_elem<DT>(pick_x(p, t), src + c);
         nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
     }
-    block_minmax(mn, mx, nan, red);
+    if (p.ext_minmax) {
+        const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
+        mn = mm[0]; mx = mm[1];
+    } else {
+        block_minmax(mn, mx, nan, red);
+    }
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
     float scale, zp;
     quant_params<DT>(mn, mx, bits, scale, zp);
@@ -151,6 +162,31 @@ __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
         float v = load_elem<DT>(pick_x(p, t), src + c);
         store_elem<DT>(pick_y(p, t), dst + c, dequant_code<DT>(quant_code<DT>(v, scale, zp, qmax_r), scale, zp));
     }
+}
+
+// Local (this rank's head shard) min/max of every kept row: out[b,r,:] = (min0, max0, min1, max1).
+// Rows past n_selected get (+inf, -inf) so that a MIN/MAX reduction over ranks ignores them.
+template <int DT>
+__global__ void __launch_bounds__(kQT) row_minmax_kernel(QGParams p, float *out)
+{
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    float *o = out + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
+    if (r >= cnt) {
+        if (threadIdx.x == 0) { o[0] = INFINITY; o[1] = -INFINITY; }
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int64_t src = ((int64_t)b * p.S + tok) * p.n;
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        const float v = load_elem<DT>(pick_x(p, t), src + c);
+        nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    block_minmax(mn, mx, nan, red);
+    if (threadIdx.x == 0) { o[0] = mn; o[1] = mx; }
 }
 
 template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st, int nrows, int nb)
@@ -318,6 +354,7 @@ static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S
     p.quantize = (labels != nullptr && bits != nullptr);
     for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
     p.row_begin = 0; p.b_begin = 0;
+    p.ext_minmax = nullptr;
     return RTKV_OK;
 }
 
@@ -386,6 +423,43 @@ extern "C" int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
     p.row_begin = row_begin; p.b_begin = b_begin;
     RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, row_count, b_count));
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                               const int32_t *sel_idx, const rtkv_row_stats *row_stats, int out_rows,
+                               float *minmax, void *stream)
+{
+    RTKV_CHECK_ARG(X0 && minmax, "rtkv_row_minmax: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_row_minmax: bad shape");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_row_minmax: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_row_minmax: out_rows > S without sel_idx");
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, nullptr, nullptr, out_rows, 0, nullptr, nullptr);
+    dim3 grid(out_rows, B, X1 ? 2 : 1);
+    RTKV_DISPATCH(dtype, (row_minmax_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, minmax)));
+    RTKV_LAUNCH_CHECK("row_minmax_kernel");
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                        const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                        const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                        const float *minmax, void *Y0, void *Y1, void *stream)
+{
+    RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1) && labels && bits && minmax, "rtkv_quant_gather_minmax: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather_minmax: bad dtype %d", dtype);
+    RTKV_CHECK_ARG(B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather_minmax: bad shape");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_minmax: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_minmax: out_rows > S without sel_idx");
+    int rc = check_bits(bits, dtype, "rtkv_quant_gather_minmax");
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    p.ext_minmax = minmax;
+    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, out_rows, B));
     return RTKV_OK;
 }
 

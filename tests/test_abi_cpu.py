@@ -148,3 +148,41 @@ def test_tracker_cumulative_scores_host_logic(built_lib):
     t.layer_scores = {3: torch.ones(1, 5)}
     with pytest.raises(KeyError):
         t.get_cumulative_scores(3)                                              # reference: layer_scores[0]
+
+
+def test_compat_tree_resolves_reference_imports(built_lib):
+    """PYTHONPATH=<pkg>/compat:<pkg> makes the reference's own import lines resolve to rtkv."""
+    import subprocess, sys
+    pkg = os.path.join(ROOT, "realtime-kv-cache-compression_b200")
+    code = ("from configs.base_config import CompressionConfig\n"
+            "from src.compression.unified_compressor import RealTimePrefillCompressor\n"
+            "from src.compression.token_importance import PromptGuidedImportanceScorer, LayerWiseImportanceTracker\n"
+            "from src.compression.dynamic_quantization import DynamicPrecisionQuantizer\n"
+            "from src.compression.selective_propagation import SelectiveTokenPropagator\n"
+            "from src.models.modified_llama import create_compressed_llama_model, CompressedLlamaForCausalLM\n"
+            "import rtkv\n"
+            "assert RealTimePrefillCompressor is rtkv.RealTimePrefillCompressor\n"
+            "c = RealTimePrefillCompressor(CompressionConfig(num_hidden_layers=4))\n"
+            "print('ok', len(c.config.layer_weights))\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(pkg, "compat") + os.pathsep + pkg)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip() == "ok 4", out.stderr
+
+
+def test_model_hook_chain_on_cpu(built_lib):
+    """set_compressor reaches every attention module; a decode step (q_len == 1) and training mode
+    never call the compressor (modified_llama.py:102), so this runs without a GPU."""
+    import rtkv
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM
+    from transformers import LlamaConfig
+    hf = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=4, vocab_size=97, max_position_embeddings=64)
+    model = CompressedLlamaForCausalLM(hf).eval()
+    comp = rtkv.RealTimePrefillCompressor(rtkv.CompressionConfig(num_hidden_layers=2, num_attention_heads=4, hidden_size=64))
+    model.set_compressor(comp)
+    assert all(l.self_attn.compressor is comp for l in model.model.layers)
+    with torch.no_grad():
+        out = model(input_ids=torch.tensor([[5]]))
+    assert out.logits.shape == (1, 1, 97) and out.compression_info == {}
+    assert model.get_compression_stats() == {}
+    model.reset_compression_state()

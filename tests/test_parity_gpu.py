@@ -362,6 +362,37 @@ def test_quant_gather_selected_rows_zero_padded(rt, dt):
         np.testing.assert_array_equal(sl.cpu().numpy()[b, :c], labels[b][mask[b] == 1])
 
 
+@pytest.mark.parametrize("R", [2, 4, 8])
+def test_head_sharded_layer_equals_single_gpu(rt, R):
+    """R ranks emulated in one process (collectives replaced by cat / min / max): the concatenated
+    rank outputs equal the single-GPU compress_layer_kv_cache bit for bit."""
+    rtkv, ops = rt
+    H, D, S, B = 16, 32, 400, 2
+    K, V, A, P = synth_layer(B, H, S, H * D, seed=R)
+    cfg = rtkv.CompressionConfig(num_attention_heads=H, hidden_size=H * D, high_precision_bits=8,
+                                 medium_precision_bits=4, low_precision_bits=2)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    layer = 25
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    k_ref, v_ref, info = comp.compress_layer_kv_cache(K, V, A, ids, layer)
+    hl, gs, wl = H // R, H // 8, H * D // R
+    parts = [ops.prompt_mass_partials(A[:, r * hl:(r + 1) * hl].contiguous(), P, gs) for r in range(R)]
+    mass = ops.mass_from_partials(torch.cat(parts, dim=-1).contiguous(), H)
+    params, _ = comp.layer_params(layer, S, ops.F32)
+    sel = ops.score_select(params, B, S, K.device, mass=mass)
+    lyr, rows = sel.read_stats()
+    ms = int(lyr["max_selected"])
+    assert ms == k_ref.shape[1]
+    np.testing.assert_array_equal(host(sel.mask), info["propagation_info"]["selection_mask"].cpu().numpy().astype(np.uint8))
+    Ks = [K[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    Vs = [V[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    mms = torch.stack([ops.row_minmax(Ks[r], Vs[r], sel, ms) for r in range(R)])
+    mm = torch.stack([mms[..., 0].amin(0), mms[..., 1].amax(0), mms[..., 2].amin(0), mms[..., 3].amax(0)], dim=-1)
+    outs = [ops.quant_gather_minmax(Ks[r], Vs[r], sel, sel.labels, (2, 4, 8), ms, mm) for r in range(R)]
+    assert torch.equal(torch.cat([o[0] for o in outs], dim=-1), k_ref)
+    assert torch.equal(torch.cat([o[1] for o in outs], dim=-1), v_ref)
+
+
 def test_whole_tensor_params_and_quantize(rt):
     rtkv, ops = rt
     q = rtkv.DynamicPrecisionQuantizer(rtkv.CompressionConfig())
@@ -668,3 +699,32 @@ def test_reference_style_scorer_tests(rt):
     assert torch.allclose(cum, (tr.layer_scores[0] + tr.layer_scores[1] + tr.layer_scores[2]) / 3)
     with pytest.raises(IndexError):
         scorer.compute_importance_scores(attn, pidx, 8)         # layer_idx >= len(layer_weights)
+
+
+def test_llama_hook_prefill_on_gpu(rt):
+    """The hook block of modified_llama.py:96-152 on a tiny random Llama: every layer is compressed,
+    statistics are attached, and the layer result equals the eager formulation recomputed by hand."""
+    rtkv, ops = rt
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM
+    from transformers import LlamaConfig
+    torch.manual_seed(0)
+    hf = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=8,
+                     num_key_value_heads=8, vocab_size=211, max_position_embeddings=256)
+    model = CompressedLlamaForCausalLM(hf).cuda().eval()
+    cfg = rtkv.CompressionConfig(num_hidden_layers=3, num_attention_heads=8, hidden_size=128, high_precision_bits=8,
+                                 medium_precision_bits=8, low_precision_bits=8)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    model.set_compressor(comp)
+    ids = torch.randint(0, 211, (2, 60), device="cuda")
+    with torch.no_grad():
+        out = model(input_ids=ids, use_cache=True)
+    assert torch.isfinite(out.logits).all() and out.logits.shape == (2, 60, 211)
+    assert sorted(comp.layer_states) == [0, 1, 2]
+    # all-8-bit: cost 1.0 per token -> exactly floor(ratio*S) tokens survive
+    assert [comp.layer_states[l]["compressed_shape"][1] for l in range(3)] == [48, 36, 24]
+    assert out.compression_info["total_layers_processed"] == 3
+    assert abs(out.compression_info["cumulative_compression"] - 24 / 60) < 1e-12
+    kept = out.past_key_values.layers[2].keys.shape[2]
+    assert kept == 24                                            # the cache entry is the compressed K/V
+    model.reset_compression_state()
+    assert comp.layer_states == {}
