@@ -131,8 +131,19 @@ def prompt_mass_partials(A_local, P, group_size):
 def mass_from_partials(partials, H):
     partials = _c(partials, np.float32)
     mass = np.empty(partials.shape[:-1], np.float32)
-    lib().orc_mass_from_partials(_p(partials), ctypes.c_int64(mass.size), int(H), _p(mass))
+    lib().orc_mass_from_partials(_p(partials), ctypes.c_int64(mass.size), int(partials.shape[-1]), int(H), _p(mass))
     return mass
+
+
+def prompt_mass_qk(Q, Kp, lse, dt, scale, causal, group_size):
+    """Q [B,H,S,D], Kp [B,H,P,D] (storage dtype dt), lse [B,H,S] f32 -> partials [B,S,H/group_size]."""
+    Q, Kp, lse = _c(Q), _c(Kp), _c(lse, np.float32)
+    B, H, S, D = Q.shape
+    P = Kp.shape[2]
+    parts = np.zeros((B, S, H // group_size), np.float32)
+    lib().orc_prompt_mass_qk(_p(Q), _p(Kp), _p(lse), int(dt), B, H, S, D, P, ctypes.c_double(scale),
+                             int(bool(causal)), int(group_size), _p(parts))
+    return parts
 
 
 def position_bias(S):

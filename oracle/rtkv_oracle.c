@@ -178,14 +178,41 @@ void orc_prompt_mass_partials(const float *A, int B, int H_local, int S,
             }
 }
 
-/* head-sharded combine: partials [B,S,8] (all groups, gathered) -> mass */
-void orc_mass_from_partials(const float *partials, int64_t n, int H, float *mass)
+/* head-sharded combine: partials [n, ng] (all groups, gathered) -> mass */
+void orc_mass_from_partials(const float *partials, int64_t n, int ng, int H, float *mass)
 {
     for (int64_t t = 0; t < n; ++t) {
-        float tot = partials[t * 8];
-        for (int g = 1; g < 8; ++g) tot = tot + partials[t * 8 + g];
+        float tot = partials[t * ng];
+        for (int g = 1; g < ng; ++g) tot = tot + partials[t * ng + g];
         mass[t] = tot / (float)H;
     }
+}
+
+/* Extension with no reference behaviour (parity unpinned by the reference): prompt mass from
+ * Q, K_prompt and the row log-sum-exp.  Q [B,H,S,D], Kp [B,H,P,D] in dtype dt, lse [B,H,S].
+ * partials[b,i,g] = sum_{h in g} sum_{j<P, j<=i} exp(scale*q.k - lse)   (double accumulation:
+ * this is the tolerance reference of the tensor-core kernel, not a bit-exact contract). */
+void orc_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dt, int B, int H, int S, int D,
+                        int P, double scale, int causal, int group_size, float *partials)
+{
+    const int ng = H / group_size;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < S; ++i)
+            for (int g = 0; g < ng; ++g) {
+                double acc = 0.0;
+                for (int h = g * group_size; h < (g + 1) * group_size; ++h) {
+                    const int64_t qo = (((int64_t)b * H + h) * S + i) * D;
+                    const double l = (double)lse[((int64_t)b * H + h) * S + i];
+                    for (int j = 0; j < P && (!causal || j <= i); ++j) {
+                        const int64_t ko = (((int64_t)b * H + h) * P + j) * D;
+                        double dot = 0.0;
+                        for (int d = 0; d < D; ++d) dot += (double)ld(Q, qo + d, dt) * (double)ld(Kp, ko + d, dt);
+                        acc += exp(scale * dot - l);
+                    }
+                }
+                partials[((int64_t)b * S + i) * ng + g] = (float)acc;
+            }
 }
 
 /* correctly rounded fp32 log (definition (2) above) */

@@ -168,16 +168,15 @@ prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, 
     }
 }
 
-// head-sharded combine: partials [n,8] -> mass [n] = (p0 + p1 + ... + p7) / H
-__global__ void mass_from_partials_kernel(const float *__restrict__ partials, int64_t n, float fH, float *mass)
+// combine: partials [n, n_groups] -> mass [n] = (p0 + p1 + ... ) / H, groups added in order
+__global__ void mass_from_partials_kernel(const float *__restrict__ partials, int64_t n, int n_groups, float fH,
+                                          float *mass)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const float4 a = reinterpret_cast<const float4 *>(partials)[2 * t];
-    const float4 c = reinterpret_cast<const float4 *>(partials)[2 * t + 1];
-    float tot = a.x;
-    tot = __fadd_rn(tot, a.y); tot = __fadd_rn(tot, a.z); tot = __fadd_rn(tot, a.w);
-    tot = __fadd_rn(tot, c.x); tot = __fadd_rn(tot, c.y); tot = __fadd_rn(tot, c.z); tot = __fadd_rn(tot, c.w);
+    const float *q = partials + t * n_groups;
+    float tot = q[0];
+    for (int g = 1; g < n_groups; ++g) tot = __fadd_rn(tot, q[g]);
     mass[t] = __fdiv_rn(tot, fH);
 }
 
@@ -235,11 +234,10 @@ extern "C" int rtkv_prompt_mass_partials(const void *A, int dtype, int B, int H_
                                  partials, (cudaStream_t)stream);
 }
 
-extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int H, float *mass, void *stream)
+extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int n_groups, int H, float *mass, void *stream)
 {
-    RTKV_CHECK_ARG(partials && mass && n > 0 && H > 0, "rtkv_mass_from_partials: bad argument");
-    RTKV_CHECK_ARG((uintptr_t)partials % 16 == 0, "rtkv_mass_from_partials: partials must be 16-byte aligned");
-    mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, (float)H, mass);
+    RTKV_CHECK_ARG(partials && mass && n > 0 && H > 0 && n_groups > 0, "rtkv_mass_from_partials: bad argument");
+    mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, n_groups, (float)H, mass);
     RTKV_LAUNCH_CHECK("mass_from_partials_kernel");
     return RTKV_OK;
 }

@@ -1,10 +1,299 @@
-// prompt_mass_qk.cu — K1b: fused Q*K_prompt^T scoring on tcgen05 (placeholder until the
-// tensor-core kernel lands; the entry point reports "unsupported" instead of guessing).
+// prompt_mass_qk.cu — K1b: prompt-attention mass straight from Q, K_prompt and the row
+// log-sum-exp, without a materialised S x S attention matrix (the reference
+// receives softmaxed attention and slices the prompt key columns, token_importance.py:41;
+// the only contraction that reproduces that slice is Q . K_prompt^T).
+//
+//   partial[b,i,g] = sum_{h in group g} sum_{j < P, j <= i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
+//   mass[b,i]      = (partial[b,i,0] + ... + partial[b,i,G-1]) / H          (rtkv_mass_from_partials)
+//
+// This is the one dense contraction of the path, so it runs on the 5th-generation tensor
+// cores: tcgen05.mma (M=128 query rows x N=128 prompt keys x K=16, bf16/f16 in, fp32
+// accumulate in TMEM), operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte
+// swizzle), one CTA per (128-row query tile, head group, batch row):
+//   warp 0        TMA producer: per head 2+2 boxes (Q tile, K_prompt tile) into a 3-stage ring
+//   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per head, tcgen05.commit -> mbarriers
+//   warps 2..5    epilogue: tcgen05.ld 32 lanes x 32 columns, exp2(s*c - lse*log2e), causal /
+//                 P mask, in-thread row sum (a thread owns a query row), accumulate over heads
+// Two 128-column accumulators in TMEM let the MMAs of head h+1 overlap the epilogue of head h.
+// Roofline: 2*B*H*S*P*D flop (4.3 GFLOP per 7B layer at S=4096) and B*H*S*D*2 bytes of Q
+// (32 MiB): memory/MUFU bound, the tensor cores are there so the contraction is not the limiter.
+#include <cuda.h>
+
 #include "common.cuh"
 
-extern "C" int rtkv_prompt_mass_qk(const void *, const void *, const float *, int, int, int, int, int, int,
-                                   float, int, float *, void *)
+namespace rtkv {
+
+constexpr int kTileM = 128;      // query rows per CTA
+constexpr int kTileN = 128;      // prompt keys (P <= 128)
+constexpr int kHeadDim = 128;    // K of the GEMM
+constexpr int kKBlock = 64;      // elements per 128-byte swizzle atom row
+constexpr int kStages = 3;
+constexpr int kOperandBytes = kTileM * kHeadDim * 2;          // 32 KiB: one Q (or K) tile
+constexpr int kStageBytes = 2 * kOperandBytes;                 // Q + K
+constexpr int kQkThreads = 192;
+constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256;
+
+// ---- raw PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    rtkv::set_error("rtkv_prompt_mass_qk: not built in this version");
-    return RTKV_EUNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 "version 1"):
+// rows 128 B apart inside an 8-row group, groups 1024 B apart (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct QkParams {
+    const float *lse;     // [B,H,S]
+    float *partials;      // [B,S,n_groups]
+    int B, H, S, P, gs, n_groups, causal;
+    float scale_log2;     // scale * log2(e)
+    uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(kQkThreads, 1)
+prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, QkParams p)
+{
+    extern __shared__ unsigned char qk_smem_raw[];
+    // 128-byte swizzle needs 1024-byte aligned tiles
+    unsigned char *smem = (unsigned char *)(((uintptr_t)qk_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + (size_t)kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int i0 = tile * kTileM;
+    const int h0 = g * p.gs, nh = p.gs;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // 256 TMEM columns: two 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int hh = 0; hh < nh; ++hh) {
+                const int s = hh % kStages;
+                const uint32_t ph = (hh / kStages) & 1;
+                mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+                const uint32_t fb = smem_u32(&full[s]);
+                mbar_expect_tx(fb, kStageBytes);
+                const uint32_t qdst = smem_u32(smem + (size_t)s * kStageBytes);
+                const uint32_t kdst = qdst + kOperandBytes;
+                const int h = h0 + hh;
+                const int qrow = (b * p.H + h) * p.S + i0;
+                const int krow = (b * p.H + h) * p.P;
+                tma_load_2d(qdst, &map_q, 0, qrow, fb);
+                tma_load_2d(qdst + kOperandBytes / 2, &map_q, kKBlock, qrow, fb);
+                tma_load_2d(kdst, &map_k, 0, krow, fb);
+                tma_load_2d(kdst + kOperandBytes / 2, &map_k, kKBlock, krow, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int hh = 0; hh < nh; ++hh) {
+                const int s = hh % kStages, a = hh & 1;
+                mbar_wait(smem_u32(&tempty[a]), ((hh >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                mbar_wait(smem_u32(&full[s]), (hh / kStages) & 1);        // TMA landed Q and K
+                tc_fence_after();
+                const uint32_t qbase = smem_u32(smem + (size_t)s * kStageBytes);
+                const uint32_t kbase = qbase + kOperandBytes;
+                const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = (uint32_t)(kb * (kOperandBytes / 2) + k * 32);   // 16 elements = 32 B
+                        umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
+                                 (uint32_t)((kb | k) != 0));
+                    }
+                umma_commit(smem_u32(&empty[s]));      // smem stage reusable once these MMAs retire
+                umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;              // accumulator row == TMEM lane
+        const int i = i0 + row;
+        const bool live = i < p.S;
+        const float kLog2e = 1.4426950408889634f;
+        float acc = 0.0f;
+        for (int hh = 0; hh < nh; ++hh) {
+            const int a = hh & 1, h = h0 + hh;
+            const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
+            mbar_wait(smem_u32(&tfull[a]), (hh >> 1) & 1);
+            tc_fence_after();
+            float rs = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kTileN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c), v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const int j = c + k;
+                    const bool ok = (j < p.P) && (!p.causal || j <= i);
+                    const float e = ex2_approx(__uint_as_float(v[k]) * p.scale_log2 - l2);
+                    rs += ok ? e : 0.0f;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
+            acc += rs;
+        }
+        if (live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_rows_map(CUtensorMap *map, const void *base, int dtype, uint64_t rows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !sym) return cuda_fail(e != cudaSuccess ? e : cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
+        fn = (EncodeTiledFn)sym;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)kHeadDim, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kHeadDim * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dtype == RTKV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RTKV_EINVAL; }
+    return RTKV_OK;
+}
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype, int B, int H, int S,
+                                   int D, int P, float scale, int causal, int group_size, float *partials,
+                                   void *stream)
+{
+    RTKV_CHECK_ARG(Q && Kp && lse && partials, "rtkv_prompt_mass_qk: null pointer");
+    if (dtype != RTKV_BF16 && dtype != RTKV_F16) {
+        set_error("rtkv_prompt_mass_qk: Q/K must be bf16 or f16 (tf32 would cost 13 mantissa bits of the logits)");
+        return RTKV_EUNSUPPORTED;
+    }
+    if (D != kHeadDim || P < 1 || P > kTileN) {
+        set_error("rtkv_prompt_mass_qk: needs head_dim == 128 and 1 <= P <= 128 (got D=%d, P=%d)", D, P);
+        return RTKV_EUNSUPPORTED;
+    }
+    RTKV_CHECK_ARG(B > 0 && H > 0 && S > 0 && group_size > 0 && H % group_size == 0, "rtkv_prompt_mass_qk: bad shape");
+    RTKV_CHECK_ARG((int64_t)B * H * S < (1ll << 31), "rtkv_prompt_mass_qk: B*H*S too large");
+    RTKV_CHECK_ARG((uintptr_t)Q % 16 == 0 && (uintptr_t)Kp % 16 == 0, "rtkv_prompt_mass_qk: Q/K must be 16-byte aligned");
+    RTKV_CHECK_ARG(B <= 65535 && H / group_size <= 65535, "rtkv_prompt_mass_qk: grid too large");
+    CUtensorMap map_q, map_k;
+    int rc = encode_rows_map(&map_q, Q, dtype, (uint64_t)B * H * S);
+    if (rc) return rc;
+    rc = encode_rows_map(&map_k, Kp, dtype, (uint64_t)B * H * P);
+    if (rc) return rc;
+    QkParams p;
+    p.lse = lse; p.partials = partials;
+    p.B = B; p.H = H; p.S = S; p.P = P; p.gs = group_size; p.n_groups = H / group_size; p.causal = causal;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    RTKV_CUDA(cudaFuncSetAttribute(prompt_mass_qk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQkSmem));
+    dim3 grid((S + kTileM - 1) / kTileM, H / group_size, B);
+    prompt_mass_qk_kernel<<<grid, kQkThreads, kQkSmem, (cudaStream_t)stream>>>(map_q, map_k, p);
+    RTKV_LAUNCH_CHECK("prompt_mass_qk_kernel");
+    return RTKV_OK;
 }

@@ -114,25 +114,34 @@ def prompt_mass_partials(attn_local, prompt_len, group_size):
 
 
 def mass_from_partials(partials, num_heads):
-    """partials [B,S,8] (all head groups, in group order) -> mass [B,S] = (p0+...+p7)/H."""
+    """partials [B,S,G] (head groups in order) -> mass [B,S] = (p0+...+p_{G-1})/H."""
     require_cuda()
     partials = partials.contiguous()
-    assert partials.shape[-1] == 8 and partials.dtype == torch.float32
+    assert partials.dtype == torch.float32
     mass = torch.empty(partials.shape[:-1], dtype=torch.float32, device=partials.device)
-    check(lib.rtkv_mass_from_partials(_ptr(partials), mass.numel(), int(num_heads), _ptr(mass), _stream()))
+    check(lib.rtkv_mass_from_partials(_ptr(partials), mass.numel(), int(partials.shape[-1]), int(num_heads),
+                                      _ptr(mass), _stream()))
     return mass
 
 
-def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
-    """Fused Q.K_prompt^T scoring: q [B,H,S,D], k_prompt [B,H,P,D], lse [B,H,S] -> mass [B,S]."""
+def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True, group_size=None):
+    """Fused Q.K_prompt^T scoring on tcgen05: q [B,H,S,128], k_prompt [B,H,P,128] (bf16/f16),
+    lse [B,H,S] f32 -> per-head-group partial sums [B,S,H/group_size]."""
     require_cuda()
     q, k_prompt, lse = q.contiguous(), k_prompt.contiguous(), lse.contiguous().float()
     B, H, S, D = q.shape
     P = k_prompt.shape[2]
-    mass = torch.empty(B, S, dtype=torch.float32, device=q.device)
+    if group_size is None:
+        group_size = H // 8 if H % 8 == 0 else H
+    parts = torch.empty(B, S, H // group_size, dtype=torch.float32, device=q.device)
     check(lib.rtkv_prompt_mass_qk(_ptr(q), _ptr(k_prompt), _ptr(lse), dtype_code(q), B, H, S, D, P,
-                                  float(scale), int(bool(causal)), _ptr(mass), _stream()))
-    return mass
+                                  float(scale), int(bool(causal)), int(group_size), _ptr(parts), _stream()))
+    return parts
+
+
+def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
+    """mass [B,S] from Q, K_prompt and the row log-sum-exp (no S x S attention matrix)."""
+    return mass_from_partials(prompt_mass_qk_partials(q, k_prompt, lse, scale, causal), q.shape[1])
 
 
 def position_bias(seq_len, device):

@@ -721,10 +721,52 @@ def test_llama_hook_prefill_on_gpu(rt):
     assert torch.isfinite(out.logits).all() and out.logits.shape == (2, 60, 211)
     assert sorted(comp.layer_states) == [0, 1, 2]
     # all-8-bit: cost 1.0 per token -> exactly floor(ratio*S) tokens survive
-    assert [comp.layer_states[l]["compressed_shape"][1] for l in range(3)] == [48, 36, 24]
+    assert [comp.layer_states[l]["compressed_shape"][1] for l in range(3)] == [36, 36, 24]   # L=3: int(0.3*3)=0 early layers, int(0.7*3)=2
     assert out.compression_info["total_layers_processed"] == 3
     assert abs(out.compression_info["cumulative_compression"] - 24 / 60) < 1e-12
     kept = out.past_key_values.layers[2].keys.shape[2]
     assert kept == 24                                            # the cache entry is the compressed K/V
     model.reset_compression_state()
     assert comp.layer_states == {}
+
+
+# ---------------------------------------------------------------- K1b fused Q.K scoring (tcgen05)
+def qk_inputs(B, H, S, P, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    D = 128
+    q = (torch.randn(B, H, S, D, generator=g, device="cuda") * 1.2).to(dtype)
+    k = (torch.randn(B, H, S, D, generator=g, device="cuda") * 1.2).to(dtype)
+    scale = D ** -0.5
+    logits = (q.float() @ k.float().transpose(-1, -2)) * scale
+    logits = logits + torch.full((S, S), float("-inf"), device="cuda").triu(1)
+    lse = torch.logsumexp(logits, dim=-1)
+    probs = torch.softmax(logits, dim=-1)[..., :P].contiguous()
+    return q, k[:, :, :P].contiguous(), lse, scale, probs
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,S,P", [(1, 8, 256, 51), (2, 16, 640, 128), (1, 32, 1000, 128), (1, 8, 130, 26)])
+def test_qk_scoring_matches_restatement(rt, dtype, B, H, S, P):
+    """tensor-core scoring vs the CPU restatement (double accumulation) and vs the probability-slice
+    kernel on the same attention: north-star tolerance for half inputs is 1e-3 relative."""
+    _, ops = rt
+    q, kp, lse, scale, probs = qk_inputs(B, H, S, P, dtype, seed=S + H)
+    gs = H // 8
+    parts = ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True, group_size=gs)
+    dt = oracle.BF16 if dtype == torch.bfloat16 else oracle.F16
+    want = oracle.prompt_mass_qk(oracle.from_torch(q)[0], oracle.from_torch(kp)[0], lse.cpu().numpy(), dt, scale, True, gs)
+    np.testing.assert_allclose(parts.cpu().numpy(), want, rtol=2e-4, atol=1e-6)
+    mass = ops.prompt_mass_qk(q, kp, lse, scale)
+    np.testing.assert_allclose(mass.cpu().numpy(), oracle.mass_from_partials(want, H), rtol=2e-4, atol=1e-6)
+    via_probs = ops.prompt_mass(probs, prompt_len=P)
+    np.testing.assert_allclose(mass.cpu().numpy(), via_probs.cpu().numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_qk_scoring_rejects_unsupported(rt):
+    _, ops = rt
+    q = torch.zeros(1, 8, 128, 128, device="cuda")
+    with pytest.raises(RuntimeError, match="bf16 or f16"):
+        ops.prompt_mass_qk_partials(q, q, torch.zeros(1, 8, 128, device="cuda"), 0.1)
+    q64 = torch.zeros(1, 8, 128, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="head_dim == 128"):
+        ops.prompt_mass_qk_partials(q64, q64, torch.zeros(1, 8, 128, device="cuda"), 0.1)
