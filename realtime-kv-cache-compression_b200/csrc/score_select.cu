@@ -238,6 +238,7 @@ __device__ void build_hist(const float *sc, const uint8_t *lb, int S, Smem &sm)
     const int shift = sm.lvl_shift[d], nb = sm.lvl_nb[d];
     for (int x = threadIdx.x; x < 3 * kNB; x += kT) (&sm.hist[0][0])[x] = 0;
     __syncthreads();
+#pragma unroll 4
     for (int i = threadIdx.x; i < S; i += kT) {
         unsigned long long k = walk_key(sc[i], i);
         if (k >= lo) {
@@ -288,6 +289,7 @@ __device__ void walk_bucket(const float *sc, const uint8_t *lb, int S, int bsel,
     const int shift = sm.lvl_shift[d];
     if (threadIdx.x == 0) sm.ncand = 0;
     __syncthreads();
+#pragma unroll 4
     for (int i = threadIdx.x; i < S; i += kT) {
         unsigned long long k = walk_key(sc[i], i);
         if (k >= lo && ((k - lo) >> shift) == (unsigned long long)bsel) {
@@ -394,39 +396,52 @@ __device__ void emit_selection(const float *sc, const uint8_t *lb, int S, uint8_
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long t0 = sm.thr[0], t1 = sm.thr[1], t2 = sm.thr[2];
-    const int chunk = ((S + 31) / 32 + 31) / 32 * 32;           // multiple of 32 tokens per warp
+    const int chunk = ((S + 31) / 32 + 127) / 128 * 128;        // multiple of 128 tokens per warp
     const int beg = warp * chunk, end = min(S, beg + chunk);
     int mine = 0;
-    for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
-        bool keep = false;
-        if (i < end) {
-            const int l = lab_at(lb, i);
-            keep = walk_key(sc[i], i) < (l == 0 ? t0 : (l == 1 ? t1 : t2));
+    for (int base = beg; base < end; base += 128) {
+        float sv[4];
+        int lv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            sv[u] = i < end ? sc[i] : 0.0f;
+            lv[u] = i < end ? lab_at(lb, i) : 0;
         }
-        mine += __popc(__ballot_sync(0xffffffffu, keep));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            const bool keep = i < end && walk_key(sv[u], i) < (lv[u] == 0 ? t0 : (lv[u] == 1 ? t1 : t2));
+            mine += __popc(__ballot_sync(0xffffffffu, keep));
+        }
     }
     int total;
     int off = block_excl_scan(lane == 0 ? mine : 0, total, sm);
     off = __shfl_sync(0xffffffffu, off, 0);
     RowAgg a = agg_identity();
-    for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
-        bool keep = false;
-        float s = 0.0f;
-        int l = 0;
-        if (i < end) {
-            s = sc[i]; l = lab_at(lb, i);
-            keep = walk_key(s, i) < (l == 0 ? t0 : (l == 1 ? t1 : t2));
-            mask[i] = keep ? 1 : 0;
+    for (int base = beg; base < end; base += 128) {
+        float sv[4];
+        int lv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            sv[u] = i < end ? sc[i] : 0.0f;
+            lv[u] = i < end ? lab_at(lb, i) : 0;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            sel_idx[off + __popc(bal & ((1u << lane) - 1u))] = i;
-            a.sum += (double)s;
-            a.n0 += (l == 0); a.n1 += (l == 1); a.n2 += (l == 2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            const int l = lv[u];
+            const bool keep = i < end && walk_key(sv[u], i) < (l == 0 ? t0 : (l == 1 ? t1 : t2));
+            if (i < end) mask[i] = keep ? 1 : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                sel_idx[off + __popc(bal & ((1u << lane) - 1u))] = i;
+                a.sum += (double)sv[u];
+                a.n0 += (l == 0); a.n1 += (l == 1); a.n2 += (l == 2);
+            }
+            off += __popc(bal);
         }
-        off += __popc(bal);
     }
     count = total;
     a = block_reduce_agg(a, sm);
@@ -456,15 +471,24 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
     if (threadIdx.x == 0) { sm.dbg = p.dbg; sm.dbg_n = 0; tick(sm); }
 
     // ---- scores (token_importance.py:134-176) ----
+    // Every loop below handles 4 independent tokens per trip (i, i+kT, i+2kT, i+3kT) with the
+    // loads issued first: the per-token chain (L2 load -> 3 IEEE divisions -> stores) is long,
+    // so instruction-level parallelism, not occupancy, is what keeps this single CTA moving.
+    const float *__restrict__ ms = p.mass ? p.mass + (int64_t)b * S : nullptr;
+    const float *__restrict__ tab = p.log_tab;
     float mn = 0.0f, den = 0.0f;
     if (p.flags & RTKV_FROM_MASS) {
-        const float *ms = p.mass + (int64_t)b * S;
         RowAgg a = agg_identity();                      // kmin/kmax hold the mass range as walk keys
-        for (int i = threadIdx.x; i < S; i += kT) {
-            const float v = ms[i];
-            a.nan |= (v != v);
-            const unsigned k = score_key_desc(v);
-            a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
+        for (int i0 = threadIdx.x; i0 < S; i0 += 4 * kT) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * kT; v[u] = i < S ? ms[i] : ms[i0]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a.nan |= (v[u] != v[u]);
+                const unsigned k = score_key_desc(v[u]);
+                a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
+            }
         }
         a = block_reduce_agg(a, sm, false);
         mn = score_of_key(a.kmax);                      // largest key = smallest value
@@ -480,28 +504,49 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         const int dt = p.score_dt;
         const bool ok = den > 1e-8f;
         const float t3 = __fmul_rn(p.gamma, p.rel);
-        const float *ms = p.mass + (int64_t)b * S;
-        for (int i = threadIdx.x; i < S; i += kT) {
-            float s;
-            if (p.flags & RTKV_FROM_MASS) {
-                float n = 0.0f;
-                if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(ms[i], mn), dt), den), dt);
-                const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
-                const float t2 = __fmul_rn(p.beta, position_bias_at(i, S, p.log_tab, p.log_tab_len, p.log_S));
-                s = __fadd_rn(__fadd_rn(t1, t2), t3);
-                sc[i] = s;
-            } else {
-                s = sc[i];
+        const bool from_mass = (p.flags & RTKV_FROM_MASS) != 0, make_labels = (p.flags & RTKV_MAKE_LABELS) != 0;
+        for (int i0 = threadIdx.x; i0 < S; i0 += 4 * kT) {
+            float sv[4], lg[4];
+            int lv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {               // loads first
+                const int i = i0 + u * kT;
+                const bool in = i < S;
+                if (from_mass) {
+                    sv[u] = in ? ms[i] : 0.0f;
+                    lg[u] = (in && i < p.log_tab_len) ? tab[i] : 0.0f;
+                } else {
+                    sv[u] = in ? sc[i] : 0.0f;
+                }
+                lv[u] = (!make_labels && in) ? lab_at(lb, i) : 0;
             }
-            int l;
-            if (p.flags & RTKV_MAKE_LABELS) { l = label_of(s, p.theta_h, p.theta_m); lb[i] = (uint8_t)l; }
-            else l = lab_at(lb, i);
-            if (p.staged) { s_sc[i] = s; s_lb[i] = (uint8_t)l; }
-            st.n0 += (l == 0); st.n1 += (l == 1); st.n2 += (l == 2);
-            st.sum += (double)s; st.sumsq += (double)s * (double)s;
-            st.nan |= (s != s);
-            const unsigned k = score_key_desc(s);
-            st.kmin = k < st.kmin ? k : st.kmin; st.kmax = k > st.kmax ? k : st.kmax;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kT;
+                if (i < S) {
+                    float s = sv[u];
+                    if (from_mass) {
+                        float n = 0.0f;
+                        if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(s, mn), dt), den), dt);
+                        const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                        float pb = 0.0f;
+                        if (S > 1) {
+                            const float l = (i < p.log_tab_len) ? lg[u] : (float)log((double)(float)(i + 1));
+                            pb = __fdiv_rn(l, p.log_S);
+                        }
+                        s = __fadd_rn(__fadd_rn(t1, __fmul_rn(p.beta, pb)), t3);
+                        sc[i] = s;
+                    }
+                    int l = lv[u];
+                    if (make_labels) { l = label_of(s, p.theta_h, p.theta_m); lb[i] = (uint8_t)l; }
+                    if (p.staged) { s_sc[i] = s; s_lb[i] = (uint8_t)l; }
+                    st.n0 += (l == 0); st.n1 += (l == 1); st.n2 += (l == 2);
+                    st.sum += (double)s; st.sumsq += (double)s * (double)s;
+                    st.nan |= (s != s);
+                    const unsigned k = score_key_desc(s);
+                    st.kmin = k < st.kmin ? k : st.kmin; st.kmax = k > st.kmax ? k : st.kmax;
+                }
+            }
         }
     }
     st = block_reduce_agg(st, sm);          // (also orders the staged writes before the reads below)

@@ -10,7 +10,9 @@ from rtkv import ops, _lib
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 B = 1
 dev = torch.device("cuda")
-cfg = rtkv.CompressionConfig(high_precision_bits=8, medium_precision_bits=4, low_precision_bits=2)
+WALK = len(sys.argv) > 2 and sys.argv[2] == "walk"
+cfg = (rtkv.CompressionConfig(high_precision_bits=16, medium_precision_bits=8, low_precision_bits=4) if WALK
+       else rtkv.CompressionConfig(high_precision_bits=8, medium_precision_bits=4, low_precision_bits=2))
 g = torch.Generator(device="cuda").manual_seed(0)
 i = torch.arange(S, device="cuda", dtype=torch.float32)
 mass = (torch.clamp(128.0 / (i + 1), max=1.0) * (1 + 0.05 * torch.rand(S, generator=g, device="cuda")))[None].contiguous()
