@@ -415,9 +415,11 @@ __device__ void emit_selection(const float *sc, const uint8_t *lb, int S, uint8_
             mine += __popc(__ballot_sync(0xffffffffu, keep));
         }
     }
+    tick(sm);   // emit: counting pass done
     int total;
     int off = block_excl_scan(lane == 0 ? mine : 0, total, sm);
     off = __shfl_sync(0xffffffffu, off, 0);
+    tick(sm);   // emit: scan done
     RowAgg a = agg_identity();
     for (int base = beg; base < end; base += 128) {
         float sv[4];
@@ -444,6 +446,7 @@ __device__ void emit_selection(const float *sc, const uint8_t *lb, int S, uint8_
         }
     }
     count = total;
+    tick(sm);   // emit: write pass done
     a = block_reduce_agg(a, sm);
     sel_sum = a.sum;
     sel_class[0] = a.n0; sel_class[1] = a.n1; sel_class[2] = a.n2;
@@ -490,6 +493,7 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
                 a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
             }
         }
+        tick(sm);   // min/max loop done
         a = block_reduce_agg(a, sm, false);
         mn = score_of_key(a.kmax);                      // largest key = smallest value
         float mx = score_of_key(a.kmin);
@@ -549,6 +553,7 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
             }
         }
     }
+    tick(sm);   // score loop done (before the statistics reduction)
     st = block_reduce_agg(st, sm);          // (also orders the staged writes before the reads below)
     float smin = score_of_key(st.kmax), smax = score_of_key(st.kmin);
     if (st.nan) smin = smax = __int_as_float(0x7fc00000);
