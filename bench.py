@@ -163,6 +163,7 @@ def cpu_baseline(layers_host, cfg, bits, S, n_layers_total, B, reps=1):
     the reference does) timed on the host cores over a bounded sample of layers."""
     import oracle
     from rtkv.selective_propagation import SelectiveTokenPropagator
+    oracle.set_num_threads(os.cpu_count() or 1)
     prop = SelectiveTokenPropagator(cfg)
     P = max(1, min(S // 5, 128))
     l0, K0, V0, A0 = layers_host[0]
@@ -180,7 +181,24 @@ def cpu_baseline(layers_host, cfg, bits, S, n_layers_total, B, reps=1):
 
 
 # ----------------------------------------------------------------------------- main
+def _emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints there
+    (e.g. "NCCL version ...") was redirected to stderr by _quiet_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -214,6 +232,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # torchrun pins OMP_NUM_THREADS=1; the reference arm uses every host core (rank 0 runs alone)
+        import oracle
+        oracle.set_num_threads(os.cpu_count() or 1)
         dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
         if dev.type == "cuda":
             torch.cuda.set_device(dev)
@@ -236,7 +257,7 @@ def main():
                                            f"CPU path (oracle/), per-layer time x {L} layers"},
                 "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ rtkv arm (GPU)
@@ -415,7 +436,7 @@ def main():
                                 "sample": f"layers {sample_layers} of {L}, once each, C/OpenMP port of the reference's "
                                           f"CPU path (oracle/): {per_layer * 1e3:.1f} ms per layer x {L} layers"}
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -88,6 +88,11 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """Override OMP_NUM_THREADS (torchrun pins it to 1) for the CPU-baseline legs of bench.py."""
+    lib().orc_set_num_threads(int(n))
+
+
 def prompt_mass(A, adt, P, idx=None):
     """A: [B,H,S,>=P] (last dim contiguous) -> mass [B,S] float32."""
     assert A.ndim == 4 and A.strides[-1] == A.itemsize

@@ -480,6 +480,16 @@ void orc_pack_codes(const float *codes, int64_t rows, int n, const uint8_t *labe
     }
 }
 
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
