@@ -216,6 +216,10 @@ RTKV_API int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int
  * buf[0] = number of ticks and buf[1..] = clock64() at its phase boundaries (row 0).  NULL: off. */
 RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);
 
+/* Testing aid: which rtkv_score_select kernel runs.  0 = automatic (a cluster of 8 CTAs per batch
+ * row when S >= 1024, else one CTA), 1 = always one CTA, 2 = cluster only (error if it does not apply). */
+RTKV_API int rtkv_debug_k2_mode(int mode);
+
 /* One layer with HOST buffers (pinned or pageable): copies K, V and the first P
  * key columns of A to the device, runs the path, copies the results back and
  * synchronises.  K_out/V_out must hold B*S*n elements; they are filled as a

@@ -92,7 +92,7 @@ def test_prompt_mass_close_to_torch(rt):
 # ---------------------------------------------------------------- scores / labels
 @pytest.mark.parametrize("adt", [oracle.F32, oracle.BF16, oracle.F16])
 @pytest.mark.parametrize("B,S", [(1, 2), (2, 17), (1, 700), (3, 4096), (1, 32768)])
-def test_scores_and_labels(rt, adt, B, S):
+def test_scores_and_labels(rt, k2_mode, adt, B, S):
     rtkv, ops = rt
     rng = np.random.default_rng(S + B)
     mass = rng.random((B, S), dtype=np.float32) * 3
@@ -135,6 +135,15 @@ def test_normalize_matches_oracle(rt):
 
 
 # ---------------------------------------------------------------- K2 selection
+@pytest.fixture(params=["single-cta", "auto-cluster"])
+def k2_mode(request, rt):
+    """Every selection test runs against both K2 kernels (one CTA per row / a cluster of 8 CTAs)."""
+    from rtkv import _lib
+    _lib.check(_lib.lib.rtkv_debug_k2_mode(1 if request.param == "single-cta" else 0))
+    yield request.param
+    _lib.check(_lib.lib.rtkv_debug_k2_mode(0))
+
+
 def run_select(ops, scores, labels, bits, budget, fallback=False, topk=None):
     B, S = scores.shape
     p = ops.LayerParams()
@@ -167,7 +176,7 @@ BITS = [(2, 4, 8), (4, 8, 16), (8, 8, 8), (4, 4, 4), (8, 4, 2), (3, 5, 7), (1, 1
 
 @pytest.mark.parametrize("bits", BITS)
 @pytest.mark.parametrize("S", [1, 2, 9, 100, 1023, 1024, 1025, 4096, 20000])
-def test_select_random_scores(rt, bits, S):
+def test_select_random_scores(rt, k2_mode, bits, S):
     _, ops = rt
     rng = np.random.default_rng(S * 7 + bits[0])
     B = 3
@@ -180,7 +189,7 @@ def test_select_random_scores(rt, bits, S):
 
 
 @pytest.mark.parametrize("S", [40, 1500, 5000, 70000])
-def test_select_ties_break_to_lowest_index(rt, S):
+def test_select_ties_break_to_lowest_index(rt, k2_mode, S):
     _, ops = rt
     rng = np.random.default_rng(S)
     labels = rng.integers(0, 3, (2, S)).astype(np.uint8)
@@ -194,7 +203,7 @@ def test_select_ties_break_to_lowest_index(rt, S):
 
 
 @pytest.mark.parametrize("S", [3000, 40000])
-def test_select_clustered_scores_force_refinement(rt, S):
+def test_select_clustered_scores_force_refinement(rt, k2_mode, S):
     """Nearly all scores inside one level-0 bucket: the boundary bucket must be refined."""
     _, ops = rt
     rng = np.random.default_rng(S + 1)
@@ -212,7 +221,7 @@ def test_select_clustered_scores_force_refinement(rt, S):
     check_select(ops, scores.astype(np.float32), labels, (2, 4, 8), S * 0.6)
 
 
-def test_select_special_values(rt):
+def test_select_special_values(rt, k2_mode):
     _, ops = rt
     S = 600
     rng = np.random.default_rng(0)
@@ -226,7 +235,7 @@ def test_select_special_values(rt):
         check_select(ops, scores, labels, (2, 4, 8), budget)
 
 
-def test_select_budget_is_double(rt):
+def test_select_budget_is_double(rt, k2_mode):
     _, ops = rt
     S = 4096
     scores = np.linspace(1, 0, S, dtype=np.float32)[None].copy()
@@ -236,7 +245,7 @@ def test_select_budget_is_double(rt):
     assert cnt[0] == 3279
 
 
-def test_select_fallback_topk(rt):
+def test_select_fallback_topk(rt, k2_mode):
     """Nothing fits (cost 2.0 > budget): every row falls back to its top max(1,int(0.1*S)) scores."""
     _, ops = rt
     rng = np.random.default_rng(4)
@@ -257,7 +266,7 @@ def test_select_fallback_topk(rt):
         assert rows["n_selected"].tolist() == cnt.tolist() and cnt[0] == 0 and cnt[1] == min(3, S)
 
 
-def test_cross_row_ticket_is_left_zeroed(rt):
+def test_cross_row_ticket_is_left_zeroed(rt, k2_mode):
     _, ops = rt
     scores = np.random.default_rng(1).random((5, 300), dtype=np.float32)
     labels = np.ones((5, 300), np.uint8)
