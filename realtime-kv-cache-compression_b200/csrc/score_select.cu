@@ -343,7 +343,7 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
     else if (b8 >= 9.0e18) p.budget_bits = LLONG_MAX / 2;
     else p.budget_bits = (long long)floor(b8);
     p.fallback_topk = prm->fallback_topk < S ? prm->fallback_topk : S;
-    if (g_k2_mode != 1 && !p.dbg) {   // one row across a cluster of 8 CTAs (8 SMs) when it applies
+    if (g_k2_mode != 1) {   // one row across a cluster of 8 CTAs (8 SMs) when it applies
         const int rc = launch_score_select_cluster(p, (cudaStream_t)stream);
         if (rc != RTKV_EUNSUPPORTED) return rc;
         if (g_k2_mode == 2) { set_error("rtkv_score_select: cluster kernel does not apply to S=%d", S); return rc; }

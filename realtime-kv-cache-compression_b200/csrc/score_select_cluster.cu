@@ -43,6 +43,7 @@ struct ClSmem {
     int ghist[3][kNB];               // cluster-wide histogram (valid on rank 0)
     XRec xch[2][kCS];
     Cmd cmd;
+    unsigned long long bar[2];       // cluster barrier: two alternating mbarriers, 8 remote arrivals per use
 };
 
 __device__ __forceinline__ XRec to_xrec(const RowAgg &a, int count)
@@ -53,20 +54,52 @@ __device__ __forceinline__ XRec to_xrec(const RowAgg &a, int count)
     return r;
 }
 
-// every CTA ends up with all 8 records (in rank order) in out[]
-__device__ void cl_allgather(cg::cluster_group &cl, ClSmem &cs, int rank, int &phase, const XRec &mine, XRec out[kCS])
+__device__ __forceinline__ void ctick(Smem &sm)
+{
+    if (threadIdx.x == 0 && sm.dbg && sm.dbg_n < 62) sm.dbg[1 + sm.dbg_n++] = clock64();
+}
+
+// Cluster-wide barrier with release/acquire semantics at cluster scope, built on one mbarrier
+// per CTA: after a CTA-local __syncthreads, 8 threads of every CTA arrive (remotely) on the 8
+// CTAs' mbarriers and everybody waits on its own.  barrier.cluster (cg::cluster_group::sync) has
+// all 8192 threads of the cluster arrive, which measured ~3000 cycles per use here.
+// Consecutive uses alternate between two mbarriers so that a fast CTA's arrival for use n+1 can
+// never be counted towards use n of a slower CTA's barrier.  `parity` counts the uses.
+__device__ __forceinline__ void cl_barrier(ClSmem &cs, unsigned &parity)
+{
+    __syncthreads();
+    const unsigned local = (unsigned)__cvta_generic_to_shared(&cs.bar[parity & 1u]);
+    const unsigned ph = (parity >> 1) & 1u;
+    if (threadIdx.x < kCS) {
+        unsigned remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((unsigned)threadIdx.x));
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    }
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(local), "r"(ph) : "memory");
+    ++parity;
+}
+
+// all-gather of one record per CTA: afterwards cs.xch[buf][0..7] (buf = returned index) holds the
+// records of all ranks, in rank order, in every CTA's shared memory
+__device__ __forceinline__ int cl_exchange(cg::cluster_group &cl, ClSmem &cs, int rank, int &phase, unsigned &parity,
+                                           const XRec &mine)
 {
     const int buf = phase & 1;
     if (threadIdx.x < kCS) *cl.map_shared_rank(&cs.xch[buf][rank], threadIdx.x) = mine;
-    cl.sync();
-#pragma unroll
-    for (int r = 0; r < kCS; ++r) out[r] = cs.xch[buf][r];
+    cl_barrier(cs, parity);
     ++phase;
+    return buf;
 }
 
 // local histogram of the chunk for one level, then reduce-scatter into rank 0's ghist
-__device__ void cl_histogram(cg::cluster_group &cl, ClSmem &cs, int rank, const float *s_sc, const uint8_t *s_lb,
-                             int beg, int end, unsigned long long lo, int shift, int nb)
+__device__ void cl_histogram(cg::cluster_group &cl, ClSmem &cs, int rank, unsigned &parity, const float *s_sc,
+                             const uint8_t *s_lb, int beg, int end, unsigned long long lo, int shift, int nb)
 {
     Smem &sm = cs.s;
     for (int x = threadIdx.x; x < 3 * kNB; x += kT) (&sm.hist[0][0])[x] = 0;
@@ -79,7 +112,7 @@ __device__ void cl_histogram(cg::cluster_group &cl, ClSmem &cs, int rank, const 
             if (bk < (unsigned long long)nb) atomicAdd(&sm.hist[s_lb[i - beg]][(int)bk], 1);
         }
     }
-    cl.sync();                                           // all local histograms complete
+    cl_barrier(cs, parity);                              // all local histograms complete
     constexpr int kSlice = 3 * kNB / kCS;                // 768 bins per CTA
     int *root_g = cl.map_shared_rank(&cs.ghist[0][0], 0);
     for (int x = rank * kSlice + threadIdx.x; x < (rank + 1) * kSlice; x += kT) {
@@ -88,7 +121,7 @@ __device__ void cl_histogram(cg::cluster_group &cl, ClSmem &cs, int rank, const 
         for (int r = 0; r < kCS; ++r) tot += cl.map_shared_rank(&sm.hist[0][0], r)[x];
         root_g[x] = tot;
     }
-    cl.sync();                                           // rank 0's ghist complete
+    cl_barrier(cs, parity);                              // rank 0's ghist complete
 }
 
 __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
@@ -108,8 +141,15 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
     const float *__restrict__ ms = p.mass ? p.mass + (int64_t)b * S : nullptr;
     const float *__restrict__ tab = p.log_tab;
     int phase = 0;
-    XRec all[kCS];
-    if (threadIdx.x == 0) { sm.dbg = nullptr; sm.dbg_n = 0; }
+    unsigned parity = 0;
+    if (threadIdx.x == 0) {
+        sm.dbg = (rank == 0 && blockIdx.x == 0) ? p.dbg : nullptr; sm.dbg_n = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&cs.bar[0])), "r"(kCS));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&cs.bar[1])), "r"(kCS));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cl.sync();       // every CTA's mbarrier exists before anybody arrives on it remotely
+    ctick(sm);
 
     // ---- mass range over the whole row ----
     float mn = 0.0f, den = 0.0f;
@@ -126,8 +166,11 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
                 a.kmin = k < a.kmin ? k : a.kmin; a.kmax = k > a.kmax ? k : a.kmax;
             }
         }
+        ctick(sm);   // 1 mass loop
         a = block_reduce_agg(a, sm, false);
-        cl_allgather(cl, cs, rank, phase, to_xrec(a, 0), all);
+        ctick(sm);   // 2 block reduce
+        const XRec *all = cs.xch[cl_exchange(cl, cs, rank, phase, parity, to_xrec(a, 0))];
+        ctick(sm);   // 3 allgather
         unsigned kmin = 0xffffffffu, kmax = 0u;
         int nan = 0;
 #pragma unroll
@@ -192,8 +235,11 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
             }
         }
     }
+    ctick(sm);       // 4 score loop
     st = block_reduce_agg(st, sm);
-    cl_allgather(cl, cs, rank, phase, to_xrec(st, 0), all);
+    ctick(sm);       // 5 block reduce
+    const XRec *all = cs.xch[cl_exchange(cl, cs, rank, phase, parity, to_xrec(st, 0))];
+    ctick(sm);       // 6 allgather
     RowAgg row = agg_identity();                         // whole-row statistics, combined in rank order
 #pragma unroll
     for (int r = 0; r < kCS; ++r) {
@@ -228,8 +274,10 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
                 sm.cur = 0; sm.depth = 0;
                 sm.lvl_lo[0] = lo; sm.lvl_shift[0] = shift; sm.lvl_nb[0] = nb; sm.lvl_resume[0] = 0;
             }
-            cl_histogram(cl, cs, rank, s_sc, s_lb, beg, end, lo, shift, nb);
+            cl_histogram(cl, cs, rank, parity, s_sc, s_lb, beg, end, lo, shift, nb);
+            ctick(sm);   // level-0 histogram
             for (;;) {
+                ctick(sm);   // round start
                 if (rank == 0) {
                     // decide the next command from the cluster-wide histogram of the current level
                     __syncthreads();
@@ -274,7 +322,9 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
                         *cl.map_shared_rank(&cs.cmd, threadIdx.x) = c;
                     }
                 }
-                cl.sync();
+                ctick(sm);   // decision made
+                cl_barrier(cs, parity);
+                ctick(sm);   // command sync
                 const Cmd c = cs.cmd;
                 if (c.op == CMD_DONE) { thr0 = c.thr[0]; thr1 = c.thr[1]; thr2 = c.thr[2]; cost_bits = c.cur; break; }
                 if (c.op == CMD_COLLECT) {
@@ -293,15 +343,16 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
                             }
                         }
                     }
-                    cl.sync();
+                    cl_barrier(cs, parity);
                     if (rank == 0) process_candidates(sm.ncand < kMaxCand ? sm.ncand : kMaxCand, cfg, sm);
                 } else {                                 // CMD_HIST: (re)build the histogram of level (lo, shift, nb)
-                    cl_histogram(cl, cs, rank, s_sc, s_lb, beg, end, c.lo, c.shift, c.nb);
+                    cl_histogram(cl, cs, rank, parity, s_sc, s_lb, beg, end, c.lo, c.shift, c.nb);
                 }
             }
         }
     }
 
+    ctick(sm);   // thresholds known
     // ---- mask + compacted index list of the chunk ----
     int count_row = 0;
     RowAgg sel = agg_identity();
@@ -327,7 +378,7 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
         int cta_total;
         int off = block_excl_scan(lane == 0 ? mine : 0, cta_total, sm);
         off = __shfl_sync(0xffffffffu, off, 0);
-        cl_allgather(cl, cs, rank, phase, to_xrec(agg_identity(), cta_total), all);
+        all = cs.xch[cl_exchange(cl, cs, rank, phase, parity, to_xrec(agg_identity(), cta_total))];
         int base_off = 0;
 #pragma unroll
         for (int r = 0; r < kCS; ++r) { if (r < rank) base_off += all[r].count; count_row += all[r].count; }
@@ -354,13 +405,15 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
             }
         }
         sel = block_reduce_agg(sel, sm);
-        cl_allgather(cl, cs, rank, phase, to_xrec(sel, 0), all);
+        all = cs.xch[cl_exchange(cl, cs, rank, phase, parity, to_xrec(sel, 0))];
         sel = agg_identity();
 #pragma unroll
         for (int r = 0; r < kCS; ++r) { sel.sum += all[r].sum; sel.n0 += all[r].n0; sel.n1 += all[r].n1; sel.n2 += all[r].n2; }
     }
     // no CTA touches another CTA's shared memory after the last all-gather: non-root CTAs may leave
     if (rank != 0) return;
+    ctick(sm);   // emit done
+    if (threadIdx.x == 0 && sm.dbg) sm.dbg[0] = sm.dbg_n;
 
     if (threadIdx.x == 0) {
         rtkv_row_stats &r = p.row_stats[b];
