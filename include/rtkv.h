@@ -217,7 +217,7 @@ RTKV_API int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int
 RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);
 
 /* Testing aid: which rtkv_score_select kernel runs.  0 = automatic (a cluster of 8 CTAs per batch
- * row when S >= 1024, else one CTA), 1 = always one CTA, 2 = cluster only (error if it does not apply). */
+ * row from 8192 tokens, else one CTA), 1 = always one CTA, 2 = the cluster kernel whenever S >= 1024. */
 RTKV_API int rtkv_debug_k2_mode(int mode);
 
 /* One layer with HOST buffers (pinned or pageable): copies K, V and the first P

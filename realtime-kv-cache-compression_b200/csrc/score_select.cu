@@ -266,7 +266,7 @@ __global__ void gather_scalars_kernel(const float *scores, const uint8_t *labels
 
 using namespace rtkv;
 
-static int g_k2_mode = 0;   // 0 auto (cluster when it applies), 1 single CTA, 2 cluster only
+static int g_k2_mode = 0;   // 0 auto (cluster from 8192 tokens), 1 single CTA, 2 cluster whenever S >= 1024
 extern "C" int rtkv_debug_k2_mode(int mode)
 {
     RTKV_CHECK_ARG(mode >= 0 && mode <= 2, "rtkv_debug_k2_mode: mode must be 0, 1 or 2");
@@ -344,9 +344,9 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
     else p.budget_bits = (long long)floor(b8);
     p.fallback_topk = prm->fallback_topk < S ? prm->fallback_topk : S;
     if (g_k2_mode != 1) {   // one row across a cluster of 8 CTAs (8 SMs) when it applies
-        const int rc = launch_score_select_cluster(p, (cudaStream_t)stream);
+        const int rc = launch_score_select_cluster(p, (cudaStream_t)stream, g_k2_mode == 2);
         if (rc != RTKV_EUNSUPPORTED) return rc;
-        if (g_k2_mode == 2) { set_error("rtkv_score_select: cluster kernel does not apply to S=%d", S); return rc; }
+        // mode 2 with a row too short (or too long) for the cluster: fall through to the single-CTA kernel
     }
     // shared memory: control block + (when it fits) the row's scores and labels
     const size_t base = ((sizeof(Smem) + 15) / 16) * 16;

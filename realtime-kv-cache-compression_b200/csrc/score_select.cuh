@@ -449,6 +449,6 @@ __device__ __forceinline__ float position_bias_at(int i, int S, const float *tab
 }
 
 // score_select_cluster.cu: K2 over a cluster of 8 CTAs; RTKV_EUNSUPPORTED = use the single-CTA kernel
-int launch_score_select_cluster(const K2Params &p, cudaStream_t st);
+int launch_score_select_cluster(const K2Params &p, cudaStream_t st, bool force);
 
 } // namespace rtkv

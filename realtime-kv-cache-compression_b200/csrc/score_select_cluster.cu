@@ -473,10 +473,12 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
 
 // Returns RTKV_EUNSUPPORTED when the cluster variant does not apply (caller falls back to the
 // single-CTA kernel), RTKV_OK after a successful launch.
-int launch_score_select_cluster(const K2Params &p, cudaStream_t st)
+int launch_score_select_cluster(const K2Params &p, cudaStream_t st, bool force)
 {
     const int S = p.S;
-    if (S < 1024) return RTKV_EUNSUPPORTED;                    // not worth 8 SMs
+    // Measured on B200 (tools/bench_kernels.py): one CTA costs ~5 us + 1.3..1.8 ns/token, the cluster
+    // ~11..21 us (a dozen ~2 us cross-CTA steps) + 0.1..0.2 ns/token: the cluster pays off from ~8k tokens.
+    if (S < (force ? 1024 : 8192)) return RTKV_EUNSUPPORTED;
     const int C = ((S + kCS - 1) / kCS + 127) / 128 * 128;
     const size_t smem = ((sizeof(ClSmem) + 15) / 16) * 16 + 4 * (size_t)C + (size_t)C + 16;
     if (smem > 200 * 1024) return RTKV_EUNSUPPORTED;

@@ -135,11 +135,12 @@ def test_normalize_matches_oracle(rt):
 
 
 # ---------------------------------------------------------------- K2 selection
-@pytest.fixture(params=["single-cta", "auto-cluster"])
+@pytest.fixture(params=["single-cta", "cluster"])
 def k2_mode(request, rt):
-    """Every selection test runs against both K2 kernels (one CTA per row / a cluster of 8 CTAs)."""
+    """Every selection test runs against both K2 kernels (one CTA per row / a cluster of 8 CTAs;
+    mode 2 forces the cluster kernel for every row of at least 1024 tokens)."""
     from rtkv import _lib
-    _lib.check(_lib.lib.rtkv_debug_k2_mode(1 if request.param == "single-cta" else 0))
+    _lib.check(_lib.lib.rtkv_debug_k2_mode(1 if request.param == "single-cta" else 2))
     yield request.param
     _lib.check(_lib.lib.rtkv_debug_k2_mode(0))
 
