@@ -85,3 +85,19 @@ class HeadShardedCompressor:
         mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, max_sel), self.group)
         k_sel, v_sel = ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), max_sel, mm)
         return k_sel, v_sel, sel
+
+    def compress_layer_async(self, key_local, value_local, attention_local, layer_idx, out_keys, out_values):
+        """Synchronisation-free variant (fixed capacity S rows, like compress_layer_kv_cache_async):
+        the two exchanges run on the full [B,S,.] extent, nothing is read back to the host."""
+        from . import ops
+        B, S, _ = key_local.shape
+        gs = self.num_heads // N_GROUPS
+        comp = self.compressor
+        params, _ = comp.layer_params(layer_idx, S, ops.F32)
+        partials = ops.prompt_mass_partials(attention_local, comp.prompt_length(S), gs)
+        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads)
+        sel = ops.score_select(params, B, S, key_local.device, mass=mass)
+        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, S), self.group)
+        ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), S, mm, zero_pad=False,
+                                out0=out_keys, out1=out_values)
+        return sel

@@ -253,13 +253,13 @@ def row_minmax(x0, x1, sel, out_rows):
     return mm
 
 
-def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=True):
+def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=True, out0=None, out1=None):
     """quant_gather with externally supplied (rank-reduced) row min/max."""
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
     B, S, n = x0.shape
-    y0 = torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
-    y1 = torch.empty_like(y0)
+    y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = out1 if out1 is not None else torch.empty_like(y0)
     lab = labels.to(torch.uint8).contiguous()
     check(lib.rtkv_quant_gather_minmax(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,
                                        _ptr(sel.sel_idx) if sel is not None else None,
