@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (description, layers, hidden, heads, intermediate, S, B, bits(low,mid,high))
     "c1": ("single layer K/V [1,32,2048,128] fp32 (configs[0])", 1, 4096, 32, 11008, 2048, 1, (2, 4, 8)),
     "c2": ("Llama-2-7B random-init, 32-layer prefill of 4096 tokens, batch 1 (configs[1])", 32, 4096, 32, 11008, 4096, 1, (2, 4, 8)),
+    "c3": ("Llama-2-7B random-init, 32-layer prefill of 32768 tokens, batch 1, KV-head-sharded over the GPUs (configs[2])", 32, 4096, 32, 11008, 32768, 1, (2, 4, 8)),
     "c4": ("Llama-2-13B random-init, 40-layer prefill of 16384 tokens, batch 1 (configs[3], mixed 8/4/2)", 40, 5120, 40, 13824, 16384, 1, (2, 4, 8)),
 }
 PEAKS_FALLBACK_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -65,7 +66,7 @@ def rmsnorm(x):
 
 
 @torch.no_grad()
-def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, keep_layers=None):
+def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, keep_layers=None, head_slice=None):
     """Random-init Llama-2 stack (N(0,0.02) weights, RoPE, causal softmax attention, SwiGLU MLP)
     run in plain torch fp32 as SETUP: yields per layer the K/V the compressor sees
     ([B,S,H*D] after RoPE, as modified_llama.py:105-108) and the first P key columns of the
@@ -99,8 +100,15 @@ def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, 
             ctx[:, :, r0:r1] = probs @ v
             del logits, probs
         if keep_layers is None or l in keep_layers:
-            out.append((l, k.transpose(1, 2).reshape(B, S, hidden).contiguous(),
-                        v.transpose(1, 2).reshape(B, S, hidden).contiguous(), A))
+            if head_slice is None:
+                out.append((l, k.transpose(1, 2).reshape(B, S, hidden).contiguous(),
+                            v.transpose(1, 2).reshape(B, S, hidden).contiguous(), A))
+            else:   # this rank's contiguous slice of the heads (identical data on every rank)
+                r, w = head_slice
+                hl = heads // w
+                out.append((l, k[:, r * hl:(r + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
+                            v[:, r * hl:(r + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
+                            A[:, r * hl:(r + 1) * hl].contiguous()))
         x = x + ctx.transpose(1, 2).reshape(B, S, hidden) @ w(hidden, hidden).T
         h = rmsnorm(x)
         gate, up = h @ w(inter, hidden).T, h @ w(inter, hidden).T
@@ -180,6 +188,78 @@ def cpu_baseline(layers_host, cfg, bits, S, n_layers_total, B, reps=1):
     return B * S / (per_layer * n_layers_total), per_layer, oracle.num_threads()
 
 
+# ----------------------------------------------------------------------------- head-sharded mode
+def bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, B, P, hidden, heads, bits):
+    """BASELINE configs[2]: one long sequence, KV heads split over the ranks (strong scaling).
+    Per layer: K1a partials -> all-gather -> K2 (replicated, identical on every rank) ->
+    row min/max of the kept rows -> MIN all-reduce -> K3.  No host synchronisation."""
+    import torch.distributed as dist
+    from rtkv import dist as rd
+    sharded = rd.HeadShardedCompressor(comp, heads)
+    w = hidden // world
+    outs = [(torch.empty(B, S, w, device=dev), torch.empty(B, S, w, device=dev)) for _ in range(2)]
+
+    def step():
+        sels = []
+        for j, (l, K, V, A) in enumerate(layers):
+            sels.append(sharded.compress_layer_async(K, V, A, l, outs[j & 1][0], outs[j & 1][1]))
+        return sels
+
+    for _ in range(args.warmup):
+        sels = step()
+    torch.cuda.synchronize()
+    mode = "eager launches"
+    graph = None
+    try:                                   # NCCL collectives can be captured; fall back to eager if not
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
+        torch.cuda.synchronize()
+        mode = "one CUDA graph per step (kernels + NCCL collectives)"
+    except Exception as e:                 # pragma: no cover
+        sys.stderr.write(f"graph capture of the head-sharded step failed ({e}); timing eager launches\n")
+        graph = None
+        torch.cuda.synchronize()
+    run = graph.replay if graph is not None else step
+    for _ in range(args.warmup):
+        run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    kept = [int(s.read_stats()[1]["n_selected"].sum()) for s in sels]
+    e = 4
+    path_bytes = sum(n * 2 * hidden * 2 * e for n in kept) + L * (B * S * heads * P * e + B * S * 16)
+    peak, peak_src = measured_hbm_peak()
+    line = {"metric": "prefill_kv_compress_tokens_per_s", "value": B * S / (ms_per_step * 1e-3), "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "clocks": clocks, "gpu_launches": 5 * L * args.steps, "launch_mode": mode,
+            "roofline": {"bound": "hbm", "kernel": "whole path, all ranks", "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world),
+                         "peak_source": peak_src + f" x {world} GPUs", "traffic": None,
+                         "retained_fraction": sum(kept) / (L * B * S)},
+            "collectives_per_layer": {"all_gather_bytes": B * S * (8 // world) * 4, "all_reduce_bytes": B * S * 16}}
+    if rank == 0:
+        _emit(line)
+    dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- main
 def _emit(line):
     """The one JSON line goes to the real stdout; everything else a library prints there
@@ -205,6 +285,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="rtkv", choices=["rtkv", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=0, help="override the number of layers (setup time)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -214,6 +295,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     desc, L, hidden, heads, inter, S, B, bits = WORKLOADS[args.workload]
+    if args.layers > 0:
+        L = args.layers
+    head_sharded = args.workload == "c3" and world > 1
     P = max(1, min(S // 5, 128))
     sample_layers = sorted({0, L // 3, (2 * L) // 3, L - 1})
 
@@ -225,7 +309,8 @@ def main():
               "prompt_len": P, "bits_low_mid_high": list(bits), "theta_h": cfg.theta_h, "theta_m": cfg.theta_m,
               "ratios": [cfg.early_layer_ratio, cfg.middle_layer_ratio, cfg.later_layer_ratio],
               "kv_dtype": "float32", "attention_input": f"[B,H,S,P={P}] probability slice, float32",
-              "sharding": "batch (one sequence per GPU, no collective)" if world > 1 else "single GPU",
+              "sharding": ("KV heads (2 small NCCL exchanges per layer: score partials, row min/max)" if head_sharded else
+                           "batch (one sequence per GPU, no collective)" if world > 1 else "single GPU"),
               "l2": "per-step working set (inputs+outputs, all layers) far exceeds the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -267,9 +352,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    layers = llama_prefill_inputs(L, hidden, heads, inter, S, B, P, 1234 + rank, dev)
+    layers = llama_prefill_inputs(L, hidden, heads, inter, S, B, P, 1234 + (0 if head_sharded else rank), dev,
+                                  head_slice=(rank, world) if head_sharded else None)
     torch.cuda.synchronize()
     comp = rtkv.RealTimePrefillCompressor(cfg)
+    if head_sharded:
+        return bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, B, P, hidden, heads, bits)
     outs = [(torch.empty_like(K), torch.empty_like(V)) for (_, K, V, _) in layers]
     ev_k3 = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in layers]
              for _ in range(args.steps)]
