@@ -104,11 +104,11 @@ def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, 
                 out.append((l, k.transpose(1, 2).reshape(B, S, hidden).contiguous(),
                             v.transpose(1, 2).reshape(B, S, hidden).contiguous(), A))
             else:   # this rank's contiguous slice of the heads (identical data on every rank)
-                r, w = head_slice
-                hl = heads // w
-                out.append((l, k[:, r * hl:(r + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
-                            v[:, r * hl:(r + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
-                            A[:, r * hl:(r + 1) * hl].contiguous()))
+                hr, hw = head_slice
+                hl = heads // hw
+                out.append((l, k[:, hr * hl:(hr + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
+                            v[:, hr * hl:(hr + 1) * hl].transpose(1, 2).reshape(B, S, hl * D).contiguous(),
+                            A[:, hr * hl:(hr + 1) * hl].contiguous()))
         x = x + ctx.transpose(1, 2).reshape(B, S, hidden) @ w(hidden, hidden).T
         h = rmsnorm(x)
         gate, up = h @ w(inter, hidden).T, h @ w(inter, hidden).T
