@@ -174,14 +174,15 @@ RTKV_API int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype, 
 /* KV-head sharding: the reference's scale spans ALL heads of a token row, so ranks first
  * compute the local min/max of their kept rows (minmax [B,out_rows,4] = min0,max0,min1,max1;
  * padding rows give +inf,-inf), reduce them over ranks (MIN / MAX), and quantise with the
- * reduced values.  With one rank this equals rtkv_quant_gather bit for bit. */
+ * reduced values.  negate_max stores -max instead of max, so ONE element-wise MIN all-reduce
+ * combines the ranks (negation is exact).  With one rank this equals rtkv_quant_gather bit for bit. */
 RTKV_API int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                       const int32_t *sel_idx, const rtkv_row_stats *row_stats, int out_rows,
-                      float *minmax, void *stream);
+                      int negate_max, float *minmax, void *stream);
 RTKV_API int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                       const int32_t *sel_idx, const rtkv_row_stats *row_stats,
                       const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
-                      const float *minmax, void *Y0, void *Y1, void *stream);
+                      const float *minmax, int negated_max, void *Y0, void *Y1, void *stream);
 
 /* Whole-tensor scale / zero-point (qparams[0] = scale, [1] = zero_point, in `dtype`,
  * stored as f32) and quantise-dequantise with given parameters. */

@@ -30,6 +30,7 @@ struct QGParams {
     int bits[3];
     int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
     const float *ext_minmax;  // [B,out_rows,4] = (min0, max0, min1, max1) of the WHOLE row (head sharding) or NULL
+    int neg_max;              // the max entries are stored negated (so that one MIN all-reduce combines ranks)
 };
 
 // no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
     }
     if (p.ext_minmax) {         // row min/max reduced over all ranks' head shards
         const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
-        mn = mm[0]; mx = mm[1];
+        mn = mm[0]; mx = p.neg_max ? -mm[1] : mm[1];
     } else {
         block_minmax(mn, mx, nan, red);
     }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
     }
     if (p.ext_minmax) {
         const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
-        mn = mm[0]; mx = mm[1];
+        mn = mm[0]; mx = p.neg_max ? -mm[1] : mm[1];
     } else {
         block_minmax(mn, mx, nan, red);
     }
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kQT) row_minmax_kernel(QGParams p, float *out)
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
     float *o = out + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
     if (r >= cnt) {
-        if (threadIdx.x == 0) { o[0] = INFINITY; o[1] = -INFINITY; }
+        if (threadIdx.x == 0) { o[0] = INFINITY; o[1] = p.neg_max ? INFINITY : -INFINITY; }
         return;
     }
     const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kQT) row_minmax_kernel(QGParams p, float *out)
         nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
     }
     block_minmax(mn, mx, nan, red);
-    if (threadIdx.x == 0) { o[0] = mn; o[1] = mx; }
+    if (threadIdx.x == 0) { o[0] = mn; o[1] = p.neg_max ? -mx : mx; }
 }
 
 template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st, int nrows, int nb)
@@ -354,7 +355,7 @@ static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S
     p.quantize = (labels != nullptr && bits != nullptr);
     for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
     p.row_begin = 0; p.b_begin = 0;
-    p.ext_minmax = nullptr;
+    p.ext_minmax = nullptr; p.neg_max = 0;
     return RTKV_OK;
 }
 
@@ -428,7 +429,7 @@ extern "C" int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype
 
 extern "C" int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                                const int32_t *sel_idx, const rtkv_row_stats *row_stats, int out_rows,
-                               float *minmax, void *stream)
+                               int negate_max, float *minmax, void *stream)
 {
     RTKV_CHECK_ARG(X0 && minmax, "rtkv_row_minmax: null pointer");
     RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_row_minmax: bad shape");
@@ -437,6 +438,7 @@ extern "C" int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B,
     if (out_rows == 0) return RTKV_OK;
     QGParams p;
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, nullptr, nullptr, out_rows, 0, nullptr, nullptr);
+    p.neg_max = negate_max != 0;
     dim3 grid(out_rows, B, X1 ? 2 : 1);
     RTKV_DISPATCH(dtype, (row_minmax_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, minmax)));
     RTKV_LAUNCH_CHECK("row_minmax_kernel");
@@ -446,7 +448,7 @@ extern "C" int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B,
 extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                                         const int32_t *sel_idx, const rtkv_row_stats *row_stats,
                                         const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
-                                        const float *minmax, void *Y0, void *Y1, void *stream)
+                                        const float *minmax, int negated_max, void *Y0, void *Y1, void *stream)
 {
     RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1) && labels && bits && minmax, "rtkv_quant_gather_minmax: null pointer");
     RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather_minmax: bad dtype %d", dtype);
@@ -458,7 +460,7 @@ extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtyp
     if (out_rows == 0) return RTKV_OK;
     QGParams p;
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
-    p.ext_minmax = minmax;
+    p.ext_minmax = minmax; p.neg_max = negated_max != 0;
     RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, out_rows, B));
     return RTKV_OK;
 }

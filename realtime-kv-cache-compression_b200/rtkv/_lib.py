@@ -68,10 +68,10 @@ PROTOTYPES = {
                                                c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                c_vp]),
     "rtkv_row_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
-                                       ctypes.c_int, c_vp, c_vp]),
+                                       ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rtkv_quant_gather_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
-                                                c_vp, c_vp, c_vp, c_vp]),
+                                                c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_quant_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_quantize_with_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_gather_scalars": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -45,16 +45,14 @@ def gather_partials(partials_local, group=None):
     return torch.cat(parts, dim=-1).contiguous()
 
 
-def reduce_minmax(minmax_local, group=None):
-    """[B,S',4] = (min0,max0,min1,max1) per rank -> element-wise MIN of the mins / MAX of the maxes.
-    One MIN all-reduce on (min0, -max0, min1, -max1): negation is exact, so this is bit-exact."""
+def reduce_minmax(minmax_negmax, group=None):
+    """[B,S',4] = (min0, -max0, min1, -max1) per rank -> element-wise MIN over the ranks, in place.
+    (ops.row_minmax(..., negate_max=True) produces this layout; negation is exact, so MIN of the
+    negated maxima is the negated MAX: one collective, bit-exact.)"""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        return minmax_local
-    sign = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=minmax_local.dtype, device=minmax_local.device)
-    t = (minmax_local * sign).contiguous()
-    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-    return t * sign
+    if world > 1:
+        dist.all_reduce(minmax_negmax, op=dist.ReduceOp.MIN, group=group)
+    return minmax_negmax
 
 
 class HeadShardedCompressor:
@@ -82,8 +80,9 @@ class HeadShardedCompressor:
         sel = ops.score_select(params, B, S, key_local.device, mass=mass)
         layer, _rows = sel.read_stats()                       # S' is a shape: one sync
         max_sel = int(layer["max_selected"])
-        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, max_sel), self.group)
-        k_sel, v_sel = ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), max_sel, mm)
+        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, max_sel, negate_max=True), self.group)
+        k_sel, v_sel = ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), max_sel, mm,
+                                               negated_max=True)
         return k_sel, v_sel, sel
 
     def compress_layer_async(self, key_local, value_local, attention_local, layer_idx, out_keys, out_values):
@@ -97,7 +96,7 @@ class HeadShardedCompressor:
         partials = ops.prompt_mass_partials(attention_local, comp.prompt_length(S), gs)
         mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads)
         sel = ops.score_select(params, B, S, key_local.device, mass=mass)
-        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, S), self.group)
+        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, S, negate_max=True), self.group)
         ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), S, mm, zero_pad=False,
-                                out0=out_keys, out1=out_values)
+                                out0=out_keys, out1=out_values, negated_max=True)
         return sel

@@ -241,19 +241,22 @@ def quant_gather(x0, x1, sel, labels, bits, out_rows, zero_pad=True, out0=None, 
     return y0, y1
 
 
-def row_minmax(x0, x1, sel, out_rows):
-    """Local min/max of the kept rows: [B,out_rows,4] = (min0, max0, min1, max1) float32."""
+def row_minmax(x0, x1, sel, out_rows, negate_max=False):
+    """Local min/max of the kept rows: [B,out_rows,4] = (min0, max0, min1, max1) float32
+    (max entries negated with negate_max, so that one MIN all-reduce combines ranks)."""
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
     B, S, n = x0.shape
     mm = torch.empty(B, out_rows, 4, dtype=torch.float32, device=x0.device)
     check(lib.rtkv_row_minmax(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,
                               _ptr(sel.sel_idx) if sel is not None else None,
-                              sel.row_stats_ptr if sel is not None else None, int(out_rows), _ptr(mm), _stream()))
+                              sel.row_stats_ptr if sel is not None else None, int(out_rows), int(bool(negate_max)),
+                              _ptr(mm), _stream()))
     return mm
 
 
-def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=True, out0=None, out1=None):
+def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=True, out0=None, out1=None,
+                        negated_max=False):
     """quant_gather with externally supplied (rank-reduced) row min/max."""
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
@@ -265,7 +268,7 @@ def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=Tr
                                        _ptr(sel.sel_idx) if sel is not None else None,
                                        sel.row_stats_ptr if sel is not None else None, _ptr(lab),
                                        _lib.bits3(bits), int(out_rows), int(bool(zero_pad)),
-                                       _ptr(minmax.contiguous()), _ptr(y0), _ptr(y1), _stream()))
+                                       _ptr(minmax.contiguous()), int(bool(negated_max)), _ptr(y0), _ptr(y1), _stream()))
     return y0, y1
 
 

@@ -38,9 +38,9 @@ def _worker(rank, world, port, q):
         # exchange 2: row min/max over the ranks' column slices == min/max of the whole row
         w = H * D // world
         kl, vl = K[..., rank * w:(rank + 1) * w], V[..., rank * w:(rank + 1) * w]
-        mm_local = np.stack([kl.min(-1), kl.max(-1), vl.min(-1), vl.max(-1)], axis=-1).astype(np.float32)
+        mm_local = np.stack([kl.min(-1), -kl.max(-1), vl.min(-1), -vl.max(-1)], axis=-1).astype(np.float32)
         mm = rd.reduce_minmax(torch.from_numpy(mm_local)).numpy()
-        want = np.stack([K.min(-1), K.max(-1), V.min(-1), V.max(-1)], axis=-1)
+        want = np.stack([K.min(-1), -K.max(-1), V.min(-1), -V.max(-1)], axis=-1)
         ok2 = np.array_equal(mm, want)
         # batch sharding covers every row exactly once
         sl = rd.batch_shard(5, rank, world)
