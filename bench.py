@@ -257,7 +257,20 @@ def bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, 
             "collectives_per_layer": {"all_gather_bytes": B * S * (8 // world) * 4, "all_reduce_bytes": B * S * 16}}
     if rank == 0:
         _emit(line)
-    dist.destroy_process_group()
+    # a live CUDA graph that holds NCCL kernels can dead-lock communicator teardown: drop it first
+    del run, graph
+    torch.cuda.synchronize()
+    _shutdown(dist)
+
+
+def _shutdown(dist):
+    """Tear the process group down, but never hang the box: hard-exit if teardown stalls."""
+    import threading
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------- main
@@ -526,7 +539,7 @@ def main():
     if rank == 0:
         _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(dist)
 
 
 if __name__ == "__main__":

@@ -190,6 +190,40 @@ __global__ void __launch_bounds__(kQT) row_minmax_kernel(QGParams p, float *out)
     if (threadIdx.x == 0) { o[0] = mn; o[1] = p.neg_max ? -mx : mx; }
 }
 
+// Vector path of row_minmax: same 128-bit streaming loads as the quantise kernel.
+template <int DT>
+__global__ void __launch_bounds__(kQT) row_minmax_vec_kernel(QGParams p, float *out)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    float *o = out + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
+    if (r >= cnt) {
+        if (threadIdx.x == 0) { o[0] = INFINITY; o[1] = p.neg_max ? INFINITY : -INFINITY; }
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int nvec = p.n / EPV;
+    const uint4 *src = (const uint4 *)((const char *)pick_x(p, t) + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += 4 * kQT) {
+        uint4 raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) raw[k] = (v0 + k * kQT < nvec) ? ldg_stream(src + v0 + k * kQT) : ldg_stream(src + v0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+        }
+    }
+    block_minmax(mn, mx, nan, red);
+    if (threadIdx.x == 0) { o[0] = mn; o[1] = p.neg_max ? -mx : mx; }
+}
+
 template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStream_t st, int nrows, int nb)
 {
     constexpr int EPV = Vec16<DT>::kElems;
@@ -440,7 +474,10 @@ extern "C" int rtkv_row_minmax(const void *X0, const void *X1, int dtype, int B,
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, nullptr, nullptr, out_rows, 0, nullptr, nullptr);
     p.neg_max = negate_max != 0;
     dim3 grid(out_rows, B, X1 ? 2 : 1);
-    RTKV_DISPATCH(dtype, (row_minmax_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, minmax)));
+    const int epv = 16 / dtype_bytes(dtype);
+    const bool vec = n % epv == 0 && (uintptr_t)X0 % 16 == 0 && (!X1 || (uintptr_t)X1 % 16 == 0);
+    if (vec) { RTKV_DISPATCH(dtype, (row_minmax_vec_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, minmax))); }
+    else { RTKV_DISPATCH(dtype, (row_minmax_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, minmax))); }
     RTKV_LAUNCH_CHECK("row_minmax_kernel");
     return RTKV_OK;
 }
