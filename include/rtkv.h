@@ -120,20 +120,21 @@ RTKV_API int rtkv_prompt_mass(const void *A, int dtype, int B, int H, int S,
 
 /* Head sharding (one rank holds H_local = n_groups*group_size consecutive heads; float32 only):
  * partials[b,i,g] = sum_p sum_{h in local group g} A[b,h,i,idx[p]],  [B,S,H_local/group_size].
- * After the ranks' partials are gathered into [B*S, 8] (group_size = H/8 of the full model),
- * rtkv_mass_from_partials (n = B*S, n_groups = 8) gives mass = (p0 + ... + p7) / H — bit-identical
- * to rtkv_prompt_mass on the unsharded tensor. */
+ * The ranks' buffers are all-gathered into [R][B*S][8/R] (all_gather_into_tensor) and
+ * rtkv_mass_from_partials (n = B*S, n_ranks = R, groups_per_rank = 8/R) adds the 8 groups in head
+ * order: mass = (p0 + ... + p7) / H — bit-identical to rtkv_prompt_mass on the unsharded tensor.
+ * (n_ranks = 1: a plain [n][n_groups] buffer.) */
 RTKV_API int rtkv_prompt_mass_partials(const void *A, int dtype, int B, int H_local, int S,
                      int64_t sb, int64_t sh, int64_t si, const int64_t *idx, int P,
                      int group_size, float *partials, void *stream);
-RTKV_API int rtkv_mass_from_partials(const float *partials, int64_t n, int n_groups, int H, float *mass,
-                     void *stream);
+RTKV_API int rtkv_mass_from_partials(const float *partials, int64_t n, int n_ranks, int groups_per_rank, int H,
+                     float *mass, void *stream);
 
 /* Same quantity without a materialised attention matrix (tcgen05 tensor cores + TMA):
  * partials[b,i,g] = sum_{h in group g} sum_{j<P, j<=i if causal} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
  * Q: [B,H,S,D], Kp: [B,H,P,D] contiguous (bf16 or f16, D == 128, P <= 128), lse: [B,H,S] natural-log
  * row log-sum-exp of the layer's attention logits; partials: [B,S,H/group_size] f32, to be combined
- * with rtkv_mass_from_partials (n_groups = H/group_size). */
+ * with rtkv_mass_from_partials (n_ranks = 1, groups_per_rank = H/group_size). */
 RTKV_API int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype,
                         int B, int H, int S, int D, int P, float scale, int causal,
                         int group_size, float *partials, void *stream);

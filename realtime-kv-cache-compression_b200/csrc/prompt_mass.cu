@@ -106,12 +106,18 @@ prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, 
 {
     using E = typename Elem<DT>::T;
     __shared__ float part[kGroups][129];
-    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rows = (int64_t)B * S;
+    // head sharding: a rank with n_groups < 8 local groups packs 8/n_groups rows into one CTA
+    const int rpc = partials ? kGroups / n_groups : 1;
+    const int g = partials ? warp % n_groups : warp;
+    const int sub = partials ? warp / n_groups : 0;
     const int h0 = g * gs, h1 = min(H, h0 + gs);
     const float fH = (float)H;
 
-    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    for (int64_t row0 = (int64_t)blockIdx.x * rpc; row0 < rows; row0 += (int64_t)gridDim.x * rpc) {
+        const int64_t row = row0 + sub;
+        if (row >= rows) continue;                       // (only possible in partials mode: no barrier below)
         const int b = (int)(row / S);
         const int i = (int)(row - (int64_t)b * S);
         const E *rowp = (const E *)A + b * sb + (int64_t)i * si;
@@ -168,15 +174,23 @@ prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, 
     }
 }
 
-// combine: partials [n, n_groups] -> mass [n] = (p0 + p1 + ... ) / H, groups added in order
-__global__ void mass_from_partials_kernel(const float *__restrict__ partials, int64_t n, int n_groups, float fH,
+// combine: mass[t] = (p0 + p1 + ...) / H, groups added in head order.  partials is laid out
+// [n_ranks][n][groups_per_rank] (n_ranks = 1: plain [n][n_groups]); this is exactly what
+// all_gather_into_tensor of the ranks' [n][groups_per_rank] buffers produces.
+__global__ void mass_from_partials_kernel(const float *__restrict__ partials, int64_t n, int n_ranks, int gpr, float fH,
                                           float *mass)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const float *q = partials + t * n_groups;
-    float tot = q[0];
-    for (int g = 1; g < n_groups; ++g) tot = __fadd_rn(tot, q[g]);
+    float tot = 0.0f;
+    bool first = true;
+    for (int r = 0; r < n_ranks; ++r) {
+        const float *q = partials + ((int64_t)r * n + t) * gpr;
+        for (int g = 0; g < gpr; ++g) {
+            tot = first ? q[g] : __fadd_rn(tot, q[g]);
+            first = false;
+        }
+    }
     mass[t] = __fdiv_rn(tot, fH);
 }
 
@@ -189,7 +203,8 @@ static int launch_mass(const void *A, int B, int H, int S, int64_t sb, int64_t s
     const int64_t quad = 4 * eb; // bytes of one lane's vector load
     const bool vec = idx == nullptr && ((uintptr_t)A % quad == 0) && (sb * eb) % quad == 0 &&
                      (sh * eb) % quad == 0 && (si * eb) % quad == 0;
-    const int64_t rows = (int64_t)B * S;
+    const int rpc = partials ? kGroups / n_groups : 1;
+    const int64_t rows = ((int64_t)B * S + rpc - 1) / rpc;
     const int grid = (int)(rows < (1 << 20) ? rows : (1 << 20));
     if (vec)
         prompt_mass_kernel<DT, true><<<grid, kGroups * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, gs, n_groups, mass, partials);
@@ -227,17 +242,21 @@ extern "C" int rtkv_prompt_mass_partials(const void *A, int dtype, int B, int H_
     RTKV_CHECK_ARG(dtype == RTKV_F32, "rtkv_prompt_mass_partials: head sharding needs float32 probabilities "
                    "(half dtypes round the per-column head mean, which does not decompose over ranks)");
     RTKV_CHECK_ARG(B > 0 && H_local > 0 && S > 0 && P > 0 && group_size > 0, "rtkv_prompt_mass_partials: bad shape");
-    RTKV_CHECK_ARG(H_local % group_size == 0 && H_local / group_size <= kGroups,
-                   "rtkv_prompt_mass_partials: H_local=%d must be a multiple of group_size=%d with at most 8 groups",
+    const int ng = H_local / group_size;
+    RTKV_CHECK_ARG(H_local % group_size == 0 && (ng == 1 || ng == 2 || ng == 4 || ng == 8),
+                   "rtkv_prompt_mass_partials: H_local=%d must be 1, 2, 4 or 8 groups of group_size=%d heads",
                    H_local, group_size);
     return launch_mass<RTKV_F32>(A, B, H_local, S, sb, sh, si, idx, P, group_size, H_local / group_size, nullptr,
                                  partials, (cudaStream_t)stream);
 }
 
-extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int n_groups, int H, float *mass, void *stream)
+extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int n_ranks, int groups_per_rank, int H,
+                                       float *mass, void *stream)
 {
-    RTKV_CHECK_ARG(partials && mass && n > 0 && H > 0 && n_groups > 0, "rtkv_mass_from_partials: bad argument");
-    mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, n_groups, (float)H, mass);
+    RTKV_CHECK_ARG(partials && mass && n > 0 && H > 0 && n_ranks > 0 && groups_per_rank > 0,
+                   "rtkv_mass_from_partials: bad argument");
+    mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, n_ranks,
+                                                                                          groups_per_rank, (float)H, mass);
     RTKV_LAUNCH_CHECK("mass_from_partials_kernel");
     return RTKV_OK;
 }

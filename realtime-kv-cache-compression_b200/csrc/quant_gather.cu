@@ -211,13 +211,16 @@ __global__ void __launch_bounds__(kQT) row_minmax_vec_kernel(QGParams p, float *
     for (int v0 = threadIdx.x; v0 < nvec; v0 += 4 * kQT) {
         uint4 raw[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) raw[k] = (v0 + k * kQT < nvec) ? ldg_stream(src + v0 + k * kQT) : ldg_stream(src + v0);
+        for (int k = 0; k < 4; ++k)
+            if (v0 + k * kQT < nvec) raw[k] = ldg_stream(src + v0 + k * kQT);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float f[EPV];
-            Vec16<DT>::unpack(raw[k], f);
+            if (v0 + k * kQT < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+            }
         }
     }
     block_minmax(mn, mx, nan, red);

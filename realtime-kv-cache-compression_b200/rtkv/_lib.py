@@ -50,7 +50,7 @@ PROTOTYPES = {
                                         c_i64, c_i64, c_i64, c_vp, ctypes.c_int, c_vp, c_vp]),
     "rtkv_prompt_mass_partials": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                  c_i64, c_i64, c_i64, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
-    "rtkv_mass_from_partials": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_mass_from_partials": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rtkv_scratch_init": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp]),
     "rtkv_prompt_mass_qk": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int,

@@ -36,13 +36,15 @@ def head_shard(num_heads, rank, world):
 
 
 def gather_partials(partials_local, group=None):
-    """[B,S,8/R] per rank -> [B,S,8] on every rank, groups in head order."""
+    """[B,S,8/R] per rank -> [R,B,S,8/R] on every rank (one all_gather_into_tensor; rank-major is
+    head order, ops.mass_from_partials(..., rank_major=True) consumes it without a transpose)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return partials_local
-    parts = [torch.empty_like(partials_local) for _ in range(world)]
-    dist.all_gather(parts, partials_local.contiguous(), group=group)
-    return torch.cat(parts, dim=-1).contiguous()
+        return partials_local.unsqueeze(0)
+    shape = tuple(partials_local.shape)
+    out = torch.empty((world * shape[0],) + shape[1:], dtype=partials_local.dtype, device=partials_local.device)
+    dist.all_gather_into_tensor(out, partials_local.contiguous(), group=group)   # concatenation along dim 0
+    return out.view((world,) + shape)
 
 
 def reduce_minmax(minmax_negmax, group=None):
@@ -76,7 +78,7 @@ class HeadShardedCompressor:
         P = comp.prompt_length(S)
         params, _ = comp.layer_params(layer_idx, S, ops.F32)
         partials = ops.prompt_mass_partials(attention_local, P, gs)
-        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads)
+        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
         sel = ops.score_select(params, B, S, key_local.device, mass=mass)
         layer, _rows = sel.read_stats()                       # S' is a shape: one sync
         max_sel = int(layer["max_selected"])
@@ -94,7 +96,7 @@ class HeadShardedCompressor:
         comp = self.compressor
         params, _ = comp.layer_params(layer_idx, S, ops.F32)
         partials = ops.prompt_mass_partials(attention_local, comp.prompt_length(S), gs)
-        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads)
+        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
         sel = ops.score_select(params, B, S, key_local.device, mass=mass)
         mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, S, negate_max=True), self.group)
         ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), S, mm, zero_pad=False,

@@ -113,14 +113,19 @@ def prompt_mass_partials(attn_local, prompt_len, group_size):
     return parts
 
 
-def mass_from_partials(partials, num_heads):
-    """partials [B,S,G] (head groups in order) -> mass [B,S] = (p0+...+p_{G-1})/H."""
+def mass_from_partials(partials, num_heads, rank_major=False):
+    """Per-head-group partial sums -> mass = (p0 + p1 + ...)/H with the groups added in head order.
+    partials: [B,S,G], or with rank_major=True the all_gather_into_tensor layout [R,B,S,G/R]."""
     require_cuda()
     partials = partials.contiguous()
     assert partials.dtype == torch.float32
-    mass = torch.empty(partials.shape[:-1], dtype=torch.float32, device=partials.device)
-    check(lib.rtkv_mass_from_partials(_ptr(partials), mass.numel(), int(partials.shape[-1]), int(num_heads),
-                                      _ptr(mass), _stream()))
+    if rank_major:
+        R, gpr, shape = partials.shape[0], partials.shape[-1], partials.shape[1:-1]
+    else:
+        R, gpr, shape = 1, partials.shape[-1], partials.shape[:-1]
+    mass = torch.empty(shape, dtype=torch.float32, device=partials.device)
+    check(lib.rtkv_mass_from_partials(_ptr(partials), mass.numel(), int(R), int(gpr), int(num_heads), _ptr(mass),
+                                      _stream()))
     return mass
 
 

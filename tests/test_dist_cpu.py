@@ -32,7 +32,8 @@ def _worker(rank, world, port, q):
         h0, h1, gs = rd.head_shard(H, rank, world)
         # exchange 1: per-group partial sums -> identical mass on every rank, equal to the unsharded oracle
         local = oracle.prompt_mass_partials(np.ascontiguousarray(A[:, h0:h1]), P, gs)
-        gathered = rd.gather_partials(torch.from_numpy(local)).numpy()
+        gathered = rd.gather_partials(torch.from_numpy(local)).numpy()          # [R,B,S,8/R], rank-major
+        gathered = np.ascontiguousarray(np.moveaxis(gathered, 0, -2)).reshape(B, S, 8)   # -> [B,S,8] in head order
         full_mass, full_parts = oracle.prompt_mass_groups(A, oracle.F32, P)
         ok1 = np.array_equal(gathered, full_parts) and np.array_equal(oracle.mass_from_partials(gathered, H), full_mass)
         # exchange 2: row min/max over the ranks' column slices == min/max of the whole row
@@ -77,4 +78,4 @@ def test_shard_arithmetic(built_lib):
     assert rd.batch_shard(3, 3, 4) == slice(3, 3)
     # single process: the exchanges are identities
     t = torch.arange(8.0).view(1, 2, 4)
-    assert torch.equal(rd.gather_partials(t), t) and torch.equal(rd.reduce_minmax(t), t)
+    assert torch.equal(rd.gather_partials(t), t.unsqueeze(0)) and torch.equal(rd.reduce_minmax(t), t)

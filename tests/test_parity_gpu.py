@@ -293,6 +293,8 @@ def test_head_sharded_partials_are_bit_identical(rt, H, S, P):
         gathered = torch.cat(parts, dim=-1)                       # what the all-gather produces
         np.testing.assert_array_equal(host(gathered), wparts)
         np.testing.assert_array_equal(host(ops.mass_from_partials(gathered, H)), want)
+        stacked = torch.stack(parts, dim=0)                       # what all_gather_into_tensor produces
+        np.testing.assert_array_equal(host(ops.mass_from_partials(stacked, H, rank_major=True)), want)
     np.testing.assert_array_equal(oracle.mass_from_partials(wparts, H), want)
 
 
