@@ -34,6 +34,7 @@ WORKLOADS = {
     "c1": ("single layer K/V [1,32,2048,128] fp32 (configs[0])", 1, 4096, 32, 11008, 2048, 1, (2, 4, 8)),
     "c2": ("Llama-2-7B random-init, 32-layer prefill of 4096 tokens, batch 1 (configs[1])", 32, 4096, 32, 11008, 4096, 1, (2, 4, 8)),
     "c3": ("Llama-2-7B random-init, 32-layer prefill of 32768 tokens, batch 1, KV-head-sharded over the GPUs (configs[2])", 32, 4096, 32, 11008, 32768, 1, (2, 4, 8)),
+    "c5": ("Llama-2-7B random-init, batch 8 per GPU x 4096-token prefill, batch-sharded (configs[4]: 64 sequences on 8 GPUs)", 32, 4096, 32, 11008, 4096, 8, (2, 4, 8)),
     "c4": ("Llama-2-13B random-init, 40-layer prefill of 16384 tokens, batch 1 (configs[3], mixed 8/4/2)", 40, 5120, 40, 13824, 16384, 1, (2, 4, 8)),
 }
 PEAKS_FALLBACK_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -299,6 +300,9 @@ def main():
     ap.add_argument("--impl", default="rtkv", choices=["rtkv", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--layers", type=int, default=0, help="override the number of layers (setup time)")
+    ap.add_argument("--bits", default="", help="low,mid,high bit widths, e.g. 8,8,8 (configs[3] precision sweep)")
+    ap.add_argument("--ablation", default="", choices=["", "quant_only"],
+                    help="quant_only: propagation ratios 1.0, every token kept (configs[4] ablation)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -310,14 +314,17 @@ def main():
     desc, L, hidden, heads, inter, S, B, bits = WORKLOADS[args.workload]
     if args.layers > 0:
         L = args.layers
+    if args.bits:
+        bits = tuple(int(x) for x in args.bits.split(","))
     head_sharded = args.workload == "c3" and world > 1
     P = max(1, min(S // 5, 128))
     sample_layers = sorted({0, L // 3, (2 * L) // 3, L - 1})
 
     import rtkv
+    ratios = {"early_layer_ratio": 1.0, "middle_layer_ratio": 1.0, "later_layer_ratio": 1.0} if args.ablation == "quant_only" else {}
     cfg = rtkv.CompressionConfig(num_hidden_layers=max(L, 2), num_attention_heads=heads, hidden_size=hidden,
                                  high_precision_bits=bits[2], medium_precision_bits=bits[1],
-                                 low_precision_bits=bits[0])
+                                 low_precision_bits=bits[0], **ratios)
     config = {"workload": desc, "layers": L, "seq_len": S, "batch_per_gpu": B, "kv_width": hidden, "heads": heads,
               "prompt_len": P, "bits_low_mid_high": list(bits), "theta_h": cfg.theta_h, "theta_m": cfg.theta_m,
               "ratios": [cfg.early_layer_ratio, cfg.middle_layer_ratio, cfg.later_layer_ratio],

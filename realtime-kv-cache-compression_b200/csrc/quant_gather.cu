@@ -238,7 +238,10 @@ template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStre
         const int nv = (p.n / EPV + kQT - 1) / kQT;
         if (nv <= 1) quant_gather_vec_kernel<DT, 1><<<grid, kQT, 0, st>>>(p);
         else if (nv <= 2) quant_gather_vec_kernel<DT, 2><<<grid, kQT, 0, st>>>(p);
+        else if (nv <= 3) quant_gather_vec_kernel<DT, 3><<<grid, kQT, 0, st>>>(p);
         else if (nv <= 4) quant_gather_vec_kernel<DT, 4><<<grid, kQT, 0, st>>>(p);
+        else if (nv <= 5) quant_gather_vec_kernel<DT, 5><<<grid, kQT, 0, st>>>(p);   // 13B rows: 5120 fp32
+        else if (nv <= 6) quant_gather_vec_kernel<DT, 6><<<grid, kQT, 0, st>>>(p);
         else quant_gather_vec_kernel<DT, kMaxVec><<<grid, kQT, 0, st>>>(p);
     } else {
         quant_gather_generic_kernel<DT><<<grid, kQT, 0, st>>>(p);
