@@ -98,9 +98,14 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
                 if (i < S) {
                     float s = sv[u];
                     if (from_mass) {
-                        float n = 0.0f;
-                        if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(s, mn), dt), den), dt);
-                        const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                        float n = 0.0f, t1;
+                        if (dt == RTKV_F32) {            // float32 attention: no per-op rounding to a half dtype
+                            if (ok) n = __fdiv_rn(__fsub_rn(s, mn), den);
+                            t1 = __fmul_rn(__fmul_rn(p.alpha, n), p.w_l);
+                        } else {
+                            if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(s, mn), dt), den), dt);
+                            t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                        }
                         float pb = 0.0f;
                         if (S > 1) {
                             const float l = (i < p.log_tab_len) ? lg[u] : (float)log((double)(float)(i + 1));
@@ -137,16 +142,20 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
         cfg.budget_bits = p.budget_bits;
         const long long all_bits = (long long)cfg.bits[0] * st.n0 + (long long)cfg.bits[1] * st.n1 +
                                    (long long)cfg.bits[2] * st.n2;
-        if (all_bits <= cfg.budget_bits) {            // the whole row fits: no walk needed
-            if (threadIdx.x == 0) { sm.thr[0] = sm.thr[1] = sm.thr[2] = ~0ull; sm.cur = all_bits; }
-            __syncthreads();
+        if (all_bits <= cfg.budget_bits) {            // the whole row fits: every token is kept, in order
+            uint8_t *mask = p.mask + (int64_t)b * S;
+            int32_t *sel_idx = p.sel_idx + (int64_t)b * S;
+            for (int i = threadIdx.x; i < S; i += kT) { mask[i] = 1; sel_idx[i] = i; }
+            cost_bits = all_bits; count = S; sel_sum = st.sum;
+            sel_class[0] = st.n0; sel_class[1] = st.n1; sel_class[2] = st.n2;
+            tick(sm);
         } else {
             select_thresholds(rsc, rlb, S, st.kmin, st.kmax, cfg, sm);
+            cost_bits = sm.cur;
+            tick(sm);   // thresholds done
+            emit_selection(rsc, rlb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
+                           sel_class, sel_sum);
         }
-        cost_bits = sm.cur;
-        tick(sm);   // thresholds done
-        emit_selection(rsc, rlb, S, p.mask + (int64_t)b * S, p.sel_idx + (int64_t)b * S, sm, count,
-                       sel_class, sel_sum);
         tick(sm);   // emit done
     }
     if (threadIdx.x == 0) {

@@ -212,9 +212,14 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
                 if (i < end) {
                     float s = sv[u];
                     if (from_mass) {
-                        float n = 0.0f;
-                        if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(s, mn), dt), den), dt);
-                        const float t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                        float n = 0.0f, t1;
+                        if (dt == RTKV_F32) {            // float32 attention: no per-op rounding to a half dtype
+                            if (ok) n = __fdiv_rn(__fsub_rn(s, mn), den);
+                            t1 = __fmul_rn(__fmul_rn(p.alpha, n), p.w_l);
+                        } else {
+                            if (ok) n = rnd_dt(__fdiv_rn(rnd_dt(__fsub_rn(s, mn), dt), den), dt);
+                            t1 = rnd_dt(__fmul_rn(rnd_dt(__fmul_rn(p.alpha, n), dt), p.w_l), dt);
+                        }
                         float pb = 0.0f;
                         if (S > 1) {
                             const float l = (i < p.log_tab_len) ? lg[u] : (float)log((double)(float)(i + 1));
@@ -356,7 +361,19 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
     // ---- mask + compacted index list of the chunk ----
     int count_row = 0;
     RowAgg sel = agg_identity();
+    bool all_fit = false;
     if (p.flags & RTKV_SELECT) {
+        const long long all_bits = (long long)cfg.bits[0] * row.n0 + (long long)cfg.bits[1] * row.n1 +
+                                   (long long)cfg.bits[2] * row.n2;
+        all_fit = all_bits <= cfg.budget_bits;
+    }
+    if (all_fit) {                                       // every token kept, in order: no exchange needed
+        uint8_t *mask = p.mask + (int64_t)b * S;
+        int32_t *sel_idx = p.sel_idx + (int64_t)b * S;
+        for (int i = beg + threadIdx.x; i < end; i += kT) { mask[i] = 1; sel_idx[i] = i; }
+        count_row = S;
+        sel.sum = row.sum; sel.n0 = row.n0; sel.n1 = row.n1; sel.n2 = row.n2;
+    } else if (p.flags & RTKV_SELECT) {
         uint8_t *mask = p.mask + (int64_t)b * S;
         int32_t *sel_idx = p.sel_idx + (int64_t)b * S;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
