@@ -463,7 +463,8 @@ def main():
     # K3 launch durations inside the graph: event-record nodes around every K3 kernel
     k3_graph_ms = None
     try:
-        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in layers]
+        gev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+               for _ in layers]
         graph3, _ = capture(False, gev)
         for _ in range(3):
             graph3.replay()
