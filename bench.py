@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--bits", default="", help="low,mid,high bit widths, e.g. 8,8,8 (configs[3] precision sweep)")
     ap.add_argument("--ablation", default="", choices=["", "quant_only"],
                     help="quant_only: propagation ratios 1.0, every token kept (configs[4] ablation)")
+    ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -376,6 +377,9 @@ def main():
                                   head_slice=(rank, world) if head_sharded else None)
     torch.cuda.synchronize()
     comp = rtkv.RealTimePrefillCompressor(cfg)
+    if args.no_pdl:
+        from rtkv import _lib as _rl
+        _rl.lib.rtkv_debug_pdl(0)
     if head_sharded:
         return bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, B, P, hidden, heads, bits)
     outs = [(torch.empty_like(K), torch.empty_like(V)) for (_, K, V, _) in layers]
@@ -522,7 +526,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "gpu_launches": 3 * L * args.steps, "roofline": roofline,
-            "launch_mode": "one CUDA graph per step (3 kernels x %d layers, single stream)" % L,
+            "launch_mode": "one CUDA graph per step (3 kernels x %d layers, single stream%s)" % (
+                L, "" if args.no_pdl else ", programmatic dependent launch"),
             "eager_ms_per_step": eager_ms_per_step,
             "two_stream": {"ms_per_step": ms_two_stream, "value": world * B * S / (ms_two_stream * 1e-3),
                            "note": "same graph with K3 of layer l on a second stream, overlapping K1/K2 of layer l+1"},

@@ -222,6 +222,9 @@ RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);
  * row from 8192 tokens, else one CTA), 1 = always one CTA, 2 = the cluster kernel whenever S >= 1024. */
 RTKV_API int rtkv_debug_k2_mode(int mode);
 
+/* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
+RTKV_API int rtkv_debug_pdl(int on);
+
 /* One layer with HOST buffers (pinned or pageable): copies K, V and the first P
  * key columns of A to the device, runs the path, copies the results back and
  * synchronises.  K_out/V_out must hold B*S*n elements; they are filled as a

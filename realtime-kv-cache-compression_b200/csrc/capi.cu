@@ -30,9 +30,17 @@ int cuda_fail(cudaError_t e, const char *what)
     return (int)e;
 }
 
+int g_use_pdl = 1;
+
 } // namespace rtkv
 
 using namespace rtkv;
+
+extern "C" int rtkv_debug_pdl(int on)
+{
+    g_use_pdl = on ? 1 : 0;
+    return RTKV_OK;
+}
 
 extern "C" int rtkv_abi_version(void) { return RTKV_ABI_VERSION; }
 extern "C" const char *rtkv_last_error(void) { return g_err; }

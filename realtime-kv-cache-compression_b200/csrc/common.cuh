@@ -198,6 +198,38 @@ template <int DT> __device__ __forceinline__ float qmax_rounded(int bits)
     return Elem<DT>::rnd((float)((1ll << bits) - 1));
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// Every hot kernel starts with pdl_wait() (the previous kernel of the stream has completed and its
+// memory is visible) followed by pdl_trigger() (the next kernel may be scheduled as soon as all CTAs
+// of this one are running): the successor's launch latency and ramp-up overlap this kernel's tail.
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_use_pdl;   // capi.cu; rtkv_debug_pdl()
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 int cluster_x, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster_x > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int dtype_bytes(int dt) { return dt == RTKV_F32 ? 4 : 2; }
 inline bool dtype_ok(int dt) { return dt == RTKV_F32 || dt == RTKV_F16 || dt == RTKV_BF16; }
 

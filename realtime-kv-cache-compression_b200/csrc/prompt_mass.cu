@@ -114,6 +114,8 @@ prompt_mass_kernel(const void *__restrict__ A, int B, int H, int S, int64_t sb, 
     const int sub = partials ? warp / n_groups : 0;
     const int h0 = g * gs, h1 = min(H, h0 + gs);
     const float fH = (float)H;
+    pdl_wait();
+    pdl_trigger();
 
     for (int64_t row0 = (int64_t)blockIdx.x * rpc; row0 < rows; row0 += (int64_t)gridDim.x * rpc) {
         const int64_t row = row0 + sub;
@@ -207,10 +209,11 @@ static int launch_mass(const void *A, int B, int H, int S, int64_t sb, int64_t s
     const int64_t rows = ((int64_t)B * S + rpc - 1) / rpc;
     const int grid = (int)(rows < (1 << 20) ? rows : (1 << 20));
     if (vec)
-        prompt_mass_kernel<DT, true><<<grid, kGroups * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, gs, n_groups, mass, partials);
+        RTKV_CUDA(launch_kernel(prompt_mass_kernel<DT, true>, dim3(grid), dim3(kGroups * 32), 0, st, 1, A, B, H, S, sb, sh, si,
+                                idx, P, gs, n_groups, mass, partials));
     else
-        prompt_mass_kernel<DT, false><<<grid, kGroups * 32, 0, st>>>(A, B, H, S, sb, sh, si, idx, P, gs, n_groups, mass, partials);
-    RTKV_LAUNCH_CHECK("prompt_mass_kernel");
+        RTKV_CUDA(launch_kernel(prompt_mass_kernel<DT, false>, dim3(grid), dim3(kGroups * 32), 0, st, 1, A, B, H, S, sb, sh, si,
+                                idx, P, gs, n_groups, mass, partials));
     return RTKV_OK;
 }
 

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
     constexpr int EPV = Vec16<DT>::kElems;
     __shared__ float red[16];
     const int r = blockIdx.x + p.row_begin, b = blockIdx.y + p.b_begin, t = blockIdx.z;
+    pdl_wait();
+    pdl_trigger();
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
     const int nvec = p.n / EPV;
     uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
@@ -236,13 +238,14 @@ template <int DT> static int launch_qg(const QGParams &p, int ntensors, cudaStre
         vec = vec && ((uintptr_t)p.x[t] % 16 == 0) && ((uintptr_t)p.y[t] % 16 == 0);
     if (vec) {
         const int nv = (p.n / EPV + kQT - 1) / kQT;
-        if (nv <= 1) quant_gather_vec_kernel<DT, 1><<<grid, kQT, 0, st>>>(p);
-        else if (nv <= 2) quant_gather_vec_kernel<DT, 2><<<grid, kQT, 0, st>>>(p);
-        else if (nv <= 3) quant_gather_vec_kernel<DT, 3><<<grid, kQT, 0, st>>>(p);
-        else if (nv <= 4) quant_gather_vec_kernel<DT, 4><<<grid, kQT, 0, st>>>(p);
-        else if (nv <= 5) quant_gather_vec_kernel<DT, 5><<<grid, kQT, 0, st>>>(p);   // 13B rows: 5120 fp32
-        else if (nv <= 6) quant_gather_vec_kernel<DT, 6><<<grid, kQT, 0, st>>>(p);
-        else quant_gather_vec_kernel<DT, kMaxVec><<<grid, kQT, 0, st>>>(p);
+        void (*kern)(QGParams) = quant_gather_vec_kernel<DT, kMaxVec>;
+        if (nv <= 1) kern = quant_gather_vec_kernel<DT, 1>;
+        else if (nv <= 2) kern = quant_gather_vec_kernel<DT, 2>;
+        else if (nv <= 3) kern = quant_gather_vec_kernel<DT, 3>;
+        else if (nv <= 4) kern = quant_gather_vec_kernel<DT, 4>;
+        else if (nv <= 5) kern = quant_gather_vec_kernel<DT, 5>;   // 13B rows: 5120 fp32
+        else if (nv <= 6) kern = quant_gather_vec_kernel<DT, 6>;
+        RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, p));
     } else {
         quant_gather_generic_kernel<DT><<<grid, kQT, 0, st>>>(p);
     }

@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
     uint8_t *s_lb = reinterpret_cast<uint8_t *>(s_sc + ((S + 3) / 4) * 4);
     const float *rsc = p.staged ? s_sc : sc;
     const uint8_t *rlb = p.staged ? s_lb : lb;
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0) { sm.dbg = p.dbg; sm.dbg_n = 0; tick(sm); }
 
     // ---- scores (token_importance.py:134-176) ----
@@ -369,8 +371,7 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
         RTKV_CUDA(cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_bytes[dev] = 200 * 1024;
     }
-    score_select_kernel<<<B, kT, smem, (cudaStream_t)stream>>>(p);
-    RTKV_LAUNCH_CHECK("score_select_kernel");
+    RTKV_CUDA(launch_kernel(score_select_kernel, dim3(B), dim3(kT), smem, (cudaStream_t)stream, 1, p));
     return RTKV_OK;
 }
 

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
     const float *__restrict__ tab = p.log_tab;
     int phase = 0;
     unsigned parity = 0;
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0) {
         sm.dbg = (rank == 0 && blockIdx.x == 0) ? p.dbg : nullptr; sm.dbg_n = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&cs.bar[0])), "r"(kCS));
@@ -506,17 +508,7 @@ int launch_score_select_cluster(const K2Params &p, cudaStream_t st, bool force)
         RTKV_CUDA(cudaFuncSetAttribute(score_select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_bytes[dev] = 200 * 1024;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p.B * kCS));
-    cfg.blockDim = dim3(kT);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    RTKV_CUDA(cudaLaunchKernelEx(&cfg, score_select_cluster_kernel, p));
+    RTKV_CUDA(launch_kernel(score_select_cluster_kernel, dim3((unsigned)(p.B * kCS)), dim3(kT), smem, st, kCS, p));
     return RTKV_OK;
 }
 
