@@ -185,6 +185,20 @@ RTKV_API int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtype,
                       const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
                       const float *minmax, int negated_max, void *Y0, void *Y1, void *stream);
 
+/* KV-head sharding, fused: min/max exchange inside the quantise kernel over peer-mapped memory
+ * (NVLink).  mailbox_ptrs [host]: `world` device pointers, entry s = rank s's mailbox as mapped into
+ * this process (symmetric memory / CUDA IPC), each rtkv_p2p_mailbox_bytes(B, out_rows, world) bytes,
+ * zero-filled once; state: 2 zero-initialised uint32 in local device memory.  Every rank must call
+ * this with the same B, out_rows, selection and call sequence, and a collective (or barrier) must
+ * separate consecutive calls that reuse a mailbox parity twice (the score all-gather does).
+ * Equals rtkv_quant_gather on the concatenated row bit for bit. */
+RTKV_API int64_t rtkv_p2p_mailbox_bytes(int B, int out_rows, int world);
+RTKV_API int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                      const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                      const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
+                      const uint64_t *mailbox_ptrs /*[host]*/, int rank, int world, uint32_t *state,
+                      void *Y0, void *Y1, void *stream);
+
 /* Whole-tensor scale / zero-point (qparams[0] = scale, [1] = zero_point, in `dtype`,
  * stored as f32) and quantise-dequantise with given parameters. */
 RTKV_API int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bits, float *qparams,

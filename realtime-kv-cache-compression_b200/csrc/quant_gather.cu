@@ -31,6 +31,10 @@ struct QGParams {
     int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
     const float *ext_minmax;  // [B,out_rows,4] = (min0, max0, min1, max1) of the WHOLE row (head sharding) or NULL
     int neg_max;              // the max entries are stored negated (so that one MIN all-reduce combines ranks)
+    // fused peer exchange (rtkv_quant_gather_p2p): mailbox of rank s as mapped into this process
+    unsigned long long mbox[8];
+    unsigned *p2p_state;      // [0] epoch of the last finished call, [1] finished-CTA counter
+    int rank, world, total_ctas;
 };
 
 // no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
@@ -122,6 +126,120 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
 #pragma unroll
             for (int e = 0; e < EPV; ++e) f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
             stg_stream(dst + v, Vec16<DT>::pack(f));
+        }
+    }
+}
+
+// ---- KV-head sharding, fused exchange ------------------------------------------------------
+// Same as quant_gather_vec_kernel, but the row's scale spans the head slices of ALL ranks
+// (dynamic_quantization.py:183-184 quantises the whole [H*D] row).  Instead of a separate min/max
+// pass + collective + second read, the CTA keeps its slice of the row in registers, pushes its local
+// (min, -max) into every rank's mailbox over NVLink (peer stores into symmetric memory) and polls its
+// own mailbox until all R partials of this row have arrived.  Mailbox words are self-validating
+// {value, epoch} pairs (8-byte granules, NCCL-LL style), so no fence or flag reset is needed; the
+// epoch lives in device memory and is bumped by the last CTA, which makes the kernel graph-replayable.
+// All ranks process the same rows in the same order, so a CTA only ever waits for a peer CTA that has
+// already been scheduled or will be without needing this CTA's resources.
+__device__ __forceinline__ void st_volatile_v4(void *p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+template <int DT, int NV>
+__global__ void __launch_bounds__(kQT) quant_gather_p2p_kernel(QGParams p)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ float red[16];
+    __shared__ float s_mm[2];
+    const int r = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    pdl_wait();
+    pdl_trigger();
+    const unsigned epoch = ((volatile unsigned *)p.p2p_state)[0] + 1u;
+    const int cnt = p.row_stats[b].n_selected;
+    const int nvec = p.n / EPV;
+    uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
+    if (r < cnt) {
+        const int tok = p.sel_idx[(int64_t)b * p.S + r];
+        const uint4 *src = (const uint4 *)((const char *)pick_x(p, t) + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+        uint4 raw[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+        }
+        float mn = INFINITY, mx = -INFINITY;
+        int nan = 0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (threadIdx.x + k * kQT < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+            }
+        }
+        block_minmax(mn, mx, nan, red);
+        // ---- exchange: slot[(parity, tensor, row, source rank)] in every rank's mailbox ----
+        const size_t rows_total = (size_t)p.B * p.out_rows;
+        const size_t slot0 = ((((size_t)(epoch & 1u) * 2 + t) * rows_total + (size_t)b * p.out_rows + r) * p.world);
+        if ((int)threadIdx.x < p.world) {
+            const int s = threadIdx.x;
+            uint4 mine = make_uint4(__float_as_uint(mn), epoch, __float_as_uint(-mx), epoch);
+            st_volatile_v4((uint4 *)p.mbox[s] + slot0 + p.rank, mine);                  // into rank s's mailbox
+            const uint4 *in = (const uint4 *)p.mbox[p.rank] + slot0 + s;               // from rank s, in my mailbox
+            uint4 got;
+            const long long t0 = clock64();
+            do {
+                got = ld_volatile_v4(in);
+                if (clock64() - t0 > 6000000000LL) __trap();                            // a peer never showed up
+            } while (got.y != epoch || got.w != epoch);
+            float pmn = __uint_as_float(got.x), pnmx = __uint_as_float(got.z);
+            int pnan = (pmn != pmn);
+            const unsigned act = (1u << p.world) - 1u;
+            for (int o = 4; o; o >>= 1) {                                               // world <= 8
+                const float omn = __shfl_xor_sync(act, pmn, o), onm = __shfl_xor_sync(act, pnmx, o);
+                const int on = __shfl_xor_sync(act, pnan, o);
+                if ((s ^ o) < p.world) { pmn = fminf(pmn, omn); pnmx = fminf(pnmx, onm); pnan |= on; }
+            }
+            if (s == 0) {
+                s_mm[0] = pnan ? __int_as_float(0x7fc00000) : pmn;
+                s_mm[1] = pnan ? __int_as_float(0x7fc00000) : -pnmx;
+            }
+        }
+        __syncthreads();
+        mn = s_mm[0]; mx = s_mm[1];
+        const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+        float scale, zp;
+        quant_params<DT>(mn, mx, bits, scale, zp);
+        const float qmax_r = qmax_rounded<DT>(bits);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            if (v < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+                stg_stream(dst + v, Vec16<DT>::pack(f));
+            }
+        }
+    } else if (p.zero_pad) {
+        for (int v = threadIdx.x; v < nvec; v += kQT) stg_stream(dst + v, make_uint4(0, 0, 0, 0));
+    }
+    // last CTA of the grid publishes the epoch for the next call
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&p.p2p_state[1], 1u) == (unsigned)(p.total_ctas - 1)) {
+            p.p2p_state[1] = 0u;
+            __threadfence();
+            ((volatile unsigned *)p.p2p_state)[0] = epoch;
         }
     }
 }
@@ -399,6 +517,8 @@ static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S
     for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
     p.row_begin = 0; p.b_begin = 0;
     p.ext_minmax = nullptr; p.neg_max = 0;
+    for (int i = 0; i < 8; ++i) p.mbox[i] = 0;
+    p.p2p_state = nullptr; p.rank = 0; p.world = 1; p.total_ctas = 0;
     return RTKV_OK;
 }
 
@@ -508,6 +628,51 @@ extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtyp
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
     p.ext_minmax = minmax; p.neg_max = negated_max != 0;
     RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, out_rows, B));
+    return RTKV_OK;
+}
+
+template <int DT> static void (*pick_p2p_kernel(int nv))(QGParams)
+{
+    if (nv <= 1) return quant_gather_p2p_kernel<DT, 1>;
+    if (nv <= 2) return quant_gather_p2p_kernel<DT, 2>;
+    if (nv <= 4) return quant_gather_p2p_kernel<DT, 4>;
+    return quant_gather_p2p_kernel<DT, kMaxVec>;
+}
+
+extern "C" int64_t rtkv_p2p_mailbox_bytes(int B, int out_rows, int world)
+{
+    if (B <= 0 || out_rows <= 0 || world <= 0 || world > 8) return -1;
+    return (int64_t)2 /*parity*/ * 2 /*K,V*/ * B * out_rows * world * 16;
+}
+
+extern "C" int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                     const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                     const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                     const uint64_t *mailbox_ptrs, int rank, int world, uint32_t *state,
+                                     void *Y0, void *Y1, void *stream)
+{
+    RTKV_CHECK_ARG(X0 && X1 && Y0 && Y1 && sel_idx && row_stats && labels && bits && mailbox_ptrs && state,
+                   "rtkv_quant_gather_p2p: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows > 0, "rtkv_quant_gather_p2p: bad shape");
+    RTKV_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "rtkv_quant_gather_p2p: bad rank/world");
+    int rc = check_bits(bits, dtype, "rtkv_quant_gather_p2p");
+    if (rc) return rc;
+    const int epv = 16 / dtype_bytes(dtype);
+    if (n % epv != 0 || n > kMaxVec * kQT * epv || (uintptr_t)X0 % 16 || (uintptr_t)X1 % 16 || (uintptr_t)Y0 % 16 ||
+        (uintptr_t)Y1 % 16) {
+        set_error("rtkv_quant_gather_p2p: rows must be 16-byte aligned vectors of at most %d elements", kMaxVec * kQT * epv);
+        return RTKV_EUNSUPPORTED;
+    }
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    for (int i = 0; i < world; ++i) p.mbox[i] = mailbox_ptrs[i];
+    p.p2p_state = state; p.rank = rank; p.world = world; p.total_ctas = out_rows * B * 2;
+    dim3 grid(out_rows, B, 2);
+    const int nv = (n / epv + kQT - 1) / kQT;
+    cudaStream_t st = (cudaStream_t)stream;
+    void (*kern)(QGParams) = nullptr;
+    RTKV_DISPATCH(dtype, kern = pick_p2p_kernel<DT>(nv));
+    RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, p));
     return RTKV_OK;
 }
 

@@ -72,6 +72,11 @@ PROTOTYPES = {
     "rtkv_quant_gather_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
                                                 c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "rtkv_p2p_mailbox_bytes": (c_i64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "rtkv_quant_gather_p2p": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp,
+                                             c_vp, c_vp, c_vp]),
     "rtkv_quant_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_quantize_with_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_gather_scalars": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -57,39 +57,66 @@ def reduce_minmax(minmax_negmax, group=None):
     return minmax_negmax
 
 
+class PeerMailbox:
+    """Symmetric (peer-mapped) mailbox for the fused min/max exchange of rtkv_quant_gather_p2p.
+    torch's symmetric memory is the plumbing: it allocates the buffer and hands out the peers'
+    device addresses (NVLink P2P); the exchange itself happens inside the rtkv kernel."""
+
+    def __init__(self, batch, rows, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.batch, self.rows = batch, rows
+        nbytes = int(_lib.lib.rtkv_p2p_mailbox_bytes(int(batch), int(rows), int(self.world)))
+        if nbytes <= 0:
+            raise ValueError("bad mailbox shape")
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                       # every mailbox is zeroed before anybody writes
+
+    def fits(self, batch, rows):
+        return batch * rows <= self.batch * self.rows
+
+
 class HeadShardedCompressor:
     """compress_layer_kv_cache for a rank that holds a contiguous slice of the KV heads.
 
     Returns this rank's slice of the compressed K/V ([B,S',HD/R]) and the (replicated) Selection.
     Concatenating the ranks' slices along the last dim reproduces the single-GPU output bit for bit.
+    p2p=True uses the fused kernel (row min/max exchanged over NVLink inside the quantise kernel,
+    K/V read once); p2p=False the two-pass scheme with a MIN all-reduce.
     """
 
-    def __init__(self, compressor, num_heads, group=None):
+    def __init__(self, compressor, num_heads, group=None, p2p=False):
         self.compressor = compressor
         self.num_heads = num_heads
         self.group = group
+        self.p2p = p2p
+        self.mailbox = None
 
-    def compress_layer_kv_cache(self, key_local, value_local, attention_local, layer_idx):
+    def _mailbox(self, batch, rows, device):
+        if self.mailbox is None or not self.mailbox.fits(batch, rows):
+            self.mailbox = PeerMailbox(batch, rows, device, self.group)
+        return self.mailbox
+
+    def _quantise(self, key_local, value_local, sel, rows, zero_pad, out_keys=None, out_values=None):
         from . import ops
-        B, S, _ = key_local.shape
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        gs = self.num_heads // N_GROUPS
         comp = self.compressor
-        P = comp.prompt_length(S)
-        params, _ = comp.layer_params(layer_idx, S, ops.F32)
-        partials = ops.prompt_mass_partials(attention_local, P, gs)
-        mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
-        sel = ops.score_select(params, B, S, key_local.device, mass=mass)
-        layer, _rows = sel.read_stats()                       # S' is a shape: one sync
-        max_sel = int(layer["max_selected"])
-        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, max_sel, negate_max=True), self.group)
-        k_sel, v_sel = ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), max_sel, mm,
-                                               negated_max=True)
-        return k_sel, v_sel, sel
+        if self.p2p:
+            mb = self._mailbox(key_local.shape[0], key_local.shape[1], key_local.device)
+            return ops.quant_gather_p2p(key_local, value_local, sel, sel.labels, comp._bits(), rows, mb.ptrs, mb.rank,
+                                        mb.world, mb.state, zero_pad=zero_pad, out0=out_keys, out1=out_values)
+        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, rows, negate_max=True), self.group)
+        return ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), rows, mm,
+                                       zero_pad=zero_pad, out0=out_keys, out1=out_values, negated_max=True)
 
-    def compress_layer_async(self, key_local, value_local, attention_local, layer_idx, out_keys, out_values):
-        """Synchronisation-free variant (fixed capacity S rows, like compress_layer_kv_cache_async):
-        the two exchanges run on the full [B,S,.] extent, nothing is read back to the host."""
+    def _select(self, key_local, attention_local, layer_idx):
         from . import ops
         B, S, _ = key_local.shape
         gs = self.num_heads // N_GROUPS
@@ -97,8 +124,18 @@ class HeadShardedCompressor:
         params, _ = comp.layer_params(layer_idx, S, ops.F32)
         partials = ops.prompt_mass_partials(attention_local, comp.prompt_length(S), gs)
         mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
-        sel = ops.score_select(params, B, S, key_local.device, mass=mass)
-        mm = reduce_minmax(ops.row_minmax(key_local, value_local, sel, S, negate_max=True), self.group)
-        ops.quant_gather_minmax(key_local, value_local, sel, sel.labels, comp._bits(), S, mm, zero_pad=False,
-                                out0=out_keys, out1=out_values, negated_max=True)
+        return ops.score_select(params, B, S, key_local.device, mass=mass)
+
+    def compress_layer_kv_cache(self, key_local, value_local, attention_local, layer_idx):
+        sel = self._select(key_local, attention_local, layer_idx)
+        layer, _rows = sel.read_stats()                       # S' is a shape: one sync
+        max_sel = int(layer["max_selected"])
+        k_sel, v_sel = self._quantise(key_local, value_local, sel, max_sel, True)
+        return k_sel, v_sel, sel
+
+    def compress_layer_async(self, key_local, value_local, attention_local, layer_idx, out_keys, out_values):
+        """Synchronisation-free variant (fixed capacity S rows, like compress_layer_kv_cache_async):
+        the exchanges run on the full [B,S,.] extent, nothing is read back to the host."""
+        sel = self._select(key_local, attention_local, layer_idx)
+        self._quantise(key_local, value_local, sel, key_local.shape[1], False, out_keys, out_values)
         return sel

@@ -277,6 +277,23 @@ def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=Tr
     return y0, y1
 
 
+def quant_gather_p2p(x0, x1, sel, labels, bits, out_rows, mailbox_ptrs, rank, world, state, zero_pad=True,
+                     out0=None, out1=None):
+    """KV-head-sharded quantise+gather with the row min/max exchanged inside the kernel over
+    peer-mapped mailboxes (mailbox_ptrs: list of `world` device addresses, see rtkv.h)."""
+    require_cuda()
+    x0, x1 = x0.contiguous(), x1.contiguous()
+    B, S, n = x0.shape
+    y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = out1 if out1 is not None else torch.empty_like(y0)
+    lab = labels.to(torch.uint8).contiguous()
+    ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in mailbox_ptrs])
+    check(lib.rtkv_quant_gather_p2p(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n, _ptr(sel.sel_idx), sel.row_stats_ptr,
+                                    _ptr(lab), _lib.bits3(bits), int(out_rows), int(bool(zero_pad)), ptrs, int(rank),
+                                    int(world), _ptr(state), _ptr(y0), _ptr(y1), _stream()))
+    return y0, y1
+
+
 def quant_params(x, bits):
     """Whole-tensor (scale, zero_point) as a float32 [2] device tensor (dynamic_quantization.py:62-95)."""
     require_cuda()

@@ -37,30 +37,34 @@ def main():
         k_ref, v_ref, info = comp.compress_layer_kv_cache(K, V, A, ids, layer)
         h0, h1, gs = rd.head_shard(H, rank, world)
         w = HD // world
-        sharded = rd.HeadShardedCompressor(comp, H)
-        k_loc, v_loc, sel = sharded.compress_layer_kv_cache(K[..., rank * w:(rank + 1) * w].contiguous(),
-                                                            V[..., rank * w:(rank + 1) * w].contiguous(),
-                                                            A[:, h0:h1].contiguous(), layer)
-        ks = [torch.empty_like(k_loc) for _ in range(world)]
-        vs = [torch.empty_like(v_loc) for _ in range(world)]
-        dist.all_gather(ks, k_loc)
-        dist.all_gather(vs, v_loc)
-        ok = (torch.equal(torch.cat(ks, -1), k_ref) and torch.equal(torch.cat(vs, -1), v_ref)
-              and torch.equal(sel.mask.view(torch.bool), info["propagation_info"]["selection_mask"]))
-        # fixed-capacity variant
-        ok2 = True
-        okb, ovb = torch.zeros(B, S, w, device="cuda"), torch.zeros(B, S, w, device="cuda")
-        sharded.compress_layer_async(K[..., rank * w:(rank + 1) * w].contiguous(), V[..., rank * w:(rank + 1) * w].contiguous(),
-                                     A[:, h0:h1].contiguous(), layer, okb, ovb)
-        ms = k_ref.shape[1]
-        ok2 = torch.equal(okb[:, :ms], k_loc) and torch.equal(ovb[:, :ms], v_loc) if B == 1 else True
-        t = torch.tensor([int(ok and ok2)], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            print(f"head-sharded R={world} B={B} H={H} S={S}: kept {k_ref.shape[1]} ->", "PASS" if int(t) else "FAIL", flush=True)
-        ok_all = ok_all and bool(int(t))
+        for p2p in (False, True):
+            sharded = rd.HeadShardedCompressor(comp, H, p2p=p2p)
+            Kl = K[..., rank * w:(rank + 1) * w].contiguous()
+            Vl = V[..., rank * w:(rank + 1) * w].contiguous()
+            Al = A[:, h0:h1].contiguous()
+            ok = True
+            for rep in range(3):                                   # repeated calls exercise epoch / parity reuse
+                k_loc, v_loc, sel = sharded.compress_layer_kv_cache(Kl, Vl, Al, layer)
+                ks = [torch.empty_like(k_loc) for _ in range(world)]
+                vs = [torch.empty_like(v_loc) for _ in range(world)]
+                dist.all_gather(ks, k_loc)
+                dist.all_gather(vs, v_loc)
+                ok = ok and (torch.equal(torch.cat(ks, -1), k_ref) and torch.equal(torch.cat(vs, -1), v_ref)
+                             and torch.equal(sel.mask.view(torch.bool), info["propagation_info"]["selection_mask"]))
+            okb, ovb = torch.zeros(B, S, w, device="cuda"), torch.zeros(B, S, w, device="cuda")
+            sharded.compress_layer_async(Kl, Vl, Al, layer, okb, ovb)
+            ms = k_ref.shape[1]
+            ok2 = (torch.equal(okb[:, :ms], k_loc) and torch.equal(ovb[:, :ms], v_loc)) if B == 1 else True
+            t = torch.tensor([int(ok and ok2)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"head-sharded R={world} B={B} H={H} S={S} p2p={p2p}: kept {k_ref.shape[1]} ->",
+                      "PASS" if int(t) else "FAIL", flush=True)
+            ok_all = ok_all and bool(int(t))
+    import threading
+    threading.Timer(15.0, lambda: os._exit(0 if ok_all else 1)).start()
     dist.destroy_process_group()
-    sys.exit(0 if ok_all else 1)
+    os._exit(0 if ok_all else 1)
 
 
 if __name__ == "__main__":
