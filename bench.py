@@ -196,7 +196,15 @@ def bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, 
     row min/max of the kept rows -> MIN all-reduce -> K3.  No host synchronisation."""
     import torch.distributed as dist
     from rtkv import dist as rd
-    sharded = rd.HeadShardedCompressor(comp, heads)
+    p2p = not args.no_p2p
+    sharded = rd.HeadShardedCompressor(comp, heads, p2p=p2p)
+    if p2p:
+        try:
+            sharded._mailbox(B, S, dev)
+        except Exception as e:            # symmetric memory unavailable: fall back to the collective scheme
+            sys.stderr.write(f"peer mailbox unavailable ({e}); using the all-reduce scheme\n")
+            sharded = rd.HeadShardedCompressor(comp, heads, p2p=False)
+            p2p = False
     w = hidden // world
     outs = [(torch.empty(B, S, w, device=dev), torch.empty(B, S, w, device=dev)) for _ in range(2)]
 
@@ -250,12 +258,16 @@ def bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, 
     line = {"metric": "prefill_kv_compress_tokens_per_s", "value": B * S / (ms_per_step * 1e-3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config, "clocks": clocks, "gpu_launches": 5 * L * args.steps, "launch_mode": mode,
+            "config": config, "clocks": clocks, "gpu_launches": (4 if p2p else 5) * L * args.steps, "launch_mode": mode,
             "roofline": {"bound": "hbm", "kernel": "whole path, all ranks", "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world),
                          "peak_source": peak_src + f" x {world} GPUs", "traffic": None,
                          "retained_fraction": sum(kept) / (L * B * S)},
-            "collectives_per_layer": {"all_gather_bytes": B * S * (8 // world) * 4, "all_reduce_bytes": B * S * 16}}
+            "exchange": ("fused: row min/max pushed to peer mailboxes over NVLink inside the quantise kernel (K/V read once)"
+                         if p2p else "two-pass: row_minmax kernel + MIN all-reduce + quantise (K/V read twice)"),
+            "collectives_per_layer": {"all_gather_bytes": B * S * (8 // world) * 4,
+                                      "all_reduce_bytes": 0 if p2p else B * S * 16,
+                                      "p2p_mailbox_bytes_per_rank": B * S * 2 * 16 * (world - 1) if p2p else 0}}
     if rank == 0:
         _emit(line)
     # a live CUDA graph that holds NCCL kernels can dead-lock communicator teardown: drop it first
@@ -303,6 +315,7 @@ def main():
     ap.add_argument("--bits", default="", help="low,mid,high bit widths, e.g. 8,8,8 (configs[3] precision sweep)")
     ap.add_argument("--ablation", default="", choices=["", "quant_only"],
                     help="quant_only: propagation ratios 1.0, every token kept (configs[4] ablation)")
+    ap.add_argument("--no-p2p", action="store_true", help="head-sharded mode: two-pass min/max + all-reduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

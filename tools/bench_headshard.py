@@ -51,6 +51,9 @@ res["row_minmax_us"] = timeit(lambda: ops.row_minmax(K, V, sel, S, negate_max=Tr
 res["all_reduce_min_us"] = timeit(lambda: dist.all_reduce(mm, op=dist.ReduceOp.MIN))
 res["k3_minmax_us"] = timeit(lambda: ops.quant_gather_minmax(K, V, sel, sel.labels, (2, 4, 8), S, mm, zero_pad=False, out0=ok, out1=ov, negated_max=True))
 res["k3_plain_us"] = timeit(lambda: ops.quant_gather(K, V, sel, sel.labels, (2, 4, 8), S, zero_pad=False, out0=ok, out1=ov))
+mb = rd.PeerMailbox(B, S, dev)
+res["k3_p2p_fused_us"] = timeit(lambda: ops.quant_gather_p2p(K, V, sel, sel.labels, (2, 4, 8), S, mb.ptrs, mb.rank, mb.world,
+                                                             mb.state, zero_pad=False, out0=ok, out1=ov))
 if rank == 0:
     print(json.dumps({k: round(v, 1) for k, v in res.items()}), flush=True)
 threading.Timer(15.0, lambda: os._exit(0)).start()
