@@ -151,8 +151,26 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void *p)
     return v;
 }
 
-template <int DT, int NV>
-__global__ void __launch_bounds__(kQT) quant_gather_p2p_kernel(QGParams p)
+// min / max / any-NaN over a CTA of NW warps
+template <int NW>
+__device__ __forceinline__ void block_minmax_n(float &mn, float &mx, int nan, float *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { red[warp] = mn; red[8 + warp] = mx; }
+    const int any_nan = __syncthreads_or(nan);
+    float a = red[0], z = red[8];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { a = fminf(a, red[w]); z = fmaxf(z, red[8 + w]); }
+    mn = a; mx = z;
+    if (any_nan) mn = mx = __int_as_float(0x7fc00000);
+}
+
+// THREADS per CTA is small (64/128) on purpose: a CTA spends most of its life waiting for the peers'
+// partials (~NVLink round trip), so what hides that latency is the number of ROWS in flight per SM
+// (32 resident 64-thread CTAs), not the width of a CTA.
+template <int DT, int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS) quant_gather_p2p_kernel(QGParams p)
 {
     constexpr int EPV = Vec16<DT>::kElems;
     __shared__ float red[16];
@@ -170,21 +188,21 @@ __global__ void __launch_bounds__(kQT) quant_gather_p2p_kernel(QGParams p)
         uint4 raw[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int v = threadIdx.x + k * kQT;
+            const int v = threadIdx.x + k * THREADS;
             raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
         }
         float mn = INFINITY, mx = -INFINITY;
         int nan = 0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            if (threadIdx.x + k * kQT < nvec) {
+            if (threadIdx.x + k * THREADS < nvec) {
                 float f[EPV];
                 Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
             }
         }
-        block_minmax(mn, mx, nan, red);
+        block_minmax_n<THREADS / 32>(mn, mx, nan, red);
         // ---- exchange: slot[(parity, tensor, row, source rank)] in every rank's mailbox ----
         const size_t rows_total = (size_t)p.B * p.out_rows;
         const size_t slot0 = ((((size_t)(epoch & 1u) * 2 + t) * rows_total + (size_t)b * p.out_rows + r) * p.world);
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_p2p_kernel(QGParams p)
         const float qmax_r = qmax_rounded<DT>(bits);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int v = threadIdx.x + k * kQT;
+            const int v = threadIdx.x + k * THREADS;
             if (v < nvec) {
                 float f[EPV];
                 Vec16<DT>::unpack(raw[k], f);
@@ -230,7 +248,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_p2p_kernel(QGParams p)
             }
         }
     } else if (p.zero_pad) {
-        for (int v = threadIdx.x; v < nvec; v += kQT) stg_stream(dst + v, make_uint4(0, 0, 0, 0));
+        for (int v = threadIdx.x; v < nvec; v += THREADS) stg_stream(dst + v, make_uint4(0, 0, 0, 0));
     }
     // last CTA of the grid publishes the epoch for the next call
     __syncthreads();
@@ -631,12 +649,14 @@ extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtyp
     return RTKV_OK;
 }
 
-template <int DT> static void (*pick_p2p_kernel(int nv))(QGParams)
+// smallest CTA whose threads hold the row slice in <= 8 vectors each
+template <int DT> static void (*pick_p2p_kernel(int nvec, int *threads))(QGParams)
 {
-    if (nv <= 1) return quant_gather_p2p_kernel<DT, 1>;
-    if (nv <= 2) return quant_gather_p2p_kernel<DT, 2>;
-    if (nv <= 4) return quant_gather_p2p_kernel<DT, 4>;
-    return quant_gather_p2p_kernel<DT, kMaxVec>;
+    if (nvec <= 64 * 4) { *threads = 64; return quant_gather_p2p_kernel<DT, 4, 64>; }
+    if (nvec <= 64 * 8) { *threads = 64; return quant_gather_p2p_kernel<DT, 8, 64>; }
+    if (nvec <= 128 * 8) { *threads = 128; return quant_gather_p2p_kernel<DT, 8, 128>; }
+    *threads = 256;
+    return quant_gather_p2p_kernel<DT, kMaxVec, 256>;
 }
 
 extern "C" int64_t rtkv_p2p_mailbox_bytes(int B, int out_rows, int world)
@@ -668,11 +688,11 @@ extern "C" int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, 
     for (int i = 0; i < world; ++i) p.mbox[i] = mailbox_ptrs[i];
     p.p2p_state = state; p.rank = rank; p.world = world; p.total_ctas = out_rows * B * 2;
     dim3 grid(out_rows, B, 2);
-    const int nv = (n / epv + kQT - 1) / kQT;
     cudaStream_t st = (cudaStream_t)stream;
     void (*kern)(QGParams) = nullptr;
-    RTKV_DISPATCH(dtype, kern = pick_p2p_kernel<DT>(nv));
-    RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, p));
+    int threads = 256;
+    RTKV_DISPATCH(dtype, kern = pick_p2p_kernel<DT>(n / epv, &threads));
+    RTKV_CUDA(launch_kernel(kern, grid, dim3(threads), 0, st, 1, p));
     return RTKV_OK;
 }
 
