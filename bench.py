@@ -196,7 +196,7 @@ def bench_head_sharded(args, layers, comp, cfg, config, dev, rank, world, L, S, 
     row min/max of the kept rows -> MIN all-reduce -> K3.  No host synchronisation."""
     import torch.distributed as dist
     from rtkv import dist as rd
-    p2p = not args.no_p2p
+    p2p = args.p2p
     sharded = rd.HeadShardedCompressor(comp, heads, p2p=p2p)
     if p2p:
         try:
@@ -315,7 +315,8 @@ def main():
     ap.add_argument("--bits", default="", help="low,mid,high bit widths, e.g. 8,8,8 (configs[3] precision sweep)")
     ap.add_argument("--ablation", default="", choices=["", "quant_only"],
                     help="quant_only: propagation ratios 1.0, every token kept (configs[4] ablation)")
-    ap.add_argument("--no-p2p", action="store_true", help="head-sharded mode: two-pass min/max + all-reduce instead of the fused peer-memory kernel")
+    ap.add_argument("--p2p", action="store_true", help="head-sharded mode: fused peer-memory min/max exchange inside the quantise kernel "
+                    "instead of the two-pass min/max + MIN all-reduce scheme")
     ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
