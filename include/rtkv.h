@@ -199,6 +199,10 @@ RTKV_API int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, in
                       const uint64_t *mailbox_ptrs /*[host]*/, int rank, int world, uint32_t *state,
                       void *Y0, void *Y1, void *stream);
 
+/* Prefetch [p, p+bytes) into L2 (one prefetch.global.L2 per 128-byte line).  Run it on a side stream
+ * while rtkv_score_select (one SM, latency bound) leaves HBM idle, over the first K rows. */
+RTKV_API int rtkv_prefetch_l2(const void *p, size_t bytes, void *stream);
+
 /* Whole-tensor scale / zero-point (qparams[0] = scale, [1] = zero_point, in `dtype`,
  * stored as f32) and quantise-dequantise with given parameters. */
 RTKV_API int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bits, float *qparams,

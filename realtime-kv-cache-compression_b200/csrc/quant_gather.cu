@@ -659,6 +659,26 @@ template <int DT> static void (*pick_p2p_kernel(int nvec, int *threads))(QGParam
     return quant_gather_p2p_kernel<DT, kMaxVec, 256>;
 }
 
+// L2 warm-up: one prefetch.global.L2 per 128-byte line of [p, p+bytes).  Meant to run on a side stream
+// while the latency-bound selection kernel (K2, one SM) leaves HBM idle: the first rows the quantise
+// kernel will read are then L2 hits.
+__global__ void prefetch_l2_kernel(const char *p, size_t lines)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+}
+
+extern "C" int rtkv_prefetch_l2(const void *p, size_t bytes, void *stream)
+{
+    RTKV_CHECK_ARG(p || bytes == 0, "rtkv_prefetch_l2: null pointer");
+    const size_t lines = bytes / 128;
+    if (lines == 0) return RTKV_OK;
+    const size_t ctas = (lines + 255) / 256;
+    prefetch_l2_kernel<<<(unsigned)(ctas < 148 * 16 ? ctas : 148 * 16), 256, 0, (cudaStream_t)stream>>>((const char *)p, lines);
+    RTKV_LAUNCH_CHECK("prefetch_l2_kernel");
+    return RTKV_OK;
+}
+
 extern "C" int64_t rtkv_p2p_mailbox_bytes(int B, int out_rows, int world)
 {
     if (B <= 0 || out_rows <= 0 || world <= 0 || world > 8) return -1;

@@ -294,6 +294,14 @@ def quant_gather_p2p(x0, x1, sel, labels, bits, out_rows, mailbox_ptrs, rank, wo
     return y0, y1
 
 
+def prefetch_l2(t, nbytes=None):
+    """Warm L2 with the first nbytes of tensor t on the current stream (prefetch.global.L2)."""
+    require_cuda()
+    total = t.numel() * t.element_size()
+    n = total if nbytes is None else min(int(nbytes), total)
+    check(lib.rtkv_prefetch_l2(_ptr(t), n, _stream()))
+
+
 def quant_params(x, bits):
     """Whole-tensor (scale, zero_point) as a float32 [2] device tensor (dynamic_quantization.py:62-95)."""
     require_cuda()

@@ -182,17 +182,29 @@ class RealTimePrefillCompressor:
     compress = compress_layer_kv_cache
 
     def compress_layer_kv_cache_async(self, key_states, value_states, attention_weights, layer_idx,
-                                      out_keys, out_values, zero_pad=False):
+                                      out_keys, out_values, zero_pad=False, prefetch_stream=None,
+                                      prefetch_bytes=40 << 20):
         """Fixed-capacity, synchronisation-free variant for pipelined prefill and CUDA graphs.
 
         out_keys/out_values: preallocated [B,S,HD]; rows [0, n_selected[b]) of batch row b hold the
         kept tokens, the rest is untouched (or zeroed with zero_pad).  Returns the device-side
-        Selection (scores, labels, mask, sel_idx, statistics); nothing is read back."""
+        Selection (scores, labels, mask, sel_idx, statistics); nothing is read back.
+        prefetch_stream: optional side stream used to prefetch the first prefetch_bytes of K into L2
+        while the selection kernel runs."""
         B, S, HD = key_states.shape
         P = self.prompt_length(S)
         params, _ = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
         mass = ops.prompt_mass(attention_weights, prompt_len=P)
+        if prefetch_stream is not None:
+            # while the selection kernel (one SM, latency bound) runs, HBM is idle: warm L2 with the first
+            # K rows on a side stream (forked after K1, joined before K3)
+            main = torch.cuda.current_stream()
+            prefetch_stream.wait_stream(main)
+            with torch.cuda.stream(prefetch_stream):
+                ops.prefetch_l2(key_states, prefetch_bytes)
         sel = ops.score_select(params, B, S, key_states.device, mass=mass)
+        if prefetch_stream is not None:
+            torch.cuda.current_stream().wait_stream(prefetch_stream)
         ops.quant_gather(key_states, value_states, sel, sel.labels, self._bits(), S, zero_pad=zero_pad,
                          out0=out_keys, out1=out_values)
         return sel
