@@ -317,8 +317,8 @@ def main():
                     help="quant_only: propagation ratios 1.0, every token kept (configs[4] ablation)")
     ap.add_argument("--p2p", action="store_true", help="head-sharded mode: fused peer-memory min/max exchange inside the quantise kernel "
                     "instead of the two-pass min/max + MIN all-reduce scheme")
-    ap.add_argument("--no-prefetch", action="store_true", help="do not prefetch K rows into L2 during the selection kernel")
-    ap.add_argument("--prefetch-mb", type=int, default=40)
+    ap.add_argument("--prefetch-mb", type=int, default=0,
+                    help="prefetch this many MB of K into L2 on a side stream during the selection kernel (measured: no gain)")
     ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -426,7 +426,7 @@ def main():
     def capture(two_stream, events=None):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev) if two_stream else None
-        pf = torch.cuda.Stream(device=dev) if not args.no_prefetch else None
+        pf = torch.cuda.Stream(device=dev) if args.prefetch_mb > 0 else None
         with torch.cuda.graph(g):
             main = torch.cuda.current_stream()
             out = []
@@ -551,7 +551,7 @@ def main():
             "clocks": clocks, "gpu_launches": 3 * L * args.steps, "roofline": roofline,
             "launch_mode": "one CUDA graph per step (3 kernels x %d layers, single stream%s)" % (
                 L, ("" if args.no_pdl else ", programmatic dependent launch") +
-                ("" if args.no_prefetch else ", L2 prefetch of %d MB of K on a side stream during K2" % args.prefetch_mb)),
+                ("" if args.prefetch_mb <= 0 else ", L2 prefetch of %d MB of K on a side stream during K2" % args.prefetch_mb)),
             "eager_ms_per_step": eager_ms_per_step,
             "two_stream": {"ms_per_step": ms_two_stream, "value": world * B * S / (ms_two_stream * 1e-3),
                            "note": "same graph with K3 of layer l on a second stream, overlapping K1/K2 of layer l+1"},
