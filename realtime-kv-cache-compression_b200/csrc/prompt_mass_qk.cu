@@ -9,12 +9,13 @@
 // This is the one dense contraction of the path, so it runs on the 5th-generation tensor
 // cores: tcgen05.mma (M=128 query rows x N=128 prompt keys x K=16, bf16/f16 in, fp32
 // accumulate in TMEM), operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte
-// swizzle), one CTA per (128-row query tile, head group, batch row):
+// swizzle), persistent CTAs (one per SM) over work items (128-row query tile, head group, batch row):
 //   warp 0        TMA producer: per head 2+2 boxes (Q tile, K_prompt tile) into a 3-stage ring
 //   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per head, tcgen05.commit -> mbarriers
 //   warps 2..5    epilogue: tcgen05.ld 32 lanes x 32 columns, exp2(s*c - lse*log2e), causal /
 //                 P mask, in-thread row sum (a thread owns a query row), accumulate over heads
-// Two 128-column accumulators in TMEM let the MMAs of head h+1 overlap the epilogue of head h.
+// Two 128-column accumulators in TMEM let the MMAs of head h+1 overlap the epilogue of head h; the
+// smem ring and the accumulators keep rolling across work items, so the pipeline is filled once per CTA.
 // Roofline: 2*B*H*S*P*D flop (4.3 GFLOP per 7B layer at S=4096) and B*H*S*D*2 bytes of Q
 // (32 MiB): memory/MUFU bound, the tensor cores are there so the contraction is not the limiter.
 #include <cuda.h>
@@ -130,9 +131,11 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
-    const int i0 = tile * kTileM;
-    const int h0 = g * p.gs, nh = p.gs;
+    // persistent CTA: work items (batch row, 128-row tile, head group) are dealt round-robin; the
+    // smem ring and the two TMEM accumulators keep rolling across items (k counts head iterations)
+    const int tiles = (p.S + kTileM - 1) / kTileM;
+    const int n_items = tiles * p.n_groups * p.B;
+    const int nh = p.gs;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
@@ -151,78 +154,88 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int hh = 0; hh < nh; ++hh) {
-                const int s = hh % kStages;
-                const uint32_t ph = (hh / kStages) & 1;
-                mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-                const uint32_t fb = smem_u32(&full[s]);
-                mbar_expect_tx(fb, kStageBytes);
-                const uint32_t qdst = smem_u32(smem + (size_t)s * kStageBytes);
-                const uint32_t kdst = qdst + kOperandBytes;
-                const int h = h0 + hh;
-                const int qrow = (b * p.H + h) * p.S + i0;
-                const int krow = (b * p.H + h) * p.P;
-                tma_load_2d(qdst, &map_q, 0, qrow, fb);
-                tma_load_2d(qdst + kOperandBytes / 2, &map_q, kKBlock, qrow, fb);
-                tma_load_2d(kdst, &map_k, 0, krow, fb);
-                tma_load_2d(kdst + kOperandBytes / 2, &map_k, kKBlock, krow, fb);
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int tile = item % tiles, g = (item / tiles) % p.n_groups, b = item / (tiles * p.n_groups);
+                for (int hh = 0; hh < nh; ++hh, ++k) {
+                    const int s = k % kStages;
+                    mbar_wait(smem_u32(&empty[s]), ((k / kStages) & 1) ^ 1);
+                    const uint32_t fb = smem_u32(&full[s]);
+                    mbar_expect_tx(fb, kStageBytes);
+                    const uint32_t qdst = smem_u32(smem + (size_t)s * kStageBytes);
+                    const uint32_t kdst = qdst + kOperandBytes;
+                    const int h = g * nh + hh;
+                    const int qrow = (b * p.H + h) * p.S + tile * kTileM;
+                    const int krow = (b * p.H + h) * p.P;
+                    tma_load_2d(qdst, &map_q, 0, qrow, fb);
+                    tma_load_2d(qdst + kOperandBytes / 2, &map_q, kKBlock, qrow, fb);
+                    tma_load_2d(kdst, &map_k, 0, krow, fb);
+                    tma_load_2d(kdst + kOperandBytes / 2, &map_k, kKBlock, krow, fb);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            for (int hh = 0; hh < nh; ++hh) {
-                const int s = hh % kStages, a = hh & 1;
-                mbar_wait(smem_u32(&tempty[a]), ((hh >> 1) & 1) ^ 1);      // epilogue drained this accumulator
-                mbar_wait(smem_u32(&full[s]), (hh / kStages) & 1);        // TMA landed Q and K
-                tc_fence_after();
-                const uint32_t qbase = smem_u32(smem + (size_t)s * kStageBytes);
-                const uint32_t kbase = qbase + kOperandBytes;
-                const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                for (int hh = 0; hh < nh; ++hh, ++k) {
+                    const int s = k % kStages, a = k & 1;
+                    mbar_wait(smem_u32(&tempty[a]), ((k >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                    mbar_wait(smem_u32(&full[s]), (k / kStages) & 1);        // TMA landed Q and K
+                    tc_fence_after();
+                    const uint32_t qbase = smem_u32(smem + (size_t)s * kStageBytes);
+                    const uint32_t kbase = qbase + kOperandBytes;
+                    const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t off = (uint32_t)(kb * (kOperandBytes / 2) + k * 32);   // 16 elements = 32 B
-                        umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
-                                 (uint32_t)((kb | k) != 0));
-                    }
-                umma_commit(smem_u32(&empty[s]));      // smem stage reusable once these MMAs retire
-                umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t off = (uint32_t)(kb * (kOperandBytes / 2) + kk * 32);   // 16 elements = 32 B
+                            umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
+                                     (uint32_t)((kb | kk) != 0));
+                        }
+                    umma_commit(smem_u32(&empty[s]));      // smem stage reusable once these MMAs retire
+                    umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
+                }
             }
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
         const int row = quad * 32 + lane;              // accumulator row == TMEM lane
-        const int i = i0 + row;
-        const bool live = i < p.S;
         const float kLog2e = 1.4426950408889634f;
-        float acc = 0.0f;
-        for (int hh = 0; hh < nh; ++hh) {
-            const int a = hh & 1, h = h0 + hh;
-            const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
-            mbar_wait(smem_u32(&tfull[a]), (hh >> 1) & 1);
-            tc_fence_after();
-            float rs = 0.0f;
+        int k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int tile = item % tiles, g = (item / tiles) % p.n_groups, b = item / (tiles * p.n_groups);
+            const int i = tile * kTileM + row;
+            const bool live = i < p.S;
+            float acc = 0.0f;
+            for (int hh = 0; hh < nh; ++hh, ++k) {
+                const int a = k & 1, h = g * nh + hh;
+                const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
+                mbar_wait(smem_u32(&tfull[a]), (k >> 1) & 1);
+                tc_fence_after();
+                float rs = 0.0f;
 #pragma unroll
-            for (int c = 0; c < kTileN; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c), v);
+                for (int c = 0; c < kTileN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c), v);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const int j = c + k;
-                    const bool ok = (j < p.P) && (!p.causal || j <= i);
-                    const float e = ex2_approx(__uint_as_float(v[k]) * p.scale_log2 - l2);
-                    rs += ok ? e : 0.0f;
+                    for (int q = 0; q < 32; ++q) {
+                        const int j = c + q;
+                        const bool ok = (j < p.P) && (!p.causal || j <= i);
+                        const float e = ex2_approx(__uint_as_float(v[q]) * p.scale_log2 - l2);
+                        rs += ok ? e : 0.0f;
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
+                acc += rs;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
-            acc += rs;
+            if (live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc;
         }
-        if (live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc;
     }
 
     tc_fence_before();
@@ -279,7 +292,6 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     RTKV_CHECK_ARG(B > 0 && H > 0 && S > 0 && group_size > 0 && H % group_size == 0, "rtkv_prompt_mass_qk: bad shape");
     RTKV_CHECK_ARG((int64_t)B * H * S < (1ll << 31), "rtkv_prompt_mass_qk: B*H*S too large");
     RTKV_CHECK_ARG((uintptr_t)Q % 16 == 0 && (uintptr_t)Kp % 16 == 0, "rtkv_prompt_mass_qk: Q/K must be 16-byte aligned");
-    RTKV_CHECK_ARG(B <= 65535 && H / group_size <= 65535, "rtkv_prompt_mass_qk: grid too large");
     CUtensorMap map_q, map_k;
     int rc = encode_rows_map(&map_q, Q, dtype, (uint64_t)B * H * S);
     if (rc) return rc;
@@ -292,7 +304,16 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     RTKV_CUDA(cudaFuncSetAttribute(prompt_mass_qk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQkSmem));
-    dim3 grid((S + kTileM - 1) / kTileM, H / group_size, B);
+    // persistent grid: one CTA per SM (193 KB of shared memory each), items dealt round-robin
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        RTKV_CUDA(cudaGetDevice(&dev));
+        RTKV_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long n_items = (long long)((S + kTileM - 1) / kTileM) * (H / group_size) * B;
+    RTKV_CHECK_ARG(n_items < (1ll << 31), "rtkv_prompt_mass_qk: too many work items");
+    dim3 grid((unsigned)(n_items < sm_count ? n_items : sm_count));
     prompt_mass_qk_kernel<<<grid, kQkThreads, kQkSmem, (cudaStream_t)stream>>>(map_q, map_k, p);
     RTKV_LAUNCH_CHECK("prompt_mass_qk_kernel");
     return RTKV_OK;

@@ -137,7 +137,7 @@ def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True, group_size=Non
     B, H, S, D = q.shape
     P = k_prompt.shape[2]
     if group_size is None:
-        group_size = H // 8 if H % 8 == 0 else H
+        group_size = 1          # per-head work items: finest balance over the persistent CTAs
     parts = torch.empty(B, S, H // group_size, dtype=torch.float32, device=q.device)
     check(lib.rtkv_prompt_mass_qk(_ptr(q), _ptr(k_prompt), _ptr(lse), dtype_code(q), B, H, S, D, P,
                                   float(scale), int(bool(causal)), int(group_size), _ptr(parts), _stream()))
