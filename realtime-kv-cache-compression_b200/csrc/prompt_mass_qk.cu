@@ -12,8 +12,9 @@
 // swizzle), persistent CTAs (one per SM) over work items (128-row query tile, head group, batch row):
 //   warp 0        TMA producer: per head 2+2 boxes (Q tile, K_prompt tile) into a 3-stage ring
 //   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per head, tcgen05.commit -> mbarriers
-//   warps 2..5    epilogue: tcgen05.ld 32 lanes x 32 columns, exp2(s*c - lse*log2e), causal /
-//                 P mask, in-thread row sum (a thread owns a query row), accumulate over heads
+//   warps 2..9    epilogue (two warps per TMEM lane quadrant, 64 columns each): tcgen05.ld 32 lanes x 32
+//                 columns, exp2(fma(s, c, -lse*log2e)), causal / P mask only where needed, in-thread row
+//                 sums (a thread owns half a query row), accumulate over heads
 // Two 128-column accumulators in TMEM let the MMAs of head h+1 overlap the epilogue of head h; the
 // smem ring and the accumulators keep rolling across work items, so the pipeline is filled once per CTA.
 // Roofline: 2*B*H*S*P*D flop (4.3 GFLOP per 7B layer at S=4096) and B*H*S*D*2 bytes of Q
@@ -31,8 +32,8 @@ constexpr int kKBlock = 64;      // elements per 128-byte swizzle atom row
 constexpr int kStages = 3;
 constexpr int kOperandBytes = kTileM * kHeadDim * 2;          // 32 KiB: one Q (or K) tile
 constexpr int kStageBytes = 2 * kOperandBytes;                 // Q + K
-constexpr int kQkThreads = 192;
-constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256;
+constexpr int kQkThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 + 2 * kTileM * sizeof(float);
 
 // ---- raw PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +130,7 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     uint64_t *bars = (uint64_t *)(smem + (size_t)kStages * kStageBytes);
     uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 4);
+    float *xsum = (float *)((unsigned char *)bars + 256);        // [2 halves][128 rows] row sums of one item
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // persistent CTA: work items (batch row, 128-row tile, head group) are dealt round-robin; the
@@ -139,7 +141,7 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // 256 TMEM columns: two 128-column fp32 accumulators
@@ -201,8 +203,9 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;              // accumulator row == TMEM lane
         const float kLog2e = 1.4426950408889634f;
         int k = 0;
@@ -210,6 +213,8 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const int tile = item % tiles, g = (item / tiles) % p.n_groups, b = item / (tiles * p.n_groups);
             const int i = tile * kTileM + row;
             const bool live = i < p.S;
+            // rows of this tile see every prompt key (no causal / P masking needed) -> branch-free body
+            const bool unmasked = (p.P == kTileN) && (!p.causal || tile * kTileM >= kTileN - 1);
             float acc = 0.0f;
             for (int hh = 0; hh < nh; ++hh, ++k) {
                 const int a = k & 1, h = g * nh + hh;
@@ -218,15 +223,21 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 tc_fence_after();
                 float rs = 0.0f;
 #pragma unroll
-                for (int c = 0; c < kTileN; c += 32) {
+                for (int c = 0; c < kTileN / 2; c += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c), v);
+                    const int c0 = half * (kTileN / 2) + c;
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c0), v);
+                    if (unmasked) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int j = c + q;
-                        const bool ok = (j < p.P) && (!p.causal || j <= i);
-                        const float e = ex2_approx(__uint_as_float(v[q]) * p.scale_log2 - l2);
-                        rs += ok ? e : 0.0f;
+                        for (int q = 0; q < 32; ++q) rs += ex2_approx(__fmaf_rn(__uint_as_float(v[q]), p.scale_log2, -l2));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const int j = c0 + q;
+                            const bool ok = (j < p.P) && (!p.causal || j <= i);
+                            const float e = ex2_approx(__fmaf_rn(__uint_as_float(v[q]), p.scale_log2, -l2));
+                            rs += ok ? e : 0.0f;
+                        }
                     }
                 }
                 tc_fence_before();
@@ -234,7 +245,11 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
                 acc += rs;
             }
-            if (live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc;
+            // combine the two column halves of every row (fixed order: half 0 + half 1), one store per row
+            if (half == 1) xsum[row] = acc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc + xsum[row];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
 
