@@ -131,13 +131,13 @@ RTKV_API int rtkv_mass_from_partials(const float *partials, int64_t n, int n_ran
                      float *mass, void *stream);
 
 /* Same quantity without a materialised attention matrix (tcgen05 tensor cores + TMA):
- * partials[b,i,g] = sum_{h in group g} sum_{j<P, j<=i if causal} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
+ * head_sums[b,i,h] = sum_{j<P, j<=i if causal} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
  * Q: [B,H,S,D], Kp: [B,H,P,D] contiguous (bf16 or f16, D == 128, P <= 128), lse: [B,H,S] natural-log
- * row log-sum-exp of the layer's attention logits; partials: [B,S,H/group_size] f32, to be combined
- * with rtkv_mass_from_partials (n_ranks = 1, groups_per_rank = H/group_size). */
+ * row log-sum-exp of the layer's attention logits; head_sums: [B,S,H] f32, to be combined with
+ * rtkv_mass_from_partials (n_ranks = 1, groups_per_rank = H; head-sharded ranks all-gather first). */
 RTKV_API int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype,
                         int B, int H, int S, int D, int P, float scale, int causal,
-                        int group_size, float *partials, void *stream);
+                        float *head_sums, void *stream);
 
 RTKV_API int rtkv_position_bias(int S, float *pb, void *stream);
 RTKV_API int rtkv_normalize_mass(const float *mass, int dtype, int B, int S, float *out, void *stream);

@@ -3,20 +3,21 @@
 // receives softmaxed attention and slices the prompt key columns, token_importance.py:41;
 // the only contraction that reproduces that slice is Q . K_prompt^T).
 //
-//   partial[b,i,g] = sum_{h in group g} sum_{j < P, j <= i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
-//   mass[b,i]      = (partial[b,i,0] + ... + partial[b,i,G-1]) / H          (rtkv_mass_from_partials)
+//   head_sum[b,i,h] = sum_{j < P, j <= i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
+//   mass[b,i]       = (head_sum[b,i,0] + ... + head_sum[b,i,H-1]) / H        (rtkv_mass_from_partials)
 //
 // This is the one dense contraction of the path, so it runs on the 5th-generation tensor
 // cores: tcgen05.mma (M=128 query rows x N=128 prompt keys x K=16, bf16/f16 in, fp32
 // accumulate in TMEM), operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte
-// swizzle), persistent CTAs (one per SM) over work items (128-row query tile, head group, batch row):
-//   warp 0        TMA producer: per head 2+2 boxes (Q tile, K_prompt tile) into a 3-stage ring
-//   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per head, tcgen05.commit -> mbarriers
+// swizzle), persistent CTAs (one per SM) over work items (batch row, head, chunk of T query tiles):
+//   warp 0        TMA producer: the head's K_prompt tile once per item (double buffered), Q tiles
+//                 through a 4-stage ring (2 boxes of 64 columns each)
+//   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per Q tile, tcgen05.commit -> mbarriers
 //   warps 2..9    epilogue (two warps per TMEM lane quadrant, 64 columns each): tcgen05.ld 32 lanes x 32
 //                 columns, exp2(fma(s, c, -lse*log2e)), causal / P mask only where needed, in-thread row
 //                 sums (a thread owns half a query row), accumulate over heads
-// Two 128-column accumulators in TMEM let the MMAs of head h+1 overlap the epilogue of head h; the
-// smem ring and the accumulators keep rolling across work items, so the pipeline is filled once per CTA.
+// Two 128-column accumulators in TMEM let the MMAs of tile t+1 overlap the epilogue of tile t; the
+// rings keep rolling across work items, so the pipeline is filled once per CTA.
 // Roofline: 2*B*H*S*P*D flop (4.3 GFLOP per 7B layer at S=4096) and B*H*S*D*2 bytes of Q
 // (32 MiB): memory/MUFU bound, the tensor cores are there so the contraction is not the limiter.
 #include <cuda.h>
@@ -29,11 +30,11 @@ constexpr int kTileM = 128;      // query rows per CTA
 constexpr int kTileN = 128;      // prompt keys (P <= 128)
 constexpr int kHeadDim = 128;    // K of the GEMM
 constexpr int kKBlock = 64;      // elements per 128-byte swizzle atom row
-constexpr int kStages = 3;
+constexpr int kStages = 4;       // Q-tile ring
 constexpr int kOperandBytes = kTileM * kHeadDim * 2;          // 32 KiB: one Q (or K) tile
-constexpr int kStageBytes = 2 * kOperandBytes;                 // Q + K
 constexpr int kQkThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 + 2 * kTileM * sizeof(float);
+// smem: 2 K tiles (double buffered across work items) + kStages Q tiles + barriers + row-sum exchange
+constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)(2 + kStages) * kOperandBytes + 256 + 2 * kTileM * sizeof(float);
 
 // ---- raw PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,6 +118,7 @@ struct QkParams {
     const float *lse;     // [B,H,S]
     float *partials;      // [B,S,n_groups]
     int B, H, S, P, gs, n_groups, causal;
+    int tiles_per_item;   // query tiles that share one K_prompt tile load
     float scale_log2;     // scale * log2(e)
     uint32_t idesc;
 };
@@ -127,21 +129,29 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     extern __shared__ unsigned char qk_smem_raw[];
     // 128-byte swizzle needs 1024-byte aligned tiles
     unsigned char *smem = (unsigned char *)(((uintptr_t)qk_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t *)(smem + (size_t)kStages * kStageBytes);
-    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 4);
-    float *xsum = (float *)((unsigned char *)bars + 256);        // [2 halves][128 rows] row sums of one item
+    unsigned char *smem_k = smem;                                   // [2][32 KiB]
+    unsigned char *smem_q = smem + 2 * kOperandBytes;               // [kStages][32 KiB]
+    uint64_t *bars = (uint64_t *)(smem + (size_t)(2 + kStages) * kOperandBytes);
+    uint64_t *qfull = bars, *qempty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+    uint64_t *kfull = bars + 2 * kStages + 4, *kempty = bars + 2 * kStages + 6;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 8);
+    float *xsum = (float *)((unsigned char *)bars + 256);        // [128 rows] row sums of the upper column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // persistent CTA: work items (batch row, 128-row tile, head group) are dealt round-robin; the
-    // smem ring and the two TMEM accumulators keep rolling across items (k counts head iterations)
+    // persistent CTA over work items (batch row, head, chunk of T query tiles): the K_prompt tile of the
+    // head is loaded once per item (double buffered), the Q tiles stream through the ring; q counts
+    // Q tiles, it counts items, both across the whole life of the CTA
     const int tiles = (p.S + kTileM - 1) / kTileM;
-    const int n_items = tiles * p.n_groups * p.B;
-    const int nh = p.gs;
+    const int T = p.tiles_per_item;
+    const int chunks = (tiles + T - 1) / T;
+    const int n_items = chunks * p.H * p.B;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 8); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&qfull[s]), 1); mbar_init(smem_u32(&qempty[s]), 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 8);
+            mbar_init(smem_u32(&kfull[a]), 1); mbar_init(smem_u32(&kempty[a]), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // 256 TMEM columns: two 128-column fp32 accumulators
@@ -156,50 +166,59 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int k = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int tile = item % tiles, g = (item / tiles) % p.n_groups, b = item / (tiles * p.n_groups);
-                for (int hh = 0; hh < nh; ++hh, ++k) {
-                    const int s = k % kStages;
-                    mbar_wait(smem_u32(&empty[s]), ((k / kStages) & 1) ^ 1);
-                    const uint32_t fb = smem_u32(&full[s]);
-                    mbar_expect_tx(fb, kStageBytes);
-                    const uint32_t qdst = smem_u32(smem + (size_t)s * kStageBytes);
-                    const uint32_t kdst = qdst + kOperandBytes;
-                    const int h = g * nh + hh;
+            int q = 0, it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int c = item % chunks, h = (item / chunks) % p.H, b = item / (chunks * p.H);
+                const int kb = it & 1;
+                mbar_wait(smem_u32(&kempty[kb]), ((it >> 1) & 1) ^ 1);
+                const uint32_t kf = smem_u32(&kfull[kb]);
+                mbar_expect_tx(kf, kOperandBytes);
+                const uint32_t kdst = smem_u32(smem_k + (size_t)kb * kOperandBytes);
+                const int krow = (b * p.H + h) * p.P;
+                tma_load_2d(kdst, &map_k, 0, krow, kf);
+                tma_load_2d(kdst + kOperandBytes / 2, &map_k, kKBlock, krow, kf);
+                const int t1 = min(tiles, (c + 1) * T);
+                for (int tile = c * T; tile < t1; ++tile, ++q) {
+                    const int s = q % kStages;
+                    mbar_wait(smem_u32(&qempty[s]), ((q / kStages) & 1) ^ 1);
+                    const uint32_t fb = smem_u32(&qfull[s]);
+                    mbar_expect_tx(fb, kOperandBytes);
+                    const uint32_t qdst = smem_u32(smem_q + (size_t)s * kOperandBytes);
                     const int qrow = (b * p.H + h) * p.S + tile * kTileM;
-                    const int krow = (b * p.H + h) * p.P;
                     tma_load_2d(qdst, &map_q, 0, qrow, fb);
                     tma_load_2d(qdst + kOperandBytes / 2, &map_q, kKBlock, qrow, fb);
-                    tma_load_2d(kdst, &map_k, 0, krow, fb);
-                    tma_load_2d(kdst + kOperandBytes / 2, &map_k, kKBlock, krow, fb);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            int k = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                for (int hh = 0; hh < nh; ++hh, ++k) {
-                    const int s = k % kStages, a = k & 1;
-                    mbar_wait(smem_u32(&tempty[a]), ((k >> 1) & 1) ^ 1);      // epilogue drained this accumulator
-                    mbar_wait(smem_u32(&full[s]), (k / kStages) & 1);        // TMA landed Q and K
+            int q = 0, it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int c = item % chunks;
+                const int kb = it & 1;
+                mbar_wait(smem_u32(&kfull[kb]), (it >> 1) & 1);          // K_prompt tile of this head landed
+                const uint32_t kbase = smem_u32(smem_k + (size_t)kb * kOperandBytes);
+                const int t1 = min(tiles, (c + 1) * T);
+                for (int tile = c * T; tile < t1; ++tile, ++q) {
+                    const int s = q % kStages, a = q & 1;
+                    mbar_wait(smem_u32(&tempty[a]), ((q >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                    mbar_wait(smem_u32(&qfull[s]), (q / kStages) & 1);       // TMA landed the Q tile
                     tc_fence_after();
-                    const uint32_t qbase = smem_u32(smem + (size_t)s * kStageBytes);
-                    const uint32_t kbase = qbase + kOperandBytes;
+                    const uint32_t qbase = smem_u32(smem_q + (size_t)s * kOperandBytes);
                     const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
+                    for (int kq = 0; kq < 2; ++kq)
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t off = (uint32_t)(kb * (kOperandBytes / 2) + kk * 32);   // 16 elements = 32 B
+                            const uint32_t off = (uint32_t)(kq * (kOperandBytes / 2) + kk * 32);   // 16 elements = 32 B
                             umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
-                                     (uint32_t)((kb | kk) != 0));
+                                     (uint32_t)((kq | kk) != 0));
                         }
-                    umma_commit(smem_u32(&empty[s]));      // smem stage reusable once these MMAs retire
+                    umma_commit(smem_u32(&qempty[s]));     // Q stage reusable once these MMAs retire
                     umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
                 }
+                umma_commit(smem_u32(&kempty[kb]));        // every MMA that reads this K tile has retired
             }
         }
     } else {
@@ -208,48 +227,47 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;              // accumulator row == TMEM lane
         const float kLog2e = 1.4426950408889634f;
-        int k = 0;
+        int q = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int tile = item % tiles, g = (item / tiles) % p.n_groups, b = item / (tiles * p.n_groups);
-            const int i = tile * kTileM + row;
-            const bool live = i < p.S;
-            // rows of this tile see every prompt key (no causal / P masking needed) -> branch-free body
-            const bool unmasked = (p.P == kTileN) && (!p.causal || tile * kTileM >= kTileN - 1);
-            float acc = 0.0f;
-            for (int hh = 0; hh < nh; ++hh, ++k) {
-                const int a = k & 1, h = g * nh + hh;
+            const int c = item % chunks, h = (item / chunks) % p.H, b = item / (chunks * p.H);
+            const int t1 = min(tiles, (c + 1) * T);
+            for (int tile = c * T; tile < t1; ++tile, ++q) {
+                const int a = q & 1;
+                const int i = tile * kTileM + row;
+                const bool live = i < p.S;
+                // rows of this tile see every prompt key (no causal / P masking needed) -> branch-free body
+                const bool unmasked = (p.P == kTileN) && (!p.causal || tile * kTileM >= kTileN - 1);
                 const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
-                mbar_wait(smem_u32(&tfull[a]), (k >> 1) & 1);
+                mbar_wait(smem_u32(&tfull[a]), (q >> 1) & 1);
                 tc_fence_after();
                 float rs = 0.0f;
 #pragma unroll
-                for (int c = 0; c < kTileN / 2; c += 32) {
+                for (int cc = 0; cc < kTileN / 2; cc += 32) {
                     uint32_t v[32];
-                    const int c0 = half * (kTileN / 2) + c;
+                    const int c0 = half * (kTileN / 2) + cc;
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c0), v);
                     if (unmasked) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) rs += ex2_approx(__fmaf_rn(__uint_as_float(v[q]), p.scale_log2, -l2));
+                        for (int e = 0; e < 32; ++e) rs += ex2_approx(__fmaf_rn(__uint_as_float(v[e]), p.scale_log2, -l2));
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const int j = c0 + q;
+                        for (int e = 0; e < 32; ++e) {
+                            const int j = c0 + e;
                             const bool ok = (j < p.P) && (!p.causal || j <= i);
-                            const float e = ex2_approx(__fmaf_rn(__uint_as_float(v[q]), p.scale_log2, -l2));
-                            rs += ok ? e : 0.0f;
+                            const float x = ex2_approx(__fmaf_rn(__uint_as_float(v[e]), p.scale_log2, -l2));
+                            rs += ok ? x : 0.0f;
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
-                acc += rs;
+                // combine the two column halves of the row (fixed order: half 0 + half 1), one store per row
+                if (half == 1) xsum[row] = rs;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && live) p.partials[((size_t)b * p.S + i) * p.H + h] = rs + xsum[row];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            // combine the two column halves of every row (fixed order: half 0 + half 1), one store per row
-            if (half == 1) xsum[row] = acc;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0 && live) p.partials[((size_t)b * p.S + i) * p.n_groups + g] = acc + xsum[row];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
 
@@ -292,10 +310,9 @@ static int encode_rows_map(CUtensorMap *map, const void *base, int dtype, uint64
 using namespace rtkv;
 
 extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype, int B, int H, int S,
-                                   int D, int P, float scale, int causal, int group_size, float *partials,
-                                   void *stream)
+                                   int D, int P, float scale, int causal, float *head_sums, void *stream)
 {
-    RTKV_CHECK_ARG(Q && Kp && lse && partials, "rtkv_prompt_mass_qk: null pointer");
+    RTKV_CHECK_ARG(Q && Kp && lse && head_sums, "rtkv_prompt_mass_qk: null pointer");
     if (dtype != RTKV_BF16 && dtype != RTKV_F16) {
         set_error("rtkv_prompt_mass_qk: Q/K must be bf16 or f16 (tf32 would cost 13 mantissa bits of the logits)");
         return RTKV_EUNSUPPORTED;
@@ -304,7 +321,7 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
         set_error("rtkv_prompt_mass_qk: needs head_dim == 128 and 1 <= P <= 128 (got D=%d, P=%d)", D, P);
         return RTKV_EUNSUPPORTED;
     }
-    RTKV_CHECK_ARG(B > 0 && H > 0 && S > 0 && group_size > 0 && H % group_size == 0, "rtkv_prompt_mass_qk: bad shape");
+    RTKV_CHECK_ARG(B > 0 && H > 0 && S > 0, "rtkv_prompt_mass_qk: bad shape");
     RTKV_CHECK_ARG((int64_t)B * H * S < (1ll << 31), "rtkv_prompt_mass_qk: B*H*S too large");
     RTKV_CHECK_ARG((uintptr_t)Q % 16 == 0 && (uintptr_t)Kp % 16 == 0, "rtkv_prompt_mass_qk: Q/K must be 16-byte aligned");
     CUtensorMap map_q, map_k;
@@ -312,23 +329,28 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     if (rc) return rc;
     rc = encode_rows_map(&map_k, Kp, dtype, (uint64_t)B * H * P);
     if (rc) return rc;
-    QkParams p;
-    p.lse = lse; p.partials = partials;
-    p.B = B; p.H = H; p.S = S; p.P = P; p.gs = group_size; p.n_groups = H / group_size; p.causal = causal;
-    p.scale_log2 = scale * 1.4426950408889634f;
-    const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
-    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    RTKV_CUDA(cudaFuncSetAttribute(prompt_mass_qk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQkSmem));
-    // persistent grid: one CTA per SM (193 KB of shared memory each), items dealt round-robin
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         RTKV_CUDA(cudaGetDevice(&dev));
         RTKV_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const long long n_items = (long long)((S + kTileM - 1) / kTileM) * (H / group_size) * B;
+    QkParams p;
+    p.lse = lse; p.partials = head_sums;
+    p.B = B; p.H = H; p.S = S; p.P = P; p.gs = 1; p.n_groups = H; p.causal = causal;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // Query tiles per work item: as many as possible (each item loads its head's K_prompt tile once)
+    // while keeping at least ~1.5 items per SM for balance.
+    const int tiles = (S + kTileM - 1) / kTileM;
+    int T = 1;
+    while (T * 2 <= tiles && (long long)((tiles + 2 * T - 1) / (2 * T)) * H * B * 2 >= 3LL * sm_count) T *= 2;
+    p.tiles_per_item = T;
+    const long long n_items = (long long)((tiles + T - 1) / T) * H * B;
     RTKV_CHECK_ARG(n_items < (1ll << 31), "rtkv_prompt_mass_qk: too many work items");
-    dim3 grid((unsigned)(n_items < sm_count ? n_items : sm_count));
+    RTKV_CUDA(cudaFuncSetAttribute(prompt_mass_qk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQkSmem));
+    dim3 grid((unsigned)(n_items < sm_count ? n_items : sm_count));      // persistent: one CTA per SM
     prompt_mass_qk_kernel<<<grid, kQkThreads, kQkSmem, (cudaStream_t)stream>>>(map_q, map_k, p);
     RTKV_LAUNCH_CHECK("prompt_mass_qk_kernel");
     return RTKV_OK;

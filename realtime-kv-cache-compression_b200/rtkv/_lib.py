@@ -54,7 +54,7 @@ PROTOTYPES = {
     "rtkv_scratch_init": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp]),
     "rtkv_prompt_mass_qk": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int,
-                                           ctypes.c_int, c_vp, c_vp]),
+                                           c_vp, c_vp]),
     "rtkv_position_bias": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp]),
     "rtkv_normalize_mass": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rtkv_score_select": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t,

@@ -129,18 +129,16 @@ def mass_from_partials(partials, num_heads, rank_major=False):
     return mass
 
 
-def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True, group_size=None):
+def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True):
     """Fused Q.K_prompt^T scoring on tcgen05: q [B,H,S,128], k_prompt [B,H,P,128] (bf16/f16),
-    lse [B,H,S] f32 -> per-head-group partial sums [B,S,H/group_size]."""
+    lse [B,H,S] f32 -> per-head prompt-mass sums [B,S,H]."""
     require_cuda()
     q, k_prompt, lse = q.contiguous(), k_prompt.contiguous(), lse.contiguous().float()
     B, H, S, D = q.shape
     P = k_prompt.shape[2]
-    if group_size is None:
-        group_size = 1          # per-head work items: finest balance over the persistent CTAs
-    parts = torch.empty(B, S, H // group_size, dtype=torch.float32, device=q.device)
+    parts = torch.empty(B, S, H, dtype=torch.float32, device=q.device)
     check(lib.rtkv_prompt_mass_qk(_ptr(q), _ptr(k_prompt), _ptr(lse), dtype_code(q), B, H, S, D, P,
-                                  float(scale), int(bool(causal)), int(group_size), _ptr(parts), _stream()))
+                                  float(scale), int(bool(causal)), _ptr(parts), _stream()))
     return parts
 
 

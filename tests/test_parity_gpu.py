@@ -757,16 +757,16 @@ def qk_inputs(B, H, S, P, dtype, seed):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,H,S,P", [(1, 8, 256, 51), (2, 16, 640, 128), (1, 32, 1000, 128), (1, 8, 130, 26)])
+@pytest.mark.parametrize("B,H,S,P", [(1, 8, 256, 51), (2, 16, 640, 128), (1, 32, 1000, 128), (1, 8, 130, 26),
+                                      (1, 32, 4096, 128), (1, 4, 8200, 128)])
 def test_qk_scoring_matches_restatement(rt, dtype, B, H, S, P):
     """tensor-core scoring vs the CPU restatement (double accumulation) and vs the probability-slice
     kernel on the same attention: north-star tolerance for half inputs is 1e-3 relative."""
     _, ops = rt
     q, kp, lse, scale, probs = qk_inputs(B, H, S, P, dtype, seed=S + H)
-    gs = H // 8
-    parts = ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True, group_size=gs)
+    parts = ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True)            # per-head sums [B,S,H]
     dt = oracle.BF16 if dtype == torch.bfloat16 else oracle.F16
-    want = oracle.prompt_mass_qk(oracle.from_torch(q)[0], oracle.from_torch(kp)[0], lse.cpu().numpy(), dt, scale, True, gs)
+    want = oracle.prompt_mass_qk(oracle.from_torch(q)[0], oracle.from_torch(kp)[0], lse.cpu().numpy(), dt, scale, True, 1)
     np.testing.assert_allclose(parts.cpu().numpy(), want, rtol=2e-4, atol=1e-6)
     mass = ops.prompt_mass_qk(q, kp, lse, scale)
     np.testing.assert_allclose(mass.cpu().numpy(), oracle.mass_from_partials(want, H), rtol=2e-4, atol=1e-6)

@@ -68,7 +68,6 @@ if only is None or "k1b" in only:
     Kp = torch.randn(B, H, P, D, generator=gen, device=dev).bfloat16()
     lse = torch.full((B, H, S), 8.0, device=dev)
     t = graph_time(lambda i: ops.prompt_mass_qk_partials(Qs[i], Kp, lse, D ** -0.5, True), nset)
-    res["k1b_groups8_us"] = graph_time(lambda i: ops.prompt_mass_qk_partials(Qs[i], Kp, lse, D ** -0.5, True, H // 8), nset)
     res["k1b_us"] = t; res["k1b_GBs"] = q_bytes / t / 1e3; res["k1b_frac_hbm"] = res["k1b_GBs"] / PEAK
     res["k1b_TFLOPs"] = 2.0 * B * H * S * P * D / t / 1e6
     del Qs
