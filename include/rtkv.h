@@ -131,13 +131,14 @@ RTKV_API int rtkv_mass_from_partials(const float *partials, int64_t n, int n_ran
                      float *mass, void *stream);
 
 /* Same quantity without a materialised attention matrix (tcgen05 tensor cores + TMA):
- * head_sums[b,i,h] = sum_{j<P, j<=i if causal} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
+ * head_sums[b,h,i] = sum_{j<P, j<=i if causal} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
  * Q: [B,H,S,D], Kp: [B,H,P,D] contiguous (bf16 or f16, D == 128, P <= 128), lse: [B,H,S] natural-log
- * row log-sum-exp of the layer's attention logits; head_sums: [B,S,H] f32, to be combined with
- * rtkv_mass_from_partials (n_ranks = 1, groups_per_rank = H; head-sharded ranks all-gather first). */
+ * row log-sum-exp of the layer's attention logits; head_sums: [B,H,S] f32 (head-major, like lse).
+ * rtkv_mass_from_head_sums adds the heads in order and divides by H. */
 RTKV_API int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype,
                         int B, int H, int S, int D, int P, float scale, int causal,
                         float *head_sums, void *stream);
+RTKV_API int rtkv_mass_from_head_sums(const float *head_sums, int B, int H, int S, float *mass, void *stream);
 
 RTKV_API int rtkv_position_bias(int S, float *pb, void *stream);
 RTKV_API int rtkv_normalize_mass(const float *mass, int dtype, int B, int S, float *out, void *stream);
@@ -239,6 +240,10 @@ RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);
 /* Testing aid: which rtkv_score_select kernel runs.  0 = automatic (a cluster of 8 CTAs per batch
  * row from 8192 tokens, else one CTA), 1 = always one CTA, 2 = the cluster kernel whenever S >= 1024. */
 RTKV_API int rtkv_debug_k2_mode(int mode);
+
+/* Profiling aid for rtkv_prompt_mass_qk (results become meaningless): 0 normal, 1 no exp in the
+ * epilogue, 2 no TMEM loads, 3 no MMAs. */
+RTKV_API int rtkv_debug_qk_mode(int mode);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);

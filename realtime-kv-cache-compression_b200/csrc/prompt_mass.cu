@@ -196,6 +196,18 @@ __global__ void mass_from_partials_kernel(const float *__restrict__ partials, in
     mass[t] = __fdiv_rn(tot, fH);
 }
 
+// head-major variant for the Q.K scoring kernel: mass[b,i] = (hs[b,0,i] + hs[b,1,i] + ...) / H
+__global__ void mass_from_head_sums_kernel(const float *__restrict__ hs, int H, int S, float *mass)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const float *q = hs + (size_t)b * H * S + i;
+    float tot = q[0];
+    for (int h = 1; h < H; ++h) tot = __fadd_rn(tot, q[(size_t)h * S]);
+    mass[(size_t)b * S + i] = __fdiv_rn(tot, (float)H);
+}
+
 template <int DT>
 static int launch_mass(const void *A, int B, int H, int S, int64_t sb, int64_t sh, int64_t si,
                        const int64_t *idx, int P, int gs, int n_groups, float *mass, float *partials,
@@ -261,5 +273,14 @@ extern "C" int rtkv_mass_from_partials(const float *partials, int64_t n, int n_r
     mass_from_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partials, n, n_ranks,
                                                                                           groups_per_rank, (float)H, mass);
     RTKV_LAUNCH_CHECK("mass_from_partials_kernel");
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_mass_from_head_sums(const float *head_sums, int B, int H, int S, float *mass, void *stream)
+{
+    RTKV_CHECK_ARG(head_sums && mass && B > 0 && B <= 65535 && H > 0 && S > 0, "rtkv_mass_from_head_sums: bad argument");
+    dim3 grid((S + 255) / 256, B);
+    mass_from_head_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(head_sums, H, S, mass);
+    RTKV_LAUNCH_CHECK("mass_from_head_sums_kernel");
     return RTKV_OK;
 }

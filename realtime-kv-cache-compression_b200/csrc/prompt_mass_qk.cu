@@ -3,8 +3,8 @@
 // receives softmaxed attention and slices the prompt key columns, token_importance.py:41;
 // the only contraction that reproduces that slice is Q . K_prompt^T).
 //
-//   head_sum[b,i,h] = sum_{j < P, j <= i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
-//   mass[b,i]       = (head_sum[b,i,0] + ... + head_sum[b,i,H-1]) / H        (rtkv_mass_from_partials)
+//   head_sum[b,h,i] = sum_{j < P, j <= i} exp(scale * q[b,h,i,:].k[b,h,j,:] - lse[b,h,i])
+//   mass[b,i]       = (head_sum[b,0,i] + ... + head_sum[b,H-1,i]) / H        (rtkv_mass_from_head_sums)
 //
 // This is the one dense contraction of the path, so it runs on the 5th-generation tensor
 // cores: tcgen05.mma (M=128 query rows x N=128 prompt keys x K=16, bf16/f16 in, fp32
@@ -13,9 +13,9 @@
 //   warp 0        TMA producer: the head's K_prompt tile once per item (double buffered), Q tiles
 //                 through a 4-stage ring (2 boxes of 64 columns each)
 //   warp 1        TMEM allocator + MMA issuer: 8 tcgen05.mma per Q tile, tcgen05.commit -> mbarriers
-//   warps 2..9    epilogue (two warps per TMEM lane quadrant, 64 columns each): tcgen05.ld 32 lanes x 32
-//                 columns, exp2(fma(s, c, -lse*log2e)), causal / P mask only where needed, in-thread row
-//                 sums (a thread owns half a query row), accumulate over heads
+//   warps 2..9    epilogue: two warpgroups, one per TMEM accumulator; tcgen05.ld 32 lanes x 32 columns
+//                 software-pipelined against exp2(fma(s, c, -lse*log2e)); causal / P mask only where
+//                 needed; a thread owns one query row, so row sums need no cross-warp combine
 // Two 128-column accumulators in TMEM let the MMAs of tile t+1 overlap the epilogue of tile t; the
 // rings keep rolling across work items, so the pipeline is filled once per CTA.
 // Roofline: 2*B*H*S*P*D flop (4.3 GFLOP per 7B layer at S=4096) and B*H*S*D*2 bytes of Q
@@ -30,11 +30,12 @@ constexpr int kTileM = 128;      // query rows per CTA
 constexpr int kTileN = 128;      // prompt keys (P <= 128)
 constexpr int kHeadDim = 128;    // K of the GEMM
 constexpr int kKBlock = 64;      // elements per 128-byte swizzle atom row
-constexpr int kStages = 4;       // Q-tile ring
+constexpr int kStages = 6;       // Q-tile ring (192 KiB in flight per SM)
+constexpr int kKBufs = 1;        // K_prompt tile buffers (1: reloaded at item boundaries after the item's MMAs retire)
 constexpr int kOperandBytes = kTileM * kHeadDim * 2;          // 32 KiB: one Q (or K) tile
 constexpr int kQkThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps
 // smem: 2 K tiles (double buffered across work items) + kStages Q tiles + barriers + row-sum exchange
-constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)(2 + kStages) * kOperandBytes + 256 + 2 * kTileM * sizeof(float);
+constexpr size_t kQkSmem = 1024 /*align slack*/ + (size_t)(kKBufs + kStages) * kOperandBytes + 256 + kTileM * sizeof(float);
 
 // ---- raw PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,6 +96,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -116,9 +129,10 @@ __device__ __forceinline__ float ex2_approx(float x)
 
 struct QkParams {
     const float *lse;     // [B,H,S]
-    float *partials;      // [B,S,n_groups]
+    float *partials;      // head sums [B,H,S]
     int B, H, S, P, gs, n_groups, causal;
     int tiles_per_item;   // query tiles that share one K_prompt tile load
+    int dbg;              // bisecting aid (rtkv_debug_qk_mode): 1 no exp, 2 no TMEM loads, 3 no MMAs
     float scale_log2;     // scale * log2(e)
     uint32_t idesc;
 };
@@ -129,9 +143,9 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     extern __shared__ unsigned char qk_smem_raw[];
     // 128-byte swizzle needs 1024-byte aligned tiles
     unsigned char *smem = (unsigned char *)(((uintptr_t)qk_smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *smem_k = smem;                                   // [2][32 KiB]
-    unsigned char *smem_q = smem + 2 * kOperandBytes;               // [kStages][32 KiB]
-    uint64_t *bars = (uint64_t *)(smem + (size_t)(2 + kStages) * kOperandBytes);
+    unsigned char *smem_k = smem;                                   // [kKBufs][32 KiB]
+    unsigned char *smem_q = smem + kKBufs * kOperandBytes;          // [kStages][32 KiB]
+    uint64_t *bars = (uint64_t *)(smem + (size_t)(kKBufs + kStages) * kOperandBytes);
     uint64_t *qfull = bars, *qempty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
     uint64_t *kfull = bars + 2 * kStages + 4, *kempty = bars + 2 * kStages + 6;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 8);
@@ -149,7 +163,7 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&qfull[s]), 1); mbar_init(smem_u32(&qempty[s]), 1); }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 8);
+            mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 4);
             mbar_init(smem_u32(&kfull[a]), 1); mbar_init(smem_u32(&kempty[a]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -169,8 +183,8 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             int q = 0, it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int c = item % chunks, h = (item / chunks) % p.H, b = item / (chunks * p.H);
-                const int kb = it & 1;
-                mbar_wait(smem_u32(&kempty[kb]), ((it >> 1) & 1) ^ 1);
+                const int kb = it % kKBufs;
+                mbar_wait(smem_u32(&kempty[kb]), ((it / kKBufs) & 1) ^ 1);
                 const uint32_t kf = smem_u32(&kfull[kb]);
                 mbar_expect_tx(kf, kOperandBytes);
                 const uint32_t kdst = smem_u32(smem_k + (size_t)kb * kOperandBytes);
@@ -196,8 +210,8 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             int q = 0, it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int c = item % chunks;
-                const int kb = it & 1;
-                mbar_wait(smem_u32(&kfull[kb]), (it >> 1) & 1);          // K_prompt tile of this head landed
+                const int kb = it % kKBufs;
+                mbar_wait(smem_u32(&kfull[kb]), (it / kKBufs) & 1);      // K_prompt tile of this head landed
                 const uint32_t kbase = smem_u32(smem_k + (size_t)kb * kOperandBytes);
                 const int t1 = min(tiles, (c + 1) * T);
                 for (int tile = c * T; tile < t1; ++tile, ++q) {
@@ -207,6 +221,7 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                     tc_fence_after();
                     const uint32_t qbase = smem_u32(smem_q + (size_t)s * kOperandBytes);
                     const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
+                    if (p.dbg < 3) {
 #pragma unroll
                     for (int kq = 0; kq < 2; ++kq)
 #pragma unroll
@@ -215,6 +230,7 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                             umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
                                      (uint32_t)((kq | kk) != 0));
                         }
+                    }
                     umma_commit(smem_u32(&qempty[s]));     // Q stage reusable once these MMAs retire
                     umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
                 }
@@ -222,9 +238,11 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             }
         }
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== epilogue: two warpgroups, one per TMEM accumulator (group = (warp-2)/4 handles the Q tiles
+        // with q % 2 == group); TMEM lane quadrant = warp % 4; a thread owns one query row of its tile, so
+        // there is no cross-warp combine, and the two groups work on consecutive tiles concurrently =====
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;
         const int row = quad * 32 + lane;              // accumulator row == TMEM lane
         const float kLog2e = 1.4426950408889634f;
         int q = 0;
@@ -232,7 +250,8 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const int c = item % chunks, h = (item / chunks) % p.H, b = item / (chunks * p.H);
             const int t1 = min(tiles, (c + 1) * T);
             for (int tile = c * T; tile < t1; ++tile, ++q) {
-                const int a = q & 1;
+                if ((q & 1) != grp) continue;
+                const int a = grp;
                 const int i = tile * kTileM + row;
                 const bool live = i < p.S;
                 // rows of this tile see every prompt key (no causal / P masking needed) -> branch-free body
@@ -240,33 +259,38 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
                 mbar_wait(smem_u32(&tfull[a]), (q >> 1) & 1);
                 tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN);
                 float rs = 0.0f;
+                uint32_t v0[32], v1[32];
+                if (p.dbg < 2 || p.dbg == 3) {
+                    // software pipeline: the TMEM load of the next 32 columns is in flight during the exp math
+                    tmem_ld32_issue(tbase, v0);
 #pragma unroll
-                for (int cc = 0; cc < kTileN / 2; cc += 32) {
-                    uint32_t v[32];
-                    const int c0 = half * (kTileN / 2) + cc;
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN + c0), v);
-                    if (unmasked) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) rs += ex2_approx(__fmaf_rn(__uint_as_float(v[e]), p.scale_log2, -l2));
-                    } else {
+                    for (int cc = 0; cc < kTileN; cc += 64) {
+                        tmem_ld_wait();
+                        tmem_ld32_issue(tbase + cc + 32, v1);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const int j = c0 + e;
-                            const bool ok = (j < p.P) && (!p.causal || j <= i);
-                            const float x = ex2_approx(__fmaf_rn(__uint_as_float(v[e]), p.scale_log2, -l2));
-                            rs += ok ? x : 0.0f;
+                            const int j = cc + e;
+                            float x = __uint_as_float(v0[e]);
+                            if (p.dbg != 1) x = ex2_approx(__fmaf_rn(x, p.scale_log2, -l2));
+                            rs += (unmasked || ((j < p.P) && (!p.causal || j <= i))) ? x : 0.0f;
+                        }
+                        tmem_ld_wait();
+                        if (cc + 64 < kTileN) tmem_ld32_issue(tbase + cc + 64, v0);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const int j = cc + 32 + e;
+                            float x = __uint_as_float(v1[e]);
+                            if (p.dbg != 1) x = ex2_approx(__fmaf_rn(x, p.scale_log2, -l2));
+                            rs += (unmasked || ((j < p.P) && (!p.causal || j <= i))) ? x : 0.0f;
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&tempty[a]));
-                // combine the two column halves of the row (fixed order: half 0 + half 1), one store per row
-                if (half == 1) xsum[row] = rs;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && live) p.partials[((size_t)b * p.S + i) * p.H + h] = rs + xsum[row];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (live) p.partials[((size_t)b * p.H + h) * p.S + i] = rs;       // head-major: coalesced
             }
         }
     }
@@ -300,7 +324,7 @@ static int encode_rows_map(CUtensorMap *map, const void *base, int dtype, uint64
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dtype == RTKV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RTKV_EINVAL; }
     return RTKV_OK;
 }
@@ -308,6 +332,9 @@ static int encode_rows_map(CUtensorMap *map, const void *base, int dtype, uint64
 } // namespace rtkv
 
 using namespace rtkv;
+
+static int g_qk_dbg = 0;
+extern "C" int rtkv_debug_qk_mode(int mode) { g_qk_dbg = mode; return RTKV_OK; }
 
 extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *lse, int dtype, int B, int H, int S,
                                    int D, int P, float scale, int causal, float *head_sums, void *stream)
@@ -347,6 +374,7 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     int T = 1;
     while (T * 2 <= tiles && (long long)((tiles + 2 * T - 1) / (2 * T)) * H * B * 2 >= 3LL * sm_count) T *= 2;
     p.tiles_per_item = T;
+    p.dbg = g_qk_dbg;
     const long long n_items = (long long)((tiles + T - 1) / T) * H * B;
     RTKV_CHECK_ARG(n_items < (1ll << 31), "rtkv_prompt_mass_qk: too many work items");
     RTKV_CUDA(cudaFuncSetAttribute(prompt_mass_qk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQkSmem));

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "rtkv_prompt_mass_qk": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int,
                                            c_vp, c_vp]),
+    "rtkv_mass_from_head_sums": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rtkv_position_bias": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp]),
     "rtkv_normalize_mass": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rtkv_score_select": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t,
@@ -92,6 +93,7 @@ PROTOTYPES = {
     "rtkv_debug_k2_timing": (ctypes.c_int, [c_vp]),
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_qk_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "rtkv_ctx_destroy": (ctypes.c_int, [c_vp]),
     "rtkv_compress_layer_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -131,12 +131,12 @@ def mass_from_partials(partials, num_heads, rank_major=False):
 
 def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True):
     """Fused Q.K_prompt^T scoring on tcgen05: q [B,H,S,128], k_prompt [B,H,P,128] (bf16/f16),
-    lse [B,H,S] f32 -> per-head prompt-mass sums [B,S,H]."""
+    lse [B,H,S] f32 -> per-head prompt-mass sums [B,H,S] (head-major, like lse)."""
     require_cuda()
     q, k_prompt, lse = q.contiguous(), k_prompt.contiguous(), lse.contiguous().float()
     B, H, S, D = q.shape
     P = k_prompt.shape[2]
-    parts = torch.empty(B, S, H, dtype=torch.float32, device=q.device)
+    parts = torch.empty(B, H, S, dtype=torch.float32, device=q.device)
     check(lib.rtkv_prompt_mass_qk(_ptr(q), _ptr(k_prompt), _ptr(lse), dtype_code(q), B, H, S, D, P,
                                   float(scale), int(bool(causal)), _ptr(parts), _stream()))
     return parts
@@ -144,7 +144,11 @@ def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True):
 
 def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
     """mass [B,S] from Q, K_prompt and the row log-sum-exp (no S x S attention matrix)."""
-    return mass_from_partials(prompt_mass_qk_partials(q, k_prompt, lse, scale, causal), q.shape[1])
+    hs = prompt_mass_qk_partials(q, k_prompt, lse, scale, causal)
+    B, H, S = hs.shape
+    mass = torch.empty(B, S, dtype=torch.float32, device=hs.device)
+    check(lib.rtkv_mass_from_head_sums(_ptr(hs), B, H, S, _ptr(mass), _stream()))
+    return mass
 
 
 def position_bias(seq_len, device):

@@ -764,10 +764,10 @@ def test_qk_scoring_matches_restatement(rt, dtype, B, H, S, P):
     kernel on the same attention: north-star tolerance for half inputs is 1e-3 relative."""
     _, ops = rt
     q, kp, lse, scale, probs = qk_inputs(B, H, S, P, dtype, seed=S + H)
-    parts = ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True)            # per-head sums [B,S,H]
+    parts = ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True)            # per-head sums [B,H,S]
     dt = oracle.BF16 if dtype == torch.bfloat16 else oracle.F16
     want = oracle.prompt_mass_qk(oracle.from_torch(q)[0], oracle.from_torch(kp)[0], lse.cpu().numpy(), dt, scale, True, 1)
-    np.testing.assert_allclose(parts.cpu().numpy(), want, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(parts.transpose(1, 2).cpu().numpy(), want, rtol=2e-4, atol=1e-6)
     mass = ops.prompt_mass_qk(q, kp, lse, scale)
     np.testing.assert_allclose(mass.cpu().numpy(), oracle.mass_from_partials(want, H), rtol=2e-4, atol=1e-6)
     via_probs = ops.prompt_mass(probs, prompt_len=P)

@@ -70,6 +70,12 @@ if only is None or "k1b" in only:
     t = graph_time(lambda i: ops.prompt_mass_qk_partials(Qs[i], Kp, lse, D ** -0.5, True), nset)
     res["k1b_us"] = t; res["k1b_GBs"] = q_bytes / t / 1e3; res["k1b_frac_hbm"] = res["k1b_GBs"] / PEAK
     res["k1b_TFLOPs"] = 2.0 * B * H * S * P * D / t / 1e6
+    if "--qk-bisect" in sys.argv:
+        from rtkv import _lib
+        for mode, tag in ((1, "no_exp"), (2, "no_tmem_ld"), (3, "no_mma"), (4, "tma_only")):
+            _lib.lib.rtkv_debug_qk_mode(mode)
+            res[f"k1b_{tag}_us"] = graph_time(lambda i: ops.prompt_mass_qk_partials(Qs[i], Kp, lse, D ** -0.5, True), nset)
+        _lib.lib.rtkv_debug_qk_mode(0)
     del Qs
 
 if only is None or "k2" in only:
