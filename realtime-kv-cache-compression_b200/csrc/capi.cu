@@ -229,7 +229,7 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     RTKV_CUDA(cudaEventRecord(c->ev_a, c->s_h2d));
     int per_row = kMaxPieces / B;                      // pieces per batch row
     if (per_row < 1) per_row = 1;
-    if (per_row > 8) per_row = 8;
+    if (per_row > 16) per_row = 16;                    // smaller pieces = shorter quantise+download tail
     const int tok_per_piece = (S + per_row - 1) / per_row;
     const bool piecewise = (B * per_row <= kMaxPieces);
     int n_pieces = 0;

@@ -381,6 +381,7 @@ class HostContext:
         require_cuda()
         self._h = ctypes.c_void_p()
         check(lib.rtkv_ctx_create(ctypes.byref(self._h)))
+        self._aux = None        # pinned staging for scores / labels / mask (pageable D2H would serialise)
 
     def close(self):
         if self._h:
@@ -406,9 +407,14 @@ class HostContext:
             k_out = torch.empty(B * S * n, dtype=K.dtype)
         if v_out is None:
             v_out = torch.empty(B * S * n, dtype=K.dtype)
-        scores = torch.empty(B, S, dtype=torch.float32) if want_aux else None
-        labels = torch.empty(B, S, dtype=torch.uint8) if want_aux else None
-        mask = torch.empty(B, S, dtype=torch.uint8) if want_aux else None
+        scores = labels = mask = None
+        if want_aux:
+            n = B * S
+            if self._aux is None or self._aux.numel() < 6 * n:
+                self._aux = torch.empty(6 * n, dtype=torch.uint8, pin_memory=True)
+            scores = self._aux[: 4 * n].view(torch.float32).view(B, S)
+            labels = self._aux[4 * n: 5 * n].view(B, S)
+            mask = self._aux[5 * n: 6 * n].view(B, S)
         rows = np.zeros(B, dtype=_lib.ROW_STATS)
         layer = _lib.LayerStats()
         ms = ctypes.c_int32(0)
@@ -418,6 +424,8 @@ class HostContext:
             ctypes.byref(ms), _ptr(scores), _ptr(labels), _ptr(mask),
             ctypes.c_void_p(rows.ctypes.data), ctypes.byref(layer)))
         m = int(ms.value)
+        if want_aux:            # hand out copies: the pinned staging is reused by the next call
+            scores, labels, mask = scores.clone(), labels.clone(), mask.clone()
         return dict(k=k_out.view(-1)[: B * m * n].view(B, m, n), v=v_out.view(-1)[: B * m * n].view(B, m, n),
                     max_selected=m, scores=scores, labels=labels, mask=mask, rows=rows,
                     used_fallback=int(layer.used_fallback))
