@@ -10,6 +10,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+#include <time.h>
+
 #include "common.cuh"
 
 namespace rtkv {
@@ -214,6 +217,9 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     const size_t row_bytes = (size_t)n * es;
     int rc = ctx_reserve(c, kv_bytes, a_bytes, B, S);
     if (rc) return rc;
+    static const bool trace = getenv("RTKV_TRACE") != nullptr;   // host-side phase times on stderr
+    const auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = trace ? now() : 0.0;
 
     // ---- uploads: prompt columns of A (a strided 2-D copy), then K/V pieces
     if (sh == (int64_t)S * si && sb == (int64_t)H * sh) {
@@ -229,7 +235,9 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     RTKV_CUDA(cudaEventRecord(c->ev_a, c->s_h2d));
     int per_row = kMaxPieces / B;                      // pieces per batch row
     if (per_row < 1) per_row = 1;
-    if (per_row > 16) per_row = 16;                    // smaller pieces = shorter quantise+download tail
+    int cap = 8;
+    if (const char *e = getenv("RTKV_HOST_PIECES")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning knob
+    if (per_row > cap) per_row = cap;
     const int tok_per_piece = (S + per_row - 1) / per_row;
     const bool piecewise = (B * per_row <= kMaxPieces);
     int n_pieces = 0;
@@ -267,6 +275,7 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     RTKV_CUDA(cudaStreamSynchronize(c->s_d2h));           // the one data-dependent shape: S' = max_selected
     const int ms = c->h_ls->max_selected;
     *max_selected = ms;
+    const double t_sel = trace ? now() : 0.0;
     if (layer_stats) *layer_stats = *c->h_ls;
     if (row_stats) memcpy(row_stats, c->h_rs, (size_t)B * sizeof(rtkv_row_stats));
 
@@ -309,9 +318,14 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     if (scores) RTKV_CUDA(cudaMemcpyAsync(scores, c->scores, bs * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     if (labels) RTKV_CUDA(cudaMemcpyAsync(labels, c->labels, bs, cudaMemcpyDeviceToHost, c->s_d2h));
     if (mask) RTKV_CUDA(cudaMemcpyAsync(mask, c->mask, bs, cudaMemcpyDeviceToHost, c->s_d2h));
+    const double t_enq = trace ? now() : 0.0;
+    RTKV_CUDA(cudaStreamSynchronize(c->s_h2d));
+    const double t_up = trace ? now() : 0.0;
     RTKV_CUDA(cudaStreamSynchronize(c->s_main));
     RTKV_CUDA(cudaStreamSynchronize(c->s_d2h));
-    RTKV_CUDA(cudaStreamSynchronize(c->s_h2d));
+    if (trace)
+        fprintf(stderr, "[rtkv host] selection ready %.2f ms, enqueued %.2f, uploads done %.2f, all done %.2f (kept %d)\n",
+                t_sel - t_begin, t_enq - t_begin, t_up - t_begin, now() - t_begin, ms);
     return RTKV_OK;
 }
 
