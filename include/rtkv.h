@@ -233,6 +233,60 @@ RTKV_API int rtkv_unpack_dequant(const uint8_t *codes, const float *qparams, int
                         const uint8_t *labels, const int32_t *bits /*[host]*/,
                         int out_rows, int64_t row_bytes, void *Y, void *stream);
 
+/* ---- extended scale granularities and outlier split ------------------------------------------
+ * BASELINE.json north star, subsystem (2): "per-channel K and per-token V group-wise scale/zero
+ * computation and outlier detection and split".  The reference has no such behaviour (its scale spans
+ * the whole [H*D] row, dynamic_quantization.py:183-184 = RTKV_Q_TOKEN without outliers, which is what a
+ * NULL or zeroed options struct selects); the semantics are defined by oracle/rtkv_oracle.c
+ * orc_fake_quant_ex and summarised here:
+ *   RTKV_Q_TOKEN        one (scale, zero-point) per kept row
+ *   RTKV_Q_TOKEN_GROUP  one per kept row and group of group_size consecutive channels (divides n)
+ *   RTKV_Q_CHANNEL      one (min, max) per channel and group of token_group (1..32) consecutive KEPT rows
+ *                       of a batch row; every row derives scale/zero-point from it with its own bits
+ *   outlier_tau_q8      0 = off, else 256*tau (tau >= 1), token modes only: an element is an outlier iff
+ *                       |x| > tau * mean|x| of its group, the mean taken in integer fixed point relative to
+ *                       the group's largest exponent (order independent, hence bit-reproducible).  Outliers
+ *                       are excluded from the group's min/max and kept exactly.
+ * mode[0] applies to X0 (keys), mode[1] to X1 (values). */
+enum { RTKV_Q_TOKEN = 0, RTKV_Q_TOKEN_GROUP = 1, RTKV_Q_CHANNEL = 2 };
+typedef struct rtkv_quant_options {
+    int32_t mode[2];
+    int32_t group_size;
+    int32_t token_group;
+    int32_t outlier_tau_q8;
+    int32_t reserved[3];
+} rtkv_quant_options; /* 32 bytes */
+
+/* rtkv_quant_gather with options.  outlier_counts: optional [B,out_rows,2] i32 (X0, X1), number of
+ * outliers kept exactly in each output row (0 for padding rows). */
+RTKV_API int rtkv_quant_gather_ex(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                         const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                         const uint8_t *labels, const int32_t *bits /*[host]*/,
+                         int out_rows, int zero_pad, const rtkv_quant_options *options /*[host]*/,
+                         void *Y0, void *Y1, int32_t *outlier_counts, void *stream);
+
+/* Packed rows with options, one tensor per call (tensor = 0: options->mode[0], 1: mode[1]).
+ *   codes    [B,out_rows,row_bytes] as rtkv_quant_pack; split outliers hold code 0
+ *   qparams  token modes: [B,out_rows,G,2] (scale, zero-point), G = rtkv_quant_groups();
+ *            RTKV_Q_CHANNEL: [B,ceil(out_rows/token_group),n,2] (min, max)
+ *   outliers (token modes with tau, else NULL/0): per output row the first outlier_cap outliers in channel
+ *            order: out_idx [B,out_rows,cap] i32, out_val [B,out_rows,cap] f32, out_cnt [B,out_rows] i32;
+ *            outliers past the cap are quantised like inliers (clamped to the code range). */
+RTKV_API int rtkv_quant_groups(int n, const rtkv_quant_options *options, int tensor);
+RTKV_API int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,
+                       const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                       const uint8_t *labels, const int32_t *bits /*[host]*/,
+                       int out_rows, int64_t row_bytes, const rtkv_quant_options *options /*[host]*/, int tensor,
+                       uint8_t *codes, float *qparams, int32_t *out_idx, float *out_val, int32_t *out_cnt,
+                       int outlier_cap, void *stream);
+RTKV_API int rtkv_unpack_dequant_ex(const uint8_t *codes, const float *qparams, const int32_t *out_idx,
+                           const float *out_val, const int32_t *out_cnt, int outlier_cap,
+                           int dtype, int B, int S, int n,
+                           const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                           const uint8_t *labels, const int32_t *bits /*[host]*/,
+                           int out_rows, int64_t row_bytes, const rtkv_quant_options *options /*[host]*/, int tensor,
+                           void *Y, void *stream);
+
 /* Profiling aid: when set to a device buffer of 64 int64, every rtkv_score_select launch writes
  * buf[0] = number of ticks and buf[1..] = clock64() at its phase boundaries (row 0).  NULL: off. */
 RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);

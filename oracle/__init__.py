@@ -203,6 +203,27 @@ def fake_quant_rows(x, dt, labels, bits, want_codes=False, want_params=False):
     return out, codes, qp
 
 
+def fake_quant_ex(x, dt, labels, bits, mode=0, group=0, tgroup=0, tau=0.0, cap=-1):
+    """Extended granularities / outlier split (project-defined, see orc_fake_quant_ex).
+    x: [rows, n] (ONE batch row's kept rows for mode 2); -> dict(out, codes, qparams, omask)."""
+    x = _c(x)
+    rows, n = x.shape
+    labels = _c(labels, np.uint8).reshape(-1)
+    assert labels.size == rows
+    out = np.empty_like(x)
+    codes = np.empty((rows, n), np.float32)
+    omask = np.zeros((rows, n), np.uint8)
+    if mode == 2:
+        qp = np.empty(((rows + tgroup - 1) // tgroup, n, 2), np.float32)
+    else:
+        g = group if mode == 1 else n
+        assert n % g == 0
+        qp = np.empty((rows, n // g, 2), np.float32)
+    lib().orc_fake_quant_ex(_p(x), dt, ctypes.c_int64(rows), n, _p(labels), _bits3(bits), int(mode), int(group),
+                            int(tgroup), int(round(tau * 256)), int(cap), _p(out), _p(codes), _p(qp), _p(omask))
+    return dict(out=out, codes=codes, qparams=qp, omask=omask)
+
+
 def select_tokens(scores, labels, bits, budget):
     scores = _c(scores, np.float32)
     labels = _c(labels, np.uint8)

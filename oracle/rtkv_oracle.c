@@ -480,6 +480,131 @@ void orc_pack_codes(const float *codes, int64_t rows, int n, const uint8_t *labe
     }
 }
 
+/* ---------- extended scale granularities + outlier split ----------
+ * North-star extras with NO reference behaviour ("parity unpinned by the reference"):
+ * this restatement DEFINES them; mode 0 without outliers is orc_fake_quant_rows (checked in tests).
+ *   mode 0  one (scale, zero-point) per row                      (the reference, dynamic_quantization.py:183-184)
+ *   mode 1  one per row and group of `group` consecutive channels (group divides n)
+ *   mode 2  one (min, max) per channel and group of `tgroup` consecutive rows; each row of the group
+ *           derives its own scale/zero-point from that pair and ITS bit width
+ * Outlier split (modes 0/1, tau_q8 = 256*tau >= 256): an element is an outlier iff |x| > tau * mean|x|
+ * of its group.  The mean is taken in integer fixed point so that it does not depend on the order of
+ * the additions: with E the exponent field of the group's largest magnitude, q_i = |x_i| * 2^(30-E)
+ * truncated to an integer (denormals -> 0), mean = floor(sum q_i / g), T = floor(tau_q8 * mean / 256),
+ * outlier <=> q_i > T.  A group holding a NaN, or whose largest magnitude is denormal/zero, has no
+ * outliers.  Outliers are kept exactly (dense output) and are left out of the group's min/max; in a
+ * row only the first `cap` outliers in channel order are split (cap < 0: all) - later ones are
+ * quantised like inliers, i.e. clamped to the code range.
+ * Outputs (each optional): out [rows,n] tensor dtype; codes [rows,n] float (split outliers: 0);
+ * qparams: modes 0/1 [rows, n/group, 2] = (scale, zero-point), mode 2 [ceil(rows/tgroup), n, 2] =
+ * (min, max); omask [rows,n] = 1 for split outliers. */
+static inline uint32_t mag_fix(uint32_t ab, uint32_t E)
+{
+    uint32_t e = ab >> 23;
+    if (e == 0) return 0;
+    uint32_t sh = E - e;
+    if (sh >= 31) return 0;
+    return (((ab & 0x7fffffu) | 0x800000u) << 7) >> sh;
+}
+
+static void qparams_from_minmax(float mn, float mx, int bits, int dt, float qp[2])
+{
+    if (mx == mn) { qp[0] = 1.0f; qp[1] = 0.0f; return; }
+    float qmax = (float)((1ll << bits) - 1);
+    qp[0] = rnd(rnd(mx - mn, dt) / qmax, dt);
+    qp[1] = rnd(0.0f - rnd(mn / qp[0], dt), dt);
+}
+
+void orc_fake_quant_ex(const void *x, int dt, int64_t rows, int n, const uint8_t *labels, const int bits[3],
+                       int mode, int group, int tgroup, int tau_q8, int cap,
+                       void *out, float *codes, float *qparams, uint8_t *omask)
+{
+    if (mode == 2) {
+        int64_t ng = (rows + tgroup - 1) / tgroup;
+#pragma omp parallel for schedule(static)
+        for (int64_t g = 0; g < ng; ++g) {
+            int64_t r0 = g * tgroup, r1 = r0 + tgroup < rows ? r0 + tgroup : rows;
+            for (int c = 0; c < n; ++c) {
+                float mn = ld(x, r0 * n + c, dt), mx = mn;
+                int has_nan = 0;
+                for (int64_t r = r0; r < r1; ++r) {
+                    float v = ld(x, r * n + c, dt);
+                    if (v != v) has_nan = 1;
+                    if (v < mn) mn = v;
+                    if (v > mx) mx = v;
+                }
+                if (has_nan) mn = mx = NAN;
+                if (qparams) { qparams[(g * n + c) * 2] = mn; qparams[(g * n + c) * 2 + 1] = mx; }
+                for (int64_t r = r0; r < r1; ++r) {
+                    int nb = bits[labels[r]];
+                    float qp[2];
+                    qparams_from_minmax(mn, mx, nb, dt, qp);
+                    float qmax_r = rnd((float)((1ll << nb) - 1), dt);
+                    float q = quant_code(ld(x, r * n + c, dt), qp[0], qp[1], qmax_r, dt);
+                    if (out) st(out, r * n + c, rnd(rnd(q - qp[1], dt) * qp[0], dt), dt);
+                    if (codes) codes[r * n + c] = q;
+                    if (omask) omask[r * n + c] = 0;
+                }
+            }
+        }
+        return;
+    }
+    int g = mode == 1 ? group : n;
+    int ngr = n / g;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; ++r) {
+        int nb = bits[labels[r]];
+        float qmax_r = rnd((float)((1ll << nb) - 1), dt);
+        int64_t off = r * (int64_t)n;
+        int split = 0;                                   /* outliers split so far in this row */
+        for (int gi = 0; gi < ngr; ++gi) {
+            int c0 = gi * g;
+            int has_nan = 0;
+            uint32_t maxab = 0;
+            for (int c = c0; c < c0 + g; ++c) {
+                float v = ld(x, off + c, dt);
+                if (v != v) has_nan = 1;
+                uint32_t ab = f_to_bits(v) & 0x7fffffffu;
+                if (ab > maxab) maxab = ab;
+            }
+            uint64_t T = ~0ull;
+            uint32_t E = maxab >> 23;
+            int use_out = tau_q8 > 0 && !has_nan && E > 0;
+            if (use_out) {
+                uint64_t sum = 0;
+                for (int c = c0; c < c0 + g; ++c) sum += mag_fix(f_to_bits(ld(x, off + c, dt)) & 0x7fffffffu, E);
+                T = ((uint64_t)tau_q8 * (sum / (uint64_t)g)) >> 8;
+            }
+            float mn = INFINITY, mx = -INFINITY;
+            for (int c = c0; c < c0 + g; ++c) {
+                float v = ld(x, off + c, dt);
+                if (use_out && mag_fix(f_to_bits(v) & 0x7fffffffu, E) > T) continue;
+                if (v < mn) mn = v;
+                if (v > mx) mx = v;
+            }
+            if (has_nan) mn = mx = NAN;
+            float qp[2];
+            qparams_from_minmax(mn, mx, nb, dt, qp);
+            if (qparams) { qparams[(r * ngr + gi) * 2] = qp[0]; qparams[(r * ngr + gi) * 2 + 1] = qp[1]; }
+            for (int c = c0; c < c0 + g; ++c) {
+                float v = ld(x, off + c, dt);
+                int is_out = use_out && mag_fix(f_to_bits(v) & 0x7fffffffu, E) > T;
+                if (is_out && (cap < 0 || split < cap)) {
+                    ++split;
+                    if (out) st(out, off + c, v, dt);
+                    if (codes) codes[off + c] = 0.0f;
+                    if (omask) omask[off + c] = 1;
+                    continue;
+                }
+                float q = quant_code(v, qp[0], qp[1], qmax_r, dt);
+                if (out) st(out, off + c, rnd(rnd(q - qp[1], dt) * qp[0], dt), dt);
+                if (codes) codes[off + c] = q;
+                if (omask) omask[off + c] = 0;
+            }
+        }
+    }
+}
+
 void orc_set_num_threads(int n)
 {
 #ifdef _OPENMP

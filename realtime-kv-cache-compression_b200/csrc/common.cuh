@@ -176,7 +176,10 @@ __device__ __forceinline__ float quant_code(float x, float scale, float zp, floa
     float t = Elem<DT>::rnd(__fdiv_rn(x, scale));
     t = Elem<DT>::rnd(__fadd_rn(t, zp));
     float q = rintf(t);                      // round half to even, like torch.round
-    if (q == q) q = fminf(fmaxf(q, 0.0f), qmax_r); // torch.clamp keeps NaN
+    // torch.clamp on the CPU is min(max(q, 0), qmax) with std::max/std::min: NaN stays NaN and -0.0 (a
+    // constant row in (-0.5, 0)) stays -0.0, which fmaxf(-0.0f, 0.0f) would turn into +0.0
+    q = q < 0.0f ? 0.0f : q;
+    q = q > qmax_r ? qmax_r : q;
     return q;
 }
 template <int DT>

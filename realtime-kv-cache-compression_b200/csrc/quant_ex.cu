@@ -1,0 +1,882 @@
+// quant_ex.cu — extended scale granularities and outlier split for the quantise+gather stage.
+//
+// BASELINE.json north star, subsystem (2): "per-channel K and per-token V group-wise scale/zero
+// computation and outlier detection and split", bit-packing with 128-bit accesses.  The reference
+// itself only has one scale per whole [H*D] token row (src/compression/dynamic_quantization.py:183-184,
+// quant_gather.cu); everything here is an extension whose semantics are defined by
+// oracle/rtkv_oracle.c orc_fake_quant_ex (see include/rtkv.h rtkv_quant_options).
+//
+// Same streaming structure as K3: each kept element is read once (128-bit, L1::no_allocate) and
+// written once; the data a scale depends on stays in registers between the statistics and the
+// quantise pass:
+//   token modes    one CTA per (kept row, tensor); a group of channels is a run of consecutive lanes,
+//                  so group statistics are xor-shuffle segments (no shared memory, no barrier)
+//   channel mode   one thread owns a 16-byte channel column of a group of <= 32 kept rows: min/max
+//                  over tokens is thread-local, no cross-thread traffic at all
+#include "quant_common.cuh"
+
+namespace rtkv {
+
+struct QXParams {
+    QGParams g;
+    int t;              // tensor handled by this launch (0 = X0, 1 = X1)
+    int group;          // token modes: channels per group (n for RTKV_Q_TOKEN)
+    int lanes;          // token modes, vector kernel: 16-byte vectors per group (power of two <= 32), 0 = whole row
+    int tgroup;         // channel mode: kept rows per group
+    unsigned tau_q8;    // 0 = no outlier split
+    int32_t *ocount;    // [B,out_rows,2] or NULL
+    // packed variants
+    int64_t row_bytes;
+    uint8_t *codes;
+    float *qparams;
+    int32_t *out_idx;
+    float *out_val;
+    int32_t *out_cnt;
+    int cap;
+};
+
+// |x| * 2^(30-E) truncated to an integer, E = exponent field of the group's largest magnitude
+__device__ __forceinline__ unsigned mag_fix(unsigned ab, unsigned E)
+{
+    const unsigned e = ab >> 23;
+    const unsigned sh = E - e;
+    if (e == 0 || sh >= 31) return 0;
+    return (((ab & 0x7fffffu) | 0x800000u) << 7) >> sh;
+}
+__device__ __forceinline__ unsigned absbits(float f) { return __float_as_uint(f) & 0x7fffffffu; }
+
+__device__ __forceinline__ unsigned block_max_u32(unsigned v, unsigned *sm)
+{
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned r = sm[0];
+#pragma unroll
+    for (int w = 1; w < kQT / 32; ++w) r = max(r, sm[w]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *sm)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = 0;
+#pragma unroll
+    for (int w = 0; w < kQT / 32; ++w) r += sm[w];
+    __syncthreads();
+    return r;
+}
+
+// ---- token modes, vector path -------------------------------------------------------------------
+template <int DT, int NV>
+__global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ float red[16];
+    __shared__ unsigned red_u[kQT / 32];
+    __shared__ unsigned long long red_s[kQT / 32];
+    __shared__ int s_count;
+    const QGParams &p = q.g;
+    const int r = blockIdx.x, b = blockIdx.y, t = q.t;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
+    int32_t *oc = q.ocount ? q.ocount + ((size_t)b * p.out_rows + r) * 2 + t : nullptr;
+    if (r >= cnt) {
+        if (p.zero_pad)
+            for (int v = threadIdx.x; v < nvec; v += kQT) stg_stream(dst + v, make_uint4(0, 0, 0, 0));
+        if (oc && threadIdx.x == 0) *oc = 0;
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint4 *src = (const uint4 *)((const char *)pick_x(p, t) + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+    uint4 raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+    if (oc && threadIdx.x == 0) s_count = 0;
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    const float qmax_r = qmax_rounded<DT>(bits);
+    const bool tau_on = q.tau_q8 != 0;
+    int n_out = 0;
+
+    if (q.lanes == 0) {
+        // ---- one group = the whole row: block-wide statistics
+        int nan = 0;
+        unsigned maxab = 0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (threadIdx.x + k * kQT < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); maxab = max(maxab, absbits(f[e])); }
+            }
+        }
+        unsigned long long T = ~0ull;
+        unsigned E = 0;
+        bool use = false;
+        if (tau_on) {
+            maxab = block_max_u32(maxab, red_u);
+            const int any_nan = __syncthreads_or(nan);
+            E = maxab >> 23;
+            use = !any_nan && E > 0;
+            if (use) {
+                unsigned long long sum = 0;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    if (threadIdx.x + k * kQT < nvec) {
+                        float f[EPV];
+                        Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) sum += mag_fix(absbits(f[e]), E);
+                    }
+                }
+                sum = block_sum_u64(sum, red_s);
+                T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)p.n)) >> 8;
+            }
+        }
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (threadIdx.x + k * kQT < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    if (use && mag_fix(absbits(f[e]), E) > T) continue;
+                    mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]);
+                }
+            }
+        }
+        block_minmax(mn, mx, nan, red);
+        float scale, zp;
+        quant_params<DT>(mn, mx, bits, scale, zp);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            if (v < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    if (use && mag_fix(absbits(f[e]), E) > T) { ++n_out; continue; }
+                    f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+                }
+                stg_stream(dst + v, Vec16<DT>::pack(f));
+            }
+        }
+    } else {
+        // ---- a group is q.lanes consecutive lanes of one 256-vector slab: xor-shuffle segments
+        const int lanes = q.lanes;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            const bool valid = v < nvec;          // uniform within a group (nvec is a multiple of lanes)
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+            int nan = 0;
+            unsigned maxab = 0;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); maxab = max(maxab, absbits(f[e])); }
+            for (int o = lanes >> 1; o; o >>= 1) nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+            unsigned long long T = ~0ull;
+            unsigned E = 0;
+            bool use = false;
+            if (tau_on) {
+                for (int o = lanes >> 1; o; o >>= 1) maxab = max(maxab, __shfl_xor_sync(0xffffffffu, maxab, o));
+                E = maxab >> 23;
+                use = !nan && E > 0;
+                unsigned long long sum = 0;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sum += mag_fix(absbits(f[e]), E);
+                for (int o = lanes >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)q.group)) >> 8;
+            }
+            float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                if (use && mag_fix(absbits(f[e]), E) > T) continue;
+                mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]);
+            }
+            for (int o = lanes >> 1; o; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (nan) mn = mx = __int_as_float(0x7fc00000);
+            float scale, zp;
+            quant_params<DT>(mn, mx, bits, scale, zp);
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    if (use && mag_fix(absbits(f[e]), E) > T) { ++n_out; continue; }
+                    f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+                }
+                stg_stream(dst + v, Vec16<DT>::pack(f));
+            }
+        }
+    }
+    if (oc) {
+        __syncthreads();                       // s_count = 0 is visible
+        n_out = warp_sum(n_out);
+        if ((threadIdx.x & 31) == 0 && n_out) atomicAdd(&s_count, n_out);
+        __syncthreads();
+        if (threadIdx.x == 0) *oc = s_count;
+    }
+}
+
+// ---- token modes, any n / group / alignment: groups one after the other, block-wide passes ----
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_token_ex_generic_kernel(QXParams q)
+{
+    __shared__ float red[16];
+    __shared__ unsigned red_u[kQT / 32];
+    __shared__ unsigned long long red_s[kQT / 32];
+    __shared__ int s_count;
+    const QGParams &p = q.g;
+    const int r = blockIdx.x, b = blockIdx.y, t = q.t;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int64_t dst = ((int64_t)b * p.out_rows + r) * p.n;
+    int32_t *oc = q.ocount ? q.ocount + ((size_t)b * p.out_rows + r) * 2 + t : nullptr;
+    if (r >= cnt) {
+        if (p.zero_pad)
+            for (int c = threadIdx.x; c < p.n; c += kQT) store_elem<DT>(pick_y(p, t), dst + c, 0.0f);
+        if (oc && threadIdx.x == 0) *oc = 0;
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int64_t src = ((int64_t)b * p.S + tok) * p.n;
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    const float qmax_r = qmax_rounded<DT>(bits);
+    if (threadIdx.x == 0) s_count = 0;
+    int n_out = 0;
+    for (int c0 = 0; c0 < p.n; c0 += q.group) {
+        int nan = 0;
+        unsigned maxab = 0;
+        for (int c = c0 + threadIdx.x; c < c0 + q.group; c += kQT) {
+            const float v = load_elem<DT>(pick_x(p, t), src + c);
+            nan |= (v != v); maxab = max(maxab, absbits(v));
+        }
+        unsigned long long T = ~0ull;
+        unsigned E = 0;
+        bool use = false;
+        if (q.tau_q8) {
+            maxab = block_max_u32(maxab, red_u);
+            const int any_nan = __syncthreads_or(nan);
+            E = maxab >> 23;
+            use = !any_nan && E > 0;
+            unsigned long long sum = 0;
+            for (int c = c0 + threadIdx.x; c < c0 + q.group; c += kQT)
+                sum += mag_fix(absbits(load_elem<DT>(pick_x(p, t), src + c)), E);
+            sum = block_sum_u64(sum, red_s);
+            T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)q.group)) >> 8;
+        }
+        float mn = INFINITY, mx = -INFINITY;
+        for (int c = c0 + threadIdx.x; c < c0 + q.group; c += kQT) {
+            const float v = load_elem<DT>(pick_x(p, t), src + c);
+            if (use && mag_fix(absbits(v), E) > T) continue;
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+        }
+        block_minmax(mn, mx, nan, red);
+        float scale, zp;
+        quant_params<DT>(mn, mx, bits, scale, zp);
+        for (int c = c0 + threadIdx.x; c < c0 + q.group; c += kQT) {
+            const float v = load_elem<DT>(pick_x(p, t), src + c);
+            if (use && mag_fix(absbits(v), E) > T) { ++n_out; store_elem<DT>(pick_y(p, t), dst + c, v); continue; }
+            store_elem<DT>(pick_y(p, t), dst + c, dequant_code<DT>(quant_code<DT>(v, scale, zp, qmax_r), scale, zp));
+        }
+        __syncthreads();                       // red[] is reused by the next group
+    }
+    if (oc) {
+        n_out = warp_sum(n_out);
+        if ((threadIdx.x & 31) == 0 && n_out) atomicAdd(&s_count, n_out);
+        __syncthreads();
+        if (threadIdx.x == 0) *oc = s_count;
+    }
+}
+
+// ---- channel mode -----------------------------------------------------------------------------
+// One thread = one 16-byte channel column of a group of <= GT kept rows (held in registers).
+template <int DT, int GT>
+__global__ void __launch_bounds__(kQT) quant_channel_kernel(QXParams q)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ int s_tok[GT], s_cls[GT];
+    const QGParams &p = q.g;
+    const int r0 = blockIdx.x * q.tgroup, b = blockIdx.y, t = q.t;
+    const int v = blockIdx.z * kQT + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    if (threadIdx.x < GT) {
+        const int r = r0 + threadIdx.x;
+        int tok = -1, cls = 0;
+        if (threadIdx.x < q.tgroup && r < cnt && r < p.out_rows) {
+            tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+            cls = p.labels[(int64_t)b * p.S + tok];
+        }
+        s_tok[threadIdx.x] = tok; s_cls[threadIdx.x] = cls;
+    }
+    __syncthreads();
+    if (v >= nvec) return;
+    const size_t row_b = (size_t)p.n * Elem<DT>::kBytes;
+    const char *xb = (const char *)pick_x(p, t) + (size_t)b * p.S * row_b;
+    char *yb = (char *)pick_y(p, t) + (size_t)b * p.out_rows * row_b;
+    uint4 raw[GT];
+#pragma unroll
+    for (int j = 0; j < GT; ++j)
+        if (s_tok[j] >= 0) raw[j] = ldg_stream((const uint4 *)(xb + (size_t)s_tok[j] * row_b) + v);
+    float mn[EPV], mx[EPV];
+    unsigned nanmask = 0;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) { mn[e] = INFINITY; mx[e] = -INFINITY; }
+#pragma unroll
+    for (int j = 0; j < GT; ++j) {
+        if (s_tok[j] >= 0) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[j], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                nanmask |= (unsigned)(f[e] != f[e]) << e;
+                mn[e] = fminf(mn[e], f[e]); mx[e] = fmaxf(mx[e], f[e]);
+            }
+        }
+    }
+    // scale / zero-point of every precision class for this thread's channels
+    float sc0[EPV], zp0[EPV], sc1[EPV], zp1[EPV], sc2[EPV], zp2[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        if ((nanmask >> e) & 1) mn[e] = mx[e] = __int_as_float(0x7fc00000);
+        quant_params<DT>(mn[e], mx[e], p.bits[0], sc0[e], zp0[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[1], sc1[e], zp1[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[2], sc2[e], zp2[e]);
+    }
+    const float qm0 = qmax_rounded<DT>(p.bits[0]), qm1 = qmax_rounded<DT>(p.bits[1]), qm2 = qmax_rounded<DT>(p.bits[2]);
+#pragma unroll
+    for (int j = 0; j < GT; ++j) {
+        const int r = r0 + j;
+        if (j >= q.tgroup || r >= p.out_rows) break;
+        uint4 *dst = (uint4 *)(yb + (size_t)r * row_b) + v;
+        if (s_tok[j] < 0) {
+            if (p.zero_pad) stg_stream(dst, make_uint4(0, 0, 0, 0));
+            continue;
+        }
+        const int cls = s_cls[j];
+        const float qm = cls == 0 ? qm0 : (cls == 1 ? qm1 : qm2);
+        float f[EPV];
+        Vec16<DT>::unpack(raw[j], f);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            const float s = cls == 0 ? sc0[e] : (cls == 1 ? sc1[e] : sc2[e]);
+            const float z = cls == 0 ? zp0[e] : (cls == 1 ? zp1[e] : zp2[e]);
+            f[e] = dequant_code<DT>(quant_code<DT>(f[e], s, z, qm), s, z);
+        }
+        stg_stream(dst, Vec16<DT>::pack(f));
+    }
+}
+
+// channel mode, any n / alignment: one thread per channel, the group's rows are read twice
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_channel_generic_kernel(QXParams q)
+{
+    const QGParams &p = q.g;
+    const int r0 = blockIdx.x * q.tgroup, b = blockIdx.y, t = q.t;
+    const int c = blockIdx.z * kQT + threadIdx.x;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    if (c >= p.n) return;
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int j = 0; j < q.tgroup; ++j) {
+        const int r = r0 + j;
+        if (r >= cnt || r >= p.out_rows) break;
+        const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+        const float v = load_elem<DT>(pick_x(p, t), ((int64_t)b * p.S + tok) * p.n + c);
+        nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    if (nan) mn = mx = __int_as_float(0x7fc00000);
+    for (int j = 0; j < q.tgroup; ++j) {
+        const int r = r0 + j;
+        if (r >= p.out_rows) break;
+        const int64_t dst = ((int64_t)b * p.out_rows + r) * p.n + c;
+        if (r >= cnt) {
+            if (p.zero_pad) store_elem<DT>(pick_y(p, t), dst, 0.0f);
+            continue;
+        }
+        const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+        const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+        float scale, zp;
+        quant_params<DT>(mn, mx, bits, scale, zp);
+        const float v = load_elem<DT>(pick_x(p, t), ((int64_t)b * p.S + tok) * p.n + c);
+        store_elem<DT>(pick_y(p, t), dst, dequant_code<DT>(quant_code<DT>(v, scale, zp, qmax_rounded<DT>(bits)), scale, zp));
+    }
+}
+
+// ---- packed rows, token modes -------------------------------------------------------------------
+// One CTA per kept row, one warp per channel group (lanes stride the group's channels).  Phase 1 leaves
+// every group's threshold / scale / zero-point / outlier count in shared memory, a scan turns the counts
+// into list offsets (outliers are listed in channel order), phase 2 emits codes and the outlier list.
+struct GroupRec { unsigned long long T; unsigned E; float scale, zp; int off; };
+
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_pack_ex_kernel(QXParams q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GroupRec *rec = (GroupRec *)smem_raw;
+    __shared__ int s_total;
+    const QGParams &p = q.g;
+    const int r = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int G = p.n / q.group;
+    const size_t orow = (size_t)b * p.out_rows + r;
+    float *qp = q.qparams + orow * (size_t)G * 2;
+    if (r >= cnt) {                                   // codes were zeroed by the host-side memset
+        for (int i = threadIdx.x; i < 2 * G; i += kQT) qp[i] = 0.0f;
+        if (q.out_cnt && threadIdx.x == 0) q.out_cnt[orow] = 0;
+        return;
+    }
+    uint8_t *dst = q.codes + orow * (size_t)q.row_bytes;
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const int64_t src = ((int64_t)b * p.S + tok) * p.n;
+    const void *X = pick_x(p, q.t);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    const float qmax_r = qmax_rounded<DT>(bits);
+
+    for (int gi = warp; gi < G; gi += kQT / 32) {
+        const int c0 = gi * q.group, c1 = c0 + q.group;
+        int nan = 0;
+        unsigned maxab = 0;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const float v = load_elem<DT>(X, src + c);
+            nan |= (v != v); maxab = max(maxab, absbits(v));
+        }
+        nan = __any_sync(0xffffffffu, nan);
+        unsigned long long T = ~0ull;
+        unsigned E = 0;
+        bool use = false;
+        if (q.tau_q8) {
+            maxab = __reduce_max_sync(0xffffffffu, maxab);
+            E = maxab >> 23;
+            use = !nan && E > 0;
+            unsigned long long sum = 0;
+            for (int c = c0 + lane; c < c1; c += 32) sum += mag_fix(absbits(load_elem<DT>(X, src + c)), E);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)q.group)) >> 8;
+        }
+        float mn = INFINITY, mx = -INFINITY;
+        int nout = 0;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const float v = load_elem<DT>(X, src + c);
+            if (use && mag_fix(absbits(v), E) > T) { ++nout; continue; }
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+        }
+        mn = warp_min(mn); mx = warp_max(mx); nout = warp_sum(nout);
+        if (nan) mn = mx = __int_as_float(0x7fc00000);
+        float scale, zp;
+        quant_params<DT>(mn, mx, bits, scale, zp);
+        if (lane == 0) {
+            rec[gi].T = use ? T : ~0ull; rec[gi].E = E; rec[gi].scale = scale; rec[gi].zp = zp; rec[gi].off = nout;
+            qp[2 * gi] = scale; qp[2 * gi + 1] = zp;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // exclusive scan of the per-group outlier counts
+        const int per = (G + 31) / 32, g0 = lane * per;
+        int run = 0;
+        for (int i = g0; i < g0 + per && i < G; ++i) run += rec[i].off;
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        int base = incl - run;
+        for (int i = g0; i < g0 + per && i < G; ++i) { const int c = rec[i].off; rec[i].off = base; base += c; }
+        if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    const int cap = q.out_idx ? q.cap : 0;
+    if (q.out_cnt && threadIdx.x == 0) q.out_cnt[orow] = s_total < cap ? s_total : cap;
+    int32_t *oi = q.out_idx ? q.out_idx + orow * (size_t)cap : nullptr;
+    float *ov = q.out_val ? q.out_val + orow * (size_t)cap : nullptr;
+    const int per = bits > 8 ? 1 : 8 / bits;
+    for (int gi = warp; gi < G; gi += kQT / 32) {
+        const int c0 = gi * q.group, c1 = c0 + q.group;
+        const unsigned long long T = rec[gi].T;
+        const unsigned E = rec[gi].E;
+        const float scale = rec[gi].scale, zp = rec[gi].zp;
+        int base = rec[gi].off;
+        for (int cb = c0; cb < c1; cb += 32) {
+            const int c = cb + lane;
+            const bool in = c < c1;
+            const float v = in ? load_elem<DT>(X, src + c) : 0.0f;
+            const bool is_out = in && T != ~0ull && mag_fix(absbits(v), E) > T;
+            const unsigned ball = __ballot_sync(0xffffffffu, is_out);
+            const int rank = base + __popc(ball & ((1u << lane) - 1u));
+            base += __popc(ball);
+            const bool split = is_out && rank < cap;
+            unsigned code = 0;
+            if (split) { oi[rank] = c; ov[rank] = v; }
+            else if (in) { const float qf = quant_code<DT>(v, scale, zp, qmax_r); code = qf == qf ? (unsigned)qf : 0u; }
+            if (bits > 8) {
+                if (in) ((uint16_t *)dst)[c] = (uint16_t)code;
+            } else {
+                unsigned acc = code;
+                for (int e = 1; e < per; ++e) acc |= __shfl_down_sync(0xffffffffu, code, e) << (e * bits);
+                if (in && (lane % per) == 0) dst[c / per] = (uint8_t)acc;
+            }
+        }
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kQT) unpack_dequant_ex_kernel(QXParams q)
+{
+    const QGParams &p = q.g;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const size_t orow = (size_t)b * p.out_rows + r;
+    const int64_t dst = (int64_t)orow * p.n;
+    void *Y = p.y[0];
+    if (r >= cnt) {
+        if (p.zero_pad) for (int c = threadIdx.x; c < p.n; c += kQT) store_elem<DT>(Y, dst + c, 0.0f);
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint8_t *src = q.codes + orow * (size_t)q.row_bytes;
+    const int G = p.n / q.group;
+    const float *qp = q.qparams + orow * (size_t)G * 2;
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    for (int c = threadIdx.x; c < p.n; c += kQT) {
+        unsigned code;
+        if (bits > 8) code = ((const uint16_t *)src)[c];
+        else { const int per = 8 / bits; code = (src[c / per] >> ((c % per) * bits)) & ((1u << bits) - 1u); }
+        const int gi = c / q.group;
+        store_elem<DT>(Y, dst + c, dequant_code<DT>((float)code, qp[2 * gi], qp[2 * gi + 1]));
+    }
+    if (q.out_cnt) {
+        __syncthreads();
+        const int no = q.out_cnt[orow];
+        for (int i = threadIdx.x; i < no; i += kQT)
+            store_elem<DT>(Y, dst + q.out_idx[orow * (size_t)q.cap + i], q.out_val[orow * (size_t)q.cap + i]);
+    }
+}
+
+// ---- packed rows, channel mode: one thread = 8 consecutive channels of a token group --------------
+template <int DT, bool UNPACK>
+__global__ void __launch_bounds__(kQT) pack_channel_kernel(QXParams q)
+{
+    const QGParams &p = q.g;
+    const int g = blockIdx.x, r0 = g * q.tgroup, b = blockIdx.y;
+    const int c8 = (blockIdx.z * kQT + threadIdx.x) * 8;
+    if (c8 >= p.n) return;
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int ngroups = (p.out_rows + q.tgroup - 1) / q.tgroup;
+    float *qp = q.qparams + (((size_t)b * ngroups + g) * p.n + c8) * 2;
+    float mn[8], mx[8];
+    if (UNPACK) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { mn[e] = qp[2 * e]; mx[e] = qp[2 * e + 1]; }
+    } else {
+        unsigned nanmask = 0;
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { mn[e] = INFINITY; mx[e] = -INFINITY; }
+        for (int j = 0; j < q.tgroup; ++j) {
+            const int r = r0 + j;
+            if (r >= cnt || r >= p.out_rows) break;
+            any = true;
+            const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+            const int64_t src = ((int64_t)b * p.S + tok) * p.n + c8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float v = load_elem<DT>(p.x[0], src + e);
+                nanmask |= (unsigned)(v != v) << e;
+                mn[e] = fminf(mn[e], v); mx[e] = fmaxf(mx[e], v);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if ((nanmask >> e) & 1) mn[e] = mx[e] = __int_as_float(0x7fc00000);
+            if (!any) mn[e] = mx[e] = 0.0f;
+            qp[2 * e] = mn[e]; qp[2 * e + 1] = mx[e];
+        }
+    }
+    for (int j = 0; j < q.tgroup; ++j) {
+        const int r = r0 + j;
+        if (r >= p.out_rows) break;
+        const size_t orow = (size_t)b * p.out_rows + r;
+        if (r >= cnt) {
+            if (UNPACK && p.zero_pad)
+                for (int e = 0; e < 8; ++e) store_elem<DT>(p.y[0], (int64_t)orow * p.n + c8 + e, 0.0f);
+            continue;                                 // packing: codes were zeroed by the host-side memset
+        }
+        const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+        const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+        const float qmax_r = qmax_rounded<DT>(bits);
+        uint8_t *row = q.codes + orow * (size_t)q.row_bytes;
+        unsigned long long acc = 0;
+        if (UNPACK && bits <= 8)
+            for (int i = 0; i < bits; ++i) acc |= (unsigned long long)row[(size_t)c8 * bits / 8 + i] << (8 * i);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float scale, zp;
+            quant_params<DT>(mn[e], mx[e], bits, scale, zp);
+            if (UNPACK) {
+                const unsigned code = bits > 8 ? ((const uint16_t *)row)[c8 + e]
+                                               : (unsigned)((acc >> (e * bits)) & ((1ull << bits) - 1ull));
+                store_elem<DT>(p.y[0], (int64_t)orow * p.n + c8 + e, dequant_code<DT>((float)code, scale, zp));
+            } else {
+                const float qf = quant_code<DT>(load_elem<DT>(p.x[0], ((int64_t)b * p.S + tok) * p.n + c8 + e), scale, zp, qmax_r);
+                const unsigned code = qf == qf ? (unsigned)qf : 0u;
+                if (bits > 8) ((uint16_t *)row)[c8 + e] = (uint16_t)code;
+                else acc |= (unsigned long long)code << (e * bits);
+            }
+        }
+        if (!UNPACK && bits <= 8)
+            for (int i = 0; i < bits; ++i) row[(size_t)c8 * bits / 8 + i] = (uint8_t)(acc >> (8 * i));
+    }
+}
+
+__global__ void zero_counts_kernel(int32_t *oc, int64_t rows, int t)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) oc[i * 2 + t] = 0;
+}
+
+template <int DT> static int launch_ex(QXParams q, int mode, cudaStream_t st)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    const QGParams &p = q.g;
+    const bool aligned = p.n % EPV == 0 && (uintptr_t)p.x[q.t] % 16 == 0 && (uintptr_t)p.y[q.t] % 16 == 0;
+    if (mode == RTKV_Q_CHANNEL) {
+        const int ngroups = (p.out_rows + q.tgroup - 1) / q.tgroup;
+        if (q.ocount) {
+            const int64_t rows = (int64_t)p.B * p.out_rows;
+            zero_counts_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(q.ocount, rows, q.t);
+        }
+        if (aligned) {
+            dim3 grid(ngroups, p.B, (p.n / EPV + kQT - 1) / kQT);
+            void (*kern)(QXParams) = quant_channel_kernel<DT, 32>;
+            if (q.tgroup <= 8) kern = quant_channel_kernel<DT, 8>;
+            else if (q.tgroup <= 16) kern = quant_channel_kernel<DT, 16>;
+            RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, q));
+        } else {
+            dim3 grid(ngroups, p.B, (p.n + kQT - 1) / kQT);
+            quant_channel_generic_kernel<DT><<<grid, kQT, 0, st>>>(q);
+        }
+        RTKV_LAUNCH_CHECK("quant_channel_kernel");
+        return RTKV_OK;
+    }
+    dim3 grid(p.out_rows, p.B, 1);
+    int lanes = -1;
+    if (aligned && p.n <= kMaxVec * kQT * EPV) {
+        if (q.group == p.n) lanes = 0;
+        else if (q.group % EPV == 0) {
+            const int l = q.group / EPV;
+            if (l <= 32 && (l & (l - 1)) == 0) lanes = l;
+        }
+    }
+    if (lanes >= 0) {
+        q.lanes = lanes;
+        const int nv = (p.n / EPV + kQT - 1) / kQT;
+        void (*kern)(QXParams) = quant_token_ex_kernel<DT, kMaxVec>;
+        if (nv <= 1) kern = quant_token_ex_kernel<DT, 1>;
+        else if (nv <= 2) kern = quant_token_ex_kernel<DT, 2>;
+        else if (nv <= 4) kern = quant_token_ex_kernel<DT, 4>;
+        else if (nv <= 5) kern = quant_token_ex_kernel<DT, 5>;
+        RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, q));
+    } else {
+        quant_token_ex_generic_kernel<DT><<<grid, kQT, 0, st>>>(q);
+    }
+    RTKV_LAUNCH_CHECK("quant_token_ex_kernel");
+    return RTKV_OK;
+}
+
+static int check_options(const rtkv_quant_options *o, int n, int ntensors, const char *who)
+{
+    for (int t = 0; t < ntensors; ++t) {
+        const int m = o->mode[t];
+        if (m < RTKV_Q_TOKEN || m > RTKV_Q_CHANNEL) { set_error("%s: mode[%d]=%d", who, t, m); return RTKV_EINVAL; }
+        if (m == RTKV_Q_TOKEN_GROUP && (o->group_size < 1 || n % o->group_size != 0)) {
+            set_error("%s: group_size %d does not divide n=%d", who, o->group_size, n);
+            return RTKV_EINVAL;
+        }
+        if (m == RTKV_Q_CHANNEL && (o->token_group < 1 || o->token_group > 32)) {
+            set_error("%s: token_group %d outside 1..32", who, o->token_group);
+            return RTKV_EINVAL;
+        }
+    }
+    if (o->outlier_tau_q8 != 0 && o->outlier_tau_q8 < 256) {
+        set_error("%s: outlier_tau_q8 %d: tau must be >= 1 (256)", who, o->outlier_tau_q8);
+        return RTKV_EINVAL;
+    }
+    return RTKV_OK;
+}
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+extern "C" int rtkv_quant_groups(int n, const rtkv_quant_options *o, int tensor)
+{
+    if (n <= 0 || tensor < 0 || tensor > 1) return -1;
+    if (!o || o->mode[tensor] == RTKV_Q_TOKEN) return 1;
+    if (o->mode[tensor] == RTKV_Q_TOKEN_GROUP) return (o->group_size > 0 && n % o->group_size == 0) ? n / o->group_size : -1;
+    return n;
+}
+
+extern "C" int rtkv_quant_gather_ex(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                    const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                    const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                    const rtkv_quant_options *opt, void *Y0, void *Y1, int32_t *outlier_counts,
+                                    void *stream)
+{
+    RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1), "rtkv_quant_gather_ex: null pointer");
+    RTKV_CHECK_ARG(labels && bits, "rtkv_quant_gather_ex: labels and bits are required");
+    RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather_ex: bad dtype %d", dtype);
+    RTKV_CHECK_ARG(B > 0 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather_ex: bad shape");
+    RTKV_CHECK_ARG(B <= 65535, "rtkv_quant_gather_ex: B > 65535");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_ex: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_ex: out_rows > S without sel_idx");
+    int rc = rtkv_check_bits(bits, dtype, "rtkv_quant_gather_ex");
+    if (rc) return rc;
+    rtkv_quant_options o = {};
+    if (opt) o = *opt;
+    const int nt = X1 ? 2 : 1;
+    rc = check_options(&o, n, nt, "rtkv_quant_gather_ex");
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool plain = o.outlier_tau_q8 == 0 && o.mode[0] == RTKV_Q_TOKEN && (nt == 1 || o.mode[1] == RTKV_Q_TOKEN);
+    if (plain) {       // the reference's semantics: the K3 kernel itself
+        if (outlier_counts) RTKV_CUDA(cudaMemsetAsync(outlier_counts, 0, (size_t)B * out_rows * 2 * sizeof(int32_t), st));
+        return rtkv_quant_gather(X0, X1, dtype, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1, stream);
+    }
+    if (outlier_counts && nt == 1)
+        RTKV_CUDA(cudaMemsetAsync(outlier_counts, 0, (size_t)B * out_rows * 2 * sizeof(int32_t), st));
+    QXParams q = {};
+    fill_params(q.g, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    q.tgroup = o.token_group; q.ocount = outlier_counts;
+    for (int t = 0; t < nt; ++t) {
+        q.t = t;
+        const int m = o.mode[t];
+        q.group = m == RTKV_Q_TOKEN_GROUP ? o.group_size : n;
+        q.tau_q8 = m == RTKV_Q_CHANNEL ? 0u : (unsigned)o.outlier_tau_q8;
+        RTKV_DISPATCH(dtype, rc = launch_ex<DT>(q, m, st));
+        if (rc) return rc;
+    }
+    return RTKV_OK;
+}
+
+static int pack_ex_common(QXParams &q, const char *who, const void *X, void *Y, int dtype, int B, int S, int n,
+                          const int32_t *sel_idx, const rtkv_row_stats *row_stats, const uint8_t *labels,
+                          const int32_t *bits, int out_rows, int64_t row_bytes, const rtkv_quant_options *opt, int tensor,
+                          const uint8_t *codes, const float *qparams, const int32_t *out_idx, const float *out_val,
+                          const int32_t *out_cnt, int cap, int *mode)
+{
+    RTKV_CHECK_ARG(codes && qparams && labels && bits, "%s: null pointer", who);
+    RTKV_CHECK_ARG(dtype_ok(dtype), "%s: bad dtype %d", who, dtype);
+    RTKV_CHECK_ARG(B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "%s: bad shape", who);
+    RTKV_CHECK_ARG(tensor == 0 || tensor == 1, "%s: tensor must be 0 or 1", who);
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "%s: sel_idx needs row_stats", who);
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "%s: out_rows > S without sel_idx", who);
+    int rc = rtkv_check_bits(bits, dtype, who);
+    if (rc) return rc;
+    int mb = 0;
+    for (int c = 0; c < 3; ++c) {
+        const int bb = bits[c];
+        if (!(bb == 1 || bb == 2 || bb == 4 || bb == 8 || (bb > 8 && bb <= 16))) {
+            set_error("%s: packed rows need bits in {1,2,4,8,9..16}, got %d", who, bb);
+            return RTKV_EUNSUPPORTED;
+        }
+        if (dtype == RTKV_BF16 && bb == 16) { set_error("%s: 16-bit codes are not representable for bf16 rows", who); return RTKV_EUNSUPPORTED; }
+        mb = bb > mb ? bb : mb;
+    }
+    RTKV_CHECK_ARG(row_bytes >= rtkv_packed_row_bytes(n, mb), "%s: row_bytes too small", who);
+    rtkv_quant_options o = {};
+    if (opt) o = *opt;
+    if (tensor == 1) o.mode[0] = o.mode[1];
+    rc = check_options(&o, n, 1, who);
+    if (rc) return rc;
+    *mode = o.mode[0];
+    q = QXParams{};
+    fill_params(q.g, X, nullptr, B, S, n, sel_idx, row_stats, labels, bits, out_rows, 1, Y, nullptr);
+    q.t = 0;
+    q.group = *mode == RTKV_Q_TOKEN_GROUP ? o.group_size : n;
+    q.tgroup = o.token_group;
+    q.tau_q8 = *mode == RTKV_Q_CHANNEL ? 0u : (unsigned)o.outlier_tau_q8;
+    q.row_bytes = row_bytes; q.codes = (uint8_t *)codes; q.qparams = (float *)qparams;
+    q.out_idx = (int32_t *)out_idx; q.out_val = (float *)out_val; q.out_cnt = (int32_t *)out_cnt; q.cap = cap;
+    if (*mode == RTKV_Q_CHANNEL) {
+        if (n % 8 != 0) { set_error("%s: RTKV_Q_CHANNEL packing needs n %% 8 == 0", who); return RTKV_EUNSUPPORTED; }
+    } else {
+        if (*mode == RTKV_Q_TOKEN_GROUP && o.group_size % 8 != 0) {
+            set_error("%s: packed group_size must be a multiple of 8", who);
+            return RTKV_EUNSUPPORTED;
+        }
+        if (n / q.group > 1024) { set_error("%s: more than 1024 groups per row", who); return RTKV_EUNSUPPORTED; }
+        if (q.tau_q8) RTKV_CHECK_ARG(out_idx && out_val && out_cnt && cap > 0, "%s: outlier split needs out_idx/out_val/out_cnt and a cap", who);
+        else { q.out_idx = nullptr; q.out_val = nullptr; q.cap = 0; }
+    }
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,
+                                  const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                  const uint8_t *labels, const int32_t *bits, int out_rows, int64_t row_bytes,
+                                  const rtkv_quant_options *opt, int tensor, uint8_t *codes, float *qparams,
+                                  int32_t *out_idx, float *out_val, int32_t *out_cnt, int cap, void *stream)
+{
+    RTKV_CHECK_ARG(X, "rtkv_quant_pack_ex: null pointer");
+    QXParams q;
+    int mode = 0;
+    int rc = pack_ex_common(q, "rtkv_quant_pack_ex", X, nullptr, dtype, B, S, n, sel_idx, row_stats, labels, bits, out_rows,
+                            row_bytes, opt, tensor, codes, qparams, out_idx, out_val, out_cnt, cap, &mode);
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RTKV_CUDA(cudaMemsetAsync(codes, 0, (size_t)B * out_rows * (size_t)row_bytes, st));
+    if (mode == RTKV_Q_CHANNEL) {
+        if (out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
+        dim3 grid((out_rows + q.tgroup - 1) / q.tgroup, B, (n / 8 + kQT - 1) / kQT);
+        RTKV_DISPATCH(dtype, (pack_channel_kernel<DT, false><<<grid, kQT, 0, st>>>(q)));
+    } else {
+        if (!q.tau_q8 && out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
+        if (!q.tau_q8) q.out_cnt = nullptr;
+        const size_t smem = (size_t)(n / q.group) * sizeof(GroupRec);
+        RTKV_DISPATCH(dtype, (quant_pack_ex_kernel<DT><<<dim3(out_rows, B), kQT, smem, st>>>(q)));
+    }
+    RTKV_LAUNCH_CHECK("rtkv_quant_pack_ex");
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_unpack_dequant_ex(const uint8_t *codes, const float *qparams, const int32_t *out_idx,
+                                      const float *out_val, const int32_t *out_cnt, int cap,
+                                      int dtype, int B, int S, int n,
+                                      const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                      const uint8_t *labels, const int32_t *bits, int out_rows, int64_t row_bytes,
+                                      const rtkv_quant_options *opt, int tensor, void *Y, void *stream)
+{
+    RTKV_CHECK_ARG(Y, "rtkv_unpack_dequant_ex: null pointer");
+    QXParams q;
+    int mode = 0;
+    int rc = pack_ex_common(q, "rtkv_unpack_dequant_ex", nullptr, Y, dtype, B, S, n, sel_idx, row_stats, labels, bits, out_rows,
+                            row_bytes, opt, tensor, codes, qparams, out_idx, out_val, out_cnt, cap, &mode);
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == RTKV_Q_CHANNEL) {
+        dim3 grid((out_rows + q.tgroup - 1) / q.tgroup, B, (n / 8 + kQT - 1) / kQT);
+        RTKV_DISPATCH(dtype, (pack_channel_kernel<DT, true><<<grid, kQT, 0, st>>>(q)));
+    } else {
+        if (!q.tau_q8) q.out_cnt = nullptr;
+        RTKV_DISPATCH(dtype, (unpack_dequant_ex_kernel<DT><<<dim3(out_rows, B), kQT, 0, st>>>(q)));
+    }
+    RTKV_LAUNCH_CHECK("rtkv_unpack_dequant_ex");
+    return RTKV_OK;
+}

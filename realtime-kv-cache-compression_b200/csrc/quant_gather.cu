@@ -13,54 +13,9 @@
 // registers (up to kMaxVec 16-byte vectors per thread), so the min/max pass and
 // the quantise pass cost no extra memory traffic.  Loads/stores are 128-bit,
 // coalesced, streaming (L1::no_allocate).
-#include "common.cuh"
+#include "quant_common.cuh"
 
 namespace rtkv {
-
-constexpr int kQT = 256;     // threads per row CTA
-constexpr int kMaxVec = 8;   // 16-byte vectors per thread held in registers
-
-struct QGParams {
-    const void *x[2];
-    void *y[2];
-    const int32_t *sel_idx;
-    const rtkv_row_stats *row_stats;
-    const uint8_t *labels;
-    int B, S, n, out_rows, zero_pad, quantize;
-    int bits[3];
-    int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
-    const float *ext_minmax;  // [B,out_rows,4] = (min0, max0, min1, max1) of the WHOLE row (head sharding) or NULL
-    int neg_max;              // the max entries are stored negated (so that one MIN all-reduce combines ranks)
-    // fused peer exchange (rtkv_quant_gather_p2p): mailbox of rank s as mapped into this process
-    unsigned long long mbox[8];
-    unsigned *p2p_state;      // [0] epoch of the last finished call, [1] finished-CTA counter
-    int rank, world, total_ctas;
-};
-
-// no dynamic indexing of the by-value parameter struct (keeps it out of local memory)
-__device__ __forceinline__ int pick_bits(const QGParams &p, int label)
-{
-    return label == 0 ? p.bits[0] : (label == 1 ? p.bits[1] : p.bits[2]);
-}
-__device__ __forceinline__ const void *pick_x(const QGParams &p, int t) { return t ? p.x[1] : p.x[0]; }
-__device__ __forceinline__ void *pick_y(const QGParams &p, int t) { return t ? p.y[1] : p.y[0]; }
-
-// block-wide min / max / any-NaN over kQT threads
-__device__ __forceinline__ void block_minmax(float &mn, float &mx, int nan, float *red)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    mn = warp_min(mn); mx = warp_max(mx);
-    if (lane == 0) { red[warp] = mn; red[8 + warp] = mx; }
-    const int any_nan = __syncthreads_or(nan);
-    float a = red[lane & 7], z = red[8 + (lane & 7)];
-#pragma unroll
-    for (int o = 4; o; o >>= 1) {
-        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        z = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, o));
-    }
-    mn = a; mx = z;
-    if (any_nan) mn = mx = __int_as_float(0x7fc00000); // torch.min/max propagate NaN
-}
 
 // NV = 16-byte vectors per thread (n <= NV * kQT * elems_per_vec, n % elems_per_vec == 0)
 template <int DT, int NV>
@@ -524,46 +479,9 @@ __global__ void __launch_bounds__(kQT) unpack_dequant_kernel(QGParams p, int64_t
     }
 }
 
-static int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S, int n,
-                       const int32_t *sel_idx, const rtkv_row_stats *row_stats, const uint8_t *labels,
-                       const int32_t *bits, int out_rows, int zero_pad, void *Y0, void *Y1)
-{
-    p.x[0] = X0; p.x[1] = X1; p.y[0] = Y0; p.y[1] = Y1;
-    p.sel_idx = sel_idx; p.row_stats = row_stats; p.labels = labels;
-    p.B = B; p.S = S; p.n = n; p.out_rows = out_rows; p.zero_pad = zero_pad;
-    p.quantize = (labels != nullptr && bits != nullptr);
-    for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
-    p.row_begin = 0; p.b_begin = 0;
-    p.ext_minmax = nullptr; p.neg_max = 0;
-    for (int i = 0; i < 8; ++i) p.mbox[i] = 0;
-    p.p2p_state = nullptr; p.rank = 0; p.world = 1; p.total_ctas = 0;
-    return RTKV_OK;
-}
-
 } // namespace rtkv
 
 using namespace rtkv;
-
-#define RTKV_DISPATCH(dt, CALL)                                 \
-    switch (dt) {                                               \
-    case RTKV_F32: { constexpr int DT = RTKV_F32; CALL; } break; \
-    case RTKV_F16: { constexpr int DT = RTKV_F16; CALL; } break; \
-    default: { constexpr int DT = RTKV_BF16; CALL; } break;      \
-    }
-
-static int check_bits(const int32_t *bits, int dtype, const char *who)
-{
-    if (!bits) return RTKV_OK;
-    for (int c = 0; c < 3; ++c) {
-        if (bits[c] < 1 || bits[c] > 24) { set_error("%s: bits[%d]=%d outside 1..24", who, c, bits[c]); return RTKV_EINVAL; }
-        // the reference raises here: torch.clamp(x, 0, 2^bits-1) overflows fp16 (dynamic_quantization.py:121)
-        if (dtype == RTKV_F16 && bits[c] >= 16) {
-            set_error("%s: value cannot be converted to type c10::Half without overflow (bits=%d)", who, bits[c]);
-            return RTKV_EUNSUPPORTED;
-        }
-    }
-    return RTKV_OK;
-}
 
 extern "C" int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int B, int S, int n,
                                  const int32_t *sel_idx, const rtkv_row_stats *row_stats,
@@ -576,7 +494,7 @@ extern "C" int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int 
     RTKV_CHECK_ARG(B <= 65535, "rtkv_quant_gather: B > 65535");
     RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather: sel_idx needs row_stats");
     RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather: out_rows > S without sel_idx");
-    int rc = check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather");
+    int rc = rtkv_check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather");
     if (rc) return rc;
     if (out_rows == 0) return RTKV_OK;
     QGParams p;
@@ -598,7 +516,7 @@ extern "C" int rtkv_quant_gather_range(const void *X0, const void *X1, int dtype
                    row_count >= 0 && row_begin + row_count <= out_rows, "rtkv_quant_gather_range: bad range");
     RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_range: sel_idx needs row_stats");
     RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_range: out_rows > S without sel_idx");
-    int rc = check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather_range");
+    int rc = rtkv_check_bits(labels ? bits : nullptr, dtype, "rtkv_quant_gather_range");
     if (rc) return rc;
     if (row_count == 0 || b_count == 0) return RTKV_OK;
     QGParams p;
@@ -639,7 +557,7 @@ extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtyp
     RTKV_CHECK_ARG(B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather_minmax: bad shape");
     RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_minmax: sel_idx needs row_stats");
     RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_minmax: out_rows > S without sel_idx");
-    int rc = check_bits(bits, dtype, "rtkv_quant_gather_minmax");
+    int rc = rtkv_check_bits(bits, dtype, "rtkv_quant_gather_minmax");
     if (rc) return rc;
     if (out_rows == 0) return RTKV_OK;
     QGParams p;
@@ -695,7 +613,7 @@ extern "C" int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, 
                    "rtkv_quant_gather_p2p: null pointer");
     RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows > 0, "rtkv_quant_gather_p2p: bad shape");
     RTKV_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "rtkv_quant_gather_p2p: bad rank/world");
-    int rc = check_bits(bits, dtype, "rtkv_quant_gather_p2p");
+    int rc = rtkv_check_bits(bits, dtype, "rtkv_quant_gather_p2p");
     if (rc) return rc;
     const int epv = 16 / dtype_bytes(dtype);
     if (n % epv != 0 || n > kMaxVec * kQT * epv || (uintptr_t)X0 % 16 || (uintptr_t)X1 % 16 || (uintptr_t)Y0 % 16 ||
@@ -721,7 +639,7 @@ extern "C" int rtkv_quant_params(const void *x, int dtype, int64_t numel, int bi
 {
     RTKV_CHECK_ARG(x && qparams && scratch && numel > 0 && dtype_ok(dtype), "rtkv_quant_params: bad argument");
     int32_t b3[3] = {bits, bits, bits};
-    int rc = check_bits(b3, dtype, "rtkv_quant_params");
+    int rc = rtkv_check_bits(b3, dtype, "rtkv_quant_params");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned *sc = (unsigned *)scratch + 16; // inside the 256-byte scratch header
@@ -738,7 +656,7 @@ extern "C" int rtkv_quantize_with_params(const void *x, int dtype, int64_t numel
 {
     RTKV_CHECK_ARG(x && y && qparams && numel > 0 && dtype_ok(dtype), "rtkv_quantize_with_params: bad argument");
     int32_t b3[3] = {bits, bits, bits};
-    int rc = check_bits(b3, dtype, "rtkv_quantize_with_params");
+    int rc = rtkv_check_bits(b3, dtype, "rtkv_quantize_with_params");
     if (rc) return rc;
     int64_t ctas = (numel + kQT * 4 - 1) / (kQT * 4);
     int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
@@ -774,7 +692,7 @@ extern "C" int rtkv_quant_pack(const void *X, int dtype, int B, int S, int n,
     RTKV_CHECK_ARG(X && labels && bits && codes && qparams, "rtkv_quant_pack: null pointer");
     RTKV_CHECK_ARG(dtype_ok(dtype) && B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_pack: bad shape");
     RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_pack: sel_idx needs row_stats");
-    int rc = check_bits(bits, dtype, "rtkv_quant_pack");
+    int rc = rtkv_check_bits(bits, dtype, "rtkv_quant_pack");
     if (!rc) rc = check_pack_bits(bits, "rtkv_quant_pack");
     if (rc) return rc;
     for (int c = 0; c < 3; ++c)

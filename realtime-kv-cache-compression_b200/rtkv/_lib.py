@@ -26,6 +26,15 @@ class LayerParams(ctypes.Structure):
                 ("fallback_topk", c_i32)]
 
 
+class QuantOptions(ctypes.Structure):
+    """rtkv_quant_options (include/rtkv.h): scale granularity per tensor + outlier split."""
+    _fields_ = [("mode", ctypes.c_int32 * 2), ("group_size", ctypes.c_int32), ("token_group", ctypes.c_int32),
+                ("outlier_tau_q8", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
+
+
+Q_TOKEN, Q_TOKEN_GROUP, Q_CHANNEL = 0, 1, 2
+
+
 class LayerStats(ctypes.Structure):
     """struct rtkv_layer_stats"""
     _fields_ = [("max_selected", c_i32), ("used_fallback", c_i32), ("reserved", c_i32 * 2)]
@@ -90,6 +99,18 @@ PROTOTYPES = {
     "rtkv_unpack_dequant": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, c_i64, c_vp,
                                            c_vp]),
+    "rtkv_quant_gather_ex": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(QuantOptions), c_vp, c_vp, c_vp, c_vp]),
+    "rtkv_quant_groups": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(QuantOptions), ctypes.c_int]),
+    "rtkv_quant_pack_ex": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
+                                          c_vp, ctypes.POINTER(c_i32), ctypes.c_int, c_i64,
+                                          ctypes.POINTER(QuantOptions), ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                          ctypes.c_int, c_vp]),
+    "rtkv_unpack_dequant_ex": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_i32),
+                                              ctypes.c_int, c_i64, ctypes.POINTER(QuantOptions), ctypes.c_int, c_vp,
+                                              c_vp]),
     "rtkv_debug_k2_timing": (ctypes.c_int, [c_vp]),
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),

@@ -374,6 +374,87 @@ def unpack_dequant(codes, qp, dtype, S, n, sel, labels, bits):
     return y
 
 
+_MODES = {"token": _lib.Q_TOKEN, "token_group": _lib.Q_TOKEN_GROUP, "channel": _lib.Q_CHANNEL}
+
+
+def quant_options(key_mode="token", value_mode="token", group_size=0, token_group=0, outlier_tau=0.0):
+    """rtkv_quant_options.  Modes: "token" (the reference: one scale per kept row), "token_group" (per row and
+    group of `group_size` channels), "channel" (per channel and group of `token_group` <= 32 kept rows).
+    outlier_tau > 0 splits elements with |x| > tau * mean|x| of their group (token modes)."""
+    o = _lib.QuantOptions()
+    o.mode[0] = _MODES[key_mode] if isinstance(key_mode, str) else int(key_mode)
+    o.mode[1] = _MODES[value_mode] if isinstance(value_mode, str) else int(value_mode)
+    o.group_size, o.token_group = int(group_size), int(token_group)
+    o.outlier_tau_q8 = int(round(float(outlier_tau) * 256))
+    return o
+
+
+def gather_rows(x, sel, out_rows, zero_pad=True):
+    """Coalesced gather of the kept rows of any [B,S,n] tensor (hidden states, K, V) into [B,out_rows,n]
+    in ascending token order (selective_propagation.py:213-232)."""
+    return quant_gather(x, None, sel, None, None, out_rows, zero_pad)[0]
+
+
+def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True, want_counts=False):
+    """quant_gather with extended scale granularities / outlier split (rtkv_quant_gather_ex)."""
+    require_cuda()
+    x0 = x0.contiguous()
+    B, S, n = x0.shape
+    if x1 is not None:
+        x1 = x1.contiguous()
+        assert x1.shape == x0.shape and x1.dtype == x0.dtype
+    y0 = torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device) if x1 is not None else None
+    oc = torch.empty(B, out_rows, 2, dtype=torch.int32, device=x0.device) if want_counts else None
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_quant_gather_ex(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,
+                                   _ptr(sel.sel_idx) if sel is not None else None,
+                                   sel.row_stats_ptr if sel is not None else None, _ptr(lab), _lib.bits3(bits),
+                                   int(out_rows), int(bool(zero_pad)), ctypes.byref(options) if options is not None else None,
+                                   _ptr(y0), _ptr(y1), _ptr(oc), _stream()))
+    return (y0, y1, oc) if want_counts else (y0, y1)
+
+
+def quant_pack_ex(x, sel, labels, bits, out_rows, options, tensor=0, outlier_cap=0):
+    """Packed codes with options -> dict(codes, qparams, out_idx, out_val, out_cnt, row_bytes)."""
+    require_cuda()
+    x = x.contiguous()
+    B, S, n = x.shape
+    rb = packed_row_bytes(n, max(bits))
+    mode = options.mode[tensor]
+    dev = x.device
+    codes = torch.empty(B, out_rows, rb, dtype=torch.uint8, device=dev)
+    if mode == _lib.Q_CHANNEL:
+        qp = torch.empty(B, (out_rows + options.token_group - 1) // options.token_group, n, 2, dtype=torch.float32, device=dev)
+    else:
+        qp = torch.empty(B, out_rows, lib.rtkv_quant_groups(n, ctypes.byref(options), tensor), 2, dtype=torch.float32, device=dev)
+    split = mode != _lib.Q_CHANNEL and options.outlier_tau_q8 > 0
+    cap = int(outlier_cap) if split else 0
+    oi = torch.empty(B, out_rows, cap, dtype=torch.int32, device=dev) if split else None
+    ov = torch.empty(B, out_rows, cap, dtype=torch.float32, device=dev) if split else None
+    ocnt = torch.empty(B, out_rows, dtype=torch.int32, device=dev) if split else None
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_quant_pack_ex(_ptr(x), dtype_code(x), B, S, n, _ptr(sel.sel_idx) if sel is not None else None,
+                                 sel.row_stats_ptr if sel is not None else None, _ptr(lab), _lib.bits3(bits),
+                                 int(out_rows), rb, ctypes.byref(options), int(tensor), _ptr(codes), _ptr(qp),
+                                 _ptr(oi), _ptr(ov), _ptr(ocnt), cap, _stream()))
+    return dict(codes=codes, qparams=qp, out_idx=oi, out_val=ov, out_cnt=ocnt, cap=cap)
+
+
+def unpack_dequant_ex(packed, dtype, S, n, sel, labels, bits, options, tensor=0):
+    require_cuda()
+    codes = packed["codes"]
+    B, out_rows, rb = codes.shape
+    y = torch.empty(B, out_rows, n, dtype=dtype, device=codes.device)
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_unpack_dequant_ex(_ptr(codes), _ptr(packed["qparams"]), _ptr(packed["out_idx"]),
+                                     _ptr(packed["out_val"]), _ptr(packed["out_cnt"]), int(packed["cap"]),
+                                     dtype_code(dtype), B, S, n, _ptr(sel.sel_idx) if sel is not None else None,
+                                     sel.row_stats_ptr if sel is not None else None, _ptr(lab), _lib.bits3(bits),
+                                     int(out_rows), rb, ctypes.byref(options), int(tensor), _ptr(y), _stream()))
+    return y
+
+
 class HostContext:
     """rtkv_ctx: device staging buffers for the host-buffer entry point."""
 
@@ -409,12 +490,12 @@ class HostContext:
             v_out = torch.empty(B * S * n, dtype=K.dtype)
         scores = labels = mask = None
         if want_aux:
-            n = B * S
-            if self._aux is None or self._aux.numel() < 6 * n:
-                self._aux = torch.empty(6 * n, dtype=torch.uint8, pin_memory=True)
-            scores = self._aux[: 4 * n].view(torch.float32).view(B, S)
-            labels = self._aux[4 * n: 5 * n].view(B, S)
-            mask = self._aux[5 * n: 6 * n].view(B, S)
+            bs = B * S
+            if self._aux is None or self._aux.numel() < 6 * bs:
+                self._aux = torch.empty(6 * bs, dtype=torch.uint8, pin_memory=True)
+            scores = self._aux[: 4 * bs].view(torch.float32).view(B, S)
+            labels = self._aux[4 * bs: 5 * bs].view(B, S)
+            mask = self._aux[5 * bs: 6 * bs].view(B, S)
         rows = np.zeros(B, dtype=_lib.ROW_STATS)
         layer = _lib.LayerStats()
         ms = ctypes.c_int32(0)
