@@ -8,8 +8,8 @@ from .config import CompressionConfig
 from .dynamic_quantization import DynamicPrecisionQuantizer
 from .selective_propagation import SelectiveTokenPropagator
 from .token_importance import LayerWiseImportanceTracker, PromptGuidedImportanceScorer
-from .unified_compressor import CompressionHook, RealTimePrefillCompressor, UnifiedCompressor
+from .unified_compressor import CompressionHook, PackedKV, RealTimePrefillCompressor, UnifiedCompressor
 
-__all__ = ["CompressionConfig", "DynamicPrecisionQuantizer", "SelectiveTokenPropagator",
+__all__ = ["CompressionConfig", "PackedKV", "DynamicPrecisionQuantizer", "SelectiveTokenPropagator",
            "LayerWiseImportanceTracker", "PromptGuidedImportanceScorer", "CompressionHook",
            "RealTimePrefillCompressor", "UnifiedCompressor"]

@@ -45,6 +45,14 @@ class CompressionConfig:
     quality_loss_tolerance: float = 0.05
     context_lengths: Optional[List[int]] = None
     batch_sizes: Optional[List[int]] = None
+    # extensions (no reference counterpart; the defaults ARE the reference: one scale per token row, no outlier
+    # split).  Modes: "token", "token_group" (per row and group of quant_group_size channels), "channel" (per channel
+    # and group of quant_token_group <= 32 kept rows).  outlier_tau > 0: |x| > tau * mean|x| of the group is kept exactly.
+    key_quant_mode: str = "token"
+    value_quant_mode: str = "token"
+    quant_group_size: int = 128
+    quant_token_group: int = 32
+    outlier_tau: float = 0.0
 
     def __post_init__(self):
         if self.layer_weights is None:
@@ -53,6 +61,10 @@ class CompressionConfig:
             self.context_lengths = [4096, 8192, 16384, 32768]
         if self.batch_sizes is None:
             self.batch_sizes = [1, 4, 8]
+
+    @property
+    def extended_quantization(self):
+        return self.key_quant_mode != "token" or self.value_quant_mode != "token" or self.outlier_tau > 0
 
     @property
     def bits(self):

@@ -47,6 +47,41 @@ def _precision_stats(rows, n_tokens):
             "high_ratio": high / n_tokens, "medium_ratio": medium / n_tokens, "low_ratio": low / n_tokens}
 
 
+class PackedKV:
+    """One layer's kept K/V rows as packed codes: codes [B,S',row_bytes] u8 (bits per row by label), scale
+    parameters, optional outlier lists, the kept token positions (sel.sel_idx, ascending) and labels."""
+
+    def __init__(self, keys, values, sel, max_selected, bits, options, dtype, seq_len, width, rows, layer_idx, ratio):
+        self.keys, self.values, self.sel, self.max_selected = keys, values, sel, max_selected
+        self.bits, self.options, self.dtype, self.seq_len, self.width = bits, options, dtype, seq_len, width
+        self.rows, self.layer_idx, self.ratio = rows, layer_idx, ratio
+
+    def nbytes(self):
+        """Bytes of the useful part of the packed representation (each kept row at ITS bit width + parameters
+        + outlier lists + positions), the number the container would occupy when rows are stored back to back."""
+        total = 0
+        lab = self.sel.labels.cpu().numpy()
+        idx = self.sel.sel_idx.cpu().numpy()
+        for b in range(lab.shape[0]):
+            c = int(self.rows["n_selected"][b])
+            for cls in range(3):
+                k = int((lab[b][idx[b, :c]] == cls).sum())
+                total += 2 * k * ops.packed_row_bytes(self.width, self.bits[cls])
+            total += 4 * c
+        for p in (self.keys, self.values):
+            total += p["qparams"].numel() * 4
+            if p["out_cnt"] is not None:
+                total += int(p["out_cnt"].sum()) * 8 + p["out_cnt"].numel() * 4
+        return total
+
+    def dequantize(self):
+        k = ops.unpack_dequant_ex(self.keys, self.dtype, self.seq_len, self.width, self.sel, self.sel.labels, self.bits,
+                                  self.options, tensor=0)
+        v = ops.unpack_dequant_ex(self.values, self.dtype, self.seq_len, self.width, self.sel, self.sel.labels,
+                                  self.bits, self.options, tensor=1)
+        return k, v
+
+
 class RealTimePrefillCompressor:
     """reference: unified_compressor.py:12-247"""
 
@@ -88,6 +123,14 @@ class RealTimePrefillCompressor:
     def _bits(self):
         c = self.config
         return (c.low_precision_bits, c.medium_precision_bits, c.high_precision_bits)
+
+    def _quant_options(self):
+        """rtkv_quant_options when the config asks for an extended mode, else None (reference semantics)."""
+        c = self.config
+        if not getattr(c, "extended_quantization", False):
+            return None
+        return ops.quant_options(c.key_quant_mode, c.value_quant_mode, c.quant_group_size, c.quant_token_group,
+                                 c.outlier_tau)
 
     def _stats_buffer(self, nbytes):
         if self._pinned is None or self._pinned.numel() < nbytes:
@@ -134,12 +177,20 @@ class RealTimePrefillCompressor:
             layer = raw[: ops.LAYER_STATS_BYTES].view(ops._lib.LAYER_STATS)[0]
             rows = raw[ops.LAYER_STATS_BYTES:].view(ops._lib.ROW_STATS).copy()
             max_selected = int(layer["max_selected"])
-            selected_keys, selected_values = ops.quant_gather(
-                key_states, value_states, sel, sel.labels, self._bits(), max_selected)
+            qopt = self._quant_options()
+            if qopt is None:
+                selected_keys, selected_values = ops.quant_gather(
+                    key_states, value_states, sel, sel.labels, self._bits(), max_selected)
+            else:
+                selected_keys, selected_values = ops.quant_gather_ex(
+                    key_states, value_states, sel, sel.labels, self._bits(), max_selected, qopt)
             scores_cpu = h_scores.clone()
             labels_np = h_labels.numpy().astype(np.int64)
             selection_mask = sel.mask.view(torch.bool)
         else:
+            if self._quant_options() is not None:
+                raise NotImplementedError("extended quantisation modes need CUDA tensors (rtkv_compress_layer_host "
+                                          "implements the reference's per-token scales only)")
             if self._host_ctx is None:
                 self._host_ctx = ops.HostContext()
             out = self._host_ctx.compress_layer(key_states, value_states, attention_weights, params,
@@ -180,6 +231,26 @@ class RealTimePrefillCompressor:
 
     # BASELINE.json wording
     compress = compress_layer_kv_cache
+
+    def compress_layer_kv_cache_packed(self, key_states, value_states, attention_weights, input_ids, layer_idx,
+                                       outlier_cap=32):
+        """Same selection as compress_layer_kv_cache, but the kept rows are stored as packed integer codes
+        (PackedKV) instead of dequantised floats: this is where the memory saving becomes real (the reference
+        keeps full-width floats).  PackedKV.dequantize() gives back the tensors
+        compress_layer_kv_cache returns (up to the sign of zeros)."""
+        B, S, HD = key_states.shape
+        P = self.prompt_length(input_ids.shape[1])
+        params, ratio = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
+        params.prompt_len = P
+        mass = ops.prompt_mass(attention_weights, prompt_len=P)
+        sel = ops.score_select(params, B, S, key_states.device, mass=mass)
+        layer, rows = sel.read_stats()
+        ms = int(layer["max_selected"])
+        qopt = self._quant_options() or ops.quant_options()
+        bits = self._bits()
+        pk = ops.quant_pack_ex(key_states, sel, sel.labels, bits, ms, qopt, tensor=0, outlier_cap=outlier_cap)
+        pv = ops.quant_pack_ex(value_states, sel, sel.labels, bits, ms, qopt, tensor=1, outlier_cap=outlier_cap)
+        return PackedKV(pk, pv, sel, ms, bits, qopt, key_states.dtype, S, HD, rows, layer_idx, ratio)
 
     def compress_layer_kv_cache_async(self, key_states, value_states, attention_weights, layer_idx,
                                       out_keys, out_values, zero_pad=False, prefetch_stream=None,

@@ -245,3 +245,63 @@ def test_hidden_state_gather(rt):
             c = int(rows["n_selected"][b])
             assert torch.equal(g[b, :c], h[b][mask[b]])
             assert int(g[b, c:].abs().sum()) == 0
+
+
+# ---------------------------------------------------------------- through the compressor
+def _layer(B=2, H=8, S=300, HD=512, seed=0):
+    from test_parity_gpu import synth_layer
+    return synth_layer(B, H, S, HD, seed)
+
+
+def test_compressor_with_extended_config(rt):
+    """key_quant_mode / value_quant_mode / outlier_tau on the config: same selection as the reference mode,
+    K/V quantised with the extended kernels (== the oracle on the kept rows)."""
+    rtkv, ops = rt
+    K, V, A, P = _layer()
+    B, S, HD = K.shape
+    base = dict(num_hidden_layers=8, num_attention_heads=8, hidden_size=HD, high_precision_bits=8,
+                medium_precision_bits=4, low_precision_bits=2)
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    ref = rtkv.RealTimePrefillCompressor(rtkv.CompressionConfig(**base))
+    k0, v0, info0 = ref.compress_layer_kv_cache(K, V, A, ids, 6)
+    cfg = rtkv.CompressionConfig(**base, key_quant_mode="channel", value_quant_mode="token_group", quant_group_size=64,
+                                 quant_token_group=16, outlier_tau=6.0)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    k1, v1, info1 = comp.compress_layer_kv_cache(K, V, A, ids, 6)
+    mask = info1["propagation_info"]["selection_mask"].cpu().numpy()
+    np.testing.assert_array_equal(mask, info0["propagation_info"]["selection_mask"].cpu().numpy())
+    labels = info1["quantization_info"]["bit_assignments"].astype(np.uint8)
+    ms = k1.shape[1]
+    wk, _ = oracle_dense(K.cpu(), oracle.F32, labels, mask, ms, (2, 4, 8), 2, 0, 16, 0.0)
+    wv, _ = oracle_dense(V.cpu(), oracle.F32, labels, mask, ms, (2, 4, 8), 1, 64, 0, 6.0)
+    same(k1, wk, oracle.F32)
+    same(v1, wv, oracle.F32)
+    # finer scales cannot be worse than one scale per row
+    kept = torch.from_numpy(mask.astype(bool)).cuda()
+    for b in range(B):
+        c = int(kept[b].sum())
+        e_ref = (v0[b, :c] - V[b][kept[b]]).abs().mean()
+        e_ext = (v1[b, :c] - V[b][kept[b]]).abs().mean()
+        assert float(e_ext) <= float(e_ref)
+    with pytest.raises(NotImplementedError):
+        comp.compress_layer_kv_cache(K.cpu(), V.cpu(), A.cpu(), ids.cpu(), 6)
+
+
+@pytest.mark.parametrize("extended", [False, True])
+def test_packed_container_roundtrip(rt, extended):
+    rtkv, ops = rt
+    K, V, A, P = _layer(seed=3)
+    B, S, HD = K.shape
+    kw = dict(num_hidden_layers=8, num_attention_heads=8, hidden_size=HD, high_precision_bits=8,
+              medium_precision_bits=4, low_precision_bits=2)
+    if extended:
+        kw.update(key_quant_mode="channel", value_quant_mode="token_group", quant_group_size=128, outlier_tau=5.0)
+    comp = rtkv.RealTimePrefillCompressor(rtkv.CompressionConfig(**kw))
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    k, v, info = comp.compress_layer_kv_cache(K, V, A, ids, 2)
+    packed = comp.compress_layer_kv_cache_packed(K, V, A, ids, 2, outlier_cap=64)
+    dk, dv = packed.dequantize()
+    assert packed.max_selected == k.shape[1]
+    assert torch.equal(dk, k) and torch.equal(dv, v)          # torch.equal: -0.0 == +0.0
+    dense_bytes = 2 * int(info["propagation_info"]["selection_mask"].sum()) * HD * 4
+    assert packed.nbytes() < dense_bytes / 3                  # 8/4/2-bit codes vs fp32 rows
