@@ -19,9 +19,10 @@ namespace rtkv {
 
 struct QXParams {
     QGParams g;
-    int t;              // tensor handled by this launch (0 = X0, 1 = X1)
+    int t;              // tensor handled by this launch (0 = X0, 1 = X1); -1: both, tensor = blockIdx.z (% 2)
     int group;          // token modes: channels per group (n for RTKV_Q_TOKEN)
     int lanes;          // token modes, vector kernel: 16-byte vectors per group (power of two <= 32), 0 = whole row
+    int group1, lanes1; // the same for X1 when t == -1
     int tgroup;         // channel mode: kept rows per group
     unsigned tau_q8;    // 0 = no outlier split
     int32_t *ocount;    // [B,out_rows,2] or NULL
@@ -70,7 +71,28 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 
 // ---- token modes, vector path -------------------------------------------------------------------
-template <int DT, int NV>
+// Issue-bound like K3 (ncu: K3 runs at 78 % issue utilisation), so instructions are what is budgeted here:
+// segment statistics are single REDUX instructions on order-preserving integer images of the floats (one
+// per slab and statistic, with the group's lane mask) instead of 5-step shuffle ladders, the outlier logic is
+// compiled out when tau == 0 (TAU), the threshold is a 32-bit compare against a cached per-element mask, and
+// the mean of a power-of-two group is a shift.
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+// threshold as a 32-bit number: magnitudes are < 2^31, so 0xffffffff means "no outliers in this group"
+__device__ __forceinline__ unsigned outlier_threshold(unsigned long long mean, unsigned tau_q8)
+{
+    const unsigned long long T = ((unsigned long long)tau_q8 * mean) >> 8;
+    return T > 0xfffffffeull ? 0xffffffffu : (unsigned)T;
+}
+
+template <int DT, int NV, bool TAU>
 __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
 {
     constexpr int EPV = Vec16<DT>::kElems;
@@ -79,7 +101,9 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
     __shared__ unsigned long long red_s[kQT / 32];
     __shared__ int s_count;
     const QGParams &p = q.g;
-    const int r = blockIdx.x, b = blockIdx.y, t = q.t;
+    const int r = blockIdx.x, b = blockIdx.y, t = q.t < 0 ? (int)blockIdx.z : q.t;
+    const int group = (q.t < 0 && t) ? q.group1 : q.group;
+    const int lanes = (q.t < 0 && t) ? q.lanes1 : q.lanes;
     pdl_wait();
     pdl_trigger();
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
@@ -103,10 +127,9 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
     if (oc && threadIdx.x == 0) s_count = 0;
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
     const float qmax_r = qmax_rounded<DT>(bits);
-    const bool tau_on = q.tau_q8 != 0;
     int n_out = 0;
 
-    if (q.lanes == 0) {
+    if (lanes == 0) {
         // ---- one group = the whole row: block-wide statistics
         int nan = 0;
         unsigned maxab = 0;
@@ -116,18 +139,15 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
                 float f[EPV];
                 Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
-                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); maxab = max(maxab, absbits(f[e])); }
+                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); if (TAU) maxab = max(maxab, absbits(f[e])); }
             }
         }
-        unsigned long long T = ~0ull;
-        unsigned E = 0;
-        bool use = false;
-        if (tau_on) {
+        unsigned T = 0xffffffffu, E = 0;
+        if (TAU) {
             maxab = block_max_u32(maxab, red_u);
             const int any_nan = __syncthreads_or(nan);
             E = maxab >> 23;
-            use = !any_nan && E > 0;
-            if (use) {
+            if (!any_nan && E > 0) {
                 unsigned long long sum = 0;
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
@@ -139,10 +159,11 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
                     }
                 }
                 sum = block_sum_u64(sum, red_s);
-                T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)p.n)) >> 8;
+                T = outlier_threshold(sum / (unsigned long long)p.n, q.tau_q8);
             }
         }
         float mn = INFINITY, mx = -INFINITY;
+        unsigned long long om = 0;                 // outlier bit per held element
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             if (threadIdx.x + k * kQT < nvec) {
@@ -150,7 +171,7 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
                 Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    if (use && mag_fix(absbits(f[e]), E) > T) continue;
+                    if (TAU && mag_fix(absbits(f[e]), E) > T) { om |= 1ull << (k * EPV + e); continue; }
                     mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]);
                 }
             }
@@ -166,68 +187,71 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
                 Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    if (use && mag_fix(absbits(f[e]), E) > T) { ++n_out; continue; }
+                    if (TAU && ((om >> (k * EPV + e)) & 1)) continue;
                     f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
                 }
                 stg_stream(dst + v, Vec16<DT>::pack(f));
             }
         }
+        if (TAU) n_out = __popcll(om);
     } else {
-        // ---- a group is q.lanes consecutive lanes of one 256-vector slab: xor-shuffle segments
-        const int lanes = q.lanes;
+        // ---- a group is `lanes` (power of two) consecutive lanes of one 256-vector slab
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned seg = lanes >= 32 ? 0xffffffffu : (((1u << lanes) - 1u) << (lane & ~(unsigned)(lanes - 1)));
+        const int gshift = 31 - __clz(group);     // group = lanes * EPV is a power of two
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int v = threadIdx.x + k * kQT;
-            const bool valid = v < nvec;          // uniform within a group (nvec is a multiple of lanes)
             float f[EPV];
             Vec16<DT>::unpack(raw[k], f);
             int nan = 0;
             unsigned maxab = 0;
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); maxab = max(maxab, absbits(f[e])); }
-            for (int o = lanes >> 1; o; o >>= 1) nan |= __shfl_xor_sync(0xffffffffu, nan, o);
-            unsigned long long T = ~0ull;
-            unsigned E = 0;
-            bool use = false;
-            if (tau_on) {
-                for (int o = lanes >> 1; o; o >>= 1) maxab = max(maxab, __shfl_xor_sync(0xffffffffu, maxab, o));
-                E = maxab >> 23;
-                use = !nan && E > 0;
+            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); if (TAU) maxab = max(maxab, absbits(f[e])); }
+            nan = (__ballot_sync(0xffffffffu, nan) & seg) != 0;
+            unsigned T = 0xffffffffu, E = 0;
+            if (TAU) {
+                E = __reduce_max_sync(seg, maxab) >> 23;
                 unsigned long long sum = 0;
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) sum += mag_fix(absbits(f[e]), E);
-                for (int o = lanes >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                T = ((unsigned long long)q.tau_q8 * (sum / (unsigned long long)q.group)) >> 8;
+                // exact 64-bit segment sum from two 32-bit REDUX adds (sum < 2^34 per lane)
+                const unsigned lo = __reduce_add_sync(seg, (unsigned)(sum & 0xfffffu));
+                const unsigned hi = __reduce_add_sync(seg, (unsigned)(sum >> 20));
+                sum = (unsigned long long)lo + ((unsigned long long)hi << 20);
+                if (!nan && E > 0) T = outlier_threshold(sum >> gshift, q.tau_q8);
             }
             float mn = INFINITY, mx = -INFINITY;
+            unsigned om = 0;
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
-                if (use && mag_fix(absbits(f[e]), E) > T) continue;
+                if (TAU && mag_fix(absbits(f[e]), E) > T) { om |= 1u << e; continue; }
                 mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]);
             }
-            for (int o = lanes >> 1; o; o >>= 1) {
-                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            }
+            mn = ord2f(__reduce_min_sync(seg, f2ord(mn)));
+            mx = ord2f(__reduce_max_sync(seg, f2ord(mx)));
             if (nan) mn = mx = __int_as_float(0x7fc00000);
-            float scale, zp;
-            quant_params<DT>(mn, mx, bits, scale, zp);
-            if (valid) {
+            if (v < nvec) {                        // uniform within a group (nvec is a multiple of lanes)
+                float scale, zp;
+                quant_params<DT>(mn, mx, bits, scale, zp);
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    if (use && mag_fix(absbits(f[e]), E) > T) { ++n_out; continue; }
+                    if (TAU && ((om >> e) & 1)) continue;
                     f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
                 }
                 stg_stream(dst + v, Vec16<DT>::pack(f));
+                if (TAU) n_out += __popc(om);
             }
         }
     }
-    if (oc) {
+    if (TAU && oc) {
         __syncthreads();                       // s_count = 0 is visible
         n_out = warp_sum(n_out);
         if ((threadIdx.x & 31) == 0 && n_out) atomicAdd(&s_count, n_out);
         __syncthreads();
         if (threadIdx.x == 0) *oc = s_count;
+    } else if (oc && threadIdx.x == 0) {
+        *oc = 0;
     }
 }
 
@@ -302,15 +326,32 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_generic_kernel(QXParams q)
 }
 
 // ---- channel mode -----------------------------------------------------------------------------
-// One thread = one 16-byte channel column of a group of <= GT kept rows (held in registers).
-template <int DT, int GT>
-__global__ void __launch_bounds__(kQT) quant_channel_kernel(QXParams q)
+// One thread = one 16-byte channel column of a group of <= GT kept rows.  The tile is staged in shared
+// memory with cp.async (global -> shared without passing through registers), so the kernel needs ~60
+// registers and many small CTAs stay resident per SM: one CTA's loads overlap another's arithmetic and
+// stores.  (The first version held the GT vectors in registers: 220 registers, 8 warps per SM, 18 % issue
+// utilisation, 0.3 of the HBM peak - profiles/README.md.)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int DT, int GT, int CT>
+__global__ void __launch_bounds__(CT) quant_channel_kernel(QXParams q)
 {
     constexpr int EPV = Vec16<DT>::kElems;
+    extern __shared__ __align__(16) unsigned char ch_smem[];
+    uint4 *tile = (uint4 *)ch_smem + threadIdx.x;          // [GT][CT] vectors, this thread's column
     __shared__ int s_tok[GT], s_cls[GT];
+    static_assert(CT >= GT, "CTA smaller than the token group");
     const QGParams &p = q.g;
-    const int r0 = blockIdx.x * q.tgroup, b = blockIdx.y, t = q.t;
-    const int v = blockIdx.z * kQT + threadIdx.x;
+    const int nslab = gridDim.z >> (q.t < 0 ? 1 : 0);
+    const int r0 = blockIdx.x * q.tgroup, b = blockIdx.y, t = q.t < 0 ? (int)(blockIdx.z / nslab) : q.t;
+    const int v = (blockIdx.z % nslab) * CT + threadIdx.x;
     pdl_wait();
     pdl_trigger();
     const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
@@ -329,19 +370,19 @@ __global__ void __launch_bounds__(kQT) quant_channel_kernel(QXParams q)
     const size_t row_b = (size_t)p.n * Elem<DT>::kBytes;
     const char *xb = (const char *)pick_x(p, t) + (size_t)b * p.S * row_b;
     char *yb = (char *)pick_y(p, t) + (size_t)b * p.out_rows * row_b;
-    uint4 raw[GT];
 #pragma unroll
     for (int j = 0; j < GT; ++j)
-        if (s_tok[j] >= 0) raw[j] = ldg_stream((const uint4 *)(xb + (size_t)s_tok[j] * row_b) + v);
+        if (s_tok[j] >= 0) cp_async16(tile + j * CT, (const uint4 *)(xb + (size_t)s_tok[j] * row_b) + v);
+    cp_async_wait_all();                                   // a thread only reads back what it copied itself
     float mn[EPV], mx[EPV];
     unsigned nanmask = 0;
 #pragma unroll
     for (int e = 0; e < EPV; ++e) { mn[e] = INFINITY; mx[e] = -INFINITY; }
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < GT; ++j) {
         if (s_tok[j] >= 0) {
             float f[EPV];
-            Vec16<DT>::unpack(raw[j], f);
+            Vec16<DT>::unpack(tile[j * CT], f);
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
                 nanmask |= (unsigned)(f[e] != f[e]) << e;
@@ -359,7 +400,7 @@ __global__ void __launch_bounds__(kQT) quant_channel_kernel(QXParams q)
         quant_params<DT>(mn[e], mx[e], p.bits[2], sc2[e], zp2[e]);
     }
     const float qm0 = qmax_rounded<DT>(p.bits[0]), qm1 = qmax_rounded<DT>(p.bits[1]), qm2 = qmax_rounded<DT>(p.bits[2]);
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < GT; ++j) {
         const int r = r0 + j;
         if (j >= q.tgroup || r >= p.out_rows) break;
@@ -371,12 +412,12 @@ __global__ void __launch_bounds__(kQT) quant_channel_kernel(QXParams q)
         const int cls = s_cls[j];
         const float qm = cls == 0 ? qm0 : (cls == 1 ? qm1 : qm2);
         float f[EPV];
-        Vec16<DT>::unpack(raw[j], f);
+        Vec16<DT>::unpack(tile[j * CT], f);
 #pragma unroll
         for (int e = 0; e < EPV; ++e) {
-            const float s = cls == 0 ? sc0[e] : (cls == 1 ? sc1[e] : sc2[e]);
+            const float sc = cls == 0 ? sc0[e] : (cls == 1 ? sc1[e] : sc2[e]);
             const float z = cls == 0 ? zp0[e] : (cls == 1 ? zp1[e] : zp2[e]);
-            f[e] = dequant_code<DT>(quant_code<DT>(f[e], s, z, qm), s, z);
+            f[e] = dequant_code<DT>(quant_code<DT>(f[e], sc, z, qm), sc, z);
         }
         stg_stream(dst, Vec16<DT>::pack(f));
     }
@@ -648,52 +689,106 @@ __global__ void zero_counts_kernel(int32_t *oc, int64_t rows, int t)
     if (i < rows) oc[i * 2 + t] = 0;
 }
 
-template <int DT> static int launch_ex(QXParams q, int mode, cudaStream_t st)
+template <int DT> static bool vec_ok(const QGParams &p, int t)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    return p.n % EPV == 0 && (uintptr_t)p.x[t] % 16 == 0 && (uintptr_t)p.y[t] % 16 == 0;
+}
+// 16-byte vectors per group for the vector kernel; 0 = whole row; -1 = needs the generic kernel
+template <int DT> static int group_lanes(const QGParams &p, int t, int group)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    if (!vec_ok<DT>(p, t) || p.n > kMaxVec * kQT * EPV) return -1;
+    if (group == p.n) return 0;
+    if (group % EPV) return -1;
+    const int l = group / EPV;
+    return (l <= 32 && (l & (l - 1)) == 0) ? l : -1;
+}
+
+// tensors [t0, t0+nt) share one launch (q.t = -1) when nt == 2
+template <int DT> static int launch_token(QXParams q, int t0, int nt, cudaStream_t st)
 {
     constexpr int EPV = Vec16<DT>::kElems;
     const QGParams &p = q.g;
-    const bool aligned = p.n % EPV == 0 && (uintptr_t)p.x[q.t] % 16 == 0 && (uintptr_t)p.y[q.t] % 16 == 0;
-    if (mode == RTKV_Q_CHANNEL) {
-        const int ngroups = (p.out_rows + q.tgroup - 1) / q.tgroup;
-        if (q.ocount) {
-            const int64_t rows = (int64_t)p.B * p.out_rows;
-            zero_counts_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(q.ocount, rows, q.t);
-        }
-        if (aligned) {
-            dim3 grid(ngroups, p.B, (p.n / EPV + kQT - 1) / kQT);
-            void (*kern)(QXParams) = quant_channel_kernel<DT, 32>;
-            if (q.tgroup <= 8) kern = quant_channel_kernel<DT, 8>;
-            else if (q.tgroup <= 16) kern = quant_channel_kernel<DT, 16>;
-            RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, q));
-        } else {
-            dim3 grid(ngroups, p.B, (p.n + kQT - 1) / kQT);
-            quant_channel_generic_kernel<DT><<<grid, kQT, 0, st>>>(q);
-        }
-        RTKV_LAUNCH_CHECK("quant_channel_kernel");
-        return RTKV_OK;
-    }
-    dim3 grid(p.out_rows, p.B, 1);
-    int lanes = -1;
-    if (aligned && p.n <= kMaxVec * kQT * EPV) {
-        if (q.group == p.n) lanes = 0;
-        else if (q.group % EPV == 0) {
-            const int l = q.group / EPV;
-            if (l <= 32 && (l & (l - 1)) == 0) lanes = l;
-        }
-    }
-    if (lanes >= 0) {
-        q.lanes = lanes;
-        const int nv = (p.n / EPV + kQT - 1) / kQT;
-        void (*kern)(QXParams) = quant_token_ex_kernel<DT, kMaxVec>;
-        if (nv <= 1) kern = quant_token_ex_kernel<DT, 1>;
-        else if (nv <= 2) kern = quant_token_ex_kernel<DT, 2>;
-        else if (nv <= 4) kern = quant_token_ex_kernel<DT, 4>;
-        else if (nv <= 5) kern = quant_token_ex_kernel<DT, 5>;
-        RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, q));
+    dim3 grid(p.out_rows, p.B, nt);
+    const int nv = (p.n / EPV + kQT - 1) / kQT;
+    void (*kern)(QXParams);
+    if (q.tau_q8) {
+        kern = quant_token_ex_kernel<DT, kMaxVec, true>;
+        if (nv <= 1) kern = quant_token_ex_kernel<DT, 1, true>;
+        else if (nv <= 2) kern = quant_token_ex_kernel<DT, 2, true>;
+        else if (nv <= 4) kern = quant_token_ex_kernel<DT, 4, true>;
+        else if (nv <= 5) kern = quant_token_ex_kernel<DT, 5, true>;
     } else {
-        quant_token_ex_generic_kernel<DT><<<grid, kQT, 0, st>>>(q);
+        kern = quant_token_ex_kernel<DT, kMaxVec, false>;
+        if (nv <= 1) kern = quant_token_ex_kernel<DT, 1, false>;
+        else if (nv <= 2) kern = quant_token_ex_kernel<DT, 2, false>;
+        else if (nv <= 4) kern = quant_token_ex_kernel<DT, 4, false>;
+        else if (nv <= 5) kern = quant_token_ex_kernel<DT, 5, false>;
     }
+    q.t = nt == 2 ? -1 : t0;
+    RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, st, 1, q));
     RTKV_LAUNCH_CHECK("quant_token_ex_kernel");
+    return RTKV_OK;
+}
+
+template <int DT> static int launch_channel(QXParams q, int t0, int nt, cudaStream_t st)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    const QGParams &p = q.g;
+    const int ngroups = (p.out_rows + q.tgroup - 1) / q.tgroup;
+    q.t = nt == 2 ? -1 : t0;
+    if (q.tgroup <= 8) {
+        dim3 grid(ngroups, p.B, (p.n / EPV + 127) / 128 * nt);
+        RTKV_CUDA(launch_kernel(quant_channel_kernel<DT, 8, 128>, grid, dim3(128), 8 * 128 * 16, st, 1, q));
+    } else if (q.tgroup <= 16) {
+        dim3 grid(ngroups, p.B, (p.n / EPV + 127) / 128 * nt);
+        RTKV_CUDA(launch_kernel(quant_channel_kernel<DT, 16, 128>, grid, dim3(128), 16 * 128 * 16, st, 1, q));
+    } else {
+        dim3 grid(ngroups, p.B, (p.n / EPV + 63) / 64 * nt);
+        RTKV_CUDA(launch_kernel(quant_channel_kernel<DT, 32, 64>, grid, dim3(64), 32 * 64 * 16, st, 1, q));
+    }
+    RTKV_LAUNCH_CHECK("quant_channel_kernel");
+    return RTKV_OK;
+}
+
+template <int DT> static int launch_ex(QXParams q, const int *mode, const int *group, int nt, cudaStream_t st)
+{
+    const QGParams &p = q.g;
+    int lanes[2] = {-1, -1};
+    bool chan_vec[2] = {false, false};
+    for (int t = 0; t < nt; ++t) {
+        if (mode[t] == RTKV_Q_CHANNEL) chan_vec[t] = vec_ok<DT>(p, t);
+        else lanes[t] = group_lanes<DT>(p, t, group[t]);
+    }
+    if (q.ocount)
+        for (int t = 0; t < nt; ++t)
+            if (mode[t] == RTKV_Q_CHANNEL) {
+                const int64_t rows = (int64_t)p.B * p.out_rows;
+                zero_counts_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(q.ocount, rows, t);
+            }
+    q.group = group[0]; q.lanes = lanes[0];
+    q.group1 = nt == 2 ? group[1] : 0; q.lanes1 = nt == 2 ? lanes[1] : 0;
+    if (nt == 2 && lanes[0] >= 0 && lanes[1] >= 0) return launch_token<DT>(q, 0, 2, st);
+    if (nt == 2 && chan_vec[0] && chan_vec[1]) return launch_channel<DT>(q, 0, 2, st);
+    for (int t = 0; t < nt; ++t) {
+        q.group = group[t]; q.lanes = lanes[t]; q.t = t;
+        int rc = RTKV_OK;
+        if (mode[t] == RTKV_Q_CHANNEL) {
+            if (chan_vec[t]) rc = launch_channel<DT>(q, t, 1, st);
+            else {
+                dim3 grid((p.out_rows + q.tgroup - 1) / q.tgroup, p.B, (p.n + kQT - 1) / kQT);
+                quant_channel_generic_kernel<DT><<<grid, kQT, 0, st>>>(q);
+                RTKV_LAUNCH_CHECK("quant_channel_generic_kernel");
+            }
+        } else if (lanes[t] >= 0) {
+            rc = launch_token<DT>(q, t, 1, st);
+        } else {
+            quant_token_ex_generic_kernel<DT><<<dim3(p.out_rows, p.B), kQT, 0, st>>>(q);
+            RTKV_LAUNCH_CHECK("quant_token_ex_generic_kernel");
+        }
+        if (rc) return rc;
+    }
     return RTKV_OK;
 }
 
@@ -762,15 +857,12 @@ extern "C" int rtkv_quant_gather_ex(const void *X0, const void *X1, int dtype, i
     QXParams q = {};
     fill_params(q.g, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
     q.tgroup = o.token_group; q.ocount = outlier_counts;
-    for (int t = 0; t < nt; ++t) {
-        q.t = t;
-        const int m = o.mode[t];
-        q.group = m == RTKV_Q_TOKEN_GROUP ? o.group_size : n;
-        q.tau_q8 = m == RTKV_Q_CHANNEL ? 0u : (unsigned)o.outlier_tau_q8;
-        RTKV_DISPATCH(dtype, rc = launch_ex<DT>(q, m, st));
-        if (rc) return rc;
-    }
-    return RTKV_OK;
+    q.tau_q8 = (unsigned)o.outlier_tau_q8;          // channel-mode tensors ignore it
+    int group[2] = {n, n};
+    for (int t = 0; t < nt; ++t)
+        if (o.mode[t] == RTKV_Q_TOKEN_GROUP) group[t] = o.group_size;
+    RTKV_DISPATCH(dtype, rc = launch_ex<DT>(q, o.mode, group, nt, st));
+    return rc;
 }
 
 static int pack_ex_common(QXParams &q, const char *who, const void *X, void *Y, int dtype, int B, int S, int n,

@@ -395,7 +395,8 @@ def gather_rows(x, sel, out_rows, zero_pad=True):
     return quant_gather(x, None, sel, None, None, out_rows, zero_pad)[0]
 
 
-def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True, want_counts=False):
+def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True, want_counts=False, out0=None,
+                    out1=None):
     """quant_gather with extended scale granularities / outlier split (rtkv_quant_gather_ex)."""
     require_cuda()
     x0 = x0.contiguous()
@@ -403,8 +404,10 @@ def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True,
     if x1 is not None:
         x1 = x1.contiguous()
         assert x1.shape == x0.shape and x1.dtype == x0.dtype
-    y0 = torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
-    y1 = torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device) if x1 is not None else None
+    y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = None
+    if x1 is not None:
+        y1 = out1 if out1 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     oc = torch.empty(B, out_rows, 2, dtype=torch.int32, device=x0.device) if want_counts else None
     lab = labels.to(torch.uint8).contiguous()
     check(lib.rtkv_quant_gather_ex(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,

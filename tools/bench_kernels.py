@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel timings at BASELINE shapes (CUDA events, rotating input sets larger than L2).
-usage: python tools/bench_kernels.py [c2|c3|c4] [--only k1a,k1b,k2,k3]"""
+usage: python tools/bench_kernels.py [c2|c3|c4] [--only k1a,k1b,k2,k3,k3ex]"""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "realtime-kv-cache-compression_b200"))
@@ -102,5 +102,31 @@ if only is None or "k3" in only:
     res["k3_us"] = t; res["k3_GBs"] = 4 * kv_bytes / t / 1e3; res["k3_frac"] = res["k3_GBs"] / PEAK
     t = graph_time(lambda i: (ok.copy_(Ks[i]), ov.copy_(Vs[i])), nset)
     res["torch_copy_same_bytes_us"] = t; res["torch_copy_GBs"] = 4 * kv_bytes / t / 1e3
+
+if only is None or "k3ex" in only:
+    # extended scale granularities / outlier split (quant_ex.cu): same algorithmic bytes as K3
+    kv_bytes = B * S * HD * 4
+    nset = max(2, int(300e6 // (2 * kv_bytes)) + 1)
+    Ks = [torch.randn(B, S, HD, generator=gen, device=dev) for _ in range(nset)]
+    Vs = [torch.randn(B, S, HD, generator=gen, device=dev) for _ in range(nset)]
+    labels = torch.randint(0, 3, (B, S), generator=gen, device=dev, dtype=torch.uint8)
+    variants = {
+        "group128": ops.quant_options("token_group", "token_group", group_size=128),
+        "group128_tau6": ops.quant_options("token_group", "token_group", group_size=128, outlier_tau=6.0),
+        "row_tau6": ops.quant_options("token", "token", outlier_tau=6.0),
+        "chanK32_groupV128": ops.quant_options("channel", "token_group", group_size=128, token_group=32),
+        "chanK16_chanV16": ops.quant_options("channel", "channel", token_group=16),
+    }
+    ok, ov = torch.empty_like(Ks[0]), torch.empty_like(Ks[0])
+    for tag, opt in variants.items():
+        t = graph_time(lambda i: ops.quant_gather_ex(Ks[i], Vs[i], None, labels, (2, 4, 8), S, opt, out0=ok, out1=ov), nset)
+        res[f"k3ex_{tag}_us"] = t; res[f"k3ex_{tag}_frac"] = 4 * kv_bytes / t / 1e3 / PEAK
+    # packed rows: read K fp32, write codes (mean 4.67 bits) + parameters
+    for tag, opt in (("row", ops.quant_options()), ("group128", variants["group128"]),
+                     ("chan32", ops.quant_options("channel", token_group=32))):
+        t = graph_time(lambda i: ops.quant_pack_ex(Ks[i], None, labels, (2, 4, 8), S, opt), nset)
+        res[f"pack_{tag}_us"] = t; res[f"pack_{tag}_read_GBs"] = kv_bytes / t / 1e3
+    t = graph_time(lambda i: ops.quant_pack(Ks[i], None, labels, (2, 4, 8), S), nset)
+    res["pack_reference_mode_us"] = t; res["pack_reference_mode_read_GBs"] = kv_bytes / t / 1e3
 
 print(json.dumps(res))
