@@ -932,6 +932,10 @@ extern "C" int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,
     if (rc) return rc;
     if (out_rows == 0) return RTKV_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode == RTKV_Q_TOKEN && !q.tau_q8) {          // the reference's scales: same layout as rtkv_quant_pack
+        if (out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
+        return rtkv_quant_pack(X, dtype, B, S, n, sel_idx, row_stats, labels, bits, out_rows, row_bytes, codes, qparams, stream);
+    }
     RTKV_CUDA(cudaMemsetAsync(codes, 0, (size_t)B * out_rows * (size_t)row_bytes, st));
     if (mode == RTKV_Q_CHANNEL) {
         if (out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));

@@ -456,6 +456,79 @@ __global__ void __launch_bounds__(kQT) quant_pack_kernel(QGParams p, int64_t row
     }
 }
 
+// Vector path of quant_pack_kernel: the K3 structure (row in registers, 128-bit streaming loads, one block
+// min/max) with a packing epilogue.  A lane's 16-byte vector becomes EPV codes = EPV*bits/8 bytes, written as
+// one 1/2/4/8-byte store; consecutive lanes write consecutive bytes, so a warp's store is one contiguous
+// 32..256-byte run.  Needs EPV*bits to be a whole number of bytes (everything but fp32 with 1-bit codes).
+template <int DT, int NV>
+__global__ void __launch_bounds__(kQT) quant_pack_vec_kernel(QGParams p, int64_t row_bytes, uint8_t *codes, float *qparams)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    __shared__ float red[16];
+    const int r = blockIdx.x, b = blockIdx.y;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    uint8_t *dst = codes + ((size_t)b * p.out_rows + r) * (size_t)row_bytes;
+    float *qp = qparams + ((size_t)b * p.out_rows + r) * 2;
+    if (r >= cnt) {
+        for (int64_t c = threadIdx.x; c < row_bytes / 16; c += kQT) ((uint4 *)dst)[c] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) { qp[0] = 0.0f; qp[1] = 0.0f; }
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint4 *src = (const uint4 *)((const char *)p.x[0] + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+    uint4 raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (threadIdx.x + k * kQT < nvec) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+        }
+    }
+    block_minmax(mn, mx, nan, red);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    float scale, zp;
+    quant_params<DT>(mn, mx, bits, scale, zp);
+    const float qmax_r = qmax_rounded<DT>(bits);
+    if (threadIdx.x == 0) { qp[0] = scale; qp[1] = zp; }
+    const int vbytes = bits > 8 ? 2 * EPV : EPV * bits / 8;       // bytes of codes per 16-byte input vector
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        if (v < nvec) {
+            float f[EPV];
+            Vec16<DT>::unpack(raw[k], f);
+            unsigned long long lo = 0, hi = 0;                    // up to 16 bytes of codes
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float qf = quant_code<DT>(f[e], scale, zp, qmax_r);
+                const unsigned long long c = qf == qf ? (unsigned long long)(unsigned)qf : 0ull;
+                const int sh = e * (bits > 8 ? 16 : bits);
+                if (sh < 64) lo |= c << sh; else hi |= c << (sh - 64);
+            }
+            uint8_t *o = dst + (size_t)v * vbytes;
+            if (vbytes == 16) *(uint4 *)o = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+            else if (vbytes == 8) *(unsigned long long *)o = lo;
+            else if (vbytes == 4) *(unsigned *)o = (unsigned)lo;
+            else if (vbytes == 2) *(uint16_t *)o = (uint16_t)lo;
+            else *o = (uint8_t)lo;
+        }
+    }
+    // zero the padding between the last code byte and row_bytes
+    for (int64_t c = (int64_t)nvec * vbytes + threadIdx.x; c < row_bytes; c += kQT) dst[c] = 0;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(kQT) unpack_dequant_kernel(QGParams p, int64_t row_bytes, const uint8_t *codes,
                                                              const float *qparams)
@@ -672,6 +745,15 @@ extern "C" int64_t rtkv_packed_row_bytes(int n, int bits)
     return (raw + 15) / 16 * 16;
 }
 
+template <int DT> static void (*pick_pack_kernel(int nv))(QGParams, int64_t, uint8_t *, float *)
+{
+    if (nv <= 1) return quant_pack_vec_kernel<DT, 1>;
+    if (nv <= 2) return quant_pack_vec_kernel<DT, 2>;
+    if (nv <= 4) return quant_pack_vec_kernel<DT, 4>;
+    if (nv <= 5) return quant_pack_vec_kernel<DT, 5>;
+    return quant_pack_vec_kernel<DT, kMaxVec>;
+}
+
 static int check_pack_bits(const int32_t *bits, const char *who)
 {
     for (int c = 0; c < 3; ++c) {
@@ -706,7 +788,18 @@ extern "C" int rtkv_quant_pack(const void *X, int dtype, int B, int S, int n,
     QGParams p;
     fill_params(p, X, nullptr, B, S, n, sel_idx, row_stats, labels, bits, out_rows, 1, nullptr, nullptr);
     dim3 grid(out_rows, B);
-    RTKV_DISPATCH(dtype, (quant_pack_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, row_bytes, codes, qparams)));
+    const int epv = 16 / dtype_bytes(dtype);
+    int minb = bits[0] < bits[1] ? bits[0] : bits[1]; minb = minb < bits[2] ? minb : bits[2];
+    const bool vec = n % epv == 0 && n <= kMaxVec * kQT * epv && (uintptr_t)X % 16 == 0 && (uintptr_t)codes % 16 == 0 &&
+                     row_bytes % 16 == 0 && (epv * minb) % 8 == 0;
+    if (vec) {
+        const int nv = (n / epv + kQT - 1) / kQT;
+        void (*kern)(QGParams, int64_t, uint8_t *, float *) = nullptr;
+        RTKV_DISPATCH(dtype, kern = pick_pack_kernel<DT>(nv));
+        RTKV_CUDA(launch_kernel(kern, grid, dim3(kQT), 0, (cudaStream_t)stream, 1, p, row_bytes, codes, qparams));
+    } else {
+        RTKV_DISPATCH(dtype, (quant_pack_kernel<DT><<<grid, kQT, 0, (cudaStream_t)stream>>>(p, row_bytes, codes, qparams)));
+    }
     RTKV_LAUNCH_CHECK("quant_pack_kernel");
     return RTKV_OK;
 }
