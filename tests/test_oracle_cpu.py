@@ -100,3 +100,37 @@ def test_position_bias_properties():
     assert pb[0] == 0 and abs(pb[-1] - 1) < 1e-6 and (np.diff(pb) >= 0).all()
     assert (oracle.position_bias(1) == 0).all()
     assert oracle.context_relevance(20, 4) == np.float32(0.2)
+
+
+def test_extended_quant_restatement_properties():
+    """orc_fake_quant_ex (project-defined extras): the default mode is the reference restatement, the outlier
+    split does not depend on the order of the channels inside a group, per-channel scales do not depend on
+    the order of the rows inside a token group."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((24, 256)).astype(np.float32)
+    x[rng.integers(0, 24, 30), rng.integers(0, 256, 30)] *= 40.0
+    lab = rng.integers(0, 3, 24).astype(np.uint8)
+    bits = (2, 4, 8)
+    ref, _, _ = oracle.fake_quant_rows(x, oracle.F32, lab, bits)
+    r0 = oracle.fake_quant_ex(x, oracle.F32, lab, bits)
+    np.testing.assert_array_equal(r0["out"].view(np.uint32), ref.view(np.uint32))
+    assert r0["omask"].sum() == 0
+    # outliers: permuting the channels of every 64-wide group permutes the result
+    r1 = oracle.fake_quant_ex(x, oracle.F32, lab, bits, mode=1, group=64, tau=5.0)
+    assert 0 < r1["omask"].sum() < 200
+    perm = np.concatenate([g * 64 + rng.permutation(64) for g in range(4)])
+    r2 = oracle.fake_quant_ex(x[:, perm], oracle.F32, lab, bits, mode=1, group=64, tau=5.0)
+    np.testing.assert_array_equal(r2["out"].view(np.uint32), r1["out"][:, perm].view(np.uint32))
+    np.testing.assert_array_equal(r2["omask"], r1["omask"][:, perm])
+    kept = r1["omask"] == 1
+    np.testing.assert_array_equal(r1["out"][kept], x[kept])                  # outliers are kept exactly
+    assert np.abs(r1["out"] - x)[~kept].mean() < np.abs(ref - x).mean()      # and the rest quantises finer
+    # per-channel mode: permuting the rows inside a token group permutes the result
+    rows = np.concatenate([g * 8 + rng.permutation(8) for g in range(3)])
+    c1 = oracle.fake_quant_ex(x, oracle.F32, lab, bits, mode=2, tgroup=8)
+    c2 = oracle.fake_quant_ex(x[rows], oracle.F32, lab[rows], bits, mode=2, tgroup=8)
+    np.testing.assert_array_equal(c2["out"].view(np.uint32), c1["out"][rows].view(np.uint32))
+    np.testing.assert_array_equal(c2["qparams"].view(np.uint32), c1["qparams"].view(np.uint32))
+    # a cap on the split outliers: later outliers are clamped codes, not exact values
+    r3 = oracle.fake_quant_ex(x, oracle.F32, lab, bits, mode=0, tau=3.0, cap=1)
+    assert r3["omask"].sum(axis=1).max() == 1
