@@ -299,6 +299,10 @@ RTKV_API int rtkv_debug_k2_mode(int mode);
  * epilogue, 2 no TMEM loads, 3 no MMAs. */
 RTKV_API int rtkv_debug_qk_mode(int mode);
 
+/* Tuning aid: kernel used for RTKV_Q_CHANNEL groups of 17..32 rows: 0 (default) re-reads the tile through L2, 1 stages it
+ * in shared memory with cp.async.  Same results. */
+RTKV_API int rtkv_debug_channel_variant(int variant);
+
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);
 

@@ -423,6 +423,100 @@ __global__ void __launch_bounds__(CT) quant_channel_kernel(QXParams q)
     }
 }
 
+// Variant for long token groups: nothing is staged, the second pass re-reads the tile, which is still in L2 (a CTA touches
+// GT rows x CT*16 bytes within a few microseconds): DRAM traffic stays algorithmic, the kernel needs neither the 32 KB of
+// shared memory nor 4*GT registers per thread, and occupancy is bounded by ~50 registers only.
+template <int DT, int GT, int CT>
+__global__ void __launch_bounds__(CT) quant_channel_l2_kernel(QXParams q)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    constexpr int U = 8;                                    // loads in flight per thread
+    __shared__ int s_tok[GT], s_cls[GT];
+    static_assert(CT >= GT && GT % U == 0, "bad tile");
+    const QGParams &p = q.g;
+    const int nslab = gridDim.z >> (q.t < 0 ? 1 : 0);
+    const int r0 = blockIdx.x * q.tgroup, b = blockIdx.y, t = q.t < 0 ? (int)(blockIdx.z / nslab) : q.t;
+    const int v = (blockIdx.z % nslab) * CT + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    if (threadIdx.x < GT) {
+        const int r = r0 + threadIdx.x;
+        int tok = -1, cls = 0;
+        if (threadIdx.x < q.tgroup && r < cnt && r < p.out_rows) {
+            tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+            cls = p.labels[(int64_t)b * p.S + tok];
+        }
+        s_tok[threadIdx.x] = tok; s_cls[threadIdx.x] = cls;
+    }
+    __syncthreads();
+    if (v >= nvec) return;
+    const size_t row_b = (size_t)p.n * Elem<DT>::kBytes;
+    const char *xb = (const char *)pick_x(p, t) + (size_t)b * p.S * row_b;
+    char *yb = (char *)pick_y(p, t) + (size_t)b * p.out_rows * row_b;
+    float mn[EPV], mx[EPV];
+    unsigned nanmask = 0;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) { mn[e] = INFINITY; mx[e] = -INFINITY; }
+#pragma unroll 1
+    for (int j0 = 0; j0 < GT; j0 += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (s_tok[j0 + u] >= 0) raw[u] = __ldg((const uint4 *)(xb + (size_t)s_tok[j0 + u] * row_b) + v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (s_tok[j0 + u] >= 0) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[u], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    nanmask |= (unsigned)(f[e] != f[e]) << e;
+                    mn[e] = fminf(mn[e], f[e]); mx[e] = fmaxf(mx[e], f[e]);
+                }
+            }
+        }
+    }
+    float sc0[EPV], zp0[EPV], sc1[EPV], zp1[EPV], sc2[EPV], zp2[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        if ((nanmask >> e) & 1) mn[e] = mx[e] = __int_as_float(0x7fc00000);
+        quant_params<DT>(mn[e], mx[e], p.bits[0], sc0[e], zp0[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[1], sc1[e], zp1[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[2], sc2[e], zp2[e]);
+    }
+    const float qm0 = qmax_rounded<DT>(p.bits[0]), qm1 = qmax_rounded<DT>(p.bits[1]), qm2 = qmax_rounded<DT>(p.bits[2]);
+#pragma unroll 1
+    for (int j0 = 0; j0 < GT; j0 += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (s_tok[j0 + u] >= 0) raw[u] = ldg_stream((const uint4 *)(xb + (size_t)s_tok[j0 + u] * row_b) + v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + u, r = r0 + j;
+            if (j >= q.tgroup || r >= p.out_rows) break;
+            uint4 *dst = (uint4 *)(yb + (size_t)r * row_b) + v;
+            if (s_tok[j] < 0) {
+                if (p.zero_pad) stg_stream(dst, make_uint4(0, 0, 0, 0));
+                continue;
+            }
+            const int cls = s_cls[j];
+            const float qm = cls == 0 ? qm0 : (cls == 1 ? qm1 : qm2);
+            float f[EPV];
+            Vec16<DT>::unpack(raw[u], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float sc = cls == 0 ? sc0[e] : (cls == 1 ? sc1[e] : sc2[e]);
+                const float z = cls == 0 ? zp0[e] : (cls == 1 ? zp1[e] : zp2[e]);
+                f[e] = dequant_code<DT>(quant_code<DT>(f[e], sc, z, qm), sc, z);
+            }
+            stg_stream(dst, Vec16<DT>::pack(f));
+        }
+    }
+}
+
 // channel mode, any n / alignment: one thread per channel, the group's rows are read twice
 template <int DT>
 __global__ void __launch_bounds__(kQT) quant_channel_generic_kernel(QXParams q)
@@ -732,6 +826,8 @@ template <int DT> static int launch_token(QXParams q, int t0, int nt, cudaStream
     return RTKV_OK;
 }
 
+static int g_channel_variant = 0;   // 0: L2 re-read kernel for 17..32-row groups, 1: cp.async-staged kernel
+
 template <int DT> static int launch_channel(QXParams q, int t0, int nt, cudaStream_t st)
 {
     constexpr int EPV = Vec16<DT>::kElems;
@@ -744,9 +840,12 @@ template <int DT> static int launch_channel(QXParams q, int t0, int nt, cudaStre
     } else if (q.tgroup <= 16) {
         dim3 grid(ngroups, p.B, (p.n / EPV + 127) / 128 * nt);
         RTKV_CUDA(launch_kernel(quant_channel_kernel<DT, 16, 128>, grid, dim3(128), 16 * 128 * 16, st, 1, q));
-    } else {
+    } else if (g_channel_variant == 1) {
         dim3 grid(ngroups, p.B, (p.n / EPV + 63) / 64 * nt);
         RTKV_CUDA(launch_kernel(quant_channel_kernel<DT, 32, 64>, grid, dim3(64), 32 * 64 * 16, st, 1, q));
+    } else {
+        dim3 grid(ngroups, p.B, (p.n / EPV + 127) / 128 * nt);
+        RTKV_CUDA(launch_kernel(quant_channel_l2_kernel<DT, 32, 128>, grid, dim3(128), 0, st, 1, q));
     }
     RTKV_LAUNCH_CHECK("quant_channel_kernel");
     return RTKV_OK;
@@ -816,6 +915,8 @@ static int check_options(const rtkv_quant_options *o, int n, int ntensors, const
 } // namespace rtkv
 
 using namespace rtkv;
+
+extern "C" int rtkv_debug_channel_variant(int v) { g_channel_variant = v; return RTKV_OK; }
 
 extern "C" int rtkv_quant_groups(int n, const rtkv_quant_options *o, int tensor)
 {

@@ -111,6 +111,7 @@ PROTOTYPES = {
                                               ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_i32),
                                               ctypes.c_int, c_i64, ctypes.POINTER(QuantOptions), ctypes.c_int, c_vp,
                                               c_vp]),
+    "rtkv_debug_channel_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_k2_timing": (ctypes.c_int, [c_vp]),
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),

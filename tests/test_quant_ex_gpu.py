@@ -119,9 +119,17 @@ def test_token_group_scales_and_outliers(rt, dt, n, group, tau):
         assert ck.sum() > 0 and cv.sum() > 0
 
 
+@pytest.fixture(params=["l2-reread", "cp.async-staged"])
+def chan_variant(request, rt):
+    from rtkv._lib import lib
+    lib.rtkv_debug_channel_variant(1 if request.param == "cp.async-staged" else 0)
+    yield request.param
+    lib.rtkv_debug_channel_variant(0)
+
+
 @pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
-@pytest.mark.parametrize("n,tg", [(512, 32), (4096, 32), (4096, 16), (5120, 8), (1024, 5), (100, 7), (8, 1)])
-def test_per_channel_keys(rt, dt, n, tg):
+@pytest.mark.parametrize("n,tg", [(512, 32), (4096, 32), (4096, 16), (5120, 8), (1024, 5), (100, 7), (8, 1), (2048, 20)])
+def test_per_channel_keys(rt, chan_variant, dt, n, tg):
     _, ops = rt
     rng = np.random.default_rng(n + tg)
     B, S, bits = 2, 75, (2, 4, 8)

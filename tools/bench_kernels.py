@@ -118,6 +118,13 @@ if only is None or "k3ex" in only:
         "chanK16_chanV16": ops.quant_options("channel", "channel", token_group=16),
     }
     ok, ov = torch.empty_like(Ks[0]), torch.empty_like(Ks[0])
+    from rtkv._lib import lib as _l
+    _l.rtkv_debug_channel_variant(1)
+    t = graph_time(lambda i: ops.quant_gather_ex(Ks[i], Vs[i], None, labels, (2, 4, 8), S, ops.quant_options("channel", "channel", token_group=32), out0=ok, out1=ov), nset)
+    res["k3ex_chan32_both_staged_us"] = t
+    _l.rtkv_debug_channel_variant(0)
+    t = graph_time(lambda i: ops.quant_gather_ex(Ks[i], Vs[i], None, labels, (2, 4, 8), S, ops.quant_options("channel", "channel", token_group=32), out0=ok, out1=ov), nset)
+    res["k3ex_chan32_both_l2_us"] = t
     for tag, opt in variants.items():
         t = graph_time(lambda i: ops.quant_gather_ex(Ks[i], Vs[i], None, labels, (2, 4, 8), S, opt, out0=ok, out1=ov), nset)
         res[f"k3ex_{tag}_us"] = t; res[f"k3ex_{tag}_frac"] = 4 * kv_bytes / t / 1e3 / PEAK
