@@ -13,6 +13,12 @@ is the reference's eager formulation in plain torch (SURVEY §8f lists fused rep
     its first S' columns (the reference's positional quirk)               (:125-140)
   * any exception inside the block prints and falls back to the uncompressed result (:144-149)
   * `outputs.compression_info`, `get_compression_stats`, `reset_compression_state`   (:310-339)
+
+Extension (off by default): `set_compressor(c, fused_scoring=True)` replaces the materialised
+`softmax(QK^T)` of the prefill by a flash attention that also returns the row log-sum-exp (torch's SDPA flash /
+efficient kernels: library code) and takes the prompt-attention mass from librtkv's tcgen05 kernel
+(`ops.prompt_mass_qk`: Q, K_prompt, LSE -> mass), so no [B,H,S,S] tensor exists and the hook works at 32k tokens.
+Needs bf16/fp16 activations, head_dim 128 and a causal mask; `attn_weights` is then returned as None.
 """
 import logging
 import math
@@ -32,6 +38,22 @@ except Exception:  # pragma: no cover
 log = logging.getLogger(__name__)
 
 
+def _flash_with_lse(q, k, v, scale):
+    """Causal attention output [B,H,S,D] and natural-log row LSE [B,H,S] (float32) from torch's fused SDPA kernels."""
+    errors = []
+    try:
+        r = torch.ops.aten._scaled_dot_product_flash_attention(q, k, v, 0.0, True, False, scale=scale)
+        return r[0], r[1].float()
+    except Exception as e:  # backend not built for this device / shape
+        errors.append(e)
+    try:
+        r = torch.ops.aten._scaled_dot_product_efficient_attention(q, k, v, None, True, 0.0, True, scale=scale)
+        return r[0], r[1][..., : q.shape[2]].float()
+    except Exception as e:
+        errors.append(e)
+    raise RuntimeError(f"no fused attention kernel with LSE output is available: {errors}")
+
+
 def _store_compressed(cache, layer_idx, keys, values):
     """Make the cache entry of this layer the compressed K/V (the reference returns the
     compressed pair as `present_key_value`, :165-166)."""
@@ -48,12 +70,46 @@ class CompressedLlamaAttention(LlamaAttention):
         super().__init__(config, layer_idx)
         self.layer_idx = layer_idx
         self.compressor = None
+        self.fused_scoring = False
         self.hidden_size = config.hidden_size
         self.num_heads = config.num_attention_heads
         self.num_key_value_heads = getattr(config, "num_key_value_heads", self.num_heads)
 
-    def set_compressor(self, compressor):
+    def set_compressor(self, compressor, fused_scoring=False):
         self.compressor = compressor
+        self.fused_scoring = bool(fused_scoring)
+
+    def _forward_fused(self, hidden_states, query_states, key_states, value_states, input_ids):
+        """Prefill without the S x S matrix: flash attention (+LSE) -> tcgen05 prompt mass -> compress ->
+        attention over the kept tokens (top-left aligned causal mask == the reference's truncated mask)."""
+        from . import ops
+        bsz, _, q_len, _ = query_states.shape
+        groups = self.num_heads // self.num_key_value_heads
+        scale = 1.0 / math.sqrt(self.head_dim)
+        k_full, v_full = repeat_kv(key_states, groups), repeat_kv(value_states, groups)
+        attn_output, lse = _flash_with_lse(query_states, k_full, v_full, scale)
+        try:
+            P = self.compressor.prompt_length(q_len)
+            mass = ops.prompt_mass_qk(query_states, k_full[:, :, :P], lse, scale, causal=True)
+            k_flat = key_states.transpose(1, 2).contiguous().view(bsz, q_len, -1)
+            v_flat = value_states.transpose(1, 2).contiguous().view(bsz, q_len, -1)
+            ids = input_ids if input_ids is not None else torch.zeros((bsz, q_len), device=hidden_states.device,
+                                                                       dtype=torch.long)
+            ck, cv, _info = self.compressor.compress_layer_kv_cache(k_flat, v_flat, None, ids, self.layer_idx,
+                                                                    prompt_mass=mass)
+            s_kept = ck.shape[1]
+            ck = ck.view(bsz, s_kept, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+            cv = cv.view(bsz, s_kept, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+            if s_kept != q_len:
+                attn_output = nn.functional.scaled_dot_product_attention(
+                    query_states, repeat_kv(ck, groups), repeat_kv(cv, groups), is_causal=True, scale=scale)
+            else:
+                attn_output = nn.functional.scaled_dot_product_attention(
+                    query_states, k_full, repeat_kv(cv, groups), is_causal=True, scale=scale)
+            return attn_output, (ck, cv)
+        except Exception as e:  # same downgrade as the reference
+            print(f"Compression failed at layer {self.layer_idx}: {e}")
+            return attn_output, None
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None,
                 input_ids=None, **kwargs):
@@ -67,6 +123,15 @@ class CompressedLlamaAttention(LlamaAttention):
             query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
         if past_key_values is not None:
             key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
+
+        if (self.fused_scoring and self.compressor is not None and not self.training and q_len > 1
+                and hidden_states.is_cuda and query_states.dtype in (torch.bfloat16, torch.float16)
+                and self.head_dim == 128 and key_states.shape[2] == q_len):
+            attn_output, kept = self._forward_fused(hidden_states, query_states, key_states, value_states, input_ids)
+            if kept is not None and past_key_values is not None:
+                _store_compressed(past_key_values, self.layer_idx, kept[0], kept[1])
+            attn_output = attn_output.transpose(1, 2).contiguous().reshape(bsz, q_len, -1)
+            return self.o_proj(attn_output), None
 
         groups = self.num_heads // self.num_key_value_heads
         k_full, v_full = repeat_kv(key_states, groups), repeat_kv(value_states, groups)
@@ -113,8 +178,8 @@ class CompressedLlamaDecoderLayer(LlamaDecoderLayer):
         self.self_attn = CompressedLlamaAttention(config, layer_idx)
         self.layer_idx = layer_idx
 
-    def set_compressor(self, compressor):
-        self.self_attn.set_compressor(compressor)
+    def set_compressor(self, compressor, fused_scoring=False):
+        self.self_attn.set_compressor(compressor, fused_scoring)
 
 
 class CompressedLlamaForCausalLM(LlamaForCausalLM):
@@ -127,10 +192,10 @@ class CompressedLlamaForCausalLM(LlamaForCausalLM):
         self.compressor = None
         self.compression_stats = {}
 
-    def set_compressor(self, compressor):
+    def set_compressor(self, compressor, fused_scoring=False):
         self.compressor = compressor
         for layer in self.model.layers:
-            layer.set_compressor(compressor)
+            layer.set_compressor(compressor, fused_scoring)
 
     def forward(self, input_ids=None, inputs_embeds=None, **kwargs):
         if input_ids is not None:

@@ -139,28 +139,37 @@ class RealTimePrefillCompressor:
 
     # -- the hot path ------------------------------------------------------------------
     def compress_layer_kv_cache(self, key_states, value_states, attention_weights, input_ids, layer_idx,
-                                out_keys=None, out_values=None):
+                                out_keys=None, out_values=None, prompt_mass=None):
         """(:95-172)  key/value [B,S,HD]; attention [B,H,S,>=P]; returns (K', V', info).
         out_keys/out_values (extension, host tensors only): flat buffers of B*S*HD elements the
-        result is written into (e.g. pinned memory); the returned tensors are views of them."""
+        result is written into (e.g. pinned memory); the returned tensors are views of them.
+        prompt_mass (extension, CUDA): float32 [B,S] prompt-attention mass computed by the caller without a
+        materialised attention matrix (ops.prompt_mass_qk from Q, K_prompt and the attention LSE);
+        attention_weights may then be None."""
         start_time = time.time()
         B, S, HD = key_states.shape
         if value_states.shape != key_states.shape or value_states.dtype != key_states.dtype:
             raise ValueError("key_states and value_states must have the same shape and dtype")
-        if attention_weights.dim() != 4 or attention_weights.shape[0] != B or attention_weights.shape[2] != S:
-            raise ValueError("attention_weights must be [batch, heads, seq_len, keys]")
         P = self.prompt_length(input_ids.shape[1])
-        if P > attention_weights.shape[-1]:
-            raise IndexError(f"prompt length {P} exceeds the attention width {attention_weights.shape[-1]}")
-        params, ratio = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
+        if prompt_mass is not None:
+            if not (key_states.is_cuda and prompt_mass.is_cuda) or tuple(prompt_mass.shape) != (B, S):
+                raise ValueError("prompt_mass must be a CUDA float32 [batch, seq_len] tensor next to CUDA key/value states")
+            params, ratio = self.layer_params(layer_idx, S, ops.F32)
+        else:
+            if attention_weights.dim() != 4 or attention_weights.shape[0] != B or attention_weights.shape[2] != S:
+                raise ValueError("attention_weights must be [batch, heads, seq_len, keys]")
+            if P > attention_weights.shape[-1]:
+                raise IndexError(f"prompt length {P} exceeds the attention width {attention_weights.shape[-1]}")
+            params, ratio = self.layer_params(layer_idx, S, ops.dtype_code(attention_weights))
         params.prompt_len = P
         n_tokens = B * S
 
         if key_states.is_cuda:
-            if not (value_states.is_cuda and attention_weights.is_cuda):
+            if not (value_states.is_cuda and (prompt_mass is not None or attention_weights.is_cuda)):
                 raise ValueError("key, value and attention tensors must live on the same device")
             dev = key_states.device
-            mass = ops.prompt_mass(attention_weights, prompt_len=P)
+            mass = (prompt_mass.float().contiguous() if prompt_mass is not None
+                    else ops.prompt_mass(attention_weights, prompt_len=P))
             sel = ops.score_select(params, B, S, dev, mass=mass)
             # one readback (statistics + scores + labels) and one synchronisation: S' is a shape
             nstat = sel.stats.numel()

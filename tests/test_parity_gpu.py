@@ -743,6 +743,85 @@ def test_llama_hook_prefill_on_gpu(rt):
     assert comp.layer_states == {}
 
 
+def test_precomputed_prompt_mass_input(rt):
+    """compress_layer_kv_cache(prompt_mass=...) skips K1a: same result as handing in the attention tensor."""
+    rtkv, ops = rt
+    K, V, A, P = synth_layer(2, 8, 300, 512, seed=4)
+    cfg = rtkv.CompressionConfig(num_hidden_layers=8, num_attention_heads=8, hidden_size=512, high_precision_bits=8,
+                                 medium_precision_bits=4, low_precision_bits=2)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    ids = torch.zeros(2, 300, dtype=torch.long, device="cuda")
+    k0, v0, i0 = comp.compress_layer_kv_cache(K, V, A, ids, 5)
+    k1, v1, i1 = comp.compress_layer_kv_cache(K, V, None, ids, 5, prompt_mass=ops.prompt_mass(A, prompt_len=P))
+    assert torch.equal(k0, k1) and torch.equal(v0, v1)
+    assert torch.equal(i0["propagation_info"]["selection_mask"], i1["propagation_info"]["selection_mask"])
+    with pytest.raises(ValueError):
+        comp.compress_layer_kv_cache(K, V, None, ids, 5, prompt_mass=torch.zeros(2, 299, device="cuda"))
+
+
+def test_llama_hook_fused_scoring_no_attention_matrix(rt):
+    """the hook with flash attention (+LSE) and the tcgen05 prompt-mass kernel instead of a
+    materialised softmax(QK^T).  Same weights as the eager hook: same kept counts, (nearly) the same layer-0
+    selection, close logits; attention weights are not returned."""
+    rtkv, ops = rt
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM
+    from transformers import LlamaConfig
+    torch.manual_seed(1)
+    hf = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=3, num_attention_heads=4,
+                     num_key_value_heads=2, vocab_size=211, max_position_embeddings=1024)
+    eager = CompressedLlamaForCausalLM(hf).cuda().to(torch.bfloat16).eval()
+    fused = CompressedLlamaForCausalLM(hf).cuda().to(torch.bfloat16).eval()
+    fused.load_state_dict(eager.state_dict())
+    kw = dict(num_hidden_layers=3, num_attention_heads=4, hidden_size=512, high_precision_bits=8,
+              medium_precision_bits=8, low_precision_bits=8)
+    c_eager, c_fused = rtkv.RealTimePrefillCompressor(rtkv.CompressionConfig(**kw)), \
+        rtkv.RealTimePrefillCompressor(rtkv.CompressionConfig(**kw))
+    eager.set_compressor(c_eager)
+    fused.set_compressor(c_fused, fused_scoring=True)
+    ids = torch.randint(0, 211, (2, 640), device="cuda")
+    with torch.no_grad():
+        o_e = eager(input_ids=ids, use_cache=True)
+        o_f = fused(input_ids=ids, use_cache=True, output_attentions=False)
+    assert torch.isfinite(o_f.logits).all()
+    assert sorted(c_fused.layer_states) == [0, 1, 2]
+    shapes = lambda c: [c.layer_states[l]["compressed_shape"][1] for l in range(3)]
+    assert shapes(c_fused) == shapes(c_eager) == [384, 384, 256]
+    m_e = c_eager.layer_states[0]["propagation_info"]["selection_mask"]
+    m_f = c_fused.layer_states[0]["propagation_info"]["selection_mask"]
+    overlap = float((m_e & m_f).sum()) / float(m_e.sum())
+    assert overlap > 0.8, overlap          # the eager bf16 path rounds the mass to bf16 like the reference does
+    assert o_f.past_key_values.layers[2].keys.shape[2] == 256
+
+
+def test_llama_hook_fused_scoring_32k_tokens(rt):
+    """BASELINE configs[2] shape through the model hook: 32 heads x 128, 32768 tokens.  The eager formulation of the
+    reference needs a [1,32,32768,32768] probability tensor (64 GiB in bf16, twice that for the fp32 softmax); the fused
+    hook never builds it."""
+    rtkv, ops = rt
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM
+    from transformers import LlamaConfig
+    torch.manual_seed(2)
+    S = 32768
+    hf = LlamaConfig(hidden_size=4096, intermediate_size=512, num_hidden_layers=2, num_attention_heads=32,
+                     num_key_value_heads=32, vocab_size=64, max_position_embeddings=S)
+    model = CompressedLlamaForCausalLM(hf).cuda().to(torch.bfloat16).eval()
+    cfg = rtkv.CompressionConfig(num_hidden_layers=2, num_attention_heads=32, hidden_size=4096, high_precision_bits=8,
+                                 medium_precision_bits=8, low_precision_bits=8)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    model.set_compressor(comp, fused_scoring=True)
+    ids = torch.randint(0, 64, (1, S), device="cuda")
+    with torch.no_grad():
+        x = model.model.embed_tokens(ids)
+        pos = torch.arange(S, device="cuda")[None]
+        pe = model.model.rotary_emb(x, pos)
+        for layer in model.model.layers:            # decoder layers directly: HF's eager mask builder would allocate S x S
+            x = layer(x, position_embeddings=pe, attention_mask=None, input_ids=ids)
+            x = x[0] if isinstance(x, tuple) else x
+    assert torch.isfinite(x).all()
+    assert [comp.layer_states[l]["compressed_shape"][1] for l in range(2)] == [int(0.6 * S), int(0.4 * S)]
+    assert torch.cuda.max_memory_allocated() < 24 << 30
+
+
 # ---------------------------------------------------------------- K1b fused Q.K scoring (tcgen05)
 def qk_inputs(B, H, S, P, dtype, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
