@@ -69,18 +69,30 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
         block_minmax(mn, mx, nan, red);
     }
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
-    float scale, zp;
-    quant_params<DT>(mn, mx, bits, scale, zp);
-    const float qmax_r = qmax_rounded<DT>(bits);
+    RowQuant<DT> rq;
+    rq.init(mn, mx, bits);
+    if (rq.fast) {                              // uniform over the CTA (row-level)
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const int v = threadIdx.x + k * kQT;
-        if (v < nvec) {
-            float f[EPV];
-            Vec16<DT>::unpack(raw[k], f);
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            if (v < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+                rq.apply_fast(f);
+                stg_stream(dst + v, Vec16<DT>::pack(f));
+            }
+        }
+    } else {
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
-            stg_stream(dst + v, Vec16<DT>::pack(f));
+        for (int k = 0; k < NV; ++k) {
+            const int v = threadIdx.x + k * kQT;
+            if (v < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) f[e] = rq.slow(f[e]);
+                stg_stream(dst + v, Vec16<DT>::pack(f));
+            }
         }
     }
 }

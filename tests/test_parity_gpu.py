@@ -325,6 +325,44 @@ def test_fake_quant_all_tokens(rt, dt, n):
     assert_same(yv, wv, dt)
 
 
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
+def test_fake_quant_dynamic_range_stress(rt, dt):
+    """Rows chosen to sit on every edge of the quantiser's row-level fast path (common.cuh RowQuant): scales from
+    2^-45 to 2^45 (inside and outside its window), elements far below the quantisation step, zeros of both signs,
+    denormals, a tiny negative minimum whose zero-point rounds to zero, constant, infinite and NaN rows.  Bit-exact
+    against the oracle (= the reference's true division and torch.clamp)."""
+    _, ops = rt
+    rng = np.random.default_rng(77)
+    n = 1024
+    rows = []
+    for k in range(-45, 46, 3):
+        r = rng.standard_normal(n).astype(np.float32) * np.float32(2.0 ** k)
+        r[rng.integers(0, n, 40)] = 0.0
+        r[rng.integers(0, n, 10)] = -0.0
+        r[rng.integers(0, n, 20)] *= np.float32(2.0 ** -40)            # far below the quantisation step
+        rows.append(r)
+    for k in (0, 20, -20):
+        r = np.abs(rng.standard_normal(n).astype(np.float32)) * np.float32(2.0 ** k)
+        r[5] = np.float32(-1e-45)                                        # tiny negative minimum: zero-point rounds to 0
+        r[6] = np.float32(1e-44)
+        rows.append(r)
+        rows.append(np.abs(r) + np.float32(2.0 ** k) * 1000)            # all positive, large offset (zp << 0)
+        rows.append(-np.abs(r))                                          # all negative (max == -0 possible)
+    r = rng.standard_normal(n).astype(np.float32); r[3] = np.inf; rows.append(r)
+    r = rng.standard_normal(n).astype(np.float32); r[3] = -np.inf; rows.append(r)
+    r = rng.standard_normal(n).astype(np.float32); r[9] = np.nan; rows.append(r)
+    rows.append(np.full(n, -0.3, np.float32)); rows.append(np.zeros(n, np.float32))
+    rows.append(rng.standard_normal(n).astype(np.float32) * np.float32(1e-42))   # denormal row
+    r = rng.standard_normal(n).astype(np.float32) * np.float32(3e38 / 6); rows.append(r)   # range near overflow
+    x = torch.from_numpy(np.stack(rows)[None]).to(TDT[dt])
+    S = x.shape[1]
+    for bits in ((2, 4, 8), (3, 6, 12)):
+        labels = rng.integers(0, 3, (1, S)).astype(np.uint8)
+        y, _ = ops.quant_gather(x.cuda(), None, None, torch.from_numpy(labels).cuda(), bits, S)
+        w, _, _ = oracle.fake_quant_rows(oracle.from_torch(x)[0], dt, labels, bits)
+        assert_same(y, w, dt)
+
+
 @pytest.mark.parametrize("dt,bits", [(oracle.F32, (4, 8, 16)), (oracle.BF16, (4, 8, 16)), (oracle.F32, (1, 12, 24)),
                                      (oracle.F16, (3, 5, 11))])
 def test_fake_quant_bit_widths(rt, dt, bits):
