@@ -225,6 +225,26 @@ template <int DT> struct RowQuant {
     {
         return dequant_code<DT>(quant_code<DT>(x, scale, zp, qmax_r), scale, zp);
     }
+    // integer-valued code of one element (packed rows); fast rows: same guard as apply_fast
+    __device__ __forceinline__ float code_slow(float x) const { return quant_code<DT>(x, scale, zp, qmax_r); }
+    template <int N> __device__ __forceinline__ void codes_fast(const float (&f)[N], float (&c)[N]) const
+    {
+        bool ok = true;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            const float q0 = __fmul_rn(f[e], rcp);
+            ok = ok && (fabsf(q0) >= 0x1p-30f);
+            float r = __fmaf_rn(-q0, scale, f[e]);
+            const float q1 = __fmaf_rn(r, rcp, q0);
+            r = __fmaf_rn(-q1, scale, f[e]);
+            const float a = __fmaf_rn(r, rcp, q1);
+            c[e] = fminf(rintf(Elem<DT>::rnd(__fadd_rn(Elem<DT>::rnd(a), zp))), qmax_r);
+        }
+        if (!ok) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) c[e] = code_slow(f[e]);
+        }
+    }
     // N elements of a fast row, branch-free per element; one guard branch per vector
     template <int N> __device__ __forceinline__ void apply_fast(float (&f)[N]) const
     {

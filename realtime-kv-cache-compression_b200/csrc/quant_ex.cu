@@ -177,19 +177,24 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
             }
         }
         block_minmax(mn, mx, nan, red);
-        float scale, zp;
-        quant_params<DT>(mn, mx, bits, scale, zp);
+        RowQuant<DT> rq;
+        rq.init(mn, mx, bits);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int v = threadIdx.x + k * kQT;
             if (v < nvec) {
-                float f[EPV];
+                float f[EPV], g[EPV];
                 Vec16<DT>::unpack(raw[k], f);
 #pragma unroll
-                for (int e = 0; e < EPV; ++e) {
-                    if (TAU && ((om >> (k * EPV + e)) & 1)) continue;
-                    f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+                for (int e = 0; e < EPV; ++e) g[e] = f[e];
+                if (rq.fast) rq.apply_fast(g);      // outliers lie outside [mn, mx]: their lanes are discarded below
+                else {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) g[e] = rq.slow(g[e]);
                 }
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    if (!(TAU && ((om >> (k * EPV + e)) & 1))) f[e] = g[e];
                 stg_stream(dst + v, Vec16<DT>::pack(f));
             }
         }
@@ -232,13 +237,19 @@ __global__ void __launch_bounds__(kQT) quant_token_ex_kernel(QXParams q)
             mx = ord2f(__reduce_max_sync(seg, f2ord(mx)));
             if (nan) mn = mx = __int_as_float(0x7fc00000);
             if (v < nvec) {                        // uniform within a group (nvec is a multiple of lanes)
-                float scale, zp;
-                quant_params<DT>(mn, mx, bits, scale, zp);
+                RowQuant<DT> rq;
+                rq.init(mn, mx, bits);
+                float g[EPV];
 #pragma unroll
-                for (int e = 0; e < EPV; ++e) {
-                    if (TAU && ((om >> e) & 1)) continue;
-                    f[e] = dequant_code<DT>(quant_code<DT>(f[e], scale, zp, qmax_r), scale, zp);
+                for (int e = 0; e < EPV; ++e) g[e] = f[e];
+                if (rq.fast) rq.apply_fast(g);
+                else {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) g[e] = rq.slow(g[e]);
                 }
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    if (!(TAU && ((om >> e) & 1))) f[e] = g[e];
                 stg_stream(dst + v, Vec16<DT>::pack(f));
                 if (TAU) n_out += __popc(om);
             }

@@ -510,21 +510,25 @@ __global__ void __launch_bounds__(kQT) quant_pack_vec_kernel(QGParams p, int64_t
     }
     block_minmax(mn, mx, nan, red);
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
-    float scale, zp;
-    quant_params<DT>(mn, mx, bits, scale, zp);
-    const float qmax_r = qmax_rounded<DT>(bits);
-    if (threadIdx.x == 0) { qp[0] = scale; qp[1] = zp; }
+    RowQuant<DT> rq;
+    rq.init(mn, mx, bits);
+    if (threadIdx.x == 0) { qp[0] = rq.scale; qp[1] = rq.zp; }
     const int vbytes = bits > 8 ? 2 * EPV : EPV * bits / 8;       // bytes of codes per 16-byte input vector
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const int v = threadIdx.x + k * kQT;
         if (v < nvec) {
-            float f[EPV];
+            float f[EPV], cf[EPV];
             Vec16<DT>::unpack(raw[k], f);
+            if (rq.fast) rq.codes_fast(f, cf);
+            else {
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) cf[e] = rq.code_slow(f[e]);
+            }
             unsigned long long lo = 0, hi = 0;                    // up to 16 bytes of codes
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
-                const float qf = quant_code<DT>(f[e], scale, zp, qmax_r);
+                const float qf = cf[e];
                 const unsigned long long c = qf == qf ? (unsigned long long)(unsigned)qf : 0ull;
                 const int sh = e * (bits > 8 ? 16 : bits);
                 if (sh < 64) lo |= c << sh; else hi |= c << (sh - 64);

@@ -325,15 +325,8 @@ def test_fake_quant_all_tokens(rt, dt, n):
     assert_same(yv, wv, dt)
 
 
-@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
-def test_fake_quant_dynamic_range_stress(rt, dt):
-    """Rows chosen to sit on every edge of the quantiser's row-level fast path (common.cuh RowQuant): scales from
-    2^-45 to 2^45 (inside and outside its window), elements far below the quantisation step, zeros of both signs,
-    denormals, a tiny negative minimum whose zero-point rounds to zero, constant, infinite and NaN rows.  Bit-exact
-    against the oracle (= the reference's true division and torch.clamp)."""
-    _, ops = rt
-    rng = np.random.default_rng(77)
-    n = 1024
+def stress_rows(rng, n):
+    """fp32 rows sitting on every edge of the quantiser's row-level fast path (see the test below)."""
     rows = []
     for k in range(-45, 46, 3):
         r = rng.standard_normal(n).astype(np.float32) * np.float32(2.0 ** k)
@@ -354,6 +347,18 @@ def test_fake_quant_dynamic_range_stress(rt, dt):
     rows.append(np.full(n, -0.3, np.float32)); rows.append(np.zeros(n, np.float32))
     rows.append(rng.standard_normal(n).astype(np.float32) * np.float32(1e-42))   # denormal row
     r = rng.standard_normal(n).astype(np.float32) * np.float32(3e38 / 6); rows.append(r)   # range near overflow
+    return rows
+
+
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
+def test_fake_quant_dynamic_range_stress(rt, dt):
+    """Rows chosen to sit on every edge of the quantiser's row-level fast path (common.cuh RowQuant): scales from
+    2^-45 to 2^45 (inside and outside its window), elements far below the quantisation step, zeros of both signs,
+    denormals, a tiny negative minimum whose zero-point rounds to zero, constant, infinite and NaN rows.  Bit-exact
+    against the oracle (= the reference's true division and torch.clamp)."""
+    _, ops = rt
+    rng = np.random.default_rng(77)
+    rows = stress_rows(rng, 1024)
     x = torch.from_numpy(np.stack(rows)[None]).to(TDT[dt])
     S = x.shape[1]
     for bits in ((2, 4, 8), (3, 6, 12)):

@@ -313,3 +313,27 @@ def test_packed_container_roundtrip(rt, extended):
     assert torch.equal(dk, k) and torch.equal(dv, v)          # torch.equal: -0.0 == +0.0
     dense_bytes = 2 * int(info["propagation_info"]["selection_mask"].sum()) * HD * 4
     assert packed.nbytes() < dense_bytes / 3                  # 8/4/2-bit codes vs fp32 rows
+
+
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16])
+def test_dynamic_range_stress_extended_and_packed(rt, dt):
+    """The fast-path edge rows of test_fake_quant_dynamic_range_stress through the group-wise kernel (with and without the
+    outlier split) and the packed reference-mode kernel."""
+    _, ops = rt
+    from test_parity_gpu import stress_rows
+    rng = np.random.default_rng(78)
+    x = torch.from_numpy(np.stack(stress_rows(rng, 1024))[None]).to(TDT[dt])
+    xn, _ = oracle.from_torch(x)
+    S, n = x.shape[1], x.shape[2]
+    bits = (2, 4, 8)
+    labels = rng.integers(0, 3, (1, S)).astype(np.uint8)
+    lab_d = torch.from_numpy(labels).cuda()
+    for mode, group, tau in (("token_group", 128, 0.0), ("token_group", 128, 6.0), ("token", 0, 6.0)):
+        opt = ops.quant_options(mode, mode, group_size=group, outlier_tau=tau)
+        y, _ = ops.quant_gather_ex(x.cuda(), None, None, lab_d, bits, S, opt)
+        r = oracle.fake_quant_ex(xn[0], dt, labels[0], bits, mode=MODE[mode], group=group, tau=tau)
+        same(y, r["out"][None], dt)
+    codes, qp = ops.quant_pack(x.cuda(), None, lab_d, bits, S)
+    out, ocodes, oqp = oracle.fake_quant_rows(xn, dt, labels, bits, True, True)
+    rb = ops.packed_row_bytes(n, max(bits))
+    np.testing.assert_array_equal(codes.cpu().numpy().reshape(S, rb), oracle.pack_codes(ocodes, labels, bits, rb))
