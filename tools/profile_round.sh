@@ -18,4 +18,4 @@ EX="python tools/profile_ex.py"
 $EX > $OUT/plain_ex_${TAG}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"quant_" -s 9 -c 9 \
     -o $OUT/prof_ex_${TAG} $EX > $OUT/ncu_ex_${TAG}.log 2>&1
-tail -2 $OUT/ncu_launches_${TAG}.log $OUT/ncu_full_${TAG}.log $OUT/ncu_qk_${TAG}.log | cut -c1-200
+for f in $OUT/ncu_launches_${TAG}.log $OUT/ncu_full_${TAG}.log $OUT/ncu_qk_${TAG}.log; do tail -n 2 $f | cut -c1-200; done
