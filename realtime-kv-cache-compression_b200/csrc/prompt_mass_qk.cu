@@ -249,6 +249,12 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int c = item % chunks, h = (item / chunks) % p.H, b = item / (chunks * p.H);
             const int t1 = min(tiles, (c + 1) * T);
+            const float *lse_row = p.lse + ((size_t)b * p.H + h) * p.S;
+            // The row's log-sum-exp is a dependent global load (~1 us under load) at the head of every tile's
+            // epilogue, i.e. on the accumulator hand-off critical path (ncu: 15 % of all stall samples sat on its
+            // first use).  It is therefore loaded one owned tile ahead, and only consumed after the wait for the MMA.
+            float lse_next = 0.0f;
+            bool have_next = false;
             for (int tile = c * T; tile < t1; ++tile, ++q) {
                 if ((q & 1) != grp) continue;
                 const int a = grp;
@@ -256,9 +262,15 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const bool live = i < p.S;
                 // rows of this tile see every prompt key (no causal / P masking needed) -> branch-free body
                 const bool unmasked = (p.P == kTileN) && (!p.causal || tile * kTileM >= kTileN - 1);
-                const float l2 = live ? p.lse[((size_t)b * p.H + h) * p.S + i] * kLog2e : 0.0f;
+                const float lse_cur = have_next ? lse_next : (live ? __ldg(lse_row + i) : 0.0f);
+                have_next = tile + 2 < t1;
+                if (have_next) {
+                    const int in = (tile + 2) * kTileM + row;
+                    lse_next = in < p.S ? __ldg(lse_row + in) : 0.0f;
+                }
                 mbar_wait(smem_u32(&tfull[a]), (q >> 1) & 1);
                 tc_fence_after();
+                const float l2 = lse_cur * kLog2e;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN);
                 float rs = 0.0f;
                 uint32_t v0[32], v1[32];
