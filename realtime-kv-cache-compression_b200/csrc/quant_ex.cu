@@ -564,6 +564,91 @@ __global__ void __launch_bounds__(kQT) quant_channel_generic_kernel(QXParams q)
     }
 }
 
+// ---- packed rows, channel groups, vector path (no outlier split) ------------------------------------
+// quant_token_ex_kernel's segment statistics with the packing epilogue of quant_pack_vec_kernel: a lane's
+// 16-byte vector becomes EPV codes = one 1..16-byte store, the group's first lane writes (scale, zero-point).
+template <int DT, int NV>
+__global__ void __launch_bounds__(kQT) quant_pack_group_vec_kernel(QXParams q)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    const QGParams &p = q.g;
+    const int r = blockIdx.x, b = blockIdx.y;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    const int G = p.n / q.group;
+    const size_t orow = (size_t)b * p.out_rows + r;
+    uint8_t *dst = q.codes + orow * (size_t)q.row_bytes;
+    float *qp = q.qparams + orow * (size_t)G * 2;
+    if (r >= cnt) {
+        for (int64_t c = threadIdx.x; c < q.row_bytes / 16; c += kQT) ((uint4 *)dst)[c] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 2 * G; i += kQT) qp[i] = 0.0f;
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint4 *src = (const uint4 *)((const char *)p.x[0] + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+    uint4 raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        raw[k] = v < nvec ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    const int lanes = q.lanes;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned seg = lanes >= 32 ? 0xffffffffu : (((1u << lanes) - 1u) << (lane & ~(unsigned)(lanes - 1)));
+    const int vbytes = bits > 8 ? 2 * EPV : EPV * bits / 8;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int v = threadIdx.x + k * kQT;
+        float f[EPV];
+        Vec16<DT>::unpack(raw[k], f);
+        int nan = 0;
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+        nan = (__ballot_sync(0xffffffffu, nan) & seg) != 0;
+        mn = ord2f(__reduce_min_sync(seg, f2ord(mn)));
+        mx = ord2f(__reduce_max_sync(seg, f2ord(mx)));
+        if (nan) mn = mx = __int_as_float(0x7fc00000);
+        if (v < nvec) {
+            RowQuant<DT> rq;
+            rq.init(mn, mx, bits);
+            if ((lane & (lanes - 1)) == 0) { const int gi = v / lanes; qp[2 * gi] = rq.scale; qp[2 * gi + 1] = rq.zp; }
+            float cf[EPV];
+            if (rq.fast) rq.codes_fast(f, cf);
+            else {
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) cf[e] = rq.code_slow(f[e]);
+            }
+            unsigned long long lo = 0, hi = 0;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const unsigned long long c = cf[e] == cf[e] ? (unsigned long long)(unsigned)cf[e] : 0ull;
+                const int sh = e * (bits > 8 ? 16 : bits);
+                if (sh < 64) lo |= c << sh; else hi |= c << (sh - 64);
+            }
+            uint8_t *o = dst + (size_t)v * vbytes;
+            if (vbytes == 16) *(uint4 *)o = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+            else if (vbytes == 8) *(unsigned long long *)o = lo;
+            else if (vbytes == 4) *(unsigned *)o = (unsigned)lo;
+            else if (vbytes == 2) *(uint16_t *)o = (uint16_t)lo;
+            else *o = (uint8_t)lo;
+        }
+    }
+    for (int64_t c = (int64_t)nvec * vbytes + threadIdx.x; c < q.row_bytes; c += kQT) dst[c] = 0;
+}
+
+template <int DT> static void (*pick_pack_group_kernel(int nv))(QXParams)
+{
+    if (nv <= 1) return quant_pack_group_vec_kernel<DT, 1>;
+    if (nv <= 2) return quant_pack_group_vec_kernel<DT, 2>;
+    if (nv <= 4) return quant_pack_group_vec_kernel<DT, 4>;
+    if (nv <= 5) return quant_pack_group_vec_kernel<DT, 5>;
+    return quant_pack_group_vec_kernel<DT, kMaxVec>;
+}
+
 // ---- packed rows, token modes -------------------------------------------------------------------
 // One CTA per kept row, one warp per channel group (lanes stride the group's channels).  Phase 1 leaves
 // every group's threshold / scale / zero-point / outlier count in shared memory, a scan turns the counts
@@ -785,6 +870,111 @@ __global__ void __launch_bounds__(kQT) pack_channel_kernel(QXParams q)
         }
         if (!UNPACK && bits <= 8)
             for (int i = 0; i < bits; ++i) row[(size_t)c8 * bits / 8 + i] = (uint8_t)(acc >> (8 * i));
+    }
+}
+
+// Vector path of pack_channel_kernel<.., false>: one thread = a 16-byte channel column of a token group; pass 1 reads the
+// column (min/max per channel, written as the group's parameter table), pass 2 re-reads it through L2 and emits each row's
+// EPV codes as one 1..16-byte store.
+template <int DT, int CT>
+__global__ void __launch_bounds__(CT) pack_channel_vec_kernel(QXParams q)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    constexpr int GT = 32, U = 8;
+    __shared__ int s_tok[GT], s_cls[GT];
+    const QGParams &p = q.g;
+    const int g = blockIdx.x, r0 = g * q.tgroup, b = blockIdx.y;
+    const int v = blockIdx.z * CT + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    const int nvec = p.n / EPV;
+    if (threadIdx.x < GT) {
+        const int r = r0 + threadIdx.x;
+        int tok = -1, cls = 0;
+        if (threadIdx.x < q.tgroup && r < cnt && r < p.out_rows) {
+            tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+            cls = p.labels[(int64_t)b * p.S + tok];
+        }
+        s_tok[threadIdx.x] = tok; s_cls[threadIdx.x] = cls;
+    }
+    __syncthreads();
+    if (v >= nvec) return;
+    const size_t row_b = (size_t)p.n * Elem<DT>::kBytes;
+    const char *xb = (const char *)p.x[0] + (size_t)b * p.S * row_b;
+    float mn[EPV], mx[EPV];
+    unsigned nanmask = 0;
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) { mn[e] = INFINITY; mx[e] = -INFINITY; }
+#pragma unroll 1
+    for (int j0 = 0; j0 < GT; j0 += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (s_tok[j0 + u] >= 0) raw[u] = __ldg((const uint4 *)(xb + (size_t)s_tok[j0 + u] * row_b) + v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (s_tok[j0 + u] >= 0) {
+                any = true;
+                float f[EPV];
+                Vec16<DT>::unpack(raw[u], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    nanmask |= (unsigned)(f[e] != f[e]) << e;
+                    mn[e] = fminf(mn[e], f[e]); mx[e] = fmaxf(mx[e], f[e]);
+                }
+            }
+        }
+    }
+    const int ngroups = (p.out_rows + q.tgroup - 1) / q.tgroup;
+    float *qp = q.qparams + (((size_t)b * ngroups + g) * p.n + (size_t)v * EPV) * 2;
+    float sc0[EPV], zp0[EPV], sc1[EPV], zp1[EPV], sc2[EPV], zp2[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        if ((nanmask >> e) & 1) mn[e] = mx[e] = __int_as_float(0x7fc00000);
+        if (!any) mn[e] = mx[e] = 0.0f;
+        quant_params<DT>(mn[e], mx[e], p.bits[0], sc0[e], zp0[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[1], sc1[e], zp1[e]);
+        quant_params<DT>(mn[e], mx[e], p.bits[2], sc2[e], zp2[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < EPV; e += 2)
+        *(float4 *)(qp + 2 * e) = make_float4(mn[e], mx[e], mn[e + 1], mx[e + 1]);
+    const float qm0 = qmax_rounded<DT>(p.bits[0]), qm1 = qmax_rounded<DT>(p.bits[1]), qm2 = qmax_rounded<DT>(p.bits[2]);
+#pragma unroll 1
+    for (int j0 = 0; j0 < GT; j0 += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (s_tok[j0 + u] >= 0) raw[u] = ldg_stream((const uint4 *)(xb + (size_t)s_tok[j0 + u] * row_b) + v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + u;
+            if (s_tok[j] < 0) continue;                      // padding rows were zeroed by the host-side memset
+            const int cls = s_cls[j];
+            const int bits = cls == 0 ? p.bits[0] : (cls == 1 ? p.bits[1] : p.bits[2]);
+            const float qm = cls == 0 ? qm0 : (cls == 1 ? qm1 : qm2);
+            float f[EPV];
+            Vec16<DT>::unpack(raw[u], f);
+            unsigned long long lo = 0, hi = 0;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float sc = cls == 0 ? sc0[e] : (cls == 1 ? sc1[e] : sc2[e]);
+                const float z = cls == 0 ? zp0[e] : (cls == 1 ? zp1[e] : zp2[e]);
+                const float qf = quant_code<DT>(f[e], sc, z, qm);
+                const unsigned long long c = qf == qf ? (unsigned long long)(unsigned)qf : 0ull;
+                const int sh = e * (bits > 8 ? 16 : bits);
+                if (sh < 64) lo |= c << sh; else hi |= c << (sh - 64);
+            }
+            const int vbytes = bits > 8 ? 2 * EPV : EPV * bits / 8;
+            uint8_t *o = q.codes + ((size_t)b * p.out_rows + r0 + j) * (size_t)q.row_bytes + (size_t)v * vbytes;
+            if (vbytes == 16) *(uint4 *)o = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+            else if (vbytes == 8) *(unsigned long long *)o = lo;
+            else if (vbytes == 4) *(unsigned *)o = (unsigned)lo;
+            else if (vbytes == 2) *(uint16_t *)o = (uint16_t)lo;
+            else *o = (uint8_t)lo;
+        }
     }
 }
 
@@ -1048,14 +1238,40 @@ extern "C" int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,
         if (out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
         return rtkv_quant_pack(X, dtype, B, S, n, sel_idx, row_stats, labels, bits, out_rows, row_bytes, codes, qparams, stream);
     }
-    RTKV_CUDA(cudaMemsetAsync(codes, 0, (size_t)B * out_rows * (size_t)row_bytes, st));
+    const size_t codes_bytes = (size_t)B * out_rows * (size_t)row_bytes;
     if (mode == RTKV_Q_CHANNEL) {
+        RTKV_CUDA(cudaMemsetAsync(codes, 0, codes_bytes, st));
         if (out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
-        dim3 grid((out_rows + q.tgroup - 1) / q.tgroup, B, (n / 8 + kQT - 1) / kQT);
-        RTKV_DISPATCH(dtype, (pack_channel_kernel<DT, false><<<grid, kQT, 0, st>>>(q)));
+        const int epv = 16 / dtype_bytes(dtype);
+        int minb = bits[0] < bits[1] ? bits[0] : bits[1]; minb = minb < bits[2] ? minb : bits[2];
+        const bool vec = n % epv == 0 && (uintptr_t)X % 16 == 0 && (uintptr_t)codes % 16 == 0 && (uintptr_t)qparams % 16 == 0 &&
+                         row_bytes % 16 == 0 && (epv * minb) % 8 == 0;
+        if (vec) {
+            dim3 grid((out_rows + q.tgroup - 1) / q.tgroup, B, (n / epv + 127) / 128);
+            RTKV_DISPATCH(dtype, (pack_channel_vec_kernel<DT, 128><<<grid, 128, 0, st>>>(q)));
+        } else {
+            dim3 grid((out_rows + q.tgroup - 1) / q.tgroup, B, (n / 8 + kQT - 1) / kQT);
+            RTKV_DISPATCH(dtype, (pack_channel_kernel<DT, false><<<grid, kQT, 0, st>>>(q)));
+        }
     } else {
         if (!q.tau_q8 && out_cnt) RTKV_CUDA(cudaMemsetAsync(out_cnt, 0, (size_t)B * out_rows * sizeof(int32_t), st));
         if (!q.tau_q8) q.out_cnt = nullptr;
+        if (!q.tau_q8) {                          // vector kernel when the shapes allow it
+            const int epv = 16 / dtype_bytes(dtype);
+            int minb = bits[0] < bits[1] ? bits[0] : bits[1]; minb = minb < bits[2] ? minb : bits[2];
+            const int l = q.group % epv == 0 ? q.group / epv : 0;
+            const bool vec = n % epv == 0 && n <= kMaxVec * kQT * epv && (uintptr_t)X % 16 == 0 && (uintptr_t)codes % 16 == 0 &&
+                             row_bytes % 16 == 0 && (epv * minb) % 8 == 0 && l >= 1 && l <= 32 && (l & (l - 1)) == 0;
+            if (vec) {
+                q.lanes = l;
+                void (*kern)(QXParams) = nullptr;
+                RTKV_DISPATCH(dtype, kern = pick_pack_group_kernel<DT>((n / epv + kQT - 1) / kQT));
+                RTKV_CUDA(launch_kernel(kern, dim3(out_rows, B), dim3(kQT), 0, st, 1, q));
+                RTKV_LAUNCH_CHECK("quant_pack_group_vec_kernel");
+                return RTKV_OK;
+            }
+        }
+        RTKV_CUDA(cudaMemsetAsync(codes, 0, codes_bytes, st));
         const size_t smem = (size_t)(n / q.group) * sizeof(GroupRec);
         RTKV_DISPATCH(dtype, (quant_pack_ex_kernel<DT><<<dim3(out_rows, B), kQT, smem, st>>>(q)));
     }

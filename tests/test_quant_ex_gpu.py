@@ -173,11 +173,12 @@ def test_bad_options_are_rejected(rt):
 @pytest.mark.parametrize("dt,bits", [(oracle.F32, (2, 4, 8)), (oracle.BF16, (2, 4, 8)), (oracle.F32, (4, 8, 16)),
                                      (oracle.F16, (1, 2, 12))])
 @pytest.mark.parametrize("mode,group,tau,cap", [("token", 0, 6.0, 16), ("token_group", 64, 0.0, 0),
-                                                ("token_group", 128, 5.0, 3), ("token", 0, 0.0, 0)])
+                                                ("token_group", 128, 5.0, 3), ("token", 0, 0.0, 0),
+                                                ("token_group", 24, 0.0, 0)])      # 24: not a power of two -> scalar kernel
 def test_packed_token_modes(rt, dt, bits, mode, group, tau, cap):
     _, ops = rt
     rng = np.random.default_rng(bits[0] * 7 + group)
-    B, S, n = 2, 48, 512
+    B, S, n = 2, 48, (480 if group == 24 else 512)
     x = make_rows(rng, B, S, n, dt)
     sel, labels, ms, rows = selection(ops, rng, B, S, bits)
     mask = sel.mask.cpu().numpy()
@@ -213,7 +214,8 @@ def test_packed_token_modes(rt, dt, bits, mode, group, tau, cap):
         assert torch.equal(torch.nan_to_num(d.float(), nan=12345.0), torch.nan_to_num(y.float(), nan=12345.0))
 
 
-@pytest.mark.parametrize("dt,bits", [(oracle.F32, (2, 4, 8)), (oracle.BF16, (1, 4, 8)), (oracle.F32, (4, 8, 16))])
+@pytest.mark.parametrize("dt,bits", [(oracle.F32, (2, 4, 8)), (oracle.BF16, (1, 4, 8)), (oracle.F32, (4, 8, 16)),
+                                     (oracle.F32, (1, 2, 4))])          # fp32 with 1-bit codes: the scalar kernels
 @pytest.mark.parametrize("n,tg", [(512, 32), (264, 5)])
 def test_packed_channel_mode(rt, dt, bits, n, tg):
     _, ops = rt
