@@ -102,6 +102,13 @@ if only is None or "k3" in only:
     res["k3_us"] = t; res["k3_GBs"] = 4 * kv_bytes / t / 1e3; res["k3_frac"] = res["k3_GBs"] / PEAK
     t = graph_time(lambda i: (ok.copy_(Ks[i]), ov.copy_(Vs[i])), nset)
     res["torch_copy_same_bytes_us"] = t; res["torch_copy_GBs"] = 4 * kv_bytes / t / 1e3
+    for hd, tag in ((torch.bfloat16, "bf16"), (torch.float16, "f16")):
+        Kh = [k.to(hd) for k in Ks] + [k.to(hd) * 0.5 for k in Ks]
+        Vh = [v.to(hd) for v in Vs] + [v.to(hd) * 0.5 for v in Vs]
+        okh, ovh = torch.empty_like(Kh[0]), torch.empty_like(Kh[0])
+        t = graph_time(lambda i: ops.quant_gather(Kh[i], Vh[i], None, labels, (2, 4, 8), S, out0=okh, out1=ovh), len(Kh))
+        res[f"k3_{tag}_us"] = t; res[f"k3_{tag}_frac"] = 2 * kv_bytes / t / 1e3 / PEAK
+        del Kh, Vh
 
 if only is None or "k3ex" in only:
     # extended scale granularities / outlier split (quant_ex.cu): same algorithmic bytes as K3
