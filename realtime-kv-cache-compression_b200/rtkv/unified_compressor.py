@@ -289,6 +289,59 @@ class RealTimePrefillCompressor:
                          out0=out_keys, out1=out_values)
         return sel
 
+    def collect_async(self, pending):
+        """Statistics of a whole prefill in ONE device-to-host transfer.
+
+        pending: list of (layer_idx, Selection, out_keys, out_values) from compress_layer_kv_cache_async.  All
+        layers' statistics blocks, scores and labels are concatenated on the device, copied once and the same
+        `compression_info` dictionaries as the synchronous call are built from them (and stored in
+        `layer_states` / `importance_tracker.layer_scores`).  Returns {layer_idx: (K', V', info)} where K', V'
+        are [B, max_selected, HD] views of the fixed-capacity output buffers (rows past a batch row's own
+        n_selected are whatever zero_pad left there)."""
+        if not pending:
+            return {}
+        t0 = time.time()
+        blobs = []
+        for _, sel, _, _ in pending:
+            blobs += [sel.stats.view(torch.uint8).reshape(-1), sel.scores.view(torch.uint8).reshape(-1),
+                      sel.labels.view(torch.uint8).reshape(-1)]
+        dev_blob = torch.cat(blobs)
+        host = self._stats_buffer(dev_blob.numel())[: dev_blob.numel()]
+        host.copy_(dev_blob, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = host.numpy()
+        results, off = {}, 0
+        share = (time.time() - t0) / len(pending)
+        for layer_idx, sel, out_keys, out_values in pending:
+            B, S = sel.B, sel.S
+            n_tokens = B * S
+            nstat = sel.stats.numel()
+            st = raw[off: off + nstat]; off += nstat
+            scores = torch.from_numpy(raw[off: off + 4 * n_tokens].view(np.float32).reshape(B, S).copy()); off += 4 * n_tokens
+            labels_np = raw[off: off + n_tokens].reshape(B, S).astype(np.int64); off += n_tokens
+            layer = st[: ops.LAYER_STATS_BYTES].view(ops._lib.LAYER_STATS)[0]
+            rows = st[ops.LAYER_STATS_BYTES:].view(ops._lib.ROW_STATS).copy()
+            ms = int(layer["max_selected"])
+            ratio = self.propagator.get_layer_propagation_ratio(layer_idx)
+            k_sel, v_sel = out_keys[:, :ms], out_values[:, :ms]
+            original = 2 * out_keys.shape[0] * S * out_keys.shape[2]
+            ratio_c = (k_sel.numel() + v_sel.numel()) / original if original else 0
+            info = {
+                "layer_idx": layer_idx, "processing_time": share,
+                "original_shape": torch.Size((B, S, out_keys.shape[2])), "compressed_shape": k_sel.shape,
+                "compression_ratio": ratio_c, "memory_savings": 1.0 - ratio_c,
+                "importance_stats": _importance_stats(rows, n_tokens),
+                "precision_stats": _precision_stats(rows, n_tokens),
+                "quantization_info": {"scales": {}, "zero_points": {}, "bit_assignments": labels_np},
+                "propagation_info": {"layer_idx": layer_idx, "propagation_ratio": ratio, "original_length": S,
+                                     "max_selected_length": ms, "selection_mask": sel.mask.view(torch.bool),
+                                     "selection_stats": selection_info_from_rows(rows, S * ratio)},
+            }
+            self.importance_tracker.layer_scores[layer_idx] = scores
+            self.layer_states[layer_idx] = info
+            results[layer_idx] = (k_sel, v_sel, info)
+        return results
+
     # -- aggregation (:174-230) ----------------------------------------------------------
     def get_overall_compression_stats(self):
         if not self.layer_states:

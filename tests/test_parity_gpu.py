@@ -700,6 +700,38 @@ def test_async_variant_matches_sync(rt):
 
 
 # ---------------------------------------------------------------- reference-style unit tests
+def test_async_prefill_statistics_in_one_transfer(rt):
+    """SURVEY 8f rank 4: a whole prefill without host synchronisation, statistics of all layers fetched once;
+    the resulting compression_info / layer_states equal the synchronous per-layer call."""
+    rtkv, ops = rt
+    L = 4
+    cfg = rtkv.CompressionConfig(num_hidden_layers=L, num_attention_heads=8, hidden_size=512, high_precision_bits=8,
+                                 medium_precision_bits=4, low_precision_bits=2)
+    sync, asyn = rtkv.RealTimePrefillCompressor(cfg), rtkv.RealTimePrefillCompressor(cfg)
+    layers = [synth_layer(2, 8, 300, 512, seed=10 + l)[:3] for l in range(L)]
+    ids = torch.zeros(2, 300, dtype=torch.long, device="cuda")
+    pending = []
+    for l, (K, V, A) in enumerate(layers):
+        ok, ov = torch.zeros_like(K), torch.zeros_like(V)
+        sel = asyn.compress_layer_kv_cache_async(K, V, A, l, ok, ov, zero_pad=True)
+        pending.append((l, sel, ok, ov))
+    got = asyn.collect_async(pending)
+    for l, (K, V, A) in enumerate(layers):
+        k, v, info = sync.compress_layer_kv_cache(K, V, A, ids, l)
+        gk, gv, ginfo = got[l]
+        assert torch.equal(gk, k) and torch.equal(gv, v)
+        for key in ("compressed_shape", "compression_ratio", "memory_savings", "importance_stats", "precision_stats"):
+            assert ginfo[key] == info[key], key
+        np.testing.assert_array_equal(ginfo["quantization_info"]["bit_assignments"], info["quantization_info"]["bit_assignments"])
+        assert torch.equal(ginfo["propagation_info"]["selection_mask"], info["propagation_info"]["selection_mask"])
+        assert ginfo["propagation_info"]["selection_stats"] == info["propagation_info"]["selection_stats"]
+        assert torch.equal(asyn.importance_tracker.layer_scores[l], sync.importance_tracker.layer_scores[l])
+    a, b = asyn.get_overall_compression_stats(), sync.get_overall_compression_stats()
+    for key in a:
+        if "time" not in key:
+            assert a[key] == b[key], key
+
+
 def test_reference_style_component_tests(rt):
     """The assertions of the reference's tests/test_compression.py and test_quantization.py."""
     rtkv, ops = rt
