@@ -287,6 +287,21 @@ RTKV_API int rtkv_unpack_dequant_ex(const uint8_t *codes, const float *qparams, 
                            int out_rows, int64_t row_bytes, const rtkv_quant_options *options /*[host]*/, int tensor,
                            void *Y, void *stream);
 
+/* Decode-step attention directly over packed rows (reference-mode packing: rtkv_quant_pack, one (scale, zero-point)
+ * per kept row; SURVEY.md 8f rank 2/3 - the consumer of the compressed cache the reference returns at
+ * src/models/modified_llama.py:165-166, without ever expanding the codes in memory):
+ *   out[b,h,:] = sum_j softmax_j(sm_scale * q[b,h,:].K'[b,j,h/(H/Hkv),:]) * V'[b,j,h/(H/Hkv),:]
+ * q [B,H,D] f32, D == 128; codes_k/codes_v [B,out_rows,row_bytes]; qparams [B,out_rows,2]; row_bits [B,out_rows] u8 = the
+ * bit width each row was packed with; row_stats[b].n_selected rows of batch row b are valid.  `splits` CTAs share the
+ * rows of one (batch row, head); workspace: rtkv_packed_attention_workspace_bytes(B,H,splits).  out [B,H,D] f32, lse
+ * [B,H] f32 (natural log) or NULL. */
+RTKV_API int64_t rtkv_packed_attention_workspace_bytes(int B, int H, int splits);
+RTKV_API int rtkv_packed_decode_attention(const float *q, const uint8_t *codes_k, const float *qparams_k,
+                                 const uint8_t *codes_v, const float *qparams_v, const uint8_t *row_bits,
+                                 const rtkv_row_stats *row_stats, int64_t row_bytes, int B, int H, int Hkv, int D,
+                                 int out_rows, float sm_scale, int splits, void *workspace, size_t workspace_bytes,
+                                 float *out, float *lse, void *stream);
+
 /* Profiling aid: when set to a device buffer of 64 int64, every rtkv_score_select launch writes
  * buf[0] = number of ticks and buf[1..] = clock64() at its phase boundaries (row 0).  NULL: off. */
 RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "rtkv", "librtkv.so")
 SOURCES = ["capi.cu", "prompt_mass.cu", "prompt_mass_qk.cu", "score_select.cu", "score_select_cluster.cu",
-           "quant_gather.cu", "quant_ex.cu"]
+           "quant_gather.cu", "quant_ex.cu", "packed_attention.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -458,6 +458,30 @@ def unpack_dequant_ex(packed, dtype, S, n, sel, labels, bits, options, tensor=0)
     return y
 
 
+def packed_decode_attention(q, codes_k, qparams_k, codes_v, qparams_v, row_bits, sel, num_kv_heads, sm_scale=None,
+                            splits=None, want_lse=False):
+    """Decode-step attention over packed rows (rtkv_packed_decode_attention).  q [B,H,128] -> out [B,H,128] f32."""
+    require_cuda()
+    q = q.float().contiguous()
+    B, H, D = q.shape
+    out_rows, rb = codes_k.shape[1], codes_k.shape[2]
+    if sm_scale is None:
+        sm_scale = D ** -0.5
+    if splits is None:                      # ~8 CTAs per SM; a CTA takes a multiple of 256 rows (one 32-row step per warp)
+        sms = torch.cuda.get_device_properties(q.device).multi_processor_count
+        want = max(1, min((8 * sms + B * H - 1) // (B * H), (out_rows + 255) // 256))
+        rows_per_cta = ((out_rows + want - 1) // want + 255) // 256 * 256
+        splits = (out_rows + rows_per_cta - 1) // rows_per_cta
+    ws = torch.empty(lib.rtkv_packed_attention_workspace_bytes(B, H, splits), dtype=torch.uint8, device=q.device)
+    out = torch.empty(B, H, D, dtype=torch.float32, device=q.device)
+    lse = torch.empty(B, H, dtype=torch.float32, device=q.device) if want_lse else None
+    check(lib.rtkv_packed_decode_attention(_ptr(q), _ptr(codes_k), _ptr(qparams_k), _ptr(codes_v), _ptr(qparams_v),
+                                           _ptr(row_bits), sel.row_stats_ptr, rb, B, H, int(num_kv_heads), D, out_rows,
+                                           float(sm_scale), int(splits), _ptr(ws), ws.numel(), _ptr(out), _ptr(lse),
+                                           _stream()))
+    return (out, lse) if want_lse else out
+
+
 class HostContext:
     """rtkv_ctx: device staging buffers for the host-buffer entry point."""
 

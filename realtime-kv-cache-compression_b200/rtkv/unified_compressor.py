@@ -74,6 +74,20 @@ class PackedKV:
                 total += int(p["out_cnt"].sum()) * 8 + p["out_cnt"].numel() * 4
         return total
 
+    def attend(self, q, num_kv_heads=None, sm_scale=None, want_lse=False):
+        """Decode-step attention of q [B,H,128] over this layer's packed rows without expanding them
+        (reference-mode packing only: one scale per kept row, no outlier split)."""
+        if self.options is not None and (self.options.mode[0] or self.options.mode[1] or self.options.outlier_tau_q8):
+            raise NotImplementedError("attend() reads reference-mode packed rows (one scale per kept row)")
+        if getattr(self, "_row_bits", None) is None:
+            _, sel_labels = ops.gather_scalars(self.sel, self.max_selected)
+            lut = torch.tensor(self.bits, dtype=torch.uint8, device=sel_labels.device)
+            self._row_bits = lut[sel_labels].contiguous()
+        hkv = num_kv_heads if num_kv_heads is not None else self.width // 128
+        return ops.packed_decode_attention(q, self.keys["codes"], self.keys["qparams"], self.values["codes"],
+                                           self.values["qparams"], self._row_bits, self.sel, hkv, sm_scale,
+                                           want_lse=want_lse)
+
     def dequantize(self):
         k = ops.unpack_dequant_ex(self.keys, self.dtype, self.seq_len, self.width, self.sel, self.sel.labels, self.bits,
                                   self.options, tensor=0)
