@@ -24,9 +24,14 @@
 
 namespace rtkv {
 
-constexpr int kPaThreads = 256;
+constexpr int kPaThreads = 128;
 constexpr int kPaWarps = kPaThreads / 32;
 constexpr int kPaD = 128;
+// per-warp staging of one 32-row step (sized for 8-bit rows): K slices at a padded stride (a lane reads its own row with
+// 16-byte loads: stride 144 keeps the 8 lanes of a wavefront on disjoint banks), V slices back to back
+constexpr int kPaKStride = 144, kPaVStride = 128;
+constexpr int kPaStageBytes = 32 * kPaKStride + 32 * kPaVStride;          // 8704
+constexpr int kPaSmemBytes = kPaWarps * 2 * kPaStageBytes;                 // two stages per warp: 69632
 
 struct PaParams {
     const float *q;            // [B,H,D]
@@ -67,20 +72,18 @@ __device__ __forceinline__ float code_f(unsigned word, int shift, unsigned mask)
     return __uint_as_float(((word >> shift) & mask) | 0x4b000000u) - 8388608.0f;
 }
 
-// sum_d q[d] * code[d] over the 128 channels of one head of one packed row (BITS x 16-byte loads).
-// qs = q pre-scaled for this bit width: qs[d] = q[d] * 2^-((d % (16/BITS)) * BITS)
+// sum_d q[d] * code[d] over the 128 channels of one head of one packed row, read from the staged copy in shared memory
+// (BITS x 16-byte loads).  qs = q pre-scaled for this bit width: qs[d] = q[d] * 2^-((d % (16/BITS)) * BITS)
 template <int BITS>
 __device__ __forceinline__ float dot_row(const uint8_t *kp, const float *qs)
 {
     constexpr int PER_HALF = 16 / BITS;             // codes per 16-bit half word
     constexpr unsigned MASK = (1u << BITS) - 1u;
-    uint4 w[BITS];
-#pragma unroll
-    for (int c = 0; c < BITS; ++c) w[c] = __ldg((const uint4 *)kp + c);
     float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int c = 0; c < BITS; ++c) {
-        const unsigned word[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
+        const uint4 w = *((const uint4 *)kp + c);
+        const unsigned word[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -95,38 +98,39 @@ __device__ __forceinline__ float dot_row(const uint8_t *kp, const float *qs)
     return (d[0] + d[1]) + (d[2] + d[3]);
 }
 
-// values of `nrows` rows that all use BITS-bit codes: acc[e] accumulates w_j * code * 2^pos(e)
+// values of `nrows` staged rows that all use BITS-bit codes: acc[e] accumulates w_j * code * 2^pos(e).
+// c4 = first of this lane's 4 channels inside the head (4 * lane)
 template <int BITS>
-__device__ __forceinline__ void value_rows(const uint8_t *vrow0, int64_t row_bytes, int c0, int nrows, const float *sw,
-                                           float (&acc)[4])
+__device__ __forceinline__ void value_rows(const uint8_t *sv, int c4, int nrows, const float *sw, float (&acc)[4])
 {
     constexpr unsigned MASK = (1u << BITS) - 1u;
-    for (int j0 = 0; j0 < nrows; j0 += 8) {
-        unsigned wv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            wv[u] = j0 + u < nrows ? load_codes4(vrow0 + (size_t)(j0 + u) * row_bytes, c0, BITS) : 0u;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float w = sw[j0 + u];                         // 0 for rows past the end
-            if (BITS == 8) {
-                const unsigned hi = wv[u] >> 16;
-                acc[0] = fmaf(w, code_scaled(wv[u], 0xffu), acc[0]);
-                acc[1] = fmaf(w, code_scaled(wv[u], 0xff00u), acc[1]);
-                acc[2] = fmaf(w, code_scaled(hi, 0xffu), acc[2]);
-                acc[3] = fmaf(w, code_scaled(hi, 0xff00u), acc[3]);
-            } else {
-                acc[0] = fmaf(w, code_scaled(wv[u], MASK), acc[0]);
-                acc[1] = fmaf(w, code_scaled(wv[u], MASK << BITS), acc[1]);
-                acc[2] = fmaf(w, code_scaled(wv[u], MASK << (2 * BITS)), acc[2]);
-                acc[3] = fmaf(w, code_scaled(wv[u], MASK << (3 * BITS)), acc[3]);
-            }
+#pragma unroll 8
+    for (int j = 0; j < nrows; ++j) {
+        const unsigned wv = load_codes4(sv + j * kPaVStride, c4, BITS);
+        const float w = sw[j];
+        if (BITS == 8) {
+            const unsigned hi = wv >> 16;
+            acc[0] = fmaf(w, code_scaled(wv, 0xffu), acc[0]);
+            acc[1] = fmaf(w, code_scaled(wv, 0xff00u), acc[1]);
+            acc[2] = fmaf(w, code_scaled(hi, 0xffu), acc[2]);
+            acc[3] = fmaf(w, code_scaled(hi, 0xff00u), acc[3]);
+        } else {
+            acc[0] = fmaf(w, code_scaled(wv, MASK), acc[0]);
+            acc[1] = fmaf(w, code_scaled(wv, MASK << BITS), acc[1]);
+            acc[2] = fmaf(w, code_scaled(wv, MASK << (2 * BITS)), acc[2]);
+            acc[3] = fmaf(w, code_scaled(wv, MASK << (3 * BITS)), acc[3]);
         }
     }
 }
 
-__global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(PaParams p)
+__device__ __forceinline__ void pa_cp_async16(void *smem, const void *gmem)
 {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaParams p)
+{
+    extern __shared__ __align__(16) unsigned char pa_smem[];
     __shared__ __align__(16) float s_q[4][kPaD];              // q pre-scaled for 1/2/4/8-bit rows
     __shared__ float s_m[kPaWarps], s_l[kPaWarps], s_acc[kPaWarps][kPaD];
     __shared__ __align__(16) float s_w[kPaWarps][32];
@@ -135,12 +139,12 @@ __global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(P
     pdl_wait();
     pdl_trigger();
     const int cnt = min(p.row_stats[b].n_selected, p.out_rows);
-    const int per = (((cnt + p.splits - 1) / p.splits) + 255) & ~255;      // every warp of the CTA gets the same number of 32-row steps
+    const int per = (((cnt + p.splits - 1) / p.splits) + kPaThreads - 1) / kPaThreads * kPaThreads;   // equal steps per warp
     const int r0 = split * per, r1 = min(cnt, r0 + per);
     const int hk = h / (p.H / p.Hkv);
     float qsum = 0.0f;
-    if (threadIdx.x < kPaD) {
-        const int d = threadIdx.x;
+    {
+        const int d = threadIdx.x;                          // kPaThreads == kPaD
         const float qd = p.q[((size_t)b * p.H + h) * kPaD + d];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(P
         }
     }
     __syncthreads();
-    {   // sum of the unscaled q (1-bit table entries with d % 16 == 0 are unscaled; simpler: recompute from the 8-bit table)
+    {
         float part = 0.0f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const int d = 4 * lane + e; part += s_q[3][d] * ((d & 1) ? 256.0f : 1.0f); }
@@ -162,46 +166,62 @@ __global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(P
     // one accumulator set per bit width (implicit scale 2^pos) + one for steps with mixed widths
     float acc1[4] = {0, 0, 0, 0}, acc2[4] = {0, 0, 0, 0}, acc4[4] = {0, 0, 0, 0}, acc8[4] = {0, 0, 0, 0}, accg[4] = {0, 0, 0, 0};
     const size_t base = (size_t)b * p.out_rows;
-    const int c0 = hk * kPaD + 4 * lane;                      // value phase: this lane's first channel in a packed row
-    // per-row metadata of the first step; every step prefetches the next one's (the K address depends on the bit width,
-    // so without this each step starts with two dependent global loads)
-    int bits_n = 0;
-    float2 kp_n = make_float2(0.0f, 0.0f), vp_n = kp_n;
-    {
-        const int rb = r0 + warp * 32;
+    unsigned char *stage0 = pa_smem + (size_t)warp * 2 * kPaStageBytes;
+    const int step_stride = kPaWarps * 32;
+
+    // Software pipeline per warp: the K and V slices of step n+1 are copied global -> shared with cp.async (a lane copies
+    // its own row's bits*16 bytes of K and of V) while step n is computed; the per-row metadata runs two steps ahead
+    // because the copy addresses depend on the bit width.
+    struct Meta { int bits; float2 kp, vp; };
+    auto load_meta = [&](int rb) {
+        Meta mt; mt.bits = 0; mt.kp = make_float2(0.0f, 0.0f); mt.vp = mt.kp;
         if (rb < r1) {
             const size_t row = base + (rb + lane < r1 ? rb + lane : rb);
-            bits_n = p.row_bits[row];
-            kp_n = *(const float2 *)(p.pk + row * 2);
-            vp_n = *(const float2 *)(p.pv + row * 2);
+            mt.bits = p.row_bits[row];
+            mt.kp = *(const float2 *)(p.pk + row * 2);
+            mt.vp = *(const float2 *)(p.pv + row * 2);
         }
-    }
-    for (int rb = r0 + warp * 32; rb < r1; rb += kPaWarps * 32) {
-        const int r = rb + lane;
-        const bool live = r < r1;
-        const int nrows = min(32, r1 - rb);
-        const size_t row = base + (live ? r : rb);
-        const int bits = bits_n;
-        const float2 kp = kp_n, vp = vp_n;
-        {
-            const int rn = rb + kPaWarps * 32;
-            if (rn < r1) {
-                const size_t rown = base + (rn + lane < r1 ? rn + lane : rn);
-                bits_n = p.row_bits[rown];
-                kp_n = *(const float2 *)(p.pk + rown * 2);
-                vp_n = *(const float2 *)(p.pv + rown * 2);
+        return mt;
+    };
+    auto issue_copies = [&](int rb, int bits, int st) {
+        if (rb + lane < r1) {
+            const size_t off = (base + rb + lane) * (size_t)p.row_bytes + (((size_t)hk * kPaD * bits) >> 3);
+            unsigned char *sk = stage0 + st * kPaStageBytes + lane * kPaKStride;
+            unsigned char *sv = stage0 + st * kPaStageBytes + 32 * kPaKStride + lane * kPaVStride;
+            for (int c = 0; c < bits; ++c) {
+                pa_cp_async16(sk + 16 * c, p.ck + off + 16 * c);
+                pa_cp_async16(sv + 16 * c, p.cv + off + 16 * c);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int rb = r0 + warp * 32;
+    Meta cur = load_meta(rb), nxt = load_meta(rb + step_stride);
+    issue_copies(rb, cur.bits, 0);
+    for (int it = 0; rb < r1; rb += step_stride, ++it) {
+        const int st = it & 1;
+        const bool live = rb + lane < r1;
+        const int nrows = min(32, r1 - rb);
+        const int bits = cur.bits;
+        const float2 kp = cur.kp, vp = cur.vp;
+        issue_copies(rb + step_stride, nxt.bits, st ^ 1);       // empty group past the end
+        cur = nxt;
+        nxt = load_meta(rb + 2 * step_stride);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // this step's copies have landed (the next one's may fly)
+        __syncwarp();
+        const unsigned char *sk = stage0 + st * kPaStageBytes + lane * kPaKStride;
+        const unsigned char *sv = stage0 + st * kPaStageBytes + 32 * kPaKStride;
         // bit width of every row of the step from two ballots (log2(bits) in 0..3)
         const int lg = 31 - __clz(bits);
         const unsigned b0 = __ballot_sync(0xffffffffu, lg & 1), b1 = __ballot_sync(0xffffffffu, lg & 2);
         // ---- scores: lane = row
-        const uint8_t *krow = p.ck + row * (size_t)p.row_bytes + (((size_t)hk * kPaD * bits) >> 3);
-        float dot;
-        if (bits == 4) dot = dot_row<4>(krow, s_q[2]);
-        else if (bits == 8) dot = dot_row<8>(krow, s_q[3]);
-        else if (bits == 2) dot = dot_row<2>(krow, s_q[1]);
-        else dot = dot_row<1>(krow, s_q[0]);
+        float dot = 0.0f;
+        if (live) {
+            if (bits == 4) dot = dot_row<4>(sk, s_q[2]);
+            else if (bits == 8) dot = dot_row<8>(sk, s_q[3]);
+            else if (bits == 2) dot = dot_row<2>(sk, s_q[1]);
+            else dot = dot_row<1>(sk, s_q[0]);
+        }
         const float s = live ? p.sm_scale_log2 * kp.x * (dot - kp.y * qsum) : -INFINITY;
         // ---- online softmax over the 32 rows of the step
         float smax = s;
@@ -225,18 +245,17 @@ __global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(P
         m = m_new;
         __syncwarp();
         // ---- values: lane = 4 channels; p_j * scale_j from shared memory (broadcast reads)
-        const uint8_t *vrow0 = p.cv + (base + rb) * (size_t)p.row_bytes;
         const bool uniform = (b0 == 0u || b0 == 0xffffffffu) && (b1 == 0u || b1 == 0xffffffffu);
         if (uniform) {
-            if (bits == 4) value_rows<4>(vrow0, p.row_bytes, c0, nrows, s_w[warp], acc4);
-            else if (bits == 8) value_rows<8>(vrow0, p.row_bytes, c0, nrows, s_w[warp], acc8);
-            else if (bits == 2) value_rows<2>(vrow0, p.row_bytes, c0, nrows, s_w[warp], acc2);
-            else value_rows<1>(vrow0, p.row_bytes, c0, nrows, s_w[warp], acc1);
+            if (bits == 4) value_rows<4>(sv, 4 * lane, nrows, s_w[warp], acc4);
+            else if (bits == 8) value_rows<8>(sv, 4 * lane, nrows, s_w[warp], acc8);
+            else if (bits == 2) value_rows<2>(sv, 4 * lane, nrows, s_w[warp], acc2);
+            else value_rows<1>(sv, 4 * lane, nrows, s_w[warp], acc1);
         } else {
             for (int j = 0; j < nrows; ++j) {
                 const int bj = 1 << ((((b1 >> j) & 1) << 1) | ((b0 >> j) & 1));
                 const unsigned mask = (1u << bj) - 1u;
-                const unsigned wv = load_codes4(vrow0 + (size_t)j * p.row_bytes, c0, bj);
+                const unsigned wv = load_codes4(sv + j * kPaVStride, 4 * lane, bj);
                 const float w = s_w[warp][j];
                 accg[0] = fmaf(w, code_f(wv, 0, mask), accg[0]);
                 accg[1] = fmaf(w, code_f(wv, bj, mask), accg[1]);
@@ -244,8 +263,9 @@ __global__ void __launch_bounds__(kPaThreads, 4) packed_attention_split_kernel(P
                 accg[3] = fmaf(w, code_f(wv, 3 * bj, mask), accg[3]);
             }
         }
-        __syncwarp();
+        __syncwarp();                                           // the stage is overwritten two steps later
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // undo the implicit 2^pos of the per-width accumulators
     float acc[4];
     acc[0] = accg[0] + acc8[0] + acc4[0] + acc2[0] + acc1[0];
@@ -324,7 +344,12 @@ extern "C" int rtkv_packed_decode_attention(const float *q, const uint8_t *codes
     p.row_stats = row_stats; p.row_bytes = row_bytes; p.B = B; p.H = H; p.Hkv = Hkv; p.out_rows = out_rows;
     p.splits = splits; p.sm_scale_log2 = sm_scale * 1.4426950408889634f; p.ws = (float *)workspace; p.out = out; p.lse = lse;
     cudaStream_t st = (cudaStream_t)stream;
-    RTKV_CUDA(launch_kernel(packed_attention_split_kernel, dim3(H, splits, B), dim3(kPaThreads), 0, st, 1, p));
+    static bool attr_done = false;
+    if (!attr_done) {
+        RTKV_CUDA(cudaFuncSetAttribute(packed_attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
+        attr_done = true;
+    }
+    RTKV_CUDA(launch_kernel(packed_attention_split_kernel, dim3(H, splits, B), dim3(kPaThreads), kPaSmemBytes, st, 1, p));
     RTKV_CUDA(launch_kernel(packed_attention_combine_kernel, dim3(H, B), dim3(kPaD), 0, st, 1, p));
     RTKV_LAUNCH_CHECK("rtkv_packed_decode_attention");
     return RTKV_OK;

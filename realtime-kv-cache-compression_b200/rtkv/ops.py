@@ -467,10 +467,10 @@ def packed_decode_attention(q, codes_k, qparams_k, codes_v, qparams_v, row_bits,
     out_rows, rb = codes_k.shape[1], codes_k.shape[2]
     if sm_scale is None:
         sm_scale = D ** -0.5
-    if splits is None:                      # ~8 CTAs per SM; a CTA takes a multiple of 256 rows (one 32-row step per warp)
+    if splits is None:                      # ~9 CTAs per SM (3 resident); a CTA takes a multiple of 128 rows (4 warps x 32)
         sms = torch.cuda.get_device_properties(q.device).multi_processor_count
-        want = max(1, min((8 * sms + B * H - 1) // (B * H), (out_rows + 255) // 256))
-        rows_per_cta = ((out_rows + want - 1) // want + 255) // 256 * 256
+        want = max(1, min((9 * sms + B * H - 1) // (B * H), (out_rows + 127) // 128))
+        rows_per_cta = ((out_rows + want - 1) // want + 127) // 128 * 128
         splits = (out_rows + rows_per_cta - 1) // rows_per_cta
     ws = torch.empty(lib.rtkv_packed_attention_workspace_bytes(B, H, splits), dtype=torch.uint8, device=q.device)
     out = torch.empty(B, H, D, dtype=torch.float32, device=q.device)
