@@ -11,7 +11,7 @@ OUT = os.path.join(HERE, "rtkv", "librtkv.so")
 SOURCES = ["capi.cu", "prompt_mass.cu", "prompt_mass_qk.cu", "score_select.cu", "score_select_cluster.cu",
            "quant_gather.cu", "quant_ex.cu", "packed_attention.cu"]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--fmad=false",            # parity-critical arithmetic: no FMA contraction anywhere
     "-Xptxas", "-v",
