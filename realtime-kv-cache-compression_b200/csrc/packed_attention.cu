@@ -31,7 +31,7 @@ constexpr int kPaD = 128;
 // 16-byte loads: stride 144 keeps the 8 lanes of a wavefront on disjoint banks), V slices back to back
 constexpr int kPaKStride = 144, kPaVStride = 128;
 constexpr int kPaStageBytes = 32 * kPaKStride + 32 * kPaVStride;          // 8704
-constexpr int kPaSmemBytes = kPaWarps * 2 * kPaStageBytes;                 // two stages per warp: 69632
+constexpr int kPaSmemBytes = kPaWarps * kPaStageBytes;                     // one K and one V buffer per warp: 34816
 
 struct PaParams {
     const float *q;            // [B,H,D]
@@ -166,12 +166,14 @@ __global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaPa
     // one accumulator set per bit width (implicit scale 2^pos) + one for steps with mixed widths
     float acc1[4] = {0, 0, 0, 0}, acc2[4] = {0, 0, 0, 0}, acc4[4] = {0, 0, 0, 0}, acc8[4] = {0, 0, 0, 0}, accg[4] = {0, 0, 0, 0};
     const size_t base = (size_t)b * p.out_rows;
-    unsigned char *stage0 = pa_smem + (size_t)warp * 2 * kPaStageBytes;
+    unsigned char *sk_w = pa_smem + (size_t)warp * kPaStageBytes;            // this warp's K buffer (32 rows)
+    unsigned char *sv_w = sk_w + 32 * kPaKStride;                           // and V buffer
     const int step_stride = kPaWarps * 32;
 
-    // Software pipeline per warp: the K and V slices of step n+1 are copied global -> shared with cp.async (a lane copies
-    // its own row's bits*16 bytes of K and of V) while step n is computed; the per-row metadata runs two steps ahead
-    // because the copy addresses depend on the bit width.
+    // Software pipeline per warp with ONE K and ONE V buffer: the K slices of step n+1 are copied global -> shared with
+    // cp.async as soon as the dot products of step n have consumed the buffer, the V slices as soon as the value phase of
+    // step n is done; each copy overlaps the other half of the step (and the other warps).  A lane copies its own row's
+    // bits*16 bytes; the per-row metadata runs ahead because the copy addresses depend on the bit width.
     struct Meta { int bits; float2 kp, vp; };
     auto load_meta = [&](int rb) {
         Meta mt; mt.bits = 0; mt.kp = make_float2(0.0f, 0.0f); mt.vp = mt.kp;
@@ -183,34 +185,25 @@ __global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaPa
         }
         return mt;
     };
-    auto issue_copies = [&](int rb, int bits, int st) {
+    auto issue_copy = [&](const uint8_t *codes, unsigned char *buf, int stride, int rb, int bits) {
         if (rb + lane < r1) {
             const size_t off = (base + rb + lane) * (size_t)p.row_bytes + (((size_t)hk * kPaD * bits) >> 3);
-            unsigned char *sk = stage0 + st * kPaStageBytes + lane * kPaKStride;
-            unsigned char *sv = stage0 + st * kPaStageBytes + 32 * kPaKStride + lane * kPaVStride;
-            for (int c = 0; c < bits; ++c) {
-                pa_cp_async16(sk + 16 * c, p.ck + off + 16 * c);
-                pa_cp_async16(sv + 16 * c, p.cv + off + 16 * c);
-            }
+            for (int c = 0; c < bits; ++c) pa_cp_async16(buf + lane * stride + 16 * c, codes + off + 16 * c);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");    // empty group past the end: keeps the accounting uniform
     };
     int rb = r0 + warp * 32;
     Meta cur = load_meta(rb), nxt = load_meta(rb + step_stride);
-    issue_copies(rb, cur.bits, 0);
-    for (int it = 0; rb < r1; rb += step_stride, ++it) {
-        const int st = it & 1;
+    issue_copy(p.ck, sk_w, kPaKStride, rb, cur.bits);           // commit order from here on: K(n), V(n), K(n+1), V(n+1), ...
+    issue_copy(p.cv, sv_w, kPaVStride, rb, cur.bits);
+    for (; rb < r1; rb += step_stride) {
         const bool live = rb + lane < r1;
         const int nrows = min(32, r1 - rb);
         const int bits = cur.bits;
         const float2 kp = cur.kp, vp = cur.vp;
-        issue_copies(rb + step_stride, nxt.bits, st ^ 1);       // empty group past the end
-        cur = nxt;
-        nxt = load_meta(rb + 2 * step_stride);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");    // this step's copies have landed (the next one's may fly)
-        __syncwarp();
-        const unsigned char *sk = stage0 + st * kPaStageBytes + lane * kPaKStride;
-        const unsigned char *sv = stage0 + st * kPaStageBytes + 32 * kPaKStride;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // K(n) landed (V(n) may still fly); a lane reads its own row only
+        const unsigned char *sk = sk_w + lane * kPaKStride;
+        const unsigned char *sv = sv_w;
         // bit width of every row of the step from two ballots (log2(bits) in 0..3)
         const int lg = 31 - __clz(bits);
         const unsigned b0 = __ballot_sync(0xffffffffu, lg & 1), b1 = __ballot_sync(0xffffffffu, lg & 2);
@@ -223,6 +216,7 @@ __global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaPa
             else dot = dot_row<1>(sk, s_q[0]);
         }
         const float s = live ? p.sm_scale_log2 * kp.x * (dot - kp.y * qsum) : -INFINITY;
+        issue_copy(p.ck, sk_w, kPaKStride, rb + step_stride, nxt.bits);      // K(n+1): the K buffer is free again
         // ---- online softmax over the 32 rows of the step
         float smax = s;
 #pragma unroll
@@ -243,7 +237,8 @@ __global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaPa
 #pragma unroll
         for (int e = 0; e < 4; ++e) { acc1[e] *= corr; acc2[e] *= corr; acc4[e] *= corr; acc8[e] *= corr; accg[e] *= corr; }
         m = m_new;
-        __syncwarp();
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // V(n) landed (K(n+1) may still fly)
+        __syncwarp();                                           // every lane's V row and weight are visible to the warp
         // ---- values: lane = 4 channels; p_j * scale_j from shared memory (broadcast reads)
         const bool uniform = (b0 == 0u || b0 == 0xffffffffu) && (b1 == 0u || b1 == 0xffffffffu);
         if (uniform) {
@@ -263,7 +258,10 @@ __global__ void __launch_bounds__(kPaThreads) packed_attention_split_kernel(PaPa
                 accg[3] = fmaf(w, code_f(wv, 3 * bj, mask), accg[3]);
             }
         }
-        __syncwarp();                                           // the stage is overwritten two steps later
+        __syncwarp();                                           // all lanes are done with the V buffer and the weights
+        issue_copy(p.cv, sv_w, kPaVStride, rb + step_stride, nxt.bits);      // V(n+1)
+        cur = nxt;
+        nxt = load_meta(rb + 2 * step_stride);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // undo the implicit 2^pos of the per-width accumulators
