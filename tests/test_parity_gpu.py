@@ -341,6 +341,11 @@ def stress_rows(rng, n):
         rows.append(r)
         rows.append(np.abs(r) + np.float32(2.0 ** k) * 1000)            # all positive, large offset (zp << 0)
         rows.append(-np.abs(r))                                          # all negative (max == -0 possible)
+    for k in (57, 59, 60, 61, 63, 90, 120):                              # both sides of the upper window edge 2^60
+        r = rng.standard_normal(n).astype(np.float32) * np.float32(2.0 ** k)
+        r[rng.integers(0, n, 30)] = 0.0
+        rows.append(r)
+        rows.append(np.abs(r) * np.float32(2.0 ** -3) + np.float32(2.0 ** k))   # narrow range far from zero
     r = rng.standard_normal(n).astype(np.float32); r[3] = np.inf; rows.append(r)
     r = rng.standard_normal(n).astype(np.float32); r[3] = -np.inf; rows.append(r)
     r = rng.standard_normal(n).astype(np.float32); r[9] = np.nan; rows.append(r)
