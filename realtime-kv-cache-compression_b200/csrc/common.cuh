@@ -209,8 +209,9 @@ template <int DT> __device__ __forceinline__ float qmax_rounded(int bits)
 // which returns the correctly rounded quotient whenever |q0| >= 2^-30 (no underflow in the residuals;
 // tools/divcheck.c: 0 mismatches in 4.6e9 guarded pairs); smaller quotients take the plain division.
 // For those elements t = x/scale + zp is finite and >= +0 (x >= row min and rounding is monotone, so
-// x/scale >= -zp), hence the lower clamp bound and the NaN / -0.0 cases of torch.clamp cannot occur and
-// the clamp is one FMNMX.  Every other row and element runs quant_code/dequant_code unchanged.
+// x/scale >= -zp; no intermediate overflows the tensor dtype - fp16 rows are additionally required to keep
+// |x|/scale inside the half range), hence the lower clamp bound and the NaN / -0.0 cases of torch.clamp
+// cannot occur and the clamp is one FMNMX.  Every other row and element runs quant_code/dequant_code unchanged.
 template <int DT> struct RowQuant {
     float scale, zp, qmax_r, rcp;
     bool fast;
@@ -219,6 +220,9 @@ template <int DT> struct RowQuant {
         quant_params<DT>(mn, mx, bits, scale, zp);
         qmax_r = qmax_rounded<DT>(bits);
         fast = (mx != mn) && scale >= 0x1p-30f && scale <= 0x1p60f && fabsf(mn) <= 0x1p60f && fabsf(mx) <= 0x1p60f;
+        // fp16 has a small exponent range: a narrow row far from zero makes x/scale and the zero-point overflow to inf, and
+        // the reference then produces NaN (inf - inf).  Such rows must take the plain path (found by test_fake_quant_fuzz).
+        if (DT == RTKV_F16) fast = fast && fabsf(mn) <= 65000.0f * scale && fabsf(mx) <= 65000.0f * scale;
         rcp = __frcp_rn(scale);
     }
     __device__ __forceinline__ float slow(float x) const

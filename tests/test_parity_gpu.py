@@ -373,6 +373,41 @@ def test_fake_quant_dynamic_range_stress(rt, dt):
         assert_same(y, w, dt)
 
 
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fake_quant_fuzz(rt, dt, seed):
+    """Differential fuzz of the quantiser (fast and plain paths) against the oracle: 1500 rows per case with random
+    magnitudes 2^-40..2^40 and ten row shapes (gaussian, one-sided, heavy tailed, sparse, integer valued, two valued, nearly
+    constant, tiny range far from zero, denormal mix, sorted ramp), three random bit-width triples per case."""
+    _, ops = rt
+    rng = np.random.default_rng(1000 + seed)
+    n, R = 512, 1500
+    x = np.empty((R, n), np.float32)
+    for r in range(R):
+        kind = r % 10
+        mag = np.float32(2.0 ** rng.uniform(-40, 40))
+        if kind == 0: v = rng.standard_normal(n)
+        elif kind == 1: v = np.abs(rng.standard_normal(n)) + rng.uniform(0, 5)
+        elif kind == 2: v = rng.standard_cauchy(n)
+        elif kind == 3: v = rng.standard_normal(n) * (rng.random(n) < 0.1)
+        elif kind == 4: v = rng.integers(-50, 50, n).astype(np.float64)
+        elif kind == 5: v = np.where(rng.random(n) < 0.5, rng.uniform(-3, 3), rng.uniform(-3, 3))
+        elif kind == 6: v = rng.uniform(-3, 3) + rng.standard_normal(n) * 1e-6
+        elif kind == 7: v = rng.uniform(100, 1000) * rng.choice([-1, 1]) + rng.random(n)
+        elif kind == 8: v = rng.standard_normal(n) * np.where(rng.random(n) < 0.3, 1e-38 / float(mag), 1.0)
+        else: v = np.sort(rng.standard_normal(n))
+        x[r] = np.clip(v.astype(np.float64) * float(mag), -3e38, 3e38).astype(np.float32)
+    xt = torch.from_numpy(x[None]).to(TDT[dt])
+    xn = oracle.from_torch(xt)[0]
+    for trial in range(3):
+        lo, mid, hi = sorted(rng.choice([1, 2, 3, 4, 5, 6, 8, 10, 12] if dt == oracle.F16 else [1, 2, 3, 4, 6, 8, 12, 16], 3))
+        labels = rng.integers(0, 3, (1, R)).astype(np.uint8)
+        bits = (int(lo), int(mid), int(hi))
+        y, _ = ops.quant_gather(xt.cuda(), None, None, torch.from_numpy(labels).cuda(), bits, R)
+        w, _, _ = oracle.fake_quant_rows(xn, dt, labels, bits)
+        assert_same(y, w, dt)
+
+
 @pytest.mark.parametrize("dt,bits", [(oracle.F32, (4, 8, 16)), (oracle.BF16, (4, 8, 16)), (oracle.F32, (1, 12, 24)),
                                      (oracle.F16, (3, 5, 11))])
 def test_fake_quant_bit_widths(rt, dt, bits):
