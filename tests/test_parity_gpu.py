@@ -373,15 +373,8 @@ def test_fake_quant_dynamic_range_stress(rt, dt):
         assert_same(y, w, dt)
 
 
-@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_fake_quant_fuzz(rt, dt, seed):
-    """Differential fuzz of the quantiser (fast and plain paths) against the oracle: 1500 rows per case with random
-    magnitudes 2^-40..2^40 and ten row shapes (gaussian, one-sided, heavy tailed, sparse, integer valued, two valued, nearly
-    constant, tiny range far from zero, denormal mix, sorted ramp), three random bit-width triples per case."""
-    _, ops = rt
-    rng = np.random.default_rng(1000 + seed)
-    n, R = 512, 1500
+def fuzz_rows(rng, R, n):
+    """R random fp32 rows: magnitudes 2^-40..2^40, ten row shapes (see test_fake_quant_fuzz)."""
     x = np.empty((R, n), np.float32)
     for r in range(R):
         kind = r % 10
@@ -397,6 +390,19 @@ def test_fake_quant_fuzz(rt, dt, seed):
         elif kind == 8: v = rng.standard_normal(n) * np.where(rng.random(n) < 0.3, 1e-38 / float(mag), 1.0)
         else: v = np.sort(rng.standard_normal(n))
         x[r] = np.clip(v.astype(np.float64) * float(mag), -3e38, 3e38).astype(np.float32)
+    return x
+
+
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fake_quant_fuzz(rt, dt, seed):
+    """Differential fuzz of the quantiser (fast and plain paths) against the oracle: 1500 rows per case with random
+    magnitudes 2^-40..2^40 and ten row shapes (gaussian, one-sided, heavy tailed, sparse, integer valued, two valued, nearly
+    constant, tiny range far from zero, denormal mix, sorted ramp), three random bit-width triples per case."""
+    _, ops = rt
+    rng = np.random.default_rng(1000 + seed)
+    R = 1500
+    x = fuzz_rows(rng, R, 512)
     xt = torch.from_numpy(x[None]).to(TDT[dt])
     xn = oracle.from_torch(xt)[0]
     for trial in range(3):

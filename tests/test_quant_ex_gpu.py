@@ -339,3 +339,31 @@ def test_dynamic_range_stress_extended_and_packed(rt, dt):
     out, ocodes, oqp = oracle.fake_quant_rows(xn, dt, labels, bits, True, True)
     rb = ops.packed_row_bytes(n, max(bits))
     np.testing.assert_array_equal(codes.cpu().numpy().reshape(S, rb), oracle.pack_codes(ocodes, labels, bits, rb))
+
+
+@pytest.mark.parametrize("dt", [oracle.F32, oracle.BF16, oracle.F16])
+def test_fuzz_extended_and_packed(rt, dt):
+    """The random rows of test_fake_quant_fuzz through the group-wise (with / without outliers), per-channel and packed
+    kernels, which share the quantiser's row-level fast path."""
+    _, ops = rt
+    from test_parity_gpu import fuzz_rows
+    rng = np.random.default_rng(4242)
+    R, n = 600, 512
+    x = torch.from_numpy(fuzz_rows(rng, R, n)[None]).to(TDT[dt])
+    xn, _ = oracle.from_torch(x)
+    bits = (2, 4, 8)
+    labels = rng.integers(0, 3, (1, R)).astype(np.uint8)
+    lab_d = torch.from_numpy(labels).cuda()
+    for mode, group, tg, tau in (("token_group", 128, 0, 0.0), ("token_group", 32, 0, 6.0), ("channel", 0, 16, 0.0),
+                                 ("channel", 0, 32, 0.0)):
+        opt = ops.quant_options(mode, mode, group_size=group, token_group=tg, outlier_tau=tau)
+        y, _ = ops.quant_gather_ex(x.cuda(), None, None, lab_d, bits, R, opt)
+        r = oracle.fake_quant_ex(xn[0], dt, labels[0], bits, mode=MODE[mode], group=group, tgroup=tg, tau=tau)
+        same(y, r["out"][None], dt)
+    rb = ops.packed_row_bytes(n, max(bits))
+    codes, qp = ops.quant_pack(x.cuda(), None, lab_d, bits, R)
+    out, ocodes, oqp = oracle.fake_quant_rows(xn, dt, labels, bits, True, True)
+    np.testing.assert_array_equal(codes.cpu().numpy().reshape(R, rb), oracle.pack_codes(np.nan_to_num(ocodes), labels, bits, rb))
+    pk = ops.quant_pack_ex(x.cuda(), None, lab_d, bits, R, ops.quant_options("token_group", group_size=128))
+    r = oracle.fake_quant_ex(xn[0], dt, labels[0], bits, mode=1, group=128)
+    np.testing.assert_array_equal(pk["codes"][0].cpu().numpy(), oracle.pack_codes(np.nan_to_num(r["codes"]), labels[0], bits, rb))
