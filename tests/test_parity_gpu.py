@@ -662,6 +662,47 @@ def test_config1_single_layer_full_size_vs_oracle(rt, bits):
         np.testing.assert_array_equal(v_sel.cpu().numpy(), o["v_sel"])
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_whole_layer_fuzz(rt, seed):
+    """Random layers through the drop-in call against oracle.compress_layer: random batch / heads / length / width,
+    dtype, attention sharpness, weights alpha-gamma, thresholds, bit widths and depth band; scores, labels, mask and the
+    compressed K/V are compared bit for bit (5 layers per seed)."""
+    rtkv, ops = rt
+    rng = np.random.default_rng(500 + seed)
+    for case in range(5):
+        B = int(rng.integers(1, 4)); H = int(rng.choice([1, 3, 8, 16, 40])); S = int(rng.choice([1, 2, 7, 64, 333, 1500, 2600]))
+        HD = int(rng.choice([8, 96, 256, 1024, 5120])); L = int(rng.choice([2, 5, 32]))
+        dt = int(rng.choice([oracle.F32, oracle.BF16, oracle.F16]))
+        bits = tuple(int(b) for b in sorted(rng.choice([1, 2, 3, 4, 6, 8, 12] if dt == oracle.F16 else [1, 2, 4, 8, 12, 16], 3)))
+        cfg = rtkv.CompressionConfig(
+            num_hidden_layers=L, num_attention_heads=H, hidden_size=HD, alpha=float(rng.uniform(0, 1)),
+            beta=float(rng.uniform(0, 1)), gamma=float(rng.uniform(0, 1)), theta_h=float(rng.uniform(0.4, 0.9)),
+            theta_m=float(rng.uniform(0.0, 0.4)), early_layer_ratio=float(rng.uniform(0.3, 1.0)),
+            middle_layer_ratio=float(rng.uniform(0.2, 0.9)), later_layer_ratio=float(rng.uniform(0.05, 0.6)),
+            low_precision_bits=bits[0], medium_precision_bits=bits[1], high_precision_bits=bits[2])
+        comp = rtkv.RealTimePrefillCompressor(cfg)
+        layer = int(rng.integers(0, L))
+        g = torch.Generator(device="cuda").manual_seed(int(rng.integers(1 << 30)))
+        P = comp.prompt_length(S)
+        sharp = float(rng.choice([0.2, 1.0, 6.0]))
+        A = torch.softmax(torch.randn(B, H, S, S, generator=g, device="cuda") * sharp +
+                          torch.triu(torch.full((S, S), -1e9, device="cuda"), 1), dim=-1).to(TDT[dt])
+        K = (torch.randn(B, S, HD, generator=g, device="cuda") * float(2.0 ** rng.uniform(-6, 6))).to(TDT[dt])
+        V = (torch.randn(B, S, HD, generator=g, device="cuda") * float(2.0 ** rng.uniform(-6, 6)) + float(rng.uniform(-2, 2))).to(TDT[dt])
+        ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+        k_sel, v_sel, info = comp.compress_layer_kv_cache(K, V, A, ids, layer)
+        o = oracle.compress_layer(host(K), host(V), dt, host(A), dt, P, cfg.alpha, cfg.beta, cfg.gamma,
+                                  cfg.layer_weights[layer], cfg.theta_h, cfg.theta_m, bits,
+                                  comp.propagator.get_layer_propagation_ratio(layer))
+        tag = f"seed {seed} case {case}: B={B} H={H} S={S} HD={HD} dt={dt} bits={bits} layer={layer}/{L}"
+        np.testing.assert_array_equal(comp.importance_tracker.layer_scores[layer].numpy(), o["scores"], err_msg=tag)
+        np.testing.assert_array_equal(info["quantization_info"]["bit_assignments"].astype(np.uint8), o["labels"], err_msg=tag)
+        np.testing.assert_array_equal(info["propagation_info"]["selection_mask"].cpu().numpy().astype(np.uint8), o["mask"], err_msg=tag)
+        assert k_sel.shape[1] == o["max_sel"], tag
+        assert_same(k_sel, o["k_sel"], dt)
+        assert_same(v_sel, o["v_sel"], dt)
+
+
 def test_config2_layer_4k_uniform_scores_all_widths(rt):
     """configs[1] shape, stage-level run with scores ~ U[0,1) so that all three widths occur
     (SURVEY.md §8d), checked against the oracle on the full [1,4096,4096] tensors."""
