@@ -703,6 +703,43 @@ def test_whole_layer_fuzz(rt, seed):
         assert_same(v_sel, o["v_sel"], dt)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_host_path_fuzz(rt, seed):
+    """rtkv_compress_layer_host (pieces of K/V uploaded, quantised and downloaded as they arrive; strided attention upload)
+    against the CUDA-tensor path on random shapes: identical tensors and statistics."""
+    rtkv, ops = rt
+    rng = np.random.default_rng(900 + seed)
+    for case in range(6):
+        B = int(rng.integers(1, 6)); H = int(rng.choice([1, 4, 8])); S = int(rng.choice([1, 5, 63, 500, 2000]))
+        HD = int(rng.choice([8, 100, 512, 1024])); L = 8
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(0, 3))]
+        cfg = rtkv.CompressionConfig(num_hidden_layers=L, num_attention_heads=H, hidden_size=HD, high_precision_bits=8,
+                                     medium_precision_bits=4, low_precision_bits=2,
+                                     early_layer_ratio=float(rng.uniform(0.1, 1.0)), theta_h=float(rng.uniform(0.4, 0.9)),
+                                     theta_m=float(rng.uniform(0.0, 0.4)))
+        dev_c, host_c = rtkv.RealTimePrefillCompressor(cfg), rtkv.RealTimePrefillCompressor(cfg)
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        P = dev_c.prompt_length(S)
+        W = int(rng.choice([P, S]))                         # a [..., :P] slice or the full matrix (strided upload)
+        A = torch.softmax(torch.randn(B, H, S, S, generator=g) * 3.0 + torch.triu(torch.full((S, S), -1e9), 1), dim=-1)
+        for b in range(B):
+            A[b] = A[b] * float(rng.uniform(0.2, 1.0))      # different counts per batch row
+        A = A.to(dtype)[..., :W]
+        K = torch.randn(B, S, HD, generator=g).to(dtype)
+        V = torch.randn(B, S, HD, generator=g).to(dtype)
+        ids = torch.zeros(B, S, dtype=torch.long)
+        kd, vd, idv = dev_c.compress_layer_kv_cache(K.cuda(), V.cuda(), A.cuda(), ids.cuda(), 1)
+        kh, vh, ih = host_c.compress_layer_kv_cache(K, V, A, ids, 1)
+        tag = f"seed {seed} case {case}: B={B} H={H} S={S} HD={HD} {dtype} W={W}"
+        assert not kh.is_cuda and kh.shape == kd.shape, tag
+        assert torch.equal(kh.view(torch.uint8), kd.cpu().view(torch.uint8)), tag
+        assert torch.equal(vh.view(torch.uint8), vd.cpu().view(torch.uint8)), tag
+        assert torch.equal(ih["propagation_info"]["selection_mask"].cpu(), idv["propagation_info"]["selection_mask"].cpu()), tag
+        for key in ("compression_ratio", "importance_stats", "precision_stats"):
+            assert repr(ih[key]) == repr(idv[key]), (tag, key)          # repr: nan == nan (std of a single token)
+        assert repr(ih["propagation_info"]["selection_stats"]) == repr(idv["propagation_info"]["selection_stats"]), tag
+
+
 def test_config2_layer_4k_uniform_scores_all_widths(rt):
     """configs[1] shape, stage-level run with scores ~ U[0,1) so that all three widths occur
     (SURVEY.md §8d), checked against the oracle on the full [1,4096,4096] tensors."""
