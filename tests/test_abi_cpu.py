@@ -36,6 +36,8 @@ int main(void){
         offsetof(rtkv_layer_params,fallback_topk), sizeof(rtkv_row_stats), offsetof(rtkv_row_stats,cost_bits),
         sizeof(rtkv_layer_stats));
  printf("%zu %zu %zu\n", offsetof(rtkv_row_stats,sel_score_sum), offsetof(rtkv_row_stats,score_min), offsetof(rtkv_row_stats,label_count));
+ printf("%zu %zu %zu %zu\n", sizeof(rtkv_quant_options), offsetof(rtkv_quant_options,group_size),
+        offsetof(rtkv_quant_options,token_group), offsetof(rtkv_quant_options,outlier_tau_q8));
  return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -52,6 +54,9 @@ int main(void){
     assert vals[6] == _lib.ROW_STATS.fields["sel_score_sum"][1]
     assert vals[7] == _lib.ROW_STATS.fields["score_min"][1]
     assert vals[8] == _lib.ROW_STATS.fields["label_count"][1]
+    assert vals[9] == ctypes.sizeof(_lib.QuantOptions) == 32
+    assert vals[10] == _lib.QuantOptions.group_size.offset and vals[11] == _lib.QuantOptions.token_group.offset
+    assert vals[12] == _lib.QuantOptions.outlier_tau_q8.offset
 
 
 def test_argument_errors_do_not_need_a_gpu(built_lib):
