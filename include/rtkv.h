@@ -270,7 +270,7 @@ RTKV_API int rtkv_quant_gather_ex(const void *X0, const void *X1, int dtype, int
  *   qparams  token modes: [B,out_rows,G,2] (scale, zero-point), G = rtkv_quant_groups();
  *            RTKV_Q_CHANNEL: [B,ceil(out_rows/token_group),n,2] (min, max)
  *   outliers (token modes with tau, else NULL/0): per output row the first outlier_cap outliers in channel
- *            order: out_idx [B,out_rows,cap] i32, out_val [B,out_rows,cap] f32, out_cnt [B,out_rows] i32;
+ *            order: out_idx [B,out_rows,cap] i32, out_val [B,out_rows,cap] f32 (slots past the count are zero), out_cnt [B,out_rows] i32;
  *            outliers past the cap are quantised like inliers (clamped to the code range). */
 RTKV_API int rtkv_quant_groups(int n, const rtkv_quant_options *options, int tensor);
 RTKV_API int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,

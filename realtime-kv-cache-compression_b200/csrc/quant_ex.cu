@@ -1272,6 +1272,10 @@ extern "C" int rtkv_quant_pack_ex(const void *X, int dtype, int B, int S, int n,
             }
         }
         RTKV_CUDA(cudaMemsetAsync(codes, 0, codes_bytes, st));
+        if (q.tau_q8) {                           // list slots past out_cnt are defined (zero), not left uninitialised
+            RTKV_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * out_rows * cap * sizeof(int32_t), st));
+            RTKV_CUDA(cudaMemsetAsync(out_val, 0, (size_t)B * out_rows * cap * sizeof(float), st));
+        }
         const size_t smem = (size_t)(n / q.group) * sizeof(GroupRec);
         RTKV_DISPATCH(dtype, (quant_pack_ex_kernel<DT><<<dim3(out_rows, B), kQT, smem, st>>>(q)));
     }

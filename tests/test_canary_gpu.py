@@ -138,3 +138,49 @@ def test_guard_detects_an_overrun(guarded_ops):
     with pytest.raises(AssertionError, match="AFTER"):
         proxy.check()
     proxy.registry.clear()
+
+
+def test_bitwise_repeatability(built_lib):
+    """No racecheck on the pool either: every kernel is run 6 times on large inputs (cluster selection kernel, tcgen05
+    scoring, group-wise / per-channel / outlier quantisers, packed attention) and must reproduce its first result bit for
+    bit; an unsynchronised access would show up as run-to-run differences."""
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    import rtkv
+    from rtkv import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, S, HD, P = 2, 32, 9000, 4096, 128
+    A = torch.softmax(torch.randn(B, H, S, P, generator=g, device="cuda") * 4, dim=-1)
+    K = torch.randn(B, S, HD, generator=g, device="cuda")
+    V = torch.randn(B, S, HD, generator=g, device="cuda") * 2 + 1
+    q = torch.randn(B, H, S, 128, generator=g, device="cuda").to(torch.bfloat16)
+    kp = torch.randn(B, H, P, 128, generator=g, device="cuda").to(torch.bfloat16)
+    lse = torch.full((B, H, S), 9.0, device="cuda")
+    qd = torch.randn(B, H, 128, generator=g, device="cuda")
+    cfg = rtkv.CompressionConfig(high_precision_bits=8, medium_precision_bits=4, low_precision_bits=2, later_layer_ratio=0.33)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    opts = [ops.quant_options("token_group", "token_group", group_size=128, outlier_tau=5.0),
+            ops.quant_options("channel", "channel", token_group=32), ops.quant_options("token", "token", outlier_tau=4.0)]
+
+    def run():
+        out = []
+        k, v, info = comp.compress_layer_kv_cache(K, V, A, ids, 30)          # S >= 8192: cluster selection kernel
+        out += [k, v, info["propagation_info"]["selection_mask"].to(torch.uint8)]
+        out.append(ops.prompt_mass_qk(q, kp, lse, 128 ** -0.5))
+        params, _ = comp.layer_params(30, S, ops.F32)
+        sel = ops.score_select(params, B, S, K.device, mass=ops.prompt_mass(A, prompt_len=P))
+        ms = int(sel.read_stats()[0]["max_selected"])
+        for o in opts:
+            out += list(ops.quant_gather_ex(K, V, sel, sel.labels, (2, 4, 8), ms, o))
+        pk = ops.quant_pack_ex(K, sel, sel.labels, (2, 4, 8), ms, opts[0], outlier_cap=8)
+        out += [pk["codes"], pk["qparams"], pk["out_idx"], pk["out_val"], pk["out_cnt"]]
+        packed = comp.compress_layer_kv_cache_packed(K, V, A, ids, 30)
+        out.append(packed.attend(qd))
+        return [t.clone() for t in out]
+
+    first = run()
+    for _ in range(5):
+        again = run()
+        for a, b in zip(first, again):
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
