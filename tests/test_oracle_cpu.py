@@ -134,3 +134,23 @@ def test_extended_quant_restatement_properties():
     # a cap on the split outliers: later outliers are clamped codes, not exact values
     r3 = oracle.fake_quant_ex(x, oracle.F32, lab, bits, mode=0, tau=3.0, cap=1)
     assert r3["omask"].sum(axis=1).max() == 1
+
+
+def test_oracle_matches_reference_on_edge_rows():
+    """tests/golden/edge_rows_f16.npz holds the REAL reference's fp16 output (oracle/pin_edge_rows.py) on the stress and
+    fuzz rows the GPU tests use: wide dynamic range, zeros of both signs, denormals, a constant row that rounds to -0.0,
+    non-finite rows and narrow rows whose x/scale overflows the half range (NaN in the reference)."""
+    import os
+    import torch
+    from test_parity_gpu import fuzz_rows, stress_rows
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edge_rows_f16.npz"))
+    rows = np.stack(stress_rows(np.random.default_rng(77), 256) + list(fuzz_rows(np.random.default_rng(1000), 400, 256)))
+    x = oracle.from_torch(torch.from_numpy(rows[None]).to(torch.float16))[0]
+    got, _, _ = oracle.fake_quant_rows(x, oracle.F16, fx["labels"][None], tuple(int(b) for b in fx["bits"]))
+    g = oracle.to_torch(got[0], oracle.F16).float().numpy()
+    w = oracle.to_torch(fx["want"], oracle.F16).float().numpy()
+    assert np.isnan(w).sum() > 10000 and ((w == 0) & np.signbit(w)).sum() > 1000        # the fixture does hold the edge cases
+    np.testing.assert_array_equal(np.isnan(g), np.isnan(w))
+    ok = ~np.isnan(w)
+    np.testing.assert_array_equal(g[ok], w[ok])
+    np.testing.assert_array_equal(np.signbit(g[ok]), np.signbit(w[ok]))
