@@ -273,21 +273,34 @@ static __device__ void process_candidates(int m, const SelCfg &cfg, Smem &sm)
         sm.sort_lab[rank] = sm.cand_lab[threadIdx.x];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        long long cur = sm.cur;
-        for (int t = 0; t < m; ++t) {
-            const int c = sm.sort_lab[t];
-            if (!sm.alive[c]) continue;
-            if (cur + cfg.bits[c] <= cfg.budget_bits) cur += cfg.bits[c];
-            else {
-                for (int c2 = 0; c2 < 3; ++c2)
-                    if (sm.alive[c2] && cfg.bits[c2] >= cfg.bits[c]) {
-                        sm.alive[c2] = 0;
-                        sm.thr[c2] = sm.sort_key[t];
-                    }
-            }
+    // The literal walk without a sequential loop.  The walk only changes regime when a token does not fit, which retires
+    // its class and every class at least as expensive, so that happens at most 3 times.  Each round: costs of the still
+    // alive classes from position `start` on -> block prefix sum -> first position that overflows; everything before it is
+    // taken, the classes are retired with that candidate's key as threshold, the next round resumes behind it.
+    int start = 0;
+    for (int round = 0; round < 4; ++round) {
+        const int t = threadIdx.x;
+        int c = 0, cost = 0;
+        if (t < m && t >= start) { c = sm.sort_lab[t]; cost = sm.alive[c] ? cfg.bits[c] : 0; }
+        if (threadIdx.x == 0) sm.found = INT_MAX;
+        int total;
+        const int excl = block_excl_scan(cost, total, sm);       // its barriers also order the sm.found reset
+        const long long cur = sm.cur;
+        if (cost > 0 && cur + excl + cost > cfg.budget_bits) atomicMin(&sm.found, t);
+        __syncthreads();
+        const int f = sm.found;
+        if (f == INT_MAX) {                                       // everything left fits
+            __syncthreads();
+            if (threadIdx.x == 0) sm.cur = cur + total;
+            break;
         }
-        sm.cur = cur;
+        if (t == f) {
+            sm.cur = cur + excl;
+            for (int c2 = 0; c2 < 3; ++c2)
+                if (sm.alive[c2] && cfg.bits[c2] >= cfg.bits[c]) { sm.alive[c2] = 0; sm.thr[c2] = sm.sort_key[f]; }
+        }
+        start = f + 1;
+        __syncthreads();
     }
     __syncthreads();
 }
