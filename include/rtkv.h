@@ -200,6 +200,34 @@ RTKV_API int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, in
                       const uint64_t *mailbox_ptrs /*[host]*/, int rank, int world, uint32_t *state,
                       void *Y0, void *Y1, void *stream);
 
+/* KV-head sharding with ONE exchange per layer (reference couplings: token_importance.py:45 head mean
+ * before min-max, dynamic_quantization.py:183-184 scale spans all heads).  Rank r of `world` (1, 2, 4 or 8) holds
+ * H_local = (8/world)*group_size consecutive heads: A [B,H_local,S,>=P] float32 and K/V row slices [B,S,n_local].
+ *   rtkv_shard_stats    streams A, K and V once and stores, for every token, the record
+ *                       (kmin, kmax, vmin, vmax, prompt-mass partial of each local head group) into the exchange
+ *                       buffer of EVERY rank (peer stores; xbuf_ptrs [host]: `world` device pointers, entry s = rank
+ *                       s's buffer as mapped into this process, rtkv_shard_exchange_bytes(B,S,world) bytes each,
+ *                       zero-filled once), then publishes an epoch flag to every rank.  No NCCL call is involved.
+ *   rtkv_shard_combine  waits for the flags of all ranks and reduces the records in rank order:
+ *                       mass [B,S] (bit-identical to rtkv_prompt_mass on the unsharded tensor) and
+ *                       minmax [B,S,4] = (kmin, kmax, vmin, vmax) of the WHOLE row, indexed by token.
+ *   rtkv_quant_gather_token_minmax   rtkv_quant_gather with those row min/max (equals rtkv_quant_gather on the
+ *                       concatenated row bit for bit).
+ * state: 4 zero-initialised uint32 in local device memory (epoch, ticket, error flag, reserved); state[2] != 0 after
+ * a call means a peer's flag never arrived (the results of that call are undefined; nothing traps).  Every rank must
+ * issue the same sequence of calls; consecutive calls alternate between two halves of the buffer, which is all the
+ * inter-rank synchronisation the scheme needs (DESIGN.md "Multi-GPU"). */
+RTKV_API int64_t rtkv_shard_exchange_bytes(int B, int S, int world);
+RTKV_API int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                      int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                      const uint64_t *xbuf_ptrs /*[host]*/, int rank, int world, uint32_t *state, void *stream);
+RTKV_API int rtkv_shard_combine(const void *xbuf_local, uint32_t *state, int B, int S, int H, int world,
+                      float *mass, float *minmax, void *stream);
+RTKV_API int rtkv_quant_gather_token_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                      const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                      const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
+                      const float *minmax_by_token, void *Y0, void *Y1, void *stream);
+
 /* Prefetch [p, p+bytes) into L2 (one prefetch.global.L2 per 128-byte line).  Run it on a side stream
  * while rtkv_score_select (one SM, latency bound) leaves HBM idle, over the first K rows. */
 RTKV_API int rtkv_prefetch_l2(const void *p, size_t bytes, void *stream);

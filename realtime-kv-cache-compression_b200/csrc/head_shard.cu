@@ -1,0 +1,264 @@
+// head_shard.cu — KV-head sharding with ONE exchange per layer.
+//
+// A rank holds H/R consecutive heads: its slice of the attention probabilities [B,H/R,S,>=P] and of the
+// K/V rows [B,S,(H/R)*D].  Two reductions of the reference span ALL heads of a token:
+//   src/compression/token_importance.py:45          A[:, :, :, prompt].mean(1).sum(-1)   (head mean of the prompt mass)
+//   src/compression/dynamic_quantization.py:183-184 per-token min/max over the whole [H*D] row
+// so every token needs one record from every rank before anything else can happen:
+//   record = (kmin, kmax, vmin, vmax, partial[0..8/R))       partial[g] = prompt mass of local head group g
+//
+// shard_stats_kernel    streams the local A slice and the local K/V rows ONCE, builds the record of every token
+//                       (one warp per token, the head-group reduction order of prompt_mass.cuh) and stores it into
+//                       the exchange buffer of EVERY rank with peer stores over NVLink (the buffers are symmetric
+//                       memory mapped into this process).  The last CTA publishes an epoch flag to every rank
+//                       (release at system scope), so the "all-gather" costs no extra launch and no NCCL call.
+// shard_combine_kernel  waits for the R epoch flags (acquire), then reduces the R records of every token in rank
+//                       order: mass = (p0 + ... + p7)/H exactly like rtkv_mass_from_partials (bit-identical to the
+//                       unsharded rtkv_prompt_mass), row min/max over ranks -> [B,S,4] indexed by TOKEN, which
+//                       rtkv_quant_gather_token_minmax consumes after the (replicated) selection.
+//
+// Buffers are double-buffered by epoch parity.  A rank can start epoch e+2 only after its own combine of e+1 has
+// seen every rank's flag e+1, i.e. after every rank has finished reading the records of epoch e: two parities are
+// enough and no other synchronisation between ranks exists.  The epoch is a device-side counter, so the kernels are
+// CUDA-graph replayable.
+#include "prompt_mass.cuh"
+
+namespace rtkv {
+
+constexpr int kXHeader = 256;        // bytes: flags[2 parities][8 sources] u32, padded
+constexpr int kShardWarps = 8;
+
+struct ShardParams {
+    const void *A;
+    int64_t sb, sh, si;
+    const void *K, *V;
+    int B, S, P, gs, ng, n;           // ng local head groups of gs heads; n = local row width in elements
+    int rank, world, rec_vecs;
+    unsigned long long xbuf[8];       // exchange buffer of rank s as mapped into this process
+    unsigned *state;                  // local: [0] epoch of the last finished call, [1] CTA ticket, [2] error flag
+};
+
+__device__ __forceinline__ void st_sys_v4(void *p, float a, float b, float c, float d)
+{
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_v4(const void *p)
+{
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ size_t record_offset(unsigned parity, int world, int src, int64_t rows, int64_t row, int rec_vecs)
+{
+    return (size_t)kXHeader + ((((size_t)parity * world + src) * (size_t)rows + (size_t)row) * rec_vecs) * 16;
+}
+
+// DT = dtype of K/V; the probabilities are float32 (half probabilities round the per-column head mean, which does
+// not decompose over ranks: rtkv_prompt_mass_partials has the same restriction).
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(kShardWarps * 32) shard_stats_kernel(ShardParams p)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    pdl_trigger();
+    const unsigned epoch = ((volatile unsigned *)p.state)[0] + 1u;
+    const unsigned parity = epoch & 1u;
+    const int64_t rows = (int64_t)p.B * p.S;
+    const int nvec = p.n / EPV;
+    unsigned long long my_dst = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+        if (lane == s) my_dst = p.xbuf[s];
+
+    for (int64_t row = (int64_t)blockIdx.x * kShardWarps + warp; row < rows; row += (int64_t)gridDim.x * kShardWarps) {
+        // ---- local min/max of the K row slice and of the V row slice ----
+        float mm[4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint4 *src = (const uint4 *)((const char *)(t ? p.V : p.K) + (size_t)row * p.n * Elem<DT>::kBytes);
+            float mn = INFINITY, mx = -INFINITY;
+            int nan = 0;
+            for (int v0 = lane; v0 < nvec; v0 += 4 * 32) {
+                uint4 raw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (v0 + 32 * k < nvec) raw[k] = ldg_stream(src + v0 + 32 * k);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (v0 + 32 * k < nvec) {
+                        float f[EPV];
+                        Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+                    }
+                }
+            }
+            mn = warp_min(mn); mx = warp_max(mx);
+            if (__any_sync(0xffffffffu, nan)) mn = mx = __int_as_float(0x7fc00000);   // torch.min/max propagate NaN
+            mm[2 * t] = mn; mm[2 * t + 1] = mx;
+        }
+        // ---- prompt mass of the local head groups (same order as prompt_mass_kernel's partials) ----
+        const int b = (int)(row / p.S);
+        const int i = (int)(row - (int64_t)b * p.S);
+        const float *rowp = (const float *)p.A + b * p.sb + (int64_t)i * p.si;
+        float pg[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            pg[g] = 0.0f;
+            if (g < p.ng) {
+                float lane_acc = 0.0f;
+                for (int c0 = 0; c0 < p.P; c0 += 128) {
+                    float s[4];
+                    group_column_sums<RTKV_F32, VEC>(rowp, p.sh, g * p.gs, (g + 1) * p.gs, c0 + 4 * lane, p.P, nullptr, s);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c0 + 4 * lane + k < p.P) lane_acc = __fadd_rn(lane_acc, s[k]);
+                }
+                pg[g] = butterfly(lane_acc);
+            }
+        }
+        // ---- one record per destination rank (lane s -> rank s), 16-byte peer stores ----
+        if (lane < p.world) {
+            char *dst = (char *)my_dst + record_offset(parity, p.world, p.rank, rows, row, p.rec_vecs);
+            st_sys_v4(dst, mm[0], mm[1], mm[2], mm[3]);
+            st_sys_v4(dst + 16, pg[0], pg[1], pg[2], pg[3]);
+            if (p.rec_vecs > 2) st_sys_v4(dst + 32, pg[4], pg[5], pg[6], pg[7]);
+        }
+    }
+    // ---- publish: every record of this rank is out before the flag ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+            p.state[1] = 0u;
+            __threadfence_system();
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (s < p.world) st_release_sys((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
+            ((volatile unsigned *)p.state)[0] = epoch;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, unsigned *state, int64_t rows, int world,
+                                                             int gpr, int rec_vecs, float fH, float *__restrict__ mass,
+                                                             float *__restrict__ minmax)
+{
+    pdl_wait();
+    pdl_trigger();
+    const unsigned epoch = ((volatile unsigned *)state)[0];      // published by this rank's shard_stats_kernel
+    const unsigned parity = epoch & 1u;
+    if ((int)threadIdx.x < world) {
+        const unsigned *flag = (const unsigned *)xlocal + parity * 8 + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != epoch) {
+            if (clock64() - t0 > 40000000000LL) {                   // ~20 s: a peer never showed up; flag it, do not trap
+                atomicExch(&state[2], 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    float tot = 0.0f;
+    float kmn = INFINITY, kmx = -INFINITY, vmn = INFINITY, vmx = -INFINITY;
+    bool knan = false, vnan = false;
+    for (int r = 0; r < world; ++r) {
+        const char *rec = xlocal + record_offset(parity, world, r, rows, t, rec_vecs);
+        const float4 m = ld_cg_v4(rec);
+        const float4 a = ld_cg_v4(rec + 16);
+        float pg[8] = {a.x, a.y, a.z, a.w, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (rec_vecs > 2) {
+            const float4 c = ld_cg_v4(rec + 32);
+            pg[4] = c.x; pg[5] = c.y; pg[6] = c.z; pg[7] = c.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            if (g < gpr) tot = (r == 0 && g == 0) ? pg[g] : __fadd_rn(tot, pg[g]);
+        knan = knan || (m.x != m.x); vnan = vnan || (m.z != m.z);
+        kmn = fminf(kmn, m.x); kmx = fmaxf(kmx, m.y); vmn = fminf(vmn, m.z); vmx = fmaxf(vmx, m.w);
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    mass[t] = __fdiv_rn(tot, fH);
+    float4 o = make_float4(knan ? qnan : kmn, knan ? qnan : kmx, vnan ? qnan : vmn, vnan ? qnan : vmx);
+    *reinterpret_cast<float4 *>(minmax + 4 * t) = o;
+}
+
+static int rec_vecs_for(int world) { return 1 + ((kGroups / world) + 3) / 4; }
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+extern "C" int64_t rtkv_shard_exchange_bytes(int B, int S, int world)
+{
+    if (B <= 0 || S <= 0 || !(world == 1 || world == 2 || world == 4 || world == 8)) return -1;
+    return (int64_t)kXHeader + (int64_t)2 * world * B * S * rec_vecs_for(world) * 16;
+}
+
+extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                                int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                                const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, void *stream)
+{
+    RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state, "rtkv_shard_stats: null pointer");
+    RTKV_CHECK_ARG(a_dtype == RTKV_F32, "rtkv_shard_stats: head sharding needs float32 probabilities "
+                   "(half dtypes round the per-column head mean, which does not decompose over ranks)");
+    RTKV_CHECK_ARG(dtype_ok(kv_dtype), "rtkv_shard_stats: bad K/V dtype %d", kv_dtype);
+    RTKV_CHECK_ARG(B > 0 && H_local > 0 && S > 0 && P > 0 && group_size > 0 && n_local > 0, "rtkv_shard_stats: bad shape");
+    RTKV_CHECK_ARG(world == 1 || world == 2 || world == 4 || world == 8, "rtkv_shard_stats: world must be 1, 2, 4 or 8");
+    RTKV_CHECK_ARG(rank >= 0 && rank < world, "rtkv_shard_stats: bad rank");
+    RTKV_CHECK_ARG(H_local == (kGroups / world) * group_size,
+                   "rtkv_shard_stats: H_local=%d must be %d groups of group_size=%d heads", H_local, kGroups / world, group_size);
+    const int epv = 16 / dtype_bytes(kv_dtype);
+    if (n_local % epv != 0 || (uintptr_t)K % 16 || (uintptr_t)V % 16) {
+        set_error("rtkv_shard_stats: K/V row slices must be 16-byte aligned vectors (n_local=%d)", n_local);
+        return RTKV_EUNSUPPORTED;
+    }
+    ShardParams p;
+    p.A = A; p.sb = sb; p.sh = sh; p.si = si; p.K = K; p.V = V;
+    p.B = B; p.S = S; p.P = P; p.gs = group_size; p.ng = kGroups / world; p.n = n_local;
+    p.rank = rank; p.world = world; p.rec_vecs = rec_vecs_for(world);
+    for (int s = 0; s < 8; ++s) p.xbuf[s] = s < world ? xbuf_ptrs[s] : 0ull;
+    for (int s = 0; s < world; ++s) RTKV_CHECK_ARG(p.xbuf[s] && p.xbuf[s] % 16 == 0, "rtkv_shard_stats: exchange buffer %d", s);
+    p.state = state;
+    const bool vec = ((uintptr_t)A % 16 == 0) && (sb * 4) % 16 == 0 && (sh * 4) % 16 == 0 && (si * 4) % 16 == 0;
+    const int64_t rows = (int64_t)B * S;
+    const int64_t ctas = (rows + kShardWarps - 1) / kShardWarps;
+    const int grid = (int)(ctas < 148 * 64 ? ctas : 148 * 64);
+    void (*kern)(ShardParams) = nullptr;
+    switch (kv_dtype) {
+    case RTKV_F32: kern = vec ? shard_stats_kernel<RTKV_F32, true> : shard_stats_kernel<RTKV_F32, false>; break;
+    case RTKV_F16: kern = vec ? shard_stats_kernel<RTKV_F16, true> : shard_stats_kernel<RTKV_F16, false>; break;
+    default: kern = vec ? shard_stats_kernel<RTKV_BF16, true> : shard_stats_kernel<RTKV_BF16, false>; break;
+    }
+    RTKV_CUDA(launch_kernel(kern, dim3(grid), dim3(kShardWarps * 32), 0, (cudaStream_t)stream, 1, p));
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_shard_combine(const void *xbuf_local, uint32_t *state, int B, int S, int H, int world,
+                                  float *mass, float *minmax, void *stream)
+{
+    RTKV_CHECK_ARG(xbuf_local && state && mass && minmax, "rtkv_shard_combine: null pointer");
+    RTKV_CHECK_ARG(B > 0 && S > 0 && H > 0, "rtkv_shard_combine: bad shape");
+    RTKV_CHECK_ARG(world == 1 || world == 2 || world == 4 || world == 8, "rtkv_shard_combine: world must be 1, 2, 4 or 8");
+    RTKV_CHECK_ARG((uintptr_t)minmax % 16 == 0, "rtkv_shard_combine: minmax must be 16-byte aligned");
+    const int64_t rows = (int64_t)B * S;
+    RTKV_CUDA(launch_kernel(shard_combine_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1,
+                            (const char *)xbuf_local, (unsigned *)state, rows, world, kGroups / world, rec_vecs_for(world),
+                            (float)H, mass, minmax));
+    return RTKV_OK;
+}

@@ -19,6 +19,7 @@ struct QGParams {
     int row_begin, b_begin;   // grid offsets (rtkv_quant_gather_range)
     const float *ext_minmax;  // [B,out_rows,4] = (min0, max0, min1, max1) of the WHOLE row (head sharding) or NULL
     int neg_max;              // the max entries are stored negated (so that one MIN all-reduce combines ranks)
+    int ext_by_token;         // ext_minmax is [B,S,4] indexed by TOKEN (rtkv_shard_combine) instead of by output row
     // fused peer exchange (rtkv_quant_gather_p2p): mailbox of rank s as mapped into this process
     unsigned long long mbox[8];
     unsigned *p2p_state;      // [0] epoch of the last finished call, [1] finished-CTA counter
@@ -32,6 +33,14 @@ __device__ __forceinline__ int pick_bits(const QGParams &p, int label)
 }
 __device__ __forceinline__ const void *pick_x(const QGParams &p, int t) { return t ? p.x[1] : p.x[0]; }
 __device__ __forceinline__ void *pick_y(const QGParams &p, int t) { return t ? p.y[1] : p.y[0]; }
+
+// externally supplied whole-row min/max of (batch row b, output row r = token tok), tensor t
+__device__ __forceinline__ void ext_row_minmax(const QGParams &p, int b, int r, int tok, int t, float &mn, float &mx)
+{
+    const size_t at = p.ext_by_token ? ((size_t)b * p.S + tok) : ((size_t)b * p.out_rows + r);
+    const float *mm = p.ext_minmax + at * 4 + 2 * t;
+    mn = mm[0]; mx = p.neg_max ? -mm[1] : mm[1];
+}
 
 // block-wide min / max / any-NaN over kQT threads
 __device__ __forceinline__ void block_minmax(float &mn, float &mx, int nan, float *red)
@@ -60,7 +69,7 @@ inline int fill_params(QGParams &p, const void *X0, const void *X1, int B, int S
     p.quantize = (labels != nullptr && bits != nullptr);
     for (int c = 0; c < 3; ++c) p.bits[c] = bits ? bits[c] : 0;
     p.row_begin = 0; p.b_begin = 0;
-    p.ext_minmax = nullptr; p.neg_max = 0;
+    p.ext_minmax = nullptr; p.neg_max = 0; p.ext_by_token = 0;
     for (int i = 0; i < 8; ++i) p.mbox[i] = 0;
     p.p2p_state = nullptr; p.rank = 0; p.world = 1; p.total_ctas = 0;
     return RTKV_OK;

@@ -63,8 +63,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
         }
     }
     if (p.ext_minmax) {         // row min/max reduced over all ranks' head shards
-        const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
-        mn = mm[0]; mx = p.neg_max ? -mm[1] : mm[1];
+        ext_row_minmax(p, b, r, tok, t, mn, mx);
     } else {
         block_minmax(mn, mx, nan, red);
     }
@@ -229,6 +228,57 @@ __global__ void __launch_bounds__(THREADS) quant_gather_p2p_kernel(QGParams p)
     }
 }
 
+// ---- KV-head sharding: narrow row slices with externally reduced min/max ------------------------
+// A rank's slice of a row is short (512 floats = 128 vectors when 8 ranks share a 4096-wide row) and its min/max
+// comes from the exchange (rtkv_shard_combine), so no reduction over the row is needed: 2^tpr_shift consecutive
+// threads own one (output row, tensor) item with exactly 4 vectors each, a 256-thread CTA processes
+// 256 >> tpr_shift items and never synchronises.  Same arithmetic (RowQuant) as quant_gather_vec_kernel.
+template <int DT>
+__global__ void __launch_bounds__(kQT) quant_gather_flat_kernel(QGParams p, int tpr_shift, int ntensors)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    constexpr int NV = 4;
+    pdl_wait();
+    pdl_trigger();
+    const int tpr = 1 << tpr_shift;
+    const long long item = ((long long)blockIdx.x * kQT + threadIdx.x) >> tpr_shift;
+    const int l = threadIdx.x & (tpr - 1);
+    if (item >= (long long)p.B * p.out_rows * ntensors) return;
+    const int t = (int)(item % ntensors);
+    const long long rr = item / ntensors;
+    const int r = (int)(rr % p.out_rows), b = (int)(rr / p.out_rows);
+    const int cnt = p.row_stats ? p.row_stats[b].n_selected : p.S;
+    uint4 *dst = (uint4 *)((char *)pick_y(p, t) + ((size_t)b * p.out_rows + r) * (size_t)p.n * Elem<DT>::kBytes);
+    if (r >= cnt) {
+        if (p.zero_pad) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) stg_stream(dst + l + k * tpr, make_uint4(0, 0, 0, 0));
+        }
+        return;
+    }
+    const int tok = p.sel_idx ? p.sel_idx[(int64_t)b * p.S + r] : r;
+    const uint4 *src = (const uint4 *)((const char *)pick_x(p, t) + ((size_t)b * p.S + tok) * (size_t)p.n * Elem<DT>::kBytes);
+    uint4 raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) raw[k] = ldg_stream(src + l + k * tpr);
+    float mn, mx;
+    ext_row_minmax(p, b, r, tok, t, mn, mx);
+    const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
+    RowQuant<DT> rq;
+    rq.init(mn, mx, bits);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        float f[EPV];
+        Vec16<DT>::unpack(raw[k], f);
+        if (rq.fast) rq.apply_fast(f);
+        else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) f[e] = rq.slow(f[e]);
+        }
+        stg_stream(dst + l + k * tpr, Vec16<DT>::pack(f));
+    }
+}
+
 // Any n / alignment: scalar accesses, the row is read twice (second read hits L1/L2).
 template <int DT>
 __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
@@ -255,8 +305,7 @@ __global__ void __launch_bounds__(kQT) quant_gather_generic_kernel(QGParams p)
         nan |= (v != v); mn = fminf(mn, v); mx = fmaxf(mx, v);
     }
     if (p.ext_minmax) {
-        const float *mm = p.ext_minmax + ((size_t)b * p.out_rows + r) * 4 + 2 * t;
-        mn = mm[0]; mx = p.neg_max ? -mm[1] : mm[1];
+        ext_row_minmax(p, b, r, tok, t, mn, mx);
     } else {
         block_minmax(mn, mx, nan, red);
     }
@@ -653,6 +702,41 @@ extern "C" int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtyp
     fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
     p.ext_minmax = minmax; p.neg_max = negated_max != 0;
     RTKV_DISPATCH(dtype, return launch_qg<DT>(p, X1 ? 2 : 1, (cudaStream_t)stream, out_rows, B));
+    return RTKV_OK;
+}
+
+extern "C" int rtkv_quant_gather_token_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
+                                              const int32_t *sel_idx, const rtkv_row_stats *row_stats,
+                                              const uint8_t *labels, const int32_t *bits, int out_rows, int zero_pad,
+                                              const float *minmax_by_token, void *Y0, void *Y1, void *stream)
+{
+    RTKV_CHECK_ARG(X0 && Y0 && (!X1 || Y1) && labels && bits && minmax_by_token, "rtkv_quant_gather_token_minmax: null pointer");
+    RTKV_CHECK_ARG(dtype_ok(dtype), "rtkv_quant_gather_token_minmax: bad dtype %d", dtype);
+    RTKV_CHECK_ARG(B > 0 && B <= 65535 && S > 0 && n > 0 && out_rows >= 0, "rtkv_quant_gather_token_minmax: bad shape");
+    RTKV_CHECK_ARG(!sel_idx || row_stats, "rtkv_quant_gather_token_minmax: sel_idx needs row_stats");
+    RTKV_CHECK_ARG(sel_idx || out_rows <= S, "rtkv_quant_gather_token_minmax: out_rows > S without sel_idx");
+    int rc = rtkv_check_bits(bits, dtype, "rtkv_quant_gather_token_minmax");
+    if (rc) return rc;
+    if (out_rows == 0) return RTKV_OK;
+    QGParams p;
+    fill_params(p, X0, X1, B, S, n, sel_idx, row_stats, labels, bits, out_rows, zero_pad, Y0, Y1);
+    p.ext_minmax = minmax_by_token; p.ext_by_token = 1;
+    const int epv = 16 / dtype_bytes(dtype);
+    const int nt = X1 ? 2 : 1;
+    const bool aligned = (uintptr_t)X0 % 16 == 0 && (uintptr_t)Y0 % 16 == 0 && (!X1 || ((uintptr_t)X1 % 16 == 0 && (uintptr_t)Y1 % 16 == 0));
+    const int nvec = n % epv == 0 ? n / epv : 0;
+    int shift = -1;
+    for (int s = 3; s <= 7; ++s)                  // 8..128 threads per row slice, 4 vectors each
+        if (nvec == (4 << s)) shift = s;
+    if (aligned && shift >= 0) {
+        const long long threads = ((long long)B * out_rows * nt) << shift;
+        const long long ctas = (threads + kQT - 1) / kQT;
+        RTKV_CHECK_ARG(ctas < (1ll << 31), "rtkv_quant_gather_token_minmax: too many rows");
+        RTKV_DISPATCH(dtype, RTKV_CUDA(launch_kernel(quant_gather_flat_kernel<DT>, dim3((unsigned)ctas), dim3(kQT), 0,
+                                                     (cudaStream_t)stream, 1, p, shift, nt)));
+        return RTKV_OK;
+    }
+    RTKV_DISPATCH(dtype, return launch_qg<DT>(p, nt, (cudaStream_t)stream, out_rows, B));
     return RTKV_OK;
 }
 

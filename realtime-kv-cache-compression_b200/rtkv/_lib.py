@@ -87,6 +87,15 @@ PROTOTYPES = {
                                              c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp,
                                              c_vp, c_vp, c_vp]),
+    "rtkv_shard_exchange_bytes": (c_i64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "rtkv_shard_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64, c_i64, c_i64,
+                                        ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_shard_combine": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
+                                          c_vp]),
+    "rtkv_quant_gather_token_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, ctypes.c_int,
+                                                      c_vp, c_vp, c_vp, c_vp]),
     "rtkv_prefetch_l2": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp]),
     "rtkv_quant_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rtkv_quantize_with_params": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),

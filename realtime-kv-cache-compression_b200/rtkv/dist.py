@@ -1,17 +1,23 @@
 """Multi-GPU sharding of the compression path (one process per GPU, torch.distributed).
 
 batch sharding   every reduction of the path is per batch row -> no collective at all; each rank
-                 compresses its own sequences (BASELINE configs[4], bench.py --gpus N).
+                 compresses its own sequences (BASELINE configs[4], bench.py --workload c5).
 KV-head sharding rank r holds heads [r*H/R, (r+1)*H/R) of Q/K/V and of the attention
-                 probabilities (BASELINE configs[2]).  Two small exchanges per layer:
-                   1. all-gather of the scalar per-head-group partial sums [B,S,8/R] -> [B,S,8];
-                      every rank adds the groups in the same fixed order, so scores, labels and the
-                      selection are bit-identical on all ranks and to the single-GPU result;
-                   2. MIN/MAX all-reduce of the kept rows' local (kmin,kmax,vmin,vmax) [B,S',4]:
-                      the reference's per-token scale spans all heads of the row.
-                 Both messages are latency-bound (<= 1 MiB at S = 32768); NCCL over NVLink/NVSwitch.
-The collectives are the only torch.distributed calls; with backend "gloo" and CPU tensors the same
-functions run on the host, which is how tests/test_dist_cpu.py covers the exchange logic.
+                 probabilities (BASELINE configs[2]).  Two reductions of the reference span all heads of a
+                 token: the head mean of the prompt mass (token_importance.py:45) and the per-token min/max of
+                 the whole [H*D] row (dynamic_quantization.py:183-184).  Three schemes, identical bits:
+                   "fused" (default)  ONE exchange per layer, inside the kernels: rtkv_shard_stats streams the
+                      local A/K/V once and peer-stores every token's (kmin,kmax,vmin,vmax, mass partials) record
+                      into every rank's symmetric-memory buffer over NVLink; rtkv_shard_combine waits for the R
+                      epoch flags and reduces the records in rank order.  No NCCL call on the data path.
+                   "collective"  all_gather_into_tensor of the mass partials, then (after the selection) row
+                      min/max of the kept rows + ONE MIN all-reduce, then quantise (two NCCL calls per layer).
+                   "p2p"  the collective all-gather + rtkv_quant_gather_p2p (row min/max exchanged through peer
+                      mailboxes inside the quantise kernel, K/V read once, latency bound).
+                 Every rank adds the partials in the same fixed order, so scores, labels and the selection are
+                 bit-identical on all ranks and to the single-GPU result.
+The NCCL collectives of the "collective" scheme are the only torch.distributed data-path calls; with backend
+"gloo" and CPU tensors the same functions run on the host, which is how tests/test_dist_cpu.py covers them.
 """
 import torch
 import torch.distributed as dist
@@ -84,26 +90,92 @@ class PeerMailbox:
         return batch * rows <= self.batch * self.rows
 
 
+class ShardExchange:
+    """Symmetric (peer-mapped) exchange buffers + local state words for rtkv_shard_stats / rtkv_shard_combine.
+    torch's symmetric memory is the plumbing (allocation + the peers' device addresses over NVLink P2P); the
+    exchange itself happens inside the rtkv kernels."""
+
+    def __init__(self, batch, seq_len, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.batch, self.seq_len = batch, seq_len
+        nbytes = ops.shard_exchange_bytes(batch, seq_len, self.world)
+        self.buf = symm_mem.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.local_ptr = self.ptrs[self.rank]
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.mass = torch.empty(batch, seq_len, dtype=torch.float32, device=device)
+        self.minmax = torch.empty(batch, seq_len, 4, dtype=torch.float32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                       # every buffer is zeroed before anybody writes
+
+    def fits(self, batch, seq_len):
+        return (batch, seq_len) == (self.batch, self.seq_len)
+
+    def error(self):
+        """True if a combine gave up waiting for a peer (synchronises)."""
+        return bool(int(self.state[2].item()))
+
+
+class LocalExchange:
+    """`world` ranks emulated on ONE device (tests, single-GPU profiling): plain device buffers instead of
+    symmetric memory; rank r uses .view(r).  Call the producer for every rank before any consumer."""
+
+    class _View:
+        pass
+
+    def __init__(self, batch, seq_len, world, device):
+        from . import ops
+        nbytes = ops.shard_exchange_bytes(batch, seq_len, world)
+        self.world = world
+        self.bufs = [torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device) for _ in range(world)]
+        self.states = [torch.zeros(4, dtype=torch.int32, device=device) for _ in range(world)]
+        self.ptrs = [int(b.data_ptr()) for b in self.bufs]
+        self.batch, self.seq_len, self.device = batch, seq_len, device
+
+    def view(self, rank):
+        v = LocalExchange._View()
+        v.rank, v.world, v.ptrs, v.local_ptr, v.state = rank, self.world, self.ptrs, self.ptrs[rank], self.states[rank]
+        v.mass = torch.empty(self.batch, self.seq_len, dtype=torch.float32, device=self.device)
+        v.minmax = torch.empty(self.batch, self.seq_len, 4, dtype=torch.float32, device=self.device)
+        v.fits = lambda b, s: (b, s) == (self.batch, self.seq_len)
+        return v
+
+
 class HeadShardedCompressor:
     """compress_layer_kv_cache for a rank that holds a contiguous slice of the KV heads.
 
     Returns this rank's slice of the compressed K/V ([B,S',HD/R]) and the (replicated) Selection.
     Concatenating the ranks' slices along the last dim reproduces the single-GPU output bit for bit.
-    p2p=True uses the fused kernel (row min/max exchanged over NVLink inside the quantise kernel,
-    K/V read once); p2p=False the two-pass scheme with a MIN all-reduce.
-    """
+    mode: "fused" (one in-kernel exchange per layer, default), "collective" (two NCCL calls per layer),
+    "p2p" (NCCL all-gather + min/max mailboxes inside the quantise kernel).  exchange: a ShardExchange /
+    LocalExchange view to use instead of allocating one (tests)."""
 
-    def __init__(self, compressor, num_heads, group=None, p2p=False):
+    def __init__(self, compressor, num_heads, group=None, p2p=False, mode=None, exchange=None):
         self.compressor = compressor
         self.num_heads = num_heads
         self.group = group
-        self.p2p = p2p
+        self.mode = mode if mode is not None else ("p2p" if p2p else "fused")
+        if self.mode not in ("fused", "collective", "p2p"):
+            raise ValueError(f"unknown head-sharding mode {self.mode!r}")
+        self.p2p = self.mode == "p2p"
         self.mailbox = None
+        self.exchange = exchange
 
     def _mailbox(self, batch, rows, device):
         if self.mailbox is None or not self.mailbox.fits(batch, rows):
             self.mailbox = PeerMailbox(batch, rows, device, self.group)
         return self.mailbox
+
+    def _exchange(self, batch, seq_len, device):
+        if self.exchange is None or not self.exchange.fits(batch, seq_len):
+            self.exchange = ShardExchange(batch, seq_len, device, self.group)
+        return self.exchange
 
     def _quantise(self, key_local, value_local, sel, rows, zero_pad, out_keys=None, out_values=None):
         from . import ops
@@ -126,7 +198,37 @@ class HeadShardedCompressor:
         mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
         return ops.score_select(params, B, S, key_local.device, mass=mass)
 
+    # ---- fused scheme: stats+push -> combine -> select -> quantise (4 launches, no NCCL) ----
+    def fused_publish(self, key_local, value_local, attention_local):
+        """Producer half (rtkv_shard_stats).  Separate from fused_finish so that a single-process emulation can
+        run every rank's producer before any consumer."""
+        from . import ops
+        B, S, _ = key_local.shape
+        x = self._exchange(B, S, key_local.device)
+        ops.shard_stats(attention_local, key_local, value_local, self.compressor.prompt_length(S),
+                        self.num_heads // N_GROUPS, x.ptrs, x.rank, x.world, x.state)
+        return x
+
+    def fused_select(self, key_local, layer_idx):
+        from . import ops
+        B, S, _ = key_local.shape
+        x = self.exchange
+        mass, mm = ops.shard_combine(x.local_ptr, x.state, B, S, self.num_heads, x.world, x.mass, x.minmax)
+        params, _ = self.compressor.layer_params(layer_idx, S, ops.F32)
+        return ops.score_select(params, B, S, key_local.device, mass=mass), mm
+
+    def _fused_quantise(self, key_local, value_local, sel, mm, rows, zero_pad, out_keys=None, out_values=None):
+        from . import ops
+        return ops.quant_gather_token_minmax(key_local, value_local, sel, sel.labels, self.compressor._bits(), rows, mm,
+                                             zero_pad=zero_pad, out0=out_keys, out1=out_values)
+
     def compress_layer_kv_cache(self, key_local, value_local, attention_local, layer_idx):
+        if self.mode == "fused":
+            self.fused_publish(key_local, value_local, attention_local)
+            sel, mm = self.fused_select(key_local, layer_idx)
+            layer, _rows = sel.read_stats()
+            k_sel, v_sel = self._fused_quantise(key_local, value_local, sel, mm, int(layer["max_selected"]), True)
+            return k_sel, v_sel, sel
         sel = self._select(key_local, attention_local, layer_idx)
         layer, _rows = sel.read_stats()                       # S' is a shape: one sync
         max_sel = int(layer["max_selected"])
@@ -136,6 +238,11 @@ class HeadShardedCompressor:
     def compress_layer_async(self, key_local, value_local, attention_local, layer_idx, out_keys, out_values):
         """Synchronisation-free variant (fixed capacity S rows, like compress_layer_kv_cache_async):
         the exchanges run on the full [B,S,.] extent, nothing is read back to the host."""
+        if self.mode == "fused":
+            self.fused_publish(key_local, value_local, attention_local)
+            sel, mm = self.fused_select(key_local, layer_idx)
+            self._fused_quantise(key_local, value_local, sel, mm, key_local.shape[1], False, out_keys, out_values)
+            return sel
         sel = self._select(key_local, attention_local, layer_idx)
         self._quantise(key_local, value_local, sel, key_local.shape[1], False, out_keys, out_values)
         return sel

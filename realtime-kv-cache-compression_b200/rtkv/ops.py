@@ -296,6 +296,63 @@ def quant_gather_p2p(x0, x1, sel, labels, bits, out_rows, mailbox_ptrs, rank, wo
     return y0, y1
 
 
+def shard_exchange_bytes(batch, seq_len, world):
+    n = int(lib.rtkv_shard_exchange_bytes(int(batch), int(seq_len), int(world)))
+    if n <= 0:
+        raise ValueError(f"head sharding needs world_size in (1,2,4,8), got {world}")
+    return n
+
+
+def shard_stats(attn_local, key_local, value_local, prompt_len, group_size, xbuf_ptrs, rank, world, state):
+    """KV-head sharding, producer half of the one exchange per layer: stream the local attention slice
+    [B,H/R,S,>=P] (float32) and the local K/V row slices [B,S,n/R] once and push every token's record
+    (kmin, kmax, vmin, vmax, prompt-mass partials) into the exchange buffer of every rank (rtkv_shard_stats)."""
+    require_cuda()
+    if attn_local.stride(-1) != 1:
+        attn_local = attn_local.contiguous()
+    key_local, value_local = key_local.contiguous(), value_local.contiguous()
+    B, Hl, S, W = attn_local.shape
+    if prompt_len > W:
+        raise IndexError(f"prompt_len {prompt_len} exceeds attention width {W}")
+    assert key_local.shape == value_local.shape and key_local.dtype == value_local.dtype and key_local.shape[:2] == (B, S)
+    ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in xbuf_ptrs])
+    check(lib.rtkv_shard_stats(_ptr(attn_local), dtype_code(attn_local), B, Hl, S, attn_local.stride(0),
+                               attn_local.stride(1), attn_local.stride(2), int(prompt_len), int(group_size),
+                               _ptr(key_local), _ptr(value_local), dtype_code(key_local), key_local.shape[2],
+                               ptrs, int(rank), int(world), _ptr(state), _stream()))
+
+
+def shard_combine(xbuf_local, state, batch, seq_len, num_heads, world, mass=None, minmax=None):
+    """Consumer half: wait for every rank's records, reduce them in rank order -> mass [B,S] f32 and the whole-row
+    (kmin, kmax, vmin, vmax) [B,S,4] f32 indexed by token (rtkv_shard_combine)."""
+    require_cuda()
+    dev = state.device
+    if mass is None:
+        mass = torch.empty(batch, seq_len, dtype=torch.float32, device=dev)
+    if minmax is None:
+        minmax = torch.empty(batch, seq_len, 4, dtype=torch.float32, device=dev)
+    ptr = xbuf_local if isinstance(xbuf_local, int) else xbuf_local.data_ptr()
+    check(lib.rtkv_shard_combine(ctypes.c_void_p(ptr), _ptr(state), int(batch), int(seq_len), int(num_heads), int(world),
+                                 _ptr(mass), _ptr(minmax), _stream()))
+    return mass, minmax
+
+
+def quant_gather_token_minmax(x0, x1, sel, labels, bits, out_rows, minmax_by_token, zero_pad=True, out0=None, out1=None):
+    """quant_gather with whole-row min/max given per TOKEN ([B,S,4], from shard_combine)."""
+    require_cuda()
+    x0, x1 = x0.contiguous(), x1.contiguous()
+    B, S, n = x0.shape
+    y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
+    y1 = out1 if out1 is not None else torch.empty_like(y0)
+    lab = labels.to(torch.uint8).contiguous()
+    check(lib.rtkv_quant_gather_token_minmax(_ptr(x0), _ptr(x1), dtype_code(x0), B, S, n,
+                                             _ptr(sel.sel_idx) if sel is not None else None,
+                                             sel.row_stats_ptr if sel is not None else None, _ptr(lab),
+                                             _lib.bits3(bits), int(out_rows), int(bool(zero_pad)),
+                                             _ptr(minmax_by_token.contiguous()), _ptr(y0), _ptr(y1), _stream()))
+    return y0, y1
+
+
 def prefetch_l2(t, nbytes=None):
     """Warm L2 with the first nbytes of tensor t on the current stream (prefetch.global.L2)."""
     require_cuda()

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Real multi-GPU check of KV-head sharding (run under torchrun on R = 2, 4 or 8 GPUs, NCCL):
-every rank compresses its head slice with the two NCCL exchanges of rtkv/dist.py; the
-concatenated result must equal the single-GPU compress_layer_kv_cache bit for bit.
+every rank compresses its head slice with each exchange scheme of rtkv/dist.py ("fused": one in-kernel
+exchange over symmetric memory, "collective": two NCCL calls, "p2p": min/max mailboxes); the concatenated
+result must equal the single-GPU compress_layer_kv_cache bit for bit.
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_check.py
 """
@@ -37,13 +38,13 @@ def main():
         k_ref, v_ref, info = comp.compress_layer_kv_cache(K, V, A, ids, layer)
         h0, h1, gs = rd.head_shard(H, rank, world)
         w = HD // world
-        for p2p in (False, True):
-            sharded = rd.HeadShardedCompressor(comp, H, p2p=p2p)
+        for mode in ("fused", "collective", "p2p"):
+            sharded = rd.HeadShardedCompressor(comp, H, mode=mode)
             Kl = K[..., rank * w:(rank + 1) * w].contiguous()
             Vl = V[..., rank * w:(rank + 1) * w].contiguous()
             Al = A[:, h0:h1].contiguous()
             ok = True
-            for rep in range(3):                                   # repeated calls exercise epoch / parity reuse
+            for rep in range(5):                                   # repeated calls exercise epoch / parity reuse
                 k_loc, v_loc, sel = sharded.compress_layer_kv_cache(Kl, Vl, Al, layer)
                 ks = [torch.empty_like(k_loc) for _ in range(world)]
                 vs = [torch.empty_like(v_loc) for _ in range(world)]
@@ -55,10 +56,12 @@ def main():
             sharded.compress_layer_async(Kl, Vl, Al, layer, okb, ovb)
             ms = k_ref.shape[1]
             ok2 = (torch.equal(okb[:, :ms], k_loc) and torch.equal(ovb[:, :ms], v_loc)) if B == 1 else True
+            if mode == "fused":
+                ok2 = ok2 and not sharded.exchange.error()
             t = torch.tensor([int(ok and ok2)], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             if rank == 0:
-                print(f"head-sharded R={world} B={B} H={H} S={S} p2p={p2p}: kept {k_ref.shape[1]} ->",
+                print(f"head-sharded R={world} B={B} H={H} S={S} mode={mode}: kept {k_ref.shape[1]} ->",
                       "PASS" if int(t) else "FAIL", flush=True)
             ok_all = ok_all and bool(int(t))
     import threading

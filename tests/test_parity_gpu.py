@@ -495,6 +495,95 @@ def test_head_sharded_layer_equals_single_gpu(rt, R):
     assert torch.equal(torch.cat([o[1] for o in outs], dim=-1), v_ref)
 
 
+@pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("R,H,D,S,B,bits", [(8, 32, 128, 600, 1, (2, 4, 8)), (4, 32, 128, 257, 2, (4, 8, 16)),
+                                            (2, 16, 128, 400, 2, (2, 4, 8)), (8, 16, 24, 333, 2, (2, 4, 8)),
+                                            (1, 8, 64, 200, 1, (2, 4, 8)), (4, 8, 64, 9000, 1, (4, 8, 16))])
+def test_head_sharded_fused_exchange_equals_single_gpu(rt, kvdt, R, H, D, S, B, bits):
+    """The one-exchange scheme (rtkv_shard_stats -> rtkv_shard_combine -> K2 -> rtkv_quant_gather_token_minmax), R ranks
+    emulated on one device with plain buffers instead of symmetric memory: records, mass, row min/max, selection and
+    the concatenated outputs equal the single-GPU path bit for bit; repeated layers exercise the epoch parity."""
+    rtkv, ops = rt
+    from rtkv import dist as rd
+    if kvdt == torch.float16 and max(bits) >= 16:
+        pytest.skip("fp16 rows cannot hold 16-bit codes (reference raises)")
+    HD = H * D
+    K, V, A, P = synth_layer(B, H, S, HD, seed=R * 7 + S)
+    K, V = (K * 3).to(kvdt), (V * 2 + 0.5).to(kvdt)
+    K[0, 5] = 1.25                                   # a constant row (scale 1 / zero-point 0 branch)
+    cfg = rtkv.CompressionConfig(num_attention_heads=H, hidden_size=HD, high_precision_bits=bits[2],
+                                 medium_precision_bits=bits[1], low_precision_bits=bits[0])
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    hl, wl = H // R, HD // R
+    Ks = [K[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    Vs = [V[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    As = [A[:, r * hl:(r + 1) * hl].contiguous() for r in range(R)]
+    xch = rd.LocalExchange(B, S, R, K.device)
+    ranks = [rd.HeadShardedCompressor(comp, H, mode="fused", exchange=xch.view(r)) for r in range(R)]
+    want_mass = ops.prompt_mass(A, prompt_len=P)
+    want_mm = torch.stack([K.float().amin(-1), K.float().amax(-1), V.float().amin(-1), V.float().amax(-1)], dim=-1)
+    for layer in (3, 12, 25, 30, 31):               # odd count: both parities, and a wrap
+        k_ref, v_ref, info = comp.compress_layer_kv_cache(K, V, A, ids, layer)
+        for r in range(R):
+            ranks[r].fused_publish(Ks[r], Vs[r], As[r])
+        outs = []
+        for r in range(R):
+            sel, mm = ranks[r].fused_select(Ks[r], layer)
+            assert torch.equal(ranks[r].exchange.mass, want_mass) and torch.equal(mm, want_mm)
+            lyr, rows = sel.read_stats()
+            ms = int(lyr["max_selected"])
+            assert ms == k_ref.shape[1]
+            assert torch.equal(sel.mask.view(torch.bool), info["propagation_info"]["selection_mask"])
+            outs.append(ranks[r]._fused_quantise(Ks[r], Vs[r], sel, mm, ms, True))
+            assert int(xch.states[r][2]) == 0
+        assert torch.equal(torch.cat([o[0] for o in outs], dim=-1), k_ref)
+        assert torch.equal(torch.cat([o[1] for o in outs], dim=-1), v_ref)
+    # fixed-capacity variant (what bench.py and CUDA graphs use): rows [0, n_selected) equal, nothing else written
+    for r in range(R):
+        ranks[r].fused_publish(Ks[r], Vs[r], As[r])
+    for r in range(R):
+        ok, ov = torch.full((B, S, wl), 7.0, device="cuda", dtype=kvdt), torch.full((B, S, wl), 7.0, device="cuda", dtype=kvdt)
+        sel, mm = ranks[r].fused_select(Ks[r], 31)
+        ranks[r]._fused_quantise(Ks[r], Vs[r], sel, mm, S, False, ok, ov)
+        _, rows = sel.read_stats()
+        for b in range(B):
+            c = int(rows["n_selected"][b])
+            assert torch.equal(ok[b, :c], k_ref[b, :c, r * wl:(r + 1) * wl]) and torch.equal(ov[b, :c], v_ref[b, :c, r * wl:(r + 1) * wl])
+            assert bool((ok[b, c:] == 7.0).all()) and bool((ov[b, c:] == 7.0).all())
+
+
+def test_head_sharded_fused_exchange_propagates_nan_rows(rt):
+    """torch.min/max propagate NaN: a NaN anywhere in a row (on any rank) makes that row's scale NaN on every rank."""
+    rtkv, ops = rt
+    from rtkv import dist as rd
+    R, H, D, S, B = 4, 8, 32, 130, 1
+    K, V, A, P = synth_layer(B, H, S, H * D, seed=99)
+    K[0, 7, 3] = float("nan")            # rank 0's slice
+    V[0, 9, H * D - 1] = float("nan")    # rank 3's slice
+    cfg = rtkv.CompressionConfig(num_attention_heads=H, hidden_size=H * D, high_precision_bits=8, medium_precision_bits=4,
+                                 low_precision_bits=2)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    k_ref, v_ref, _ = comp.compress_layer_kv_cache(K, V, A, torch.zeros(B, S, dtype=torch.long, device="cuda"), 2)
+    wl, hl = H * D // R, H // R
+    xch = rd.LocalExchange(B, S, R, K.device)
+    ranks = [rd.HeadShardedCompressor(comp, H, mode="fused", exchange=xch.view(r)) for r in range(R)]
+    sl = [(K[..., r * wl:(r + 1) * wl].contiguous(), V[..., r * wl:(r + 1) * wl].contiguous(), A[:, r * hl:(r + 1) * hl].contiguous())
+          for r in range(R)]
+    for r in range(R):
+        ranks[r].fused_publish(*sl[r])
+    ks, vs = [], []
+    for r in range(R):
+        sel, mm = ranks[r].fused_select(sl[r][0], 2)
+        lyr, _ = sel.read_stats()
+        k, v = ranks[r]._fused_quantise(sl[r][0], sl[r][1], sel, mm, int(lyr["max_selected"]), True)
+        ks.append(k); vs.append(v)
+    got_k, got_v = torch.cat(ks, -1), torch.cat(vs, -1)
+    assert torch.equal(torch.isnan(got_k), torch.isnan(k_ref)) and torch.equal(torch.isnan(got_v), torch.isnan(v_ref))
+    assert bool(torch.isnan(k_ref[0]).any()) and torch.equal(torch.nan_to_num(got_k), torch.nan_to_num(k_ref))
+    assert torch.equal(torch.nan_to_num(got_v), torch.nan_to_num(v_ref))
+
+
 def test_whole_tensor_params_and_quantize(rt):
     rtkv, ops = rt
     q = rtkv.DynamicPrecisionQuantizer(rtkv.CompressionConfig())
