@@ -279,6 +279,24 @@ extern "C" int rtkv_compress_layer_host(rtkv_ctx *c, const void *K, const void *
     if (layer_stats) *layer_stats = *c->h_ls;
     if (row_stats) memcpy(row_stats, c->h_rs, (size_t)B * sizeof(rtkv_row_stats));
 
+    // fp16 rows cannot hold 16-bit codes: the reference's torch.clamp raises (dynamic_quantization.py:121) - but only
+    // for a class that HAS tokens (empty classes are skipped, :165).  An empty class's width is never used.
+    if (dtype == RTKV_F16) {
+        long long cnt[3] = {0, 0, 0};
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < 3; ++k) cnt[k] += c->h_rs[b].label_count[k];
+        for (int k = 0; k < 3; ++k) {
+            if (lp.bits[k] < 16) continue;
+            if (cnt[k] > 0) {
+                cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_main); cudaStreamSynchronize(c->s_d2h);
+                set_error("rtkv_compress_layer_host: value cannot be converted to type c10::Half without overflow (bits=%d)",
+                          lp.bits[k]);
+                return RTKV_EUNSUPPORTED;
+            }
+            lp.bits[k] = 15;
+        }
+    }
+
     // ---- quantise + download piece by piece
     if (piecewise) {
         int piece = 0;

@@ -368,11 +368,13 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     if (rc) return rc;
     rc = encode_rows_map(&map_k, Kp, dtype, (uint64_t)B * H * P);
     if (rc) return rc;
-    static int sm_count = 0;
+    static int sm_counts[64] = {0};                 // per device (a process may drive several GPUs)
+    int dev = 0;
+    RTKV_CUDA(cudaGetDevice(&dev));
+    int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
     if (!sm_count) {
-        int dev = 0;
-        RTKV_CUDA(cudaGetDevice(&dev));
         RTKV_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_counts[dev] = sm_count;
     }
     QkParams p;
     p.lse = lse; p.partials = head_sums;

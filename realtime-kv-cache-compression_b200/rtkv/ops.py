@@ -5,6 +5,7 @@ computation is a librtkv kernel.  All functions take CUDA tensors, enqueue on
 torch's current stream and do not synchronise unless their docstring says so.
 """
 import ctypes
+import functools
 
 import numpy as np
 import torch
@@ -34,12 +35,66 @@ def _ptr(t):
 
 
 def _stream():
+    """The caller's stream on the CURRENT device; every public op runs under _device_guard, which makes the
+    device of its tensors current first."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_devices(obj, found):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.append(obj.device)
+    elif isinstance(obj, torch.device):
+        if obj.type == "cuda":
+            found.append(obj if obj.index is not None else torch.device("cuda", torch.cuda.current_device()))
+    elif isinstance(obj, Selection):
+        found.append(obj.scores.device)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _cuda_devices(v, found)
+
+
+def _device_guard(fn):
+    """Launch on the device that owns the tensors, not on whatever device happens to be current: the C entries
+    use the current device and torch's current stream of that device (HF device_map / pipeline sharding puts
+    layers on several GPUs of one process).  Tensors spread over different devices are refused."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        found = []
+        for a in args:
+            _cuda_devices(a, found)
+        for a in kwargs.values():
+            _cuda_devices(a, found)
+        if not found:
+            return fn(*args, **kwargs)
+        dev = found[0]
+        for d in found[1:]:
+            if d != dev:
+                raise ValueError(f"rtkv: tensors live on different devices ({dev} and {d})")
+        if dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def _check_out(out, like, shape, what):
+    """A caller-supplied output buffer must be able to hold the result: same dtype and device as the input,
+    contiguous, at least prod(shape) elements."""
+    if out is None:
+        return
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if out.dtype != like.dtype or out.device != like.device or not out.is_contiguous() or out.numel() < n:
+        raise ValueError(f"{what}: need a contiguous {like.dtype} buffer on {like.device} with at least {n} elements, got "
+                         f"{out.dtype} on {out.device}, {out.numel()} elements, contiguous={out.is_contiguous()}")
 
 
 _scratch = {}
 
 
+@_device_guard
 def scratch(device, seq_len=1):
     """Per-device scratch (rtkv_scratch_init): header + position-bias log table for seq_len
     entries.  Grown (and re-initialised on the current stream) when a longer sequence shows up."""
@@ -70,6 +125,7 @@ def make_params(config, layer_idx, seq_len, prompt_len, ratio, score_dtype=F32):
     return p
 
 
+@_device_guard
 def prompt_mass(attn, prompt_len=None, prompt_indices=None):
     """mass[b,i] = sum_p mean_h attn[b,h,i,idx[p]] -> float32 [B,S] (token_importance.py:41-45)."""
     require_cuda()
@@ -98,6 +154,7 @@ def prompt_mass(attn, prompt_len=None, prompt_indices=None):
     return mass
 
 
+@_device_guard
 def prompt_mass_partials(attn_local, prompt_len, group_size):
     """Head-sharded K1a: per-head-group scalar partial sums [B,S,H_local/group_size] (float32 only)."""
     require_cuda()
@@ -113,6 +170,7 @@ def prompt_mass_partials(attn_local, prompt_len, group_size):
     return parts
 
 
+@_device_guard
 def mass_from_partials(partials, num_heads, rank_major=False):
     """Per-head-group partial sums -> mass = (p0 + p1 + ...)/H with the groups added in head order.
     partials: [B,S,G], or with rank_major=True the all_gather_into_tensor layout [R,B,S,G/R]."""
@@ -129,6 +187,7 @@ def mass_from_partials(partials, num_heads, rank_major=False):
     return mass
 
 
+@_device_guard
 def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True):
     """Fused Q.K_prompt^T scoring on tcgen05: q [B,H,S,128], k_prompt [B,H,P,128] (bf16/f16),
     lse [B,H,S] f32 -> per-head prompt-mass sums [B,H,S] (head-major, like lse)."""
@@ -142,6 +201,7 @@ def prompt_mass_qk_partials(q, k_prompt, lse, scale, causal=True):
     return parts
 
 
+@_device_guard
 def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
     """mass [B,S] from Q, K_prompt and the row log-sum-exp (no S x S attention matrix)."""
     hs = prompt_mass_qk_partials(q, k_prompt, lse, scale, causal)
@@ -151,6 +211,7 @@ def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
     return mass
 
 
+@_device_guard
 def position_bias(seq_len, device):
     require_cuda()
     pb = torch.empty(seq_len, dtype=torch.float32, device=device)
@@ -158,6 +219,7 @@ def position_bias(seq_len, device):
     return pb
 
 
+@_device_guard
 def normalize_mass(mass, dt=F32):
     require_cuda()
     mass = mass.contiguous()
@@ -169,11 +231,12 @@ def normalize_mass(mass, dt=F32):
 
 class Selection:
     """Device-side result of rtkv_score_select."""
-    __slots__ = ("scores", "labels", "mask", "sel_idx", "stats", "B", "S")
+    __slots__ = ("scores", "labels", "mask", "sel_idx", "stats", "B", "S", "deferred_fp16_check")
 
     def __init__(self, scores, labels, mask, sel_idx, stats, B, S):
         self.scores, self.labels, self.mask, self.sel_idx, self.stats = scores, labels, mask, sel_idx, stats
         self.B, self.S = B, S
+        self.deferred_fp16_check = False
 
     @property
     def row_stats_ptr(self):
@@ -184,13 +247,14 @@ class Selection:
         host = pinned if pinned is not None else torch.empty(self.stats.numel(), dtype=torch.uint8, pin_memory=True)
         host = host[: self.stats.numel()]
         host.copy_(self.stats, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.stats.device).synchronize()
         raw = host.numpy()
         layer = raw[:LAYER_STATS_BYTES].view(_lib.LAYER_STATS)[0]
         rows = raw[LAYER_STATS_BYTES:].view(_lib.ROW_STATS)
         return layer.copy(), rows.copy()
 
 
+@_device_guard
 def score_select(params, B, S, device, mass=None, scores=None, labels=None, select=True, fallback=True):
     """Scores -> labels -> budgeted selection (one launch).
 
@@ -226,6 +290,7 @@ def score_select(params, B, S, device, mass=None, scores=None, labels=None, sele
     return Selection(scores, labels, mask, sel_idx, stats, B, S)
 
 
+@_device_guard
 def quant_gather(x0, x1, sel, labels, bits, out_rows, zero_pad=True, out0=None, out1=None):
     """Fake-quantise (bits given) or copy (bits None) the kept rows of x0/x1 [B,S,n] into
     [B,out_rows,n].  sel: Selection or None (identity: all rows, out_rows <= S)."""
@@ -235,6 +300,8 @@ def quant_gather(x0, x1, sel, labels, bits, out_rows, zero_pad=True, out0=None, 
     if x1 is not None:
         x1 = x1.contiguous()
         assert x1.shape == x0.shape and x1.dtype == x0.dtype
+    _check_out(out0, x0, (B, out_rows, n), "quant_gather out0")
+    _check_out(out1, x0, (B, out_rows, n), "quant_gather out1")
     y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     y1 = None
     if x1 is not None:
@@ -248,6 +315,7 @@ def quant_gather(x0, x1, sel, labels, bits, out_rows, zero_pad=True, out0=None, 
     return y0, y1
 
 
+@_device_guard
 def row_minmax(x0, x1, sel, out_rows, negate_max=False):
     """Local min/max of the kept rows: [B,out_rows,4] = (min0, max0, min1, max1) float32
     (max entries negated with negate_max, so that one MIN all-reduce combines ranks)."""
@@ -262,12 +330,15 @@ def row_minmax(x0, x1, sel, out_rows, negate_max=False):
     return mm
 
 
+@_device_guard
 def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=True, out0=None, out1=None,
                         negated_max=False):
     """quant_gather with externally supplied (rank-reduced) row min/max."""
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
     B, S, n = x0.shape
+    _check_out(out0, x0, (B, out_rows, n), "out0")
+    _check_out(out1, x0, (B, out_rows, n), "out1")
     y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     y1 = out1 if out1 is not None else torch.empty_like(y0)
     lab = labels.to(torch.uint8).contiguous()
@@ -279,6 +350,7 @@ def quant_gather_minmax(x0, x1, sel, labels, bits, out_rows, minmax, zero_pad=Tr
     return y0, y1
 
 
+@_device_guard
 def quant_gather_p2p(x0, x1, sel, labels, bits, out_rows, mailbox_ptrs, rank, world, state, zero_pad=True,
                      out0=None, out1=None):
     """KV-head-sharded quantise+gather with the row min/max exchanged inside the kernel over
@@ -286,6 +358,8 @@ def quant_gather_p2p(x0, x1, sel, labels, bits, out_rows, mailbox_ptrs, rank, wo
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
     B, S, n = x0.shape
+    _check_out(out0, x0, (B, out_rows, n), "out0")
+    _check_out(out1, x0, (B, out_rows, n), "out1")
     y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     y1 = out1 if out1 is not None else torch.empty_like(y0)
     lab = labels.to(torch.uint8).contiguous()
@@ -303,6 +377,7 @@ def shard_exchange_bytes(batch, seq_len, world):
     return n
 
 
+@_device_guard
 def shard_stats(attn_local, key_local, value_local, prompt_len, group_size, xbuf_ptrs, rank, world, state):
     """KV-head sharding, producer half of the one exchange per layer: stream the local attention slice
     [B,H/R,S,>=P] (float32) and the local K/V row slices [B,S,n/R] once and push every token's record
@@ -322,6 +397,7 @@ def shard_stats(attn_local, key_local, value_local, prompt_len, group_size, xbuf
                                ptrs, int(rank), int(world), _ptr(state), _stream()))
 
 
+@_device_guard
 def shard_combine(xbuf_local, state, batch, seq_len, num_heads, world, mass=None, minmax=None):
     """Consumer half: wait for every rank's records, reduce them in rank order -> mass [B,S] f32 and the whole-row
     (kmin, kmax, vmin, vmax) [B,S,4] f32 indexed by token (rtkv_shard_combine)."""
@@ -337,11 +413,14 @@ def shard_combine(xbuf_local, state, batch, seq_len, num_heads, world, mass=None
     return mass, minmax
 
 
+@_device_guard
 def quant_gather_token_minmax(x0, x1, sel, labels, bits, out_rows, minmax_by_token, zero_pad=True, out0=None, out1=None):
     """quant_gather with whole-row min/max given per TOKEN ([B,S,4], from shard_combine)."""
     require_cuda()
     x0, x1 = x0.contiguous(), x1.contiguous()
     B, S, n = x0.shape
+    _check_out(out0, x0, (B, out_rows, n), "out0")
+    _check_out(out1, x0, (B, out_rows, n), "out1")
     y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     y1 = out1 if out1 is not None else torch.empty_like(y0)
     lab = labels.to(torch.uint8).contiguous()
@@ -353,6 +432,7 @@ def quant_gather_token_minmax(x0, x1, sel, labels, bits, out_rows, minmax_by_tok
     return y0, y1
 
 
+@_device_guard
 def prefetch_l2(t, nbytes=None):
     """Warm L2 with the first nbytes of tensor t on the current stream (prefetch.global.L2)."""
     require_cuda()
@@ -361,15 +441,18 @@ def prefetch_l2(t, nbytes=None):
     check(lib.rtkv_prefetch_l2(_ptr(t), n, _stream()))
 
 
+@_device_guard
 def quant_params(x, bits):
     """Whole-tensor (scale, zero_point) as a float32 [2] device tensor (dynamic_quantization.py:62-95)."""
     require_cuda()
     x = x.contiguous()
     qp = torch.empty(2, dtype=torch.float32, device=x.device)
-    check(lib.rtkv_quant_params(_ptr(x), dtype_code(x), x.numel(), int(bits), _ptr(qp), _ptr(scratch(x.device)), _stream()))
+    words = torch.empty(256, dtype=torch.uint8, device=x.device)   # per call: min / max / NaN flag / ticket words
+    check(lib.rtkv_quant_params(_ptr(x), dtype_code(x), x.numel(), int(bits), _ptr(qp), _ptr(words), _stream()))
     return qp
 
 
+@_device_guard
 def quantize_with_params(x, bits, qp):
     require_cuda()
     x = x.contiguous()
@@ -378,6 +461,7 @@ def quantize_with_params(x, bits, qp):
     return y
 
 
+@_device_guard
 def gather_scalars(sel, out_rows):
     """selected_scores [B,out_rows] f32, selected_labels [B,out_rows] i64 (zero padded)."""
     require_cuda()
@@ -389,6 +473,7 @@ def gather_scalars(sel, out_rows):
     return ss, sl
 
 
+@_device_guard
 def labels_to_i64(labels):
     require_cuda()
     labels = labels.contiguous()
@@ -404,6 +489,7 @@ def packed_row_bytes(n, bits):
     return int(v)
 
 
+@_device_guard
 def quant_pack(x, sel, labels, bits, out_rows):
     """Packed integer codes [B,out_rows,row_bytes] u8 + (scale, zero_point) [B,out_rows,2] f32."""
     require_cuda()
@@ -419,6 +505,7 @@ def quant_pack(x, sel, labels, bits, out_rows):
     return codes, qp
 
 
+@_device_guard
 def unpack_dequant(codes, qp, dtype, S, n, sel, labels, bits):
     require_cuda()
     B, out_rows, rb = codes.shape
@@ -446,12 +533,14 @@ def quant_options(key_mode="token", value_mode="token", group_size=0, token_grou
     return o
 
 
+@_device_guard
 def gather_rows(x, sel, out_rows, zero_pad=True):
     """Coalesced gather of the kept rows of any [B,S,n] tensor (hidden states, K, V) into [B,out_rows,n]
     in ascending token order (selective_propagation.py:213-232)."""
     return quant_gather(x, None, sel, None, None, out_rows, zero_pad)[0]
 
 
+@_device_guard
 def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True, want_counts=False, out0=None,
                     out1=None):
     """quant_gather with extended scale granularities / outlier split (rtkv_quant_gather_ex)."""
@@ -461,6 +550,8 @@ def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True,
     if x1 is not None:
         x1 = x1.contiguous()
         assert x1.shape == x0.shape and x1.dtype == x0.dtype
+    _check_out(out0, x0, (B, out_rows, n), "quant_gather_ex out0")
+    _check_out(out1, x0, (B, out_rows, n), "quant_gather_ex out1")
     y0 = out0 if out0 is not None else torch.empty(B, out_rows, n, dtype=x0.dtype, device=x0.device)
     y1 = None
     if x1 is not None:
@@ -475,6 +566,7 @@ def quant_gather_ex(x0, x1, sel, labels, bits, out_rows, options, zero_pad=True,
     return (y0, y1, oc) if want_counts else (y0, y1)
 
 
+@_device_guard
 def quant_pack_ex(x, sel, labels, bits, out_rows, options, tensor=0, outlier_cap=0):
     """Packed codes with options -> dict(codes, qparams, out_idx, out_val, out_cnt, row_bytes)."""
     require_cuda()
@@ -501,6 +593,7 @@ def quant_pack_ex(x, sel, labels, bits, out_rows, options, tensor=0, outlier_cap
     return dict(codes=codes, qparams=qp, out_idx=oi, out_val=ov, out_cnt=ocnt, cap=cap)
 
 
+@_device_guard
 def unpack_dequant_ex(packed, dtype, S, n, sel, labels, bits, options, tensor=0):
     require_cuda()
     codes = packed["codes"]
@@ -515,6 +608,7 @@ def unpack_dequant_ex(packed, dtype, S, n, sel, labels, bits, options, tensor=0)
     return y
 
 
+@_device_guard
 def packed_decode_attention(q, codes_k, qparams_k, codes_v, qparams_v, row_bits, sel, num_kv_heads, sm_scale=None,
                             splits=None, want_lse=False):
     """Decode-step attention over packed rows (rtkv_packed_decode_attention).  q [B,H,128] -> out [B,H,128] f32."""
@@ -568,6 +662,9 @@ class HostContext:
             attn = attn.contiguous()
         B, S, n = K.shape
         H = attn.shape[1]
+        for name, o in (("k_out", k_out), ("v_out", v_out)):
+            if o is not None and (o.is_cuda or o.dtype != K.dtype or not o.is_contiguous() or o.numel() < B * S * n):
+                raise ValueError(f"{name}: need a contiguous host {K.dtype} buffer with at least {B * S * n} elements")
         if k_out is None:
             k_out = torch.empty(B * S * n, dtype=K.dtype)
         if v_out is None:

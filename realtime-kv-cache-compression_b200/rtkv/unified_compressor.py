@@ -29,8 +29,8 @@ def _importance_stats(rows, n_tokens):
     ss = float(rows["score_sumsq"].sum())
     mean = s / n_tokens
     if n_tokens > 1:
-        var = max(0.0, (ss - s * s / n_tokens) / (n_tokens - 1))
-        std = math.sqrt(var)
+        var = (ss - s * s / n_tokens) / (n_tokens - 1)
+        std = float("nan") if math.isnan(var) else math.sqrt(max(0.0, var))      # NaN scores give a NaN std, like torch.std
     else:
         std = float("nan")
     mins, maxs = rows["score_min"], rows["score_max"]
@@ -138,6 +138,20 @@ class RealTimePrefillCompressor:
         c = self.config
         return (c.low_precision_bits, c.medium_precision_bits, c.high_precision_bits)
 
+    def _kernel_bits(self, dtype, label_count):
+        """Bit widths handed to the quantise kernel.  fp16 rows cannot hold 16-bit codes: the reference's
+        torch.clamp(x, 0, 65535) raises on a Half tensor (dynamic_quantization.py:121) - but only for a precision class
+        that HAS tokens, empty classes are skipped (:165).  label_count: tokens per class over all B*S tokens."""
+        bits = list(self._bits())
+        if dtype == torch.float16:
+            for c in range(3):
+                if bits[c] >= 16:
+                    if int(label_count[c]) > 0:
+                        raise RuntimeError("value cannot be converted to type at::Half without overflow "
+                                           f"({int(label_count[c])} tokens at {bits[c]} bits in float16 rows)")
+                    bits[c] = 15          # never used: the class is empty
+        return tuple(bits)
+
     def _quant_options(self):
         """rtkv_quant_options when the config asks for an extended mode, else None (reference semantics)."""
         c = self.config
@@ -195,18 +209,19 @@ class RealTimePrefillCompressor:
             h_stat.copy_(sel.stats, non_blocking=True)
             h_scores.copy_(sel.scores, non_blocking=True)
             h_labels.copy_(sel.labels, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(dev).synchronize()
             raw = h_stat.numpy()
             layer = raw[: ops.LAYER_STATS_BYTES].view(ops._lib.LAYER_STATS)[0]
             rows = raw[ops.LAYER_STATS_BYTES:].view(ops._lib.ROW_STATS).copy()
             max_selected = int(layer["max_selected"])
             qopt = self._quant_options()
+            kbits = self._kernel_bits(key_states.dtype, rows["label_count"].sum(axis=0))
             if qopt is None:
                 selected_keys, selected_values = ops.quant_gather(
-                    key_states, value_states, sel, sel.labels, self._bits(), max_selected)
+                    key_states, value_states, sel, sel.labels, kbits, max_selected)
             else:
                 selected_keys, selected_values = ops.quant_gather_ex(
-                    key_states, value_states, sel, sel.labels, self._bits(), max_selected, qopt)
+                    key_states, value_states, sel, sel.labels, kbits, max_selected, qopt)
             scores_cpu = h_scores.clone()
             labels_np = h_labels.numpy().astype(np.int64)
             selection_mask = sel.mask.view(torch.bool)
@@ -270,7 +285,7 @@ class RealTimePrefillCompressor:
         layer, rows = sel.read_stats()
         ms = int(layer["max_selected"])
         qopt = self._quant_options() or ops.quant_options()
-        bits = self._bits()
+        bits = self._kernel_bits(key_states.dtype, rows["label_count"].sum(axis=0))
         pk = ops.quant_pack_ex(key_states, sel, sel.labels, bits, ms, qopt, tensor=0, outlier_cap=outlier_cap)
         pv = ops.quant_pack_ex(value_states, sel, sel.labels, bits, ms, qopt, tensor=1, outlier_cap=outlier_cap)
         return PackedKV(pk, pv, sel, ms, bits, qopt, key_states.dtype, S, HD, rows, layer_idx, ratio)
@@ -299,7 +314,13 @@ class RealTimePrefillCompressor:
         sel = ops.score_select(params, B, S, key_states.device, mass=mass)
         if prefetch_stream is not None:
             torch.cuda.current_stream().wait_stream(prefetch_stream)
-        ops.quant_gather(key_states, value_states, sel, sel.labels, self._bits(), S, zero_pad=zero_pad,
+        bits = self._bits()
+        if key_states.dtype == torch.float16 and max(bits) >= 16:
+            # the label counts are not known on the host here: quantise with a representable stand-in width and let
+            # collect_async raise (like the reference does) if the 16-bit class turns out to be populated
+            bits = tuple(15 if b >= 16 else b for b in bits)
+            sel.deferred_fp16_check = True
+        ops.quant_gather(key_states, value_states, sel, sel.labels, bits, S, zero_pad=zero_pad,
                          out0=out_keys, out1=out_values)
         return sel
 
@@ -322,7 +343,7 @@ class RealTimePrefillCompressor:
         dev_blob = torch.cat(blobs)
         host = self._stats_buffer(dev_blob.numel())[: dev_blob.numel()]
         host.copy_(dev_blob, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(dev_blob.device).synchronize()
         raw = host.numpy()
         results, off = {}, 0
         share = (time.time() - t0) / len(pending)
@@ -335,6 +356,8 @@ class RealTimePrefillCompressor:
             labels_np = raw[off: off + n_tokens].reshape(B, S).astype(np.int64); off += n_tokens
             layer = st[: ops.LAYER_STATS_BYTES].view(ops._lib.LAYER_STATS)[0]
             rows = st[ops.LAYER_STATS_BYTES:].view(ops._lib.ROW_STATS).copy()
+            if getattr(sel, "deferred_fp16_check", False):
+                self._kernel_bits(torch.float16, rows["label_count"].sum(axis=0))     # raises if the class is populated
             ms = int(layer["max_selected"])
             ratio = self.propagator.get_layer_propagation_ratio(layer_idx)
             k_sel, v_sel = out_keys[:, :ms], out_values[:, :ms]
