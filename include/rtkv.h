@@ -346,6 +346,10 @@ RTKV_API int rtkv_debug_qk_mode(int mode);
  * in shared memory with cp.async.  Same results. */
 RTKV_API int rtkv_debug_channel_variant(int variant);
 
+/* Testing aid: rtkv_shard_stats kernel: 0 (default) the bulk-copy staged kernel when the shape allows, 1 always the
+ * generic register kernel.  Same results. */
+RTKV_API int rtkv_debug_shard_variant(int variant);
+
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);
 

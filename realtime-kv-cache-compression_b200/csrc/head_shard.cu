@@ -64,10 +64,11 @@ __device__ __forceinline__ size_t record_offset(unsigned parity, int world, int 
     return (size_t)kXHeader + ((((size_t)parity * world + src) * (size_t)rows + (size_t)row) * rec_vecs) * 16;
 }
 
+// Generic path (any P, any strides): one warp per token, loads straight into registers.
 // DT = dtype of K/V; the probabilities are float32 (half probabilities round the per-column head mean, which does
 // not decompose over ranks: rtkv_prompt_mass_partials has the same restriction).
 template <int DT, bool VEC>
-__global__ void __launch_bounds__(kShardWarps * 32) shard_stats_kernel(ShardParams p)
+__global__ void __launch_bounds__(kShardWarps * 32) shard_stats_generic_kernel(ShardParams p)
 {
     constexpr int EPV = Vec16<DT>::kElems;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,6 +154,184 @@ __global__ void __launch_bounds__(kShardWarps * 32) shard_stats_kernel(ShardPara
     }
 }
 
+// ---- staged path: bulk async copies (TMA engine, cp.async.bulk) into a ring of shared-memory stages ----
+// The register kernel above is latency bound (one row per warp, three dependent load phases: 1.1 - 3.4 TB/s measured).
+// Here a producer thread asks the copy engine for whole BLOCKS of rows (completion counted in bytes on an mbarrier),
+// so up to ~200 KB per SM are in flight with no registers held, while 8 consumer warps reduce the block that has landed.
+// Same arithmetic and the same reduction order as the generic kernel (and as prompt_mass_kernel): bit-identical records.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct StagedCfg {
+    int rb, stages, stage_bytes, kv_bytes, a_bytes;   // rb rows per block; a_bytes = P*4 bytes of one head's prompt columns
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_sys_v2(void *p, float a, float b)
+{
+    asm volatile("st.volatile.global.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+}
+
+constexpr int kStagedThreads = (kShardWarps + 1) * 32;      // 8 consumer warps + 1 producer warp
+
+// One CTA per SM, persistent over blocks of `rb` consecutive token rows of one batch row.  Per block the producer
+// thread issues 2 + H_local bulk copies (K rows, V rows: contiguous; per head the rb prompt-column runs of A, which
+// are contiguous when A is a [B,H,S,P] slice) - a few LARGE copies, because the copy engine costs ~45 ns per copy
+// whatever its size (measured: per-row 512-byte copies ran at 2.5 TB/s).  The 8 consumer warps share the block's
+// 3*rb items (row, task) with task = K min/max | V min/max | prompt-mass partials; each item writes its own part of
+// the token's record.
+template <int DT>
+__global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(ShardParams p, StagedCfg c)
+{
+    constexpr int EPV = Vec16<DT>::kElems;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 64;               // [stages] each (stages <= 8)
+    unsigned char *data = smem + 1024;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < c.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kShardWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    const unsigned epoch = ((volatile unsigned *)p.state)[0] + 1u;
+    const unsigned parity = epoch & 1u;
+    const int64_t rows = (int64_t)p.B * p.S;
+    const int nvec = p.n / EPV;
+    const int Hl = p.ng * p.gs;
+    const int bpb = (p.S + c.rb - 1) / c.rb;                   // blocks per batch row
+    const int64_t n_blocks = (int64_t)p.B * bpb;
+
+    if (warp == kShardWarps) {
+        // ---- producer ----
+        if (lane == 0) {
+            int64_t k = 0;
+            for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
+                const int st = (int)(k % c.stages);
+                mbar_wait(empty0 + 8 * st, (uint32_t)(((k / c.stages) & 1) ^ 1));
+                const int b = (int)(blk / bpb);
+                const int i0 = (int)(blk - (int64_t)b * bpb) * c.rb;
+                const int nr = min(c.rb, p.S - i0);
+                const uint32_t bar = full0 + 8 * st;
+                const uint32_t dst = smem_u32(data + (size_t)st * c.stage_bytes);
+                mbar_expect_tx(bar, (uint32_t)nr * (2u * c.kv_bytes + (uint32_t)Hl * c.a_bytes));
+                const size_t row0 = (size_t)b * p.S + i0;
+                bulk_g2s(dst, (const char *)p.K + row0 * c.kv_bytes, nr * c.kv_bytes, bar);
+                bulk_g2s(dst + c.rb * c.kv_bytes, (const char *)p.V + row0 * c.kv_bytes, nr * c.kv_bytes, bar);
+                const float *a0 = (const float *)p.A + b * p.sb + (int64_t)i0 * p.si;
+                for (int h = 0; h < Hl; ++h)
+                    bulk_g2s(dst + 2 * c.rb * c.kv_bytes + h * c.rb * c.a_bytes, a0 + (int64_t)h * p.sh, nr * c.a_bytes, bar);
+            }
+        }
+    } else {
+        // ---- consumers ----
+        unsigned long long my_dst = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (lane == s) my_dst = p.xbuf[s];
+        const int a_vecs = c.a_bytes / 16;                     // float4 per head row (P/4)
+        int64_t k = 0;
+        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
+            const int st = (int)(k % c.stages);
+            const int b = (int)(blk / bpb);
+            const int i0 = (int)(blk - (int64_t)b * bpb) * c.rb;
+            const int nr = min(c.rb, p.S - i0);
+            mbar_wait(full0 + 8 * st, (uint32_t)((k / c.stages) & 1));
+            const unsigned char *sd = data + (size_t)st * c.stage_bytes;
+            for (int item = warp; item < 3 * nr; item += kShardWarps) {
+                const int r = item / 3, task = item - 3 * r;
+                const int64_t row = (int64_t)b * p.S + i0 + r;
+                char *rec = (char *)my_dst + record_offset(parity, p.world, p.rank, rows, row, p.rec_vecs);
+                if (task < 2) {
+                    // local min/max of the K (task 0) or V (task 1) row slice
+                    const uint4 *src = reinterpret_cast<const uint4 *>(sd + (size_t)task * c.rb * c.kv_bytes + (size_t)r * c.kv_bytes);
+                    float mn = INFINITY, mx = -INFINITY;
+                    int nan = 0;
+                    for (int v0 = lane; v0 < nvec; v0 += 4 * 32) {
+                        uint4 raw[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v0 + 32 * q < nvec) raw[q] = src[v0 + 32 * q];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (v0 + 32 * q < nvec) {
+                                float f[EPV];
+                                Vec16<DT>::unpack(raw[q], f);
+#pragma unroll
+                                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+                            }
+                        }
+                    }
+                    mn = warp_min(mn); mx = warp_max(mx);
+                    if (__any_sync(0xffffffffu, nan)) mn = mx = __int_as_float(0x7fc00000);   // torch.min/max propagate NaN
+                    if (lane < p.world) st_sys_v2(rec + 8 * task, mn, mx);
+                } else {
+                    // prompt mass of the local head groups: heads of a group added in order per column, the lane's 4 columns
+                    // in order, xor butterfly (== group_column_sums + butterfly of prompt_mass.cuh)
+                    const float4 *ap = reinterpret_cast<const float4 *>(sd + 2 * (size_t)c.rb * c.kv_bytes);
+                    float pg[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        pg[g] = 0.0f;
+                        if (g < p.ng) {
+                            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, lane_acc = 0.0f;
+                            if (lane < a_vecs) {
+                                for (int h = g * p.gs; h < (g + 1) * p.gs; ++h) {
+                                    const float4 v = ap[((size_t)h * c.rb + r) * a_vecs + lane];
+                                    s0 = __fadd_rn(s0, v.x); s1 = __fadd_rn(s1, v.y); s2 = __fadd_rn(s2, v.z); s3 = __fadd_rn(s3, v.w);
+                                }
+                                lane_acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(lane_acc, s0), s1), s2), s3);
+                            }
+                            pg[g] = butterfly(lane_acc);
+                        }
+                    }
+                    if (lane < p.world) {
+                        st_sys_v4(rec + 16, pg[0], pg[1], pg[2], pg[3]);
+                        if (p.rec_vecs > 2) st_sys_v4(rec + 32, pg[4], pg[5], pg[6], pg[7]);
+                    }
+                }
+            }
+            __syncwarp();                                  // every lane is done with this stage's shared memory
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+            p.state[1] = 0u;
+            __threadfence_system();
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (s < p.world) st_release_sys((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
+            ((volatile unsigned *)p.state)[0] = epoch;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, unsigned *state, int64_t rows, int world,
                                                              int gpr, int rec_vecs, float fH, float *__restrict__ mass,
                                                              float *__restrict__ minmax)
@@ -204,6 +383,14 @@ static int rec_vecs_for(int world) { return 1 + ((kGroups / world) + 3) / 4; }
 
 using namespace rtkv;
 
+static int g_shard_variant = 0;     // 0 automatic (staged when the shape allows), 1 always the generic register kernel
+extern "C" int rtkv_debug_shard_variant(int variant)
+{
+    RTKV_CHECK_ARG(variant == 0 || variant == 1, "rtkv_debug_shard_variant: 0 or 1");
+    g_shard_variant = variant;
+    return RTKV_OK;
+}
+
 extern "C" int64_t rtkv_shard_exchange_bytes(int B, int S, int world)
 {
     if (B <= 0 || S <= 0 || !(world == 1 || world == 2 || world == 4 || world == 8)) return -1;
@@ -237,13 +424,39 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     p.state = state;
     const bool vec = ((uintptr_t)A % 16 == 0) && (sb * 4) % 16 == 0 && (sh * 4) % 16 == 0 && (si * 4) % 16 == 0;
     const int64_t rows = (int64_t)B * S;
+    // staged path: every copy must be a 16-byte multiple at a 16-byte aligned address, P <= 128 columns, and the
+    // prompt-column runs of consecutive rows must be adjacent (A is a [B,H,S,P] slice: si == P)
+    StagedCfg c;
+    c.kv_bytes = n_local * dtype_bytes(kv_dtype);
+    c.a_bytes = P * 4;
+    const int row_bytes = 2 * c.kv_bytes + H_local * c.a_bytes;
+    const int budget = 200 * 1024;
+    c.rb = budget / 2 / row_bytes;                              // at least two stages
+    if (c.rb > 8) c.rb = 8;
+    const bool staged = g_shard_variant != 1 && vec && P % 4 == 0 && P <= 128 && si == P && c.kv_bytes % 16 == 0 && c.rb >= 1;
+    if (staged) {
+        c.stage_bytes = ((c.rb * row_bytes + 127) / 128) * 128;
+        c.stages = budget / c.stage_bytes < 4 ? budget / c.stage_bytes : 4;
+        const size_t smem = 1024 + (size_t)c.stages * c.stage_bytes;
+        int dev = 0, sms = 0;
+        RTKV_CUDA(cudaGetDevice(&dev));
+        RTKV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t n_blocks = (int64_t)B * ((S + c.rb - 1) / c.rb);
+        const int grid = (int)(n_blocks < sms ? n_blocks : sms);
+        void (*kern)(ShardParams, StagedCfg) = shard_stats_staged_kernel<RTKV_BF16>;
+        if (kv_dtype == RTKV_F32) kern = shard_stats_staged_kernel<RTKV_F32>;
+        else if (kv_dtype == RTKV_F16) kern = shard_stats_staged_kernel<RTKV_F16>;
+        RTKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + budget));
+        RTKV_CUDA(launch_kernel(kern, dim3(grid), dim3(kStagedThreads), smem, (cudaStream_t)stream, 1, p, c));
+        return RTKV_OK;
+    }
     const int64_t ctas = (rows + kShardWarps - 1) / kShardWarps;
     const int grid = (int)(ctas < 148 * 64 ? ctas : 148 * 64);
     void (*kern)(ShardParams) = nullptr;
     switch (kv_dtype) {
-    case RTKV_F32: kern = vec ? shard_stats_kernel<RTKV_F32, true> : shard_stats_kernel<RTKV_F32, false>; break;
-    case RTKV_F16: kern = vec ? shard_stats_kernel<RTKV_F16, true> : shard_stats_kernel<RTKV_F16, false>; break;
-    default: kern = vec ? shard_stats_kernel<RTKV_BF16, true> : shard_stats_kernel<RTKV_BF16, false>; break;
+    case RTKV_F32: kern = vec ? shard_stats_generic_kernel<RTKV_F32, true> : shard_stats_generic_kernel<RTKV_F32, false>; break;
+    case RTKV_F16: kern = vec ? shard_stats_generic_kernel<RTKV_F16, true> : shard_stats_generic_kernel<RTKV_F16, false>; break;
+    default: kern = vec ? shard_stats_generic_kernel<RTKV_BF16, true> : shard_stats_generic_kernel<RTKV_BF16, false>; break;
     }
     RTKV_CUDA(launch_kernel(kern, dim3(grid), dim3(kShardWarps * 32), 0, (cudaStream_t)stream, 1, p));
     return RTKV_OK;

@@ -128,6 +128,7 @@ PROTOTYPES = {
     "rtkv_debug_k2_timing": (ctypes.c_int, [c_vp]),
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_shard_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_qk_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "rtkv_ctx_destroy": (ctypes.c_int, [c_vp]),

@@ -499,7 +499,8 @@ def test_head_sharded_layer_equals_single_gpu(rt, R):
 @pytest.mark.parametrize("R,H,D,S,B,bits", [(8, 32, 128, 600, 1, (2, 4, 8)), (4, 32, 128, 257, 2, (4, 8, 16)),
                                             (2, 16, 128, 400, 2, (2, 4, 8)), (8, 16, 24, 333, 2, (2, 4, 8)),
                                             (1, 8, 64, 200, 1, (2, 4, 8)), (4, 8, 64, 9000, 1, (4, 8, 16))])
-def test_head_sharded_fused_exchange_equals_single_gpu(rt, kvdt, R, H, D, S, B, bits):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_head_sharded_fused_exchange_equals_single_gpu(rt, variant, kvdt, R, H, D, S, B, bits):
     """The one-exchange scheme (rtkv_shard_stats -> rtkv_shard_combine -> K2 -> rtkv_quant_gather_token_minmax), R ranks
     emulated on one device with plain buffers instead of symmetric memory: records, mass, row min/max, selection and
     the concatenated outputs equal the single-GPU path bit for bit; repeated layers exercise the epoch parity."""
@@ -507,6 +508,14 @@ def test_head_sharded_fused_exchange_equals_single_gpu(rt, kvdt, R, H, D, S, B, 
     from rtkv import dist as rd
     if kvdt == torch.float16 and max(bits) >= 16:
         pytest.skip("fp16 rows cannot hold 16-bit codes (reference raises)")
+    ops.lib.rtkv_debug_shard_variant(variant)        # 0: bulk-copy staged statistics kernel, 1: generic register kernel
+    try:
+        _fused_exchange_case(rtkv, ops, rd, kvdt, R, H, D, S, B, bits)
+    finally:
+        ops.lib.rtkv_debug_shard_variant(0)
+
+
+def _fused_exchange_case(rtkv, ops, rd, kvdt, R, H, D, S, B, bits):
     HD = H * D
     K, V, A, P = synth_layer(B, H, S, HD, seed=R * 7 + S)
     K, V = (K * 3).to(kvdt), (V * 2 + 0.5).to(kvdt)
