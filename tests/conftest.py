@@ -26,7 +26,7 @@ def load_golden(name):
 
 
 LAYER_CASES = ["layer_f32_s64", "layer_f32_b2_s96", "layer_f32_s256_l31", "layer_f32_s700_888",
-               "layer_bf16_s128", "layer_f16_s128", "layer_f32_tiny_fallback"]
+               "layer_bf16_s128", "layer_f16_s128", "layer_f32_tiny_fallback", "layer_f16_16_8_4_nohigh"]
 STAGE_CASES = ["stage_f32_8_4_2", "stage_f32_16_8_4", "stage_bf16_8_4_2", "stage_f16_8_4_2"]
 
 

@@ -691,6 +691,40 @@ def test_golden_layer_through_drop_in_api(rt, name, on_host):
     assert overall["cumulative_compression"] == m["compressed_shape"][1] / m["S"]
 
 
+@pytest.mark.parametrize("how", ["cuda-tensors", "host-tensors", "async"])
+def test_fp16_default_widths_raise_only_when_the_wide_class_is_populated(rt, how):
+    """fp16 K/V with the reference's default 16/8/4: the reference raises (torch.clamp overflow, dynamic_quantization.py:121)
+    only if a HIGH token exists (:165 skips empty classes).  Fixture made by the reference (oracle/pin_fp16_wide.py); the
+    populated-class counterpart of the layer_f16_16_8_4_nohigh golden layer."""
+    rtkv, ops = rt
+    g = load_golden("layer_f16_16_8_4_high_raises")
+    m = g["meta"]
+    cfg = rtkv.CompressionConfig(num_hidden_layers=m["L"], num_attention_heads=m["H"], hidden_size=m["HD"])   # 16/8/4
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    place = (lambda t: t) if how == "host-tensors" else (lambda t: t.cuda())
+    K, V, A = (place(oracle.to_torch(g[k], m["dt"])) for k in ("K", "V", "A"))
+    ids = place(torch.zeros(m["B"], m["S"], dtype=torch.long))
+    if how == "async":
+        ok, ov = torch.empty_like(K), torch.empty_like(V)
+        sel = comp.compress_layer_kv_cache_async(K, V, A, m["layer_idx"], ok, ov)       # nothing is read back here ...
+        with pytest.raises(RuntimeError, match="Half"):
+            comp.collect_async([(m["layer_idx"], sel, ok, ov)])                          # ... the check is deferred to here
+        # and a layer without HIGH tokens goes through the same async path cleanly
+        g2 = load_golden("layer_f16_16_8_4_nohigh")
+        m2 = g2["meta"]
+        comp2 = build_compressor(rtkv, m2)
+        K2, V2, A2 = (oracle.to_torch(g2[k], m2["dt"]).cuda() for k in ("K", "V", "A"))
+        ok2, ov2 = torch.empty_like(K2), torch.empty_like(V2)
+        sel2 = comp2.compress_layer_kv_cache_async(K2, V2, A2, m2["layer_idx"], ok2, ov2)
+        res = comp2.collect_async([(m2["layer_idx"], sel2, ok2, ov2)])
+        k_sel, v_sel, _ = res[m2["layer_idx"]]
+        assert_same(k_sel, g2["k_sel"], m2["dt"])
+        assert_same(v_sel, g2["v_sel"], m2["dt"])
+        return
+    with pytest.raises(RuntimeError, match="Half"):
+        comp.compress_layer_kv_cache(K, V, A, ids, m["layer_idx"])
+
+
 @pytest.mark.parametrize("name", STAGE_CASES)
 def test_golden_stages_through_component_api(rt, name):
     rtkv, ops = rt
@@ -1012,8 +1046,9 @@ def test_reference_style_scorer_tests(rt):
 
 
 def test_llama_hook_prefill_on_gpu(rt):
-    """The hook block of modified_llama.py:96-152 on a tiny random Llama: every layer is compressed,
-    statistics are attached, and the layer result equals the eager formulation recomputed by hand."""
+    """The hook contract of modified_llama.py:96-152 on a tiny random Llama, model level: every layer is compressed,
+    statistics are attached, the cache entry is the compressed K/V.  (The numerics of the block are checked against
+    a hand recomputation in test_llama_hook_block_equals_hand_recomputation.)"""
     rtkv, ops = rt
     from rtkv.llama_hooks import CompressedLlamaForCausalLM
     from transformers import LlamaConfig
@@ -1038,6 +1073,79 @@ def test_llama_hook_prefill_on_gpu(rt):
     assert kept == 24                                            # the cache entry is the compressed K/V
     model.reset_compression_state()
     assert comp.layer_states == {}
+
+
+@pytest.mark.parametrize("bits,prunes", [((8, 8, 8), True), ((2, 4, 8), False)])
+def test_llama_hook_block_equals_hand_recomputation(rt, bits, prunes):
+    """Row a19: the hook block of CompressedLlamaAttention.forward (modified_llama.py:96-152) recomputed by hand in
+    plain torch, with the ORACLE doing the compression step: eager softmax(QK^T/sqrt(d) + mask), compressor fed
+    K/V as [B,S,H*D] and the probabilities, then either attention recomputed over the kept tokens with the additive
+    mask truncated to its first S' columns (:125-140, S' != S) or attn_weights @ V_quant (S' == S), o_proj.  Also the
+    downgrade when the compressor raises (:144-149)."""
+    rtkv, ops = rt
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    torch.manual_seed(1)
+    Hh, D, S, B, Lh = 8, 16, 60, 2, 3
+    hf = LlamaConfig(hidden_size=Hh * D, intermediate_size=256, num_hidden_layers=Lh, num_attention_heads=Hh,
+                     num_key_value_heads=Hh, vocab_size=211, max_position_embeddings=256)
+    model = CompressedLlamaForCausalLM(hf).cuda().eval()
+    cfg = rtkv.CompressionConfig(num_hidden_layers=Lh, num_attention_heads=Hh, hidden_size=Hh * D, high_precision_bits=bits[2],
+                                 medium_precision_bits=bits[1], low_precision_bits=bits[0])
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    model.set_compressor(comp)
+    layer = 2
+    attn = model.model.layers[layer].self_attn
+    x = torch.randn(B, S, Hh * D, device="cuda")
+    pos = torch.arange(S, device="cuda")[None].expand(B, -1)
+    cos, sin = model.model.rotary_emb(x, pos)
+    mask = torch.full((S, S), torch.finfo(torch.float32).min, device="cuda").triu(1)[None, None].expand(B, 1, S, S)
+    ids = torch.zeros(B, S, dtype=torch.long, device="cuda")
+    with torch.no_grad():
+        got, got_w = attn(x, position_embeddings=(cos, sin), attention_mask=mask, input_ids=ids)
+        # ---- by hand ----
+        shp = (B, S, Hh, D)
+        q = torch.nn.functional.linear(x, attn.q_proj.weight).view(shp).transpose(1, 2)
+        k = torch.nn.functional.linear(x, attn.k_proj.weight).view(shp).transpose(1, 2)
+        v = torch.nn.functional.linear(x, attn.v_proj.weight).view(shp).transpose(1, 2)
+        q, k = apply_rotary_pos_emb(q, k, cos, sin)
+        w = torch.softmax(q @ k.transpose(2, 3) / D ** 0.5 + mask, dim=-1, dtype=torch.float32)
+        assert torch.equal(got_w, w)                      # the probabilities the reference hands to the compressor (:88-94)
+        k_flat = k.transpose(1, 2).contiguous().view(B, S, Hh * D)
+        v_flat = v.transpose(1, 2).contiguous().view(B, S, Hh * D)
+        P = max(1, min(S // 5, 128))
+        o = oracle.compress_layer(host(k_flat), host(v_flat), oracle.F32, host(w[..., :P].contiguous()), oracle.F32, P,
+                                  cfg.alpha, cfg.beta, cfg.gamma, cfg.layer_weights[layer], cfg.theta_h, cfg.theta_m, bits,
+                                  comp.propagator.get_layer_propagation_ratio(layer))
+        ck, cv = torch.from_numpy(o["k_sel"]).cuda(), torch.from_numpy(o["v_sel"]).cuda()
+        s_kept = ck.shape[1]
+        assert (s_kept != S) == prunes
+        ck = ck.view(B, s_kept, Hh, D).transpose(1, 2)
+        cv = cv.view(B, s_kept, Hh, D).transpose(1, 2)
+        if s_kept != S:
+            w2 = torch.softmax(q @ ck.transpose(2, 3) / D ** 0.5 + mask[..., :s_kept], dim=-1, dtype=torch.float32)
+            ctx = w2 @ cv
+        else:
+            ctx = w @ cv
+        want = torch.nn.functional.linear(ctx.transpose(1, 2).contiguous().reshape(B, S, -1), attn.o_proj.weight)
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+        assert comp.layer_states[layer]["compressed_shape"][1] == s_kept
+        # ---- downgrade: a failing compressor leaves the plain attention result (:144-149) ----
+
+        class Boom:
+            def compress_layer_kv_cache(self, *a, **k):
+                raise RuntimeError("boom")
+        attn.set_compressor(Boom())
+        got2, _ = attn(x, position_embeddings=(cos, sin), attention_mask=mask, input_ids=ids)
+        plain = torch.nn.functional.linear((w @ v).transpose(1, 2).contiguous().reshape(B, S, -1), attn.o_proj.weight)
+        torch.testing.assert_close(got2, plain, rtol=1e-5, atol=1e-6)
+        # training mode / decode step (q_len == 1): the block is skipped (:102)
+        attn.set_compressor(comp)
+        comp.reset_compression_state()
+        attn.train()
+        attn(x, position_embeddings=(cos, sin), attention_mask=mask, input_ids=ids)
+        assert comp.layer_states == {}
 
 
 def test_precomputed_prompt_mass_input(rt):
