@@ -189,9 +189,12 @@ RTKV_API int rtkv_quant_gather_minmax(const void *X0, const void *X1, int dtype,
 /* KV-head sharding, fused: min/max exchange inside the quantise kernel over peer-mapped memory
  * (NVLink).  mailbox_ptrs [host]: `world` device pointers, entry s = rank s's mailbox as mapped into
  * this process (symmetric memory / CUDA IPC), each rtkv_p2p_mailbox_bytes(B, out_rows, world) bytes,
- * zero-filled once; state: 2 zero-initialised uint32 in local device memory.  Every rank must call
- * this with the same B, out_rows, selection and call sequence, and a collective (or barrier) must
- * separate consecutive calls that reuse a mailbox parity twice (the score all-gather does).
+ * zero-filled once; state: 4 zero-initialised uint32 in local device memory (epoch, ticket, error flag, reserved).
+ * Every rank must call this with the same B, out_rows, selection and call sequence, launched concurrently (a CTA
+ * waits for the peers' CTAs of the same row), and a collective (or barrier) must separate consecutive calls that
+ * reuse a mailbox parity twice (the score all-gather does).  If a peer's words do not arrive within ~20 s the
+ * kernel sets state[2] = 1 and continues with its local min/max (results of that call are then not the reference's);
+ * it never traps.
  * Equals rtkv_quant_gather on the concatenated row bit for bit. */
 RTKV_API int64_t rtkv_p2p_mailbox_bytes(int B, int out_rows, int world);
 RTKV_API int rtkv_quant_gather_p2p(const void *X0, const void *X1, int dtype, int B, int S, int n,

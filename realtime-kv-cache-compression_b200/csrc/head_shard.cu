@@ -21,6 +21,8 @@
 // seen every rank's flag e+1, i.e. after every rank has finished reading the records of epoch e: two parities are
 // enough and no other synchronisation between ranks exists.  The epoch is a device-side counter, so the kernels are
 // CUDA-graph replayable.
+#include <stdlib.h>
+
 #include "prompt_mass.cuh"
 
 namespace rtkv {
@@ -33,7 +35,8 @@ struct ShardParams {
     int64_t sb, sh, si;
     const void *K, *V;
     int B, S, P, gs, ng, n;           // ng local head groups of gs heads; n = local row width in elements
-    int rank, world, rec_vecs;
+    int rank, world, rec_vecs, dbg, kv_keep;   // kv_keep: ask L2 to keep the K/V rows (they fit and are re-read soon)
+    //    // dbg (rtkv_debug_shard_variant): 2 no consumer math, 3 no record stores
     unsigned long long xbuf[8];       // exchange buffer of rank s as mapped into this process
     unsigned *state;                  // local: [0] epoch of the last finished call, [1] CTA ticket, [2] error flag
 };
@@ -42,14 +45,14 @@ __device__ __forceinline__ void st_sys_v4(void *p, float a, float b, float c, fl
 {
     asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+__device__ __forceinline__ void st_sys_u32(unsigned *p, unsigned v)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+__device__ __forceinline__ unsigned ld_sys_u32(const unsigned *p)
 {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float4 ld_cg_v4(const void *p)
@@ -62,6 +65,27 @@ __device__ __forceinline__ float4 ld_cg_v4(const void *p)
 __device__ __forceinline__ size_t record_offset(unsigned parity, int world, int src, int64_t rows, int64_t row, int rec_vecs)
 {
     return (size_t)kXHeader + ((((size_t)parity * world + src) * (size_t)rows + (size_t)row) * rec_vecs) * 16;
+}
+
+// End of a statistics kernel: every record of this rank must be visible at every peer before the epoch flag is.
+// Every thread fences its own record stores at system scope (in parallel: one fence latency), the CTA barrier orders
+// them before thread 0's ticket, and the LAST CTA fences once more (acquire of the other CTAs' tickets + release of
+// everything they ordered before them) and then writes the flags with plain system-scope stores.  One fence per
+// thread plus one in the last CTA: a chain of st.release.sys (a system fence each, ~2.3 us apiece) measured 25 us.
+__device__ __forceinline__ void publish_epoch(const ShardParams &p, unsigned parity, unsigned epoch)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+            p.state[1] = 0u;
+            __threadfence_system();
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (s < p.world) st_sys_u32((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
+            ((volatile unsigned *)p.state)[0] = epoch;
+        }
+    }
 }
 
 // Generic path (any P, any strides): one warp per token, loads straight into registers.
@@ -139,19 +163,7 @@ __global__ void __launch_bounds__(kShardWarps * 32) shard_stats_generic_kernel(S
         }
     }
     // ---- publish: every record of this rank is out before the flag ----
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
-            p.state[1] = 0u;
-            __threadfence_system();
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (s < p.world) st_release_sys((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
-            ((volatile unsigned *)p.state)[0] = epoch;
-        }
-    }
+    publish_epoch(p, parity, epoch);
 }
 
 // ---- staged path: bulk async copies (TMA engine, cp.async.bulk) into a ring of shared-memory stages ----
@@ -174,10 +186,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// L2 residency: the K/V rows are read again by the quantise kernel a few tens of microseconds later (after the
+// exchange and the selection), the probability slice never again.  With 8 ranks a rank's K/V slice of a 32k-token layer
+// is 64 MiB - it fits the 126 MB L2 if the 64 MiB of probabilities streaming through do not evict it.
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 
 struct StagedCfg {
@@ -193,14 +220,25 @@ __device__ __forceinline__ void st_sys_v2(void *p, float a, float b)
     asm volatile("st.volatile.global.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(a), "f"(b) : "memory");
 }
 
-constexpr int kStagedThreads = (kShardWarps + 1) * 32;      // 8 consumer warps + 1 producer warp
+constexpr int kStagedConsumers = 16;                          // consumer warps (one row of the block each)
+constexpr int kStagedThreads = (kStagedConsumers + 1) * 32;   // + 1 producer warp
+
+// order-preserving unsigned image of a float: warp min/max become single REDUX instructions
+__device__ __forceinline__ unsigned f2ord_u(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f_u(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
 
 // One CTA per SM, persistent over blocks of `rb` consecutive token rows of one batch row.  Per block the producer
 // thread issues 2 + H_local bulk copies (K rows, V rows: contiguous; per head the rb prompt-column runs of A, which
 // are contiguous when A is a [B,H,S,P] slice) - a few LARGE copies, because the copy engine costs ~45 ns per copy
-// whatever its size (measured: per-row 512-byte copies ran at 2.5 TB/s).  The 8 consumer warps share the block's
-// 3*rb items (row, task) with task = K min/max | V min/max | prompt-mass partials; each item writes its own part of
-// the token's record.
+// whatever its size (measured: per-row 512-byte copies ran at 2.5 TB/s).  16 consumer warps share the block's
+// 3*rb (row, task) items: K min/max, V min/max (one REDUX each) or the prompt-mass partials of a row.
 template <int DT>
 __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(ShardParams p, StagedCfg c)
 {
@@ -210,7 +248,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 64;               // [stages] each (stages <= 8)
     unsigned char *data = smem + 1024;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < c.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kShardWarps); }
+        for (int s = 0; s < c.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kStagedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -224,9 +262,11 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
     const int bpb = (p.S + c.rb - 1) / c.rb;                   // blocks per batch row
     const int64_t n_blocks = (int64_t)p.B * bpb;
 
-    if (warp == kShardWarps) {
+    if (warp == kStagedConsumers) {
         // ---- producer ----
         if (lane == 0) {
+            const uint64_t pol_kv = p.kv_keep ? l2_policy_evict_last() : l2_policy_evict_first();
+            const uint64_t pol_a = l2_policy_evict_first();
             int64_t k = 0;
             for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
                 const int st = (int)(k % c.stages);
@@ -238,11 +278,11 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
                 const uint32_t dst = smem_u32(data + (size_t)st * c.stage_bytes);
                 mbar_expect_tx(bar, (uint32_t)nr * (2u * c.kv_bytes + (uint32_t)Hl * c.a_bytes));
                 const size_t row0 = (size_t)b * p.S + i0;
-                bulk_g2s(dst, (const char *)p.K + row0 * c.kv_bytes, nr * c.kv_bytes, bar);
-                bulk_g2s(dst + c.rb * c.kv_bytes, (const char *)p.V + row0 * c.kv_bytes, nr * c.kv_bytes, bar);
+                bulk_g2s(dst, (const char *)p.K + row0 * c.kv_bytes, nr * c.kv_bytes, bar, pol_kv);
+                bulk_g2s(dst + c.rb * c.kv_bytes, (const char *)p.V + row0 * c.kv_bytes, nr * c.kv_bytes, bar, pol_kv);
                 const float *a0 = (const float *)p.A + b * p.sb + (int64_t)i0 * p.si;
                 for (int h = 0; h < Hl; ++h)
-                    bulk_g2s(dst + 2 * c.rb * c.kv_bytes + h * c.rb * c.a_bytes, a0 + (int64_t)h * p.sh, nr * c.a_bytes, bar);
+                    bulk_g2s(dst + 2 * c.rb * c.kv_bytes + h * c.rb * c.a_bytes, a0 + (int64_t)h * p.sh, nr * c.a_bytes, bar, pol_a);
             }
         }
     } else {
@@ -260,12 +300,16 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
             const int nr = min(c.rb, p.S - i0);
             mbar_wait(full0 + 8 * st, (uint32_t)((k / c.stages) & 1));
             const unsigned char *sd = data + (size_t)st * c.stage_bytes;
-            for (int item = warp; item < 3 * nr; item += kShardWarps) {
+            // items = (row of the block, task): task 0 / 1 = min/max of the K / V row slice, 2 = prompt-mass partials;
+            // each item writes its own part of the token's record (8 + 8 + 16 bytes)
+            for (int item = warp; item < 3 * nr && p.dbg != 2; item += kStagedConsumers) {
                 const int r = item / 3, task = item - 3 * r;
                 const int64_t row = (int64_t)b * p.S + i0 + r;
                 char *rec = (char *)my_dst + record_offset(parity, p.world, p.rank, rows, row, p.rec_vecs);
                 if (task < 2) {
-                    // local min/max of the K (task 0) or V (task 1) row slice
+                    // per lane fminf/fmaxf, across lanes ONE REDUX per value on the order-preserving unsigned image (same
+                    // value as the shuffle tree of the generic kernel; only the sign of a zero extreme could differ, and
+                    // -0.0 == +0.0 everywhere downstream: scale, zero-point, mx == mn)
                     const uint4 *src = reinterpret_cast<const uint4 *>(sd + (size_t)task * c.rb * c.kv_bytes + (size_t)r * c.kv_bytes);
                     float mn = INFINITY, mx = -INFINITY;
                     int nan = 0;
@@ -284,12 +328,13 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
                             }
                         }
                     }
-                    mn = warp_min(mn); mx = warp_max(mx);
+                    mn = ord2f_u(__reduce_min_sync(0xffffffffu, f2ord_u(mn)));
+                    mx = ord2f_u(__reduce_max_sync(0xffffffffu, f2ord_u(mx)));
                     if (__any_sync(0xffffffffu, nan)) mn = mx = __int_as_float(0x7fc00000);   // torch.min/max propagate NaN
-                    if (lane < p.world) st_sys_v2(rec + 8 * task, mn, mx);
+                    if (lane < p.world && (p.dbg != 3 || mn == 12345.678f)) st_sys_v2(rec + 8 * task, mn, mx);
                 } else {
-                    // prompt mass of the local head groups: heads of a group added in order per column, the lane's 4 columns
-                    // in order, xor butterfly (== group_column_sums + butterfly of prompt_mass.cuh)
+                    // heads of a group added in order per column, the lane's 4 columns in order, xor butterfly
+                    // (== group_column_sums + butterfly of prompt_mass.cuh)
                     const float4 *ap = reinterpret_cast<const float4 *>(sd + 2 * (size_t)c.rb * c.kv_bytes);
                     float pg[8];
 #pragma unroll
@@ -307,7 +352,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
                             pg[g] = butterfly(lane_acc);
                         }
                     }
-                    if (lane < p.world) {
+                    if (lane < p.world && (p.dbg != 3 || pg[0] == 12345.678f)) {
                         st_sys_v4(rec + 16, pg[0], pg[1], pg[2], pg[3]);
                         if (p.rec_vecs > 2) st_sys_v4(rec + 32, pg[4], pg[5], pg[6], pg[7]);
                     }
@@ -317,19 +362,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
-            p.state[1] = 0u;
-            __threadfence_system();
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (s < p.world) st_release_sys((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
-            ((volatile unsigned *)p.state)[0] = epoch;
-        }
-    }
+    publish_epoch(p, parity, epoch);
 }
 
 __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, unsigned *state, int64_t rows, int world,
@@ -343,12 +376,13 @@ __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, 
     if ((int)threadIdx.x < world) {
         const unsigned *flag = (const unsigned *)xlocal + parity * 8 + threadIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys(flag) != epoch) {
+        while (ld_sys_u32(flag) != epoch) {                        // relaxed polling, one acquire fence afterwards
             if (clock64() - t0 > 40000000000LL) {                   // ~20 s: a peer never showed up; flag it, do not trap
                 atomicExch(&state[2], 1u);
                 break;
             }
         }
+        __threadfence_system();
     }
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,7 +420,7 @@ using namespace rtkv;
 static int g_shard_variant = 0;     // 0 automatic (staged when the shape allows), 1 always the generic register kernel
 extern "C" int rtkv_debug_shard_variant(int variant)
 {
-    RTKV_CHECK_ARG(variant == 0 || variant == 1, "rtkv_debug_shard_variant: 0 or 1");
+    RTKV_CHECK_ARG(variant >= 0 && variant <= 3, "rtkv_debug_shard_variant: 0..3");
     g_shard_variant = variant;
     return RTKV_OK;
 }
@@ -418,7 +452,9 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     ShardParams p;
     p.A = A; p.sb = sb; p.sh = sh; p.si = si; p.K = K; p.V = V;
     p.B = B; p.S = S; p.P = P; p.gs = group_size; p.ng = kGroups / world; p.n = n_local;
-    p.rank = rank; p.world = world; p.rec_vecs = rec_vecs_for(world);
+    p.rank = rank; p.world = world; p.rec_vecs = rec_vecs_for(world); p.dbg = g_shard_variant;
+    // keep the local K/V slice in L2 when it fits comfortably (the quantise kernel re-reads the kept rows)
+    p.kv_keep = (2.0 * B * S * n_local * dtype_bytes(kv_dtype) <= 80e6) && !getenv("RTKV_SHARD_NO_L2_KEEP");
     for (int s = 0; s < 8; ++s) p.xbuf[s] = s < world ? xbuf_ptrs[s] : 0ull;
     for (int s = 0; s < world; ++s) RTKV_CHECK_ARG(p.xbuf[s] && p.xbuf[s] % 16 == 0, "rtkv_shard_stats: exchange buffer %d", s);
     p.state = state;
@@ -432,11 +468,14 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     const int row_bytes = 2 * c.kv_bytes + H_local * c.a_bytes;
     const int budget = 200 * 1024;
     c.rb = budget / 2 / row_bytes;                              // at least two stages
-    if (c.rb > 8) c.rb = 8;
+    if (c.rb > kStagedConsumers) c.rb = kStagedConsumers;
+    int want_stages = 4;
+    if (const char *e = getenv("RTKV_SHARD_RB")) { const int v = atoi(e); if (v >= 1 && v <= c.rb) c.rb = v; }      // tuning knobs
+    if (const char *e = getenv("RTKV_SHARD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 8) want_stages = v; }
     const bool staged = g_shard_variant != 1 && vec && P % 4 == 0 && P <= 128 && si == P && c.kv_bytes % 16 == 0 && c.rb >= 1;
     if (staged) {
         c.stage_bytes = ((c.rb * row_bytes + 127) / 128) * 128;
-        c.stages = budget / c.stage_bytes < 4 ? budget / c.stage_bytes : 4;
+        c.stages = budget / c.stage_bytes < want_stages ? budget / c.stage_bytes : want_stages;
         const size_t smem = 1024 + (size_t)c.stages * c.stage_bytes;
         int dev = 0, sms = 0;
         RTKV_CUDA(cudaGetDevice(&dev));

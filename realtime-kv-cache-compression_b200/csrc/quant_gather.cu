@@ -179,17 +179,24 @@ __global__ void __launch_bounds__(THREADS) quant_gather_p2p_kernel(QGParams p)
             const uint4 *in = (const uint4 *)p.mbox[p.rank] + slot0 + s;               // from rank s, in my mailbox
             uint4 got;
             const long long t0 = clock64();
+            bool timed_out = false;
             do {
                 got = ld_volatile_v4(in);
-                if (clock64() - t0 > 6000000000LL) __trap();                            // a peer never showed up
+                if (clock64() - t0 > 40000000000LL) { timed_out = true; break; }        // ~20 s: a peer never showed up
             } while (got.y != epoch || got.w != epoch);
+            if (timed_out) {        // never trap (that would kill the CUDA context): flag it and go on with the local values
+                atomicExch(&p.p2p_state[2], 1u);
+                got = make_uint4(__float_as_uint(mn), epoch, __float_as_uint(-mx), epoch);
+            }
             float pmn = __uint_as_float(got.x), pnmx = __uint_as_float(got.z);
             int pnan = (pmn != pmn);
             const unsigned act = (1u << p.world) - 1u;
             for (int o = 4; o; o >>= 1) {                                               // world <= 8
-                const float omn = __shfl_xor_sync(act, pmn, o), onm = __shfl_xor_sync(act, pnmx, o);
-                const int on = __shfl_xor_sync(act, pnan, o);
-                if ((s ^ o) < p.world) { pmn = fminf(pmn, omn); pnmx = fminf(pnmx, onm); pnan |= on; }
+                // a partner lane outside the mask (world < 8) must not be read: shuffle from the own lane instead
+                const int src = (s ^ o) < p.world ? (s ^ o) : s;
+                const float omn = __shfl_sync(act, pmn, src), onm = __shfl_sync(act, pnmx, src);
+                const int on = __shfl_sync(act, pnan, src);
+                pmn = fminf(pmn, omn); pnmx = fminf(pnmx, onm); pnan |= on;
             }
             if (s == 0) {
                 s_mm[0] = pnan ? __int_as_float(0x7fc00000) : pmn;

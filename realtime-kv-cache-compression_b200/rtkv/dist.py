@@ -82,12 +82,16 @@ class PeerMailbox:
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                       # every mailbox is zeroed before anybody writes
 
     def fits(self, batch, rows):
         return batch * rows <= self.batch * self.rows
+
+    def error(self):
+        """True if a kernel gave up waiting for a peer's words (synchronises)."""
+        return bool(int(self.state[2].item()))
 
 
 class ShardExchange:

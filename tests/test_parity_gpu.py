@@ -1075,7 +1075,7 @@ def test_llama_hook_prefill_on_gpu(rt):
     assert comp.layer_states == {}
 
 
-@pytest.mark.parametrize("bits,prunes", [((8, 8, 8), True), ((2, 4, 8), False)])
+@pytest.mark.parametrize("bits,prunes", [((8, 8, 8), True), ((2, 2, 2), False)])
 def test_llama_hook_block_equals_hand_recomputation(rt, bits, prunes):
     """Row a19: the hook block of CompressedLlamaAttention.forward (modified_llama.py:96-152) recomputed by hand in
     plain torch, with the ORACLE doing the compression step: eager softmax(QK^T/sqrt(d) + mask), compressor fed

@@ -92,6 +92,36 @@ for R in [int(x) for x in os.environ.get("WORLDS", "2,4,8").split(",")]:
     res["k3_GBs"] = res["kept"] * w * 4 * 4 / res["k3_token_minmax_us"] / 1e3
     res["k3_plain_us"] = timeit(lambda it: ops.quant_gather(Ks[it % NBUF], Vs[it % NBUF], sel, sel.labels, bits, S, zero_pad=False, out0=ok, out1=ov))
     res["sum_us"] = res["shard_stats_us"] + res["combine_us"] + res["k2_us"] + res["k3_token_minmax_us"]
+    # rank 0's whole layer as it runs in a real job: the other ranks' records are already there (published first),
+    # then stats -> combine -> K2 -> K3 back to back; external events inside the graph bracket rank 0's chain
+    NL = 4
+    ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(NL)]
+
+    def chain(timed):
+        for l in range(NL):
+            for r in range(1, R):
+                v = views[r]
+                ops.shard_stats(As[l % NBUF], Ks[l % NBUF], Vs[l % NBUF], P, gs, v.ptrs, r, R, v.state)
+            if timed:
+                ev[l][0].record()
+            ops.shard_stats(As[l % NBUF], Ks[l % NBUF], Vs[l % NBUF], P, gs, v0.ptrs, 0, R, v0.state)
+            m_, mm_ = ops.shard_combine(v0.local_ptr, v0.state, B, S, H, R, v0.mass, v0.minmax)
+            sel_ = ops.score_select(params, B, S, dev, mass=m_)
+            ops.quant_gather_token_minmax(Ks[l % NBUF], Vs[l % NBUF], sel_, sel_.labels, bits, S, mm_, zero_pad=False, out0=ok, out1=ov)
+            if timed:
+                ev[l][1].record()
+    chain(False)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        chain(True)
+    acc = []
+    for _ in range(6):
+        g.replay()
+        torch.cuda.synchronize()
+        acc.append(sum(a.elapsed_time(b) for a, b in ev) * 1e3 / NL)
+    acc.sort()
+    res["chain_us_per_layer"] = acc[len(acc) // 2]
     print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in res.items()}), flush=True)
     del As, Ks, Vs, xch, views
     torch.cuda.empty_cache()
