@@ -484,6 +484,8 @@ def bench_head_sharded(args, rtkv, ops, layers, cfg, config, dev, rank, world, L
     from rtkv import dist as rd
     comp = rtkv.RealTimePrefillCompressor(cfg)
     mode = args.shard_mode
+    if os.environ.get("RTKV_SHARD_VARIANT"):      # bisecting aid (timing experiments only; 2/3 give wrong results)
+        ops.lib.rtkv_debug_shard_variant(int(os.environ["RTKV_SHARD_VARIANT"]))
     sharded = rd.HeadShardedCompressor(comp, heads, mode=mode)
     try:
         if mode == "fused":

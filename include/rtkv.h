@@ -226,6 +226,15 @@ RTKV_API int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, in
                       const uint64_t *xbuf_ptrs /*[host]*/, int rank, int world, uint32_t *state, void *stream);
 RTKV_API int rtkv_shard_combine(const void *xbuf_local, uint32_t *state, int B, int S, int H, int world,
                       float *mass, float *minmax, void *stream);
+/* rtkv_shard_stats and rtkv_shard_combine in ONE kernel (real multi-GPU only: every rank must be running the same call
+ * concurrently).  CTA c of every rank works on the same token blocks, so after pushing its records it raises a per-CTA
+ * flag at every rank, waits for the flags of the peers' CTA c and reduces its own tokens: no grid-wide flag, no second
+ * launch.  Needs the staged kernel (A a [B,H_local,S,P] slice, P % 4 == 0, P <= 128), else RTKV_EUNSUPPORTED.  Same
+ * results as the two-call scheme; the two schemes may be mixed from call to call as long as all ranks agree. */
+RTKV_API int rtkv_shard_stats_combine(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                      int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                      const uint64_t *xbuf_ptrs /*[host]*/, int rank, int world, uint32_t *state, int H,
+                      float *mass, float *minmax, void *stream);
 RTKV_API int rtkv_quant_gather_token_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                       const int32_t *sel_idx, const rtkv_row_stats *row_stats,
                       const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
@@ -352,6 +361,9 @@ RTKV_API int rtkv_debug_channel_variant(int variant);
 /* Testing aid: rtkv_shard_stats kernel: 0 (default) the bulk-copy staged kernel when the shape allows, 1 always the
  * generic register kernel.  Same results. */
 RTKV_API int rtkv_debug_shard_variant(int variant);
+/* Testing aid: cap the persistent grid of the staged statistics kernel (0 = one CTA per SM), so that several emulated
+ * ranks can be co-resident on one GPU for rtkv_shard_stats_combine. */
+RTKV_API int rtkv_debug_shard_grid(int max_ctas);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);

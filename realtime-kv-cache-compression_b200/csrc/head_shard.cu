@@ -27,7 +27,8 @@
 
 namespace rtkv {
 
-constexpr int kXHeader = 256;        // bytes: flags[2 parities][8 sources] u32, padded
+constexpr int kMaxShardCtas = 256;   // per-CTA flags of the fused statistics+combine kernel (grid <= SM count)
+constexpr int kXHeader = 256 + 2 * 8 * kMaxShardCtas * 4;   // bytes: flags[2 parities][8 sources] u32 (padded to 256) + CTA flags[2][8][256] u32
 constexpr int kShardWarps = 8;
 
 struct ShardParams {
@@ -39,6 +40,9 @@ struct ShardParams {
     //    // dbg (rtkv_debug_shard_variant): 2 no consumer math, 3 no record stores
     unsigned long long xbuf[8];       // exchange buffer of rank s as mapped into this process
     unsigned *state;                  // local: [0] epoch of the last finished call, [1] CTA ticket, [2] error flag
+    // fused combine (rtkv_shard_stats_combine): this rank's outputs, NULL = publish only
+    float *mass, *minmax;
+    float fH;
 };
 
 __device__ __forceinline__ void st_sys_v4(void *p, float a, float b, float c, float d)
@@ -65,6 +69,34 @@ __device__ __forceinline__ float4 ld_cg_v4(const void *p)
 __device__ __forceinline__ size_t record_offset(unsigned parity, int world, int src, int64_t rows, int64_t row, int rec_vecs)
 {
     return (size_t)kXHeader + ((((size_t)parity * world + src) * (size_t)rows + (size_t)row) * rec_vecs) * 16;
+}
+
+// mass and whole-row min/max of one token from the R records of epoch `parity` in this rank's exchange buffer
+__device__ __forceinline__ void combine_token(const char *xlocal, unsigned parity, int world, int gpr, int rec_vecs, int64_t rows,
+                                              int64_t t, float fH, float *__restrict__ mass, float *__restrict__ minmax)
+{
+    float tot = 0.0f;
+    float kmn = INFINITY, kmx = -INFINITY, vmn = INFINITY, vmx = -INFINITY;
+    bool knan = false, vnan = false;
+    for (int r = 0; r < world; ++r) {
+        const char *rec = xlocal + record_offset(parity, world, r, rows, t, rec_vecs);
+        const float4 m = ld_cg_v4(rec);
+        const float4 a = ld_cg_v4(rec + 16);
+        float pg[8] = {a.x, a.y, a.z, a.w, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (rec_vecs > 2) {
+            const float4 c = ld_cg_v4(rec + 32);
+            pg[4] = c.x; pg[5] = c.y; pg[6] = c.z; pg[7] = c.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            if (g < gpr) tot = (r == 0 && g == 0) ? pg[g] : __fadd_rn(tot, pg[g]);
+        knan = knan || (m.x != m.x); vnan = vnan || (m.z != m.z);
+        kmn = fminf(kmn, m.x); kmx = fmaxf(kmx, m.y); vmn = fminf(vmn, m.z); vmx = fmaxf(vmx, m.w);
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    mass[t] = __fdiv_rn(tot, fH);
+    float4 o = make_float4(knan ? qnan : kmn, knan ? qnan : kmx, vnan ? qnan : vmn, vnan ? qnan : vmx);
+    *reinterpret_cast<float4 *>(minmax + 4 * t) = o;
 }
 
 // End of a statistics kernel: every record of this rank must be visible at every peer before the epoch flag is.
@@ -222,6 +254,7 @@ __device__ __forceinline__ void st_sys_v2(void *p, float a, float b)
 
 constexpr int kStagedConsumers = 16;                          // consumer warps (one row of the block each)
 constexpr int kStagedThreads = (kStagedConsumers + 1) * 32;   // + 1 producer warp
+constexpr int kStagedHeader = 1024 + 8 * kStagedConsumers * 48;   // barriers + record staging (8 stages x 16 rows x 48 B)
 
 // order-preserving unsigned image of a float: warp min/max become single REDUX instructions
 __device__ __forceinline__ unsigned f2ord_u(float f)
@@ -246,7 +279,8 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 64;               // [stages] each (stages <= 8)
-    unsigned char *data = smem + 1024;
+    float *rec_s = reinterpret_cast<float *>(smem + 1024);                     // [stages][rb][4*rec_vecs] record staging
+    unsigned char *data = smem + kStagedHeader;
     if (threadIdx.x == 0) {
         for (int s = 0; s < c.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kStagedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -287,10 +321,6 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
         }
     } else {
         // ---- consumers ----
-        unsigned long long my_dst = 0;
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-            if (lane == s) my_dst = p.xbuf[s];
         const int a_vecs = c.a_bytes / 16;                     // float4 per head row (P/4)
         int64_t k = 0;
         for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
@@ -301,11 +331,11 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
             mbar_wait(full0 + 8 * st, (uint32_t)((k / c.stages) & 1));
             const unsigned char *sd = data + (size_t)st * c.stage_bytes;
             // items = (row of the block, task): task 0 / 1 = min/max of the K / V row slice, 2 = prompt-mass partials;
-            // each item writes its own part of the token's record (8 + 8 + 16 bytes)
+            // each item writes its part of the token's record into the stage's record staging area
+            float *rec_st = rec_s + (size_t)st * kStagedConsumers * 12;
             for (int item = warp; item < 3 * nr && p.dbg != 2; item += kStagedConsumers) {
                 const int r = item / 3, task = item - 3 * r;
-                const int64_t row = (int64_t)b * p.S + i0 + r;
-                char *rec = (char *)my_dst + record_offset(parity, p.world, p.rank, rows, row, p.rec_vecs);
+                float *rs = rec_st + r * 4 * p.rec_vecs;
                 if (task < 2) {
                     // per lane fminf/fmaxf, across lanes ONE REDUX per value on the order-preserving unsigned image (same
                     // value as the shuffle tree of the generic kernel; only the sign of a zero extreme could differ, and
@@ -331,7 +361,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
                     mn = ord2f_u(__reduce_min_sync(0xffffffffu, f2ord_u(mn)));
                     mx = ord2f_u(__reduce_max_sync(0xffffffffu, f2ord_u(mx)));
                     if (__any_sync(0xffffffffu, nan)) mn = mx = __int_as_float(0x7fc00000);   // torch.min/max propagate NaN
-                    if (lane < p.world && (p.dbg != 3 || mn == 12345.678f)) st_sys_v2(rec + 8 * task, mn, mx);
+                    if (lane == 0) { rs[2 * task] = mn; rs[2 * task + 1] = mx; }
                 } else {
                     // heads of a group added in order per column, the lane's 4 columns in order, xor butterfly
                     // (== group_column_sums + butterfly of prompt_mass.cuh)
@@ -352,15 +382,80 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
                             pg[g] = butterfly(lane_acc);
                         }
                     }
-                    if (lane < p.world && (p.dbg != 3 || pg[0] == 12345.678f)) {
-                        st_sys_v4(rec + 16, pg[0], pg[1], pg[2], pg[3]);
-                        if (p.rec_vecs > 2) st_sys_v4(rec + 32, pg[4], pg[5], pg[6], pg[7]);
+                    if (lane == 0) {
+                        rs[4] = pg[0]; rs[5] = pg[1]; rs[6] = pg[2]; rs[7] = pg[3];
+                        if (p.rec_vecs > 2) { rs[8] = pg[4]; rs[9] = pg[5]; rs[10] = pg[6]; rs[11] = pg[7]; }
                     }
+                }
+            }
+            // The block's records are contiguous in every rank's buffer (nr x 32 bytes): once all items are done, warp w
+            // sends them to rank w as 16-byte vectors, a warp-wide store covering whole 128-byte lines.  (Per-item 8/16-byte
+            // peer stores were 688k tiny NVLink packets per layer and cost ~30 us per layer on 8 GPUs.)
+            asm volatile("bar.sync 1, %0;" ::"n"(kStagedConsumers * 32) : "memory");
+            if (warp < p.world && p.dbg < 2) {
+                unsigned long long base = 0;
+#pragma unroll
+                for (int sdst = 0; sdst < 8; ++sdst)
+                    if (warp == sdst) base = p.xbuf[sdst];
+                const int64_t row0 = (int64_t)b * p.S + i0;
+                float4 *dst = reinterpret_cast<float4 *>((char *)base + record_offset(parity, p.world, p.rank, rows, row0, p.rec_vecs));
+                const float4 *srcv = reinterpret_cast<const float4 *>(rec_st);
+                for (int v = lane; v < nr * p.rec_vecs; v += 32) {
+                    const float4 x = srcv[v];
+                    st_sys_v4(dst + v, x.x, x.y, x.z, x.w);
                 }
             }
             __syncwarp();                                  // every lane is done with this stage's shared memory
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
         }
+        if (p.mass) {
+            // ---- fused combine: CTA c of every rank handles the same token blocks, so this CTA only needs the records
+            // of the peers' CTA c.  Point-to-point: fence my record stores, raise my CTA flag at every rank, wait for the
+            // R flags of CTA c here, then reduce my own tokens.  No grid-wide flag, no second kernel.
+            __threadfence_system();
+            asm volatile("bar.sync 1, %0;" ::"n"(kStagedConsumers * 32) : "memory");
+            if (warp == 0 && lane < p.world) {
+                unsigned long long base = 0;
+#pragma unroll
+                for (int sdst = 0; sdst < 8; ++sdst)
+                    if (lane == sdst) base = p.xbuf[sdst];
+                st_sys_u32((unsigned *)(base + 256) + ((size_t)parity * 8 + p.rank) * kMaxShardCtas + blockIdx.x, epoch);
+                unsigned long long mine = 0;
+#pragma unroll
+                for (int sdst = 0; sdst < 8; ++sdst)
+                    if (p.rank == sdst) mine = p.xbuf[sdst];
+                const unsigned *flag = (const unsigned *)(mine + 256) + ((size_t)parity * 8 + lane) * kMaxShardCtas + blockIdx.x;
+                const long long t0 = clock64();
+                while (ld_sys_u32(flag) != epoch) {
+                    if (clock64() - t0 > 40000000000LL) { atomicExch(&p.state[2], 1u); break; }     // ~20 s: flag it, never trap
+                }
+                __threadfence_system();
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kStagedConsumers * 32) : "memory");
+            unsigned long long mine = 0;
+#pragma unroll
+            for (int sdst = 0; sdst < 8; ++sdst)
+                if (p.rank == sdst) mine = p.xbuf[sdst];
+            const int per_blk = c.rb;
+            const int64_t my_blocks = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            for (int64_t idx = threadIdx.x; idx < my_blocks * per_blk; idx += kStagedConsumers * 32) {
+                const int64_t blk = blockIdx.x + (idx / per_blk) * gridDim.x;
+                const int r = (int)(idx % per_blk);
+                const int b = (int)(blk / bpb);
+                const int i = (int)(blk - (int64_t)b * bpb) * c.rb + r;
+                if (i < p.S)
+                    combine_token((const char *)mine, parity, p.world, p.ng, p.rec_vecs, rows, (int64_t)b * p.S + i, p.fH, p.mass, p.minmax);
+            }
+        }
+    }
+    if (p.mass) {       // only the epoch counter is left to advance (local; the flags were point-to-point)
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+            p.state[1] = 0u;
+            __threadfence();
+            ((volatile unsigned *)p.state)[0] = epoch;
+        }
+        return;
     }
     publish_epoch(p, parity, epoch);
 }
@@ -387,28 +482,7 @@ __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, 
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows) return;
-    float tot = 0.0f;
-    float kmn = INFINITY, kmx = -INFINITY, vmn = INFINITY, vmx = -INFINITY;
-    bool knan = false, vnan = false;
-    for (int r = 0; r < world; ++r) {
-        const char *rec = xlocal + record_offset(parity, world, r, rows, t, rec_vecs);
-        const float4 m = ld_cg_v4(rec);
-        const float4 a = ld_cg_v4(rec + 16);
-        float pg[8] = {a.x, a.y, a.z, a.w, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (rec_vecs > 2) {
-            const float4 c = ld_cg_v4(rec + 32);
-            pg[4] = c.x; pg[5] = c.y; pg[6] = c.z; pg[7] = c.w;
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-            if (g < gpr) tot = (r == 0 && g == 0) ? pg[g] : __fadd_rn(tot, pg[g]);
-        knan = knan || (m.x != m.x); vnan = vnan || (m.z != m.z);
-        kmn = fminf(kmn, m.x); kmx = fmaxf(kmx, m.y); vmn = fminf(vmn, m.z); vmx = fmaxf(vmx, m.w);
-    }
-    const float qnan = __int_as_float(0x7fc00000);
-    mass[t] = __fdiv_rn(tot, fH);
-    float4 o = make_float4(knan ? qnan : kmn, knan ? qnan : kmx, vnan ? qnan : vmn, vnan ? qnan : vmx);
-    *reinterpret_cast<float4 *>(minmax + 4 * t) = o;
+    combine_token(xlocal, parity, world, gpr, rec_vecs, rows, t, fH, mass, minmax);
 }
 
 static int rec_vecs_for(int world) { return 1 + ((kGroups / world) + 3) / 4; }
@@ -431,9 +505,18 @@ extern "C" int64_t rtkv_shard_exchange_bytes(int B, int S, int world)
     return (int64_t)kXHeader + (int64_t)2 * world * B * S * rec_vecs_for(world) * 16;
 }
 
-extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
-                                int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
-                                const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, void *stream)
+static int g_shard_grid_cap = 0;    // testing aid: cap the persistent grid (several emulated ranks co-resident on one GPU)
+extern "C" int rtkv_debug_shard_grid(int max_ctas)
+{
+    RTKV_CHECK_ARG(max_ctas >= 0, "rtkv_debug_shard_grid: negative");
+    g_shard_grid_cap = max_ctas;
+    return RTKV_OK;
+}
+
+static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                            int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                            const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, int H_total, float *mass,
+                            float *minmax, void *stream)
 {
     RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state, "rtkv_shard_stats: null pointer");
     RTKV_CHECK_ARG(a_dtype == RTKV_F32, "rtkv_shard_stats: head sharding needs float32 probabilities "
@@ -458,6 +541,7 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     for (int s = 0; s < 8; ++s) p.xbuf[s] = s < world ? xbuf_ptrs[s] : 0ull;
     for (int s = 0; s < world; ++s) RTKV_CHECK_ARG(p.xbuf[s] && p.xbuf[s] % 16 == 0, "rtkv_shard_stats: exchange buffer %d", s);
     p.state = state;
+    p.mass = mass; p.minmax = minmax; p.fH = (float)H_total;
     const bool vec = ((uintptr_t)A % 16 == 0) && (sb * 4) % 16 == 0 && (sh * 4) % 16 == 0 && (si * 4) % 16 == 0;
     const int64_t rows = (int64_t)B * S;
     // staged path: every copy must be a 16-byte multiple at a 16-byte aligned address, P <= 128 columns, and the
@@ -476,18 +560,25 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     if (staged) {
         c.stage_bytes = ((c.rb * row_bytes + 127) / 128) * 128;
         c.stages = budget / c.stage_bytes < want_stages ? budget / c.stage_bytes : want_stages;
-        const size_t smem = 1024 + (size_t)c.stages * c.stage_bytes;
+        const size_t smem = kStagedHeader + (size_t)c.stages * c.stage_bytes;
         int dev = 0, sms = 0;
         RTKV_CUDA(cudaGetDevice(&dev));
         RTKV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int64_t n_blocks = (int64_t)B * ((S + c.rb - 1) / c.rb);
-        const int grid = (int)(n_blocks < sms ? n_blocks : sms);
+        int grid = (int)(n_blocks < sms ? n_blocks : sms);
+        if (g_shard_grid_cap > 0 && grid > g_shard_grid_cap) grid = g_shard_grid_cap;
+        if (mass && grid > kMaxShardCtas) grid = kMaxShardCtas;
         void (*kern)(ShardParams, StagedCfg) = shard_stats_staged_kernel<RTKV_BF16>;
         if (kv_dtype == RTKV_F32) kern = shard_stats_staged_kernel<RTKV_F32>;
         else if (kv_dtype == RTKV_F16) kern = shard_stats_staged_kernel<RTKV_F16>;
-        RTKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + budget));
+        RTKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedHeader + budget));
         RTKV_CUDA(launch_kernel(kern, dim3(grid), dim3(kStagedThreads), smem, (cudaStream_t)stream, 1, p, c));
         return RTKV_OK;
+    }
+    if (mass) {
+        set_error("rtkv_shard_stats_combine: needs the staged kernel (A as a [B,H,S,P] slice with P %% 4 == 0, P <= 128, 16-byte "
+                  "aligned rows); use rtkv_shard_stats + rtkv_shard_combine for this shape");
+        return RTKV_EUNSUPPORTED;
     }
     const int64_t ctas = (rows + kShardWarps - 1) / kShardWarps;
     const int grid = (int)(ctas < 148 * 64 ? ctas : 148 * 64);
@@ -499,6 +590,25 @@ extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, 
     }
     RTKV_CUDA(launch_kernel(kern, dim3(grid), dim3(kShardWarps * 32), 0, (cudaStream_t)stream, 1, p));
     return RTKV_OK;
+}
+
+extern "C" int rtkv_shard_stats(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                                int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                                const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, void *stream)
+{
+    return shard_stats_impl(A, a_dtype, B, H_local, S, sb, sh, si, P, group_size, K, V, kv_dtype, n_local, xbuf_ptrs, rank, world,
+                            state, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int rtkv_shard_stats_combine(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
+                                        int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                                        const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, int H,
+                                        float *mass, float *minmax, void *stream)
+{
+    RTKV_CHECK_ARG(mass && minmax && H > 0, "rtkv_shard_stats_combine: null output");
+    RTKV_CHECK_ARG((uintptr_t)minmax % 16 == 0, "rtkv_shard_stats_combine: minmax must be 16-byte aligned");
+    return shard_stats_impl(A, a_dtype, B, H_local, S, sb, sh, si, P, group_size, K, V, kv_dtype, n_local, xbuf_ptrs, rank, world,
+                            state, H, mass, minmax, stream);
 }
 
 extern "C" int rtkv_shard_combine(const void *xbuf_local, uint32_t *state, int B, int S, int H, int world,

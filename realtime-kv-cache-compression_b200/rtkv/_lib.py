@@ -91,6 +91,10 @@ PROTOTYPES = {
     "rtkv_shard_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64, c_i64, c_i64,
                                         ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rtkv_shard_stats_combine": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64, c_i64, c_i64,
+                                                ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
+                                                c_vp, c_vp, c_vp]),
     "rtkv_shard_combine": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
                                           c_vp]),
     "rtkv_quant_gather_token_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -129,6 +133,7 @@ PROTOTYPES = {
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_variant": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_shard_grid": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_qk_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "rtkv_ctx_destroy": (ctypes.c_int, [c_vp]),

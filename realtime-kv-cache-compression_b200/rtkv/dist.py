@@ -115,6 +115,7 @@ class ShardExchange:
         self.state = torch.zeros(4, dtype=torch.int32, device=device)
         self.mass = torch.empty(batch, seq_len, dtype=torch.float32, device=device)
         self.minmax = torch.empty(batch, seq_len, 4, dtype=torch.float32, device=device)
+        self.concurrent = True                         # one process per rank: all ranks run the same kernel at the same time
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                       # every buffer is zeroed before anybody writes
 
@@ -148,6 +149,7 @@ class LocalExchange:
         v.mass = torch.empty(self.batch, self.seq_len, dtype=torch.float32, device=self.device)
         v.minmax = torch.empty(self.batch, self.seq_len, 4, dtype=torch.float32, device=self.device)
         v.fits = lambda b, s: (b, s) == (self.batch, self.seq_len)
+        v.concurrent = False      # ranks run one after the other here: the one-kernel scheme would wait for itself
         return v
 
 
@@ -202,7 +204,33 @@ class HeadShardedCompressor:
         mass = ops.mass_from_partials(gather_partials(partials, self.group), self.num_heads, rank_major=True)
         return ops.score_select(params, B, S, key_local.device, mass=mass)
 
-    # ---- fused scheme: stats+push -> combine -> select -> quantise (4 launches, no NCCL) ----
+    # ---- fused scheme: stats + push (+ combine) -> select -> quantise (3 or 4 launches, no NCCL) ----
+    def fused_mass_minmax(self, key_local, value_local, attention_local):
+        """mass [B,S] and whole-row min/max [B,S,4] of this layer.  Real multi-GPU: ONE kernel (statistics, peer
+        stores, per-CTA flags, reduction: rtkv_shard_stats_combine); shapes that kernel cannot take, and ranks emulated
+        in one process, use the two-kernel scheme (rtkv_shard_stats + rtkv_shard_combine)."""
+        from . import ops
+        from ._lib import RtkvError
+        B, S, _ = key_local.shape
+        x = self._exchange(B, S, key_local.device)
+        P, gs = self.compressor.prompt_length(S), self.num_heads // N_GROUPS
+        if getattr(x, "concurrent", False) and not getattr(self, "_two_kernels", False):
+            try:
+                return ops.shard_stats_combine(attention_local, key_local, value_local, P, gs, x.ptrs, x.rank, x.world,
+                                               x.state, self.num_heads, x.mass, x.minmax)
+            except RtkvError as e:
+                if e.code != -2:                     # RTKV_EUNSUPPORTED: same verdict on every rank (same shapes)
+                    raise
+                self._two_kernels = True
+        ops.shard_stats(attention_local, key_local, value_local, P, gs, x.ptrs, x.rank, x.world, x.state)
+        return ops.shard_combine(x.local_ptr, x.state, B, S, self.num_heads, x.world, x.mass, x.minmax)
+
+    def _fused_select(self, key_local, mass, layer_idx):
+        from . import ops
+        B, S, _ = key_local.shape
+        params, _ = self.compressor.layer_params(layer_idx, S, ops.F32)
+        return ops.score_select(params, B, S, key_local.device, mass=mass)
+
     def fused_publish(self, key_local, value_local, attention_local):
         """Producer half (rtkv_shard_stats).  Separate from fused_finish so that a single-process emulation can
         run every rank's producer before any consumer."""
@@ -228,8 +256,8 @@ class HeadShardedCompressor:
 
     def compress_layer_kv_cache(self, key_local, value_local, attention_local, layer_idx):
         if self.mode == "fused":
-            self.fused_publish(key_local, value_local, attention_local)
-            sel, mm = self.fused_select(key_local, layer_idx)
+            mass, mm = self.fused_mass_minmax(key_local, value_local, attention_local)
+            sel = self._fused_select(key_local, mass, layer_idx)
             layer, _rows = sel.read_stats()
             k_sel, v_sel = self._fused_quantise(key_local, value_local, sel, mm, int(layer["max_selected"]), True)
             return k_sel, v_sel, sel
@@ -243,8 +271,8 @@ class HeadShardedCompressor:
         """Synchronisation-free variant (fixed capacity S rows, like compress_layer_kv_cache_async):
         the exchanges run on the full [B,S,.] extent, nothing is read back to the host."""
         if self.mode == "fused":
-            self.fused_publish(key_local, value_local, attention_local)
-            sel, mm = self.fused_select(key_local, layer_idx)
+            mass, mm = self.fused_mass_minmax(key_local, value_local, attention_local)
+            sel = self._fused_select(key_local, mass, layer_idx)
             self._fused_quantise(key_local, value_local, sel, mm, key_local.shape[1], False, out_keys, out_values)
             return sel
         sel = self._select(key_local, attention_local, layer_idx)

@@ -398,6 +398,27 @@ def shard_stats(attn_local, key_local, value_local, prompt_len, group_size, xbuf
 
 
 @_device_guard
+def shard_stats_combine(attn_local, key_local, value_local, prompt_len, group_size, xbuf_ptrs, rank, world, state, num_heads,
+                        mass, minmax):
+    """shard_stats + shard_combine in one kernel (per-CTA peer flags; every rank must run it concurrently):
+    fills mass [B,S] and minmax [B,S,4].  Raises RtkvError(RTKV_EUNSUPPORTED) for shapes the staged kernel cannot take."""
+    require_cuda()
+    if attn_local.stride(-1) != 1:
+        attn_local = attn_local.contiguous()
+    key_local, value_local = key_local.contiguous(), value_local.contiguous()
+    B, Hl, S, W = attn_local.shape
+    if prompt_len > W:
+        raise IndexError(f"prompt_len {prompt_len} exceeds attention width {W}")
+    ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in xbuf_ptrs])
+    check(lib.rtkv_shard_stats_combine(_ptr(attn_local), dtype_code(attn_local), B, Hl, S, attn_local.stride(0),
+                                       attn_local.stride(1), attn_local.stride(2), int(prompt_len), int(group_size),
+                                       _ptr(key_local), _ptr(value_local), dtype_code(key_local), key_local.shape[2],
+                                       ptrs, int(rank), int(world), _ptr(state), int(num_heads), _ptr(mass), _ptr(minmax),
+                                       _stream()))
+    return mass, minmax
+
+
+@_device_guard
 def shard_combine(xbuf_local, state, batch, seq_len, num_heads, world, mass=None, minmax=None):
     """Consumer half: wait for every rank's records, reduce them in rank order -> mass [B,S] f32 and the whole-row
     (kmin, kmax, vmin, vmax) [B,S,4] f32 indexed by token (rtkv_shard_combine)."""
