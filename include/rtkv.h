@@ -342,6 +342,22 @@ RTKV_API int rtkv_packed_decode_attention(const float *q, const uint8_t *codes_k
                                  int out_rows, float sm_scale, int splits, void *workspace, size_t workspace_bytes,
                                  float *out, float *lse, void *stream);
 
+/* Prefill attention on tcgen05 tensor cores + TMA, for the two neighbours of the compression call:
+ *   upstream (src/models/modified_llama.py:88-94): causal softmax(Q K^T * sm_scale) V without the [B,H,S,S] tensor, returning
+ *     out, the natural-log row LSE [B,H,Sq] and head_sums[b,h,i] = sum_{j<P, visible} softmax_ij - the prompt-column mass the
+ *     reference slices out of the materialised probabilities (token_importance.py:41-45); rtkv_mass_from_head_sums turns it
+ *     into the mass rtkv_score_select consumes;
+ *   downstream (src/models/modified_llama.py:125-142): the same kernel with Skv = S' kept tokens: with causal != 0 query i sees
+ *     kept slots j <= i, which is the reference's "mask truncated to its first S' columns".
+ * Q [B,H,Sq,128], K/V [B,Hkv,Skv,128] (H % Hkv == 0), bf16 or f16, any strides (q/k/v/o_strides [host]: batch, head, token
+ * strides in ELEMENTS, multiples of 8; unit stride in the last dim) - e.g. the transposed view of a [B,S,H,128] projection.
+ * out: same dtype, written with o_strides (so a [B,Sq,H,128] result needs no transpose).  lse / head_sums may be NULL.
+ * Logits, softmax and accumulation in float32; P is rounded to the input dtype for the second product. */
+RTKV_API int rtkv_flash_prefill(const void *Q, const void *K, const void *V, int dtype, int B, int H, int Hkv, int Sq, int Skv, int D,
+                       const int64_t *q_strides, const int64_t *k_strides, const int64_t *v_strides,
+                       float sm_scale, int causal, int P, void *out, const int64_t *o_strides,
+                       float *lse, float *head_sums, void *stream);
+
 /* Profiling aid: when set to a device buffer of 64 int64, every rtkv_score_select launch writes
  * buf[0] = number of ticks and buf[1..] = clock64() at its phase boundaries (row 0).  NULL: off. */
 RTKV_API int rtkv_debug_k2_timing(void *device_buffer_64_i64);

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "rtkv", "librtkv.so")
 SOURCES = ["capi.cu", "prompt_mass.cu", "prompt_mass_qk.cu", "score_select.cu", "score_select_cluster.cu",
-           "quant_gather.cu", "quant_ex.cu", "packed_attention.cu", "head_shard.cu"]
+           "quant_gather.cu", "quant_ex.cu", "packed_attention.cu", "head_shard.cu", "flash_prefill.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -1,0 +1,353 @@
+// flash_prefill.cu — prefill attention on the 5th-generation tensor cores, written for the compression path's two
+// neighbours:
+//   upstream   src/models/modified_llama.py:88-94    softmax(Q K^T / sqrt(d) + causal mask), materialised [B,H,S,S]
+//              -> here: no S x S tensor; the kernel returns the attention output, the row log-sum-exp AND the
+//              prompt-column mass  head_sum[b,h,i] = sum_{j<P, j<=i} softmax_ij  that token_importance.py:41-45 takes
+//              from the materialised probabilities (it is a by-product of the first key tile: free).
+//   downstream src/models/modified_llama.py:125-142  softmax(Q K_sel^T / sqrt(d) + mask[..., :S']) V_sel over the
+//              S' kept (fake-quantised) tokens, with the reference's truncated mask: query i sees kept slots j <= i
+//              -> the same kernel with kv_len = S' < q_len.
+//
+// One CTA = 128 query rows of one (batch row, head); keys/values stream through in tiles of 128:
+//   warp 0      TMA producer: Q tile once, K and V tiles through 2-stage rings (4-D tensor maps: any [B,H,S,128]
+//               view with unit stride in the last dim, e.g. the transposed view of a [B,S,H,128] projection)
+//   warp 1      MMA issuer (one thread): S_t = Q K_t^T (tcgen05.mma 128x128x16, both operands K-major, fp32 in TMEM,
+//               two S buffers so that S_{t+1} is computed while softmax works on S_t), then O += P_t V_t with P from
+//               shared memory (K-major, written by the softmax warps in the 128-byte swizzle) and V as an MN-major
+//               operand straight from the TMA tile (no transpose anywhere)
+//   warps 2..5  softmax: a thread owns one query row (TMEM lane), tcgen05.ld of the 128 logits, running max with LAZY
+//               rescaling (the accumulator in TMEM is only rescaled when the row max grows by more than 2^8, which keeps
+//               P <= 256 and makes the TMEM read-modify-write of O rare), exp2, row sum, bf16 P tile to shared memory
+// Numerics: logits and row sums in fp32, P rounded to the input dtype for the second MMA (flash-attention practice);
+// O accumulates in fp32 in TMEM; LSE = ln2 * (m + log2(l)).
+#include "umma.cuh"
+
+namespace rtkv {
+
+constexpr int kFT = 128;                         // tile: 128 query rows x 128 keys, head_dim 128
+constexpr int kFTileBytes = kFT * 128 * 2;       // 32 KiB: one Q / K / V / P tile (bf16 or f16)
+constexpr int kFHalf = kFTileBytes / 2;          // the two 64-column (128-byte) halves of a tile
+constexpr int kFThreads = 64 + 128;              // TMA warp, MMA warp, 4 softmax warps
+constexpr size_t kFSmem = 1024 + 6 * (size_t)kFTileBytes + 256;   // Q, K[2], V[2], P + barriers
+
+struct FlashParams {
+    void *out;                 // [B,H,Sq,128] elements of the input dtype, strides below (in elements)
+    int64_t o_sb, o_sh, o_ss;
+    float *lse;                // [B,H,Sq] or NULL
+    float *head_sums;          // [B,H,Sq] or NULL: prompt-column mass
+    int B, H, Hkv, Sq, Skv, P, causal, is_bf16;
+    float scale_log2;          // sm_scale * log2(e)
+    uint32_t idesc_qk, idesc_pv;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16)
+{
+    if (is_bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, FlashParams p)
+{
+    extern __shared__ unsigned char fp_smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)fp_smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_q = smem, *smem_k = smem + kFTileBytes, *smem_v = smem + 3 * kFTileBytes, *smem_p = smem + 5 * kFTileBytes;
+    uint64_t *bars = (uint64_t *)(smem + 6 * (size_t)kFTileBytes);
+    uint64_t *qfull = bars, *kfull = bars + 1, *kempty = bars + 3, *vfull = bars + 5, *vempty = bars + 7;
+    uint64_t *sfull = bars + 9, *sfree = bars + 11, *pfull = bars + 13, *pvdone = bars + 14;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_qt = (p.Sq + kFT - 1) / kFT;
+    const int qt = n_qt - 1 - (int)(blockIdx.x % n_qt);          // heaviest (last) query tiles first
+    const int h = (int)((blockIdx.x / n_qt) % p.H), b = (int)(blockIdx.x / ((size_t)n_qt * p.H));
+    const int hk = h / (p.H / p.Hkv);
+    int T = (p.Skv + kFT - 1) / kFT;                             // key tiles this query tile sees
+    if (p.causal && qt + 1 < T) T = qt + 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(qfull), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&kfull[s]), 1); mbar_init(smem_u32(&kempty[s]), 1);
+            mbar_init(smem_u32(&vfull[s]), 1); mbar_init(smem_u32(&vempty[s]), 1);
+            mbar_init(smem_u32(&sfull[s]), 1); mbar_init(smem_u32(&sfree[s]), 4);
+        }
+        mbar_init(smem_u32(pfull), 4); mbar_init(smem_u32(pvdone), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // 512 TMEM columns: S0 [0,128), S1 [128,256), O [256,384)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t qf = smem_u32(qfull);
+            mbar_expect_tx(qf, kFTileBytes);
+            tma_load_4d(smem_u32(smem_q), &map_q, 0, qt * kFT, h, b, qf);
+            tma_load_4d(smem_u32(smem_q) + kFHalf, &map_q, 64, qt * kFT, h, b, qf);
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                const uint32_t par = (uint32_t)(((t >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&kempty[s]), par);
+                const uint32_t kf = smem_u32(&kfull[s]);
+                mbar_expect_tx(kf, kFTileBytes);
+                const uint32_t kd = smem_u32(smem_k + (size_t)s * kFTileBytes);
+                tma_load_4d(kd, &map_k, 0, t * kFT, hk, b, kf);
+                tma_load_4d(kd + kFHalf, &map_k, 64, t * kFT, hk, b, kf);
+                mbar_wait(smem_u32(&vempty[s]), par);
+                const uint32_t vf = smem_u32(&vfull[s]);
+                mbar_expect_tx(vf, kFTileBytes);
+                const uint32_t vd = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                tma_load_4d(vd, &map_v, 0, t * kFT, hk, b, vf);
+                tma_load_4d(vd + kFHalf, &map_v, 64, t * kFT, hk, b, vf);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t qbase = smem_u32(smem_q), pbase = smem_u32(smem_p);
+            auto issue_qk = [&](int t) {
+                const int s = t & 1;
+                mbar_wait(smem_u32(&kfull[s]), (uint32_t)((t >> 1) & 1));
+                mbar_wait(smem_u32(&sfree[s]), (uint32_t)(((t >> 1) & 1) ^ 1));      // softmax has S_{t-2} in registers
+                tc_fence_after();
+                const uint32_t kbase = smem_u32(smem_k + (size_t)s * kFTileBytes);
+                const uint32_t dcol = tmem_base + (uint32_t)(s * kFT);
+#pragma unroll
+                for (int kq = 0; kq < 2; ++kq)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t off = (uint32_t)(kq * kFHalf + kk * 32);       // 16 head-dim elements = 32 B
+                        umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc_qk, (uint32_t)((kq | kk) != 0));
+                    }
+                umma_commit(smem_u32(&kempty[s]));
+                umma_commit(smem_u32(&sfull[s]));
+            };
+            mbar_wait(smem_u32(qfull), 0);
+            issue_qk(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) issue_qk(t + 1);                                      // overlaps softmax of tile t
+                const int s = t & 1;
+                mbar_wait(smem_u32(pfull), (uint32_t)(t & 1));                       // P_t in shared memory, O rescaled
+                mbar_wait(smem_u32(&vfull[s]), (uint32_t)((t >> 1) & 1));
+                tc_fence_after();
+                const uint32_t vbase = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                const uint32_t ocol = tmem_base + 2 * kFT;
+#pragma unroll
+                for (int kq = 0; kq < 2; ++kq)          // keys 0..63 / 64..127: the two halves of the P tile
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {    // 16 keys per MMA
+                        const uint32_t poff = (uint32_t)(kq * kFHalf + kk * 32);
+                        const uint32_t voff = (uint32_t)((kq * 64 + kk * 16) * 128);  // 16 key rows of 128 B in each head-dim half
+                        umma_f16(ocol, umma_desc_sw128(pbase + poff), umma_desc_sw128_mn(vbase + voff, kFHalf), p.idesc_pv,
+                                 (uint32_t)((t | kq | kk) != 0));
+                    }
+                umma_commit(smem_u32(&vempty[s]));
+                umma_commit(smem_u32(pvdone));
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: thread = query row =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int i = qt * kFT + row;                          // query index
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1;
+            mbar_wait(smem_u32(&sfull[s]), (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            uint32_t raw[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32_issue(lane_base + (uint32_t)(s * kFT + 32 * c), raw[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sfree[s]));
+            // scaled logits (log2 domain), masks only where a tile needs them
+            const int j0 = t * kFT;
+            const bool need_mask = (p.causal && j0 + kFT - 1 > qt * kFT) || (j0 + kFT > p.Skv);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    float x = __uint_as_float(raw[c][e]) * p.scale_log2;
+                    if (need_mask) {
+                        const int j = j0 + 32 * c + e;
+                        if (j >= p.Skv || (p.causal && j > i)) x = -INFINITY;
+                    }
+                    raw[c][e] = __float_as_uint(x);
+                    mx = fmaxf(mx, x);
+                }
+            // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
+            float alpha = 1.0f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f) {
+                rescale = m_used != -INFINITY;
+                alpha = rescale ? ex2_approx(m_used - mx) : 0.0f;
+                m_used = mx;
+            }
+            if (t > 0) {                                         // PV_{t-1} has retired: P tile free, O stable
+                mbar_wait(smem_u32(pvdone), (uint32_t)((t - 1) & 1));
+                tc_fence_after();
+            }
+            if (__any_sync(0xffffffffu, rescale)) {              // warp-uniform: tcgen05.ld/st are warp-wide
+                const float a = rescale ? alpha : 1.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * a);
+                    tmem_st32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+                }
+                tmem_st_wait();
+            }
+            if (rescale) { l *= alpha; mass_acc *= alpha; }
+            // p = 2^(x - m), row sum, prompt-column share, bf16/f16 P tile (K-major, 128-byte swizzle) to shared memory
+            float rs = 0.0f, ps = 0.0f;
+            unsigned char *prow = smem_p + (size_t)row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const float p0 = ex2_approx(__uint_as_float(raw[c][e]) - m_used);
+                    const float p1 = ex2_approx(__uint_as_float(raw[c][e + 1]) - m_used);
+                    rs += p0 + p1;
+                    if (t == 0) {
+                        const int j = 32 * c + e;
+                        ps += (j < p.P ? p0 : 0.0f) + (j + 1 < p.P ? p1 : 0.0f);
+                    }
+                    pk[e >> 1] = pack2(p0, p1, p.is_bf16);
+                }
+                // columns 32c..32c+31 = 64 bytes = four 16-byte chunks of half (c >> 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(prow + (size_t)(c >> 1) * kFHalf + chunk * 16) =
+                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l += rs;
+            if (t == 0) mass_acc = ps;
+            fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(pfull));
+        }
+        // ---- epilogue: O / l, LSE, prompt mass ----
+        mbar_wait(smem_u32(pvdone), (uint32_t)((T - 1) & 1));
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const bool live = i < p.Sq;
+        unsigned char *orow = (unsigned char *)p.out + ((size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)i * p.o_ss) * 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pack2(__uint_as_float(o[8 * q + 2 * e]) * inv_l, __uint_as_float(o[8 * q + 2 * e + 1]) * inv_l, p.is_bf16);
+                    *reinterpret_cast<uint4 *>(orow + (size_t)(32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        if (live) {
+            const size_t at = ((size_t)b * p.H + h) * p.Sq + i;
+            if (p.lse) p.lse[at] = (m_used + log2f(l)) * 0.6931471805599453f;
+            if (p.head_sums) p.head_sums[at] = mass_acc * inv_l;
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// [B,H,S,128] view with unit stride in the last dim -> 4-D tensor map {128, S, H, B}, box {64, 128, 1, 1}, 128-byte swizzle
+static int encode_bhsd_map(CUtensorMap *map, const void *base, int dtype, int B, int H, int S, int64_t sb, int64_t sh, int64_t ss)
+{
+    EncodeTiledFn fn = tensor_map_encoder();
+    if (!fn) return cuda_fail(cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
+    const cuuint64_t dims[4] = {128, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)kFT, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, dtype == RTKV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RTKV_EINVAL; }
+    return RTKV_OK;
+}
+
+} // namespace rtkv
+
+using namespace rtkv;
+
+extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, int dtype, int B, int H, int Hkv, int Sq, int Skv, int D,
+                                  const int64_t *q_strides, const int64_t *k_strides, const int64_t *v_strides,
+                                  float sm_scale, int causal, int P, void *out, const int64_t *o_strides,
+                                  float *lse, float *head_sums, void *stream)
+{
+    RTKV_CHECK_ARG(Q && K && V && out && q_strides && k_strides && v_strides && o_strides, "rtkv_flash_prefill: null pointer");
+    if (dtype != RTKV_BF16 && dtype != RTKV_F16) {
+        set_error("rtkv_flash_prefill: Q/K/V must be bf16 or f16");
+        return RTKV_EUNSUPPORTED;
+    }
+    if (D != 128) {
+        set_error("rtkv_flash_prefill: head_dim must be 128 (got %d)", D);
+        return RTKV_EUNSUPPORTED;
+    }
+    RTKV_CHECK_ARG(B > 0 && H > 0 && Hkv > 0 && H % Hkv == 0 && Sq > 0 && Skv > 0, "rtkv_flash_prefill: bad shape");
+    RTKV_CHECK_ARG(P >= 0 && P <= kFT, "rtkv_flash_prefill: prompt length must be <= 128 (got %d)", P);
+    RTKV_CHECK_ARG(!head_sums || P > 0, "rtkv_flash_prefill: head_sums needs P > 0");
+    for (int k = 0; k < 3; ++k) {
+        RTKV_CHECK_ARG(q_strides[k] % 8 == 0 && k_strides[k] % 8 == 0 && v_strides[k] % 8 == 0 && o_strides[k] % 8 == 0,
+                       "rtkv_flash_prefill: strides must be multiples of 8 elements (16 bytes)");
+    }
+    RTKV_CHECK_ARG((uintptr_t)Q % 16 == 0 && (uintptr_t)K % 16 == 0 && (uintptr_t)V % 16 == 0 && (uintptr_t)out % 16 == 0,
+                   "rtkv_flash_prefill: tensors must be 16-byte aligned");
+    CUtensorMap mq, mk, mv;
+    int rc = encode_bhsd_map(&mq, Q, dtype, B, H, Sq, q_strides[0], q_strides[1], q_strides[2]);
+    if (!rc) rc = encode_bhsd_map(&mk, K, dtype, B, Hkv, Skv, k_strides[0], k_strides[1], k_strides[2]);
+    if (!rc) rc = encode_bhsd_map(&mv, V, dtype, B, Hkv, Skv, v_strides[0], v_strides[1], v_strides[2]);
+    if (rc) return rc;
+    FlashParams p;
+    p.out = out; p.o_sb = o_strides[0]; p.o_sh = o_strides[1]; p.o_ss = o_strides[2];
+    p.lse = lse; p.head_sums = head_sums;
+    p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Skv = Skv; p.P = P; p.causal = causal != 0; p.is_bf16 = dtype == RTKV_BF16;
+    p.scale_log2 = sm_scale * 1.4426950408889634f;
+    const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
+    p.idesc_qk = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kFT >> 3) << 17) | ((uint32_t)(kFT >> 4) << 24);
+    p.idesc_pv = p.idesc_qk | (1u << 16);                       // B operand (V) is MN-major
+    const int n_qt = (Sq + kFT - 1) / kFT;
+    const long long ctas = (long long)n_qt * H * B;
+    RTKV_CHECK_ARG(ctas < (1ll << 31), "rtkv_flash_prefill: too many tiles");
+    RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+    flash_prefill_kernel<<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    RTKV_LAUNCH_CHECK("flash_prefill_kernel");
+    return RTKV_OK;
+}

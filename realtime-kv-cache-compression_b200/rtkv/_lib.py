@@ -128,6 +128,10 @@ PROTOTYPES = {
     "rtkv_packed_decode_attention": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int,
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                     ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, c_vp, c_vp]),
+    "rtkv_flash_prefill": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                          ctypes.POINTER(c_i64), ctypes.c_float, ctypes.c_int, ctypes.c_int, c_vp,
+                                          ctypes.POINTER(c_i64), c_vp, c_vp, c_vp]),
     "rtkv_debug_channel_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_k2_timing": (ctypes.c_int, [c_vp]),
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),

@@ -212,6 +212,34 @@ def prompt_mass_qk(q, k_prompt, lse, scale, causal=True):
 
 
 @_device_guard
+def flash_prefill(q, k, v, sm_scale=None, causal=True, prompt_len=0, want_lse=True, out_layout="bhsd"):
+    """Prefill attention on tcgen05 (rtkv_flash_prefill).  q [B,H,Sq,128], k/v [B,Hkv,Skv,128] bf16/f16 views with unit stride
+    in the last dim.  Returns (out, lse [B,H,Sq] f32 or None, head_sums [B,H,Sq] f32 or None): head_sums is the per-head
+    prompt-column mass (prompt_len > 0), out is [B,H,Sq,128] ("bhsd") or [B,Sq,H,128] ("bshd") contiguous."""
+    require_cuda()
+    B, H, Sq, D = q.shape
+    Hkv, Skv = k.shape[1], k.shape[2]
+    assert k.shape == v.shape and k.shape[0] == B and k.shape[3] == D and q.dtype == k.dtype == v.dtype
+    fix = lambda t: t if (t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0) else t.contiguous()
+    q, k, v = fix(q), fix(k), fix(v)
+    if sm_scale is None:
+        sm_scale = D ** -0.5
+    if out_layout == "bshd":
+        out = torch.empty(B, Sq, H, D, dtype=q.dtype, device=q.device)
+        o_str = (out.stride(0), out.stride(2), out.stride(1))
+    else:
+        out = torch.empty(B, H, Sq, D, dtype=q.dtype, device=q.device)
+        o_str = (out.stride(0), out.stride(1), out.stride(2))
+    lse = torch.empty(B, H, Sq, dtype=torch.float32, device=q.device) if want_lse else None
+    hs = torch.empty(B, H, Sq, dtype=torch.float32, device=q.device) if prompt_len > 0 else None
+    i64x3 = lambda s: (ctypes.c_int64 * 3)(int(s[0]), int(s[1]), int(s[2]))
+    check(lib.rtkv_flash_prefill(_ptr(q), _ptr(k), _ptr(v), dtype_code(q), B, H, Hkv, Sq, Skv, D, i64x3(q.stride()),
+                                 i64x3(k.stride()), i64x3(v.stride()), float(sm_scale), int(bool(causal)), int(prompt_len),
+                                 _ptr(out), i64x3(o_str), _ptr(lse), _ptr(hs), _stream()))
+    return out, lse, hs
+
+
+@_device_guard
 def position_bias(seq_len, device):
     require_cuda()
     pb = torch.empty(seq_len, dtype=torch.float32, device=device)

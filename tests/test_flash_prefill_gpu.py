@@ -1,0 +1,113 @@
+"""rtkv_flash_prefill (tcgen05 + TMA prefill attention with LSE and fused prompt-column mass) against a plain PyTorch
+fp32 reference of the same op: the reference's eager formulation softmax(Q K^T / sqrt(d) + mask) V of
+src/models/modified_llama.py:88-94 (and :125-142 with the mask truncated to the first S' columns when the keys are the
+S' kept tokens).  Floating point kernel: tolerances are written next to every comparison (north star: 1e-3 relative for
+bf16 scales; the attention output itself is a bf16/f16 tensor, i.e. 2^-8 / 2^-11 relative per element)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    import rtkv  # noqa: F401
+    from rtkv import ops
+    return ops
+
+
+def reference(q, k, v, scale, causal, P):
+    """fp32 eager attention on the (already rounded) half-precision inputs."""
+    B, H, Sq, D = q.shape
+    Hkv, Skv = k.shape[1], k.shape[2]
+    qf, kf, vf = q.float(), k.float().repeat_interleave(H // Hkv, dim=1), v.float().repeat_interleave(H // Hkv, dim=1)
+    logits = qf @ kf.transpose(-1, -2) * scale
+    if causal:
+        i = torch.arange(Sq, device=q.device)[:, None]
+        j = torch.arange(Skv, device=q.device)[None, :]
+        logits = logits.masked_fill(j > i, float("-inf"))
+    lse = torch.logsumexp(logits, dim=-1)
+    probs = torch.softmax(logits, dim=-1)
+    out = probs @ vf
+    hs = probs[..., :P].sum(-1) if P > 0 else None
+    return out, lse, hs
+
+
+CASES = [
+    # B, H, Hkv, Sq, Skv, causal, P, dtype, qscale
+    (1, 2, 2, 128, 128, True, 128, torch.bfloat16, 1.0),
+    (2, 4, 2, 300, 300, True, 60, torch.bfloat16, 1.0),
+    (1, 2, 2, 1000, 1000, True, 128, torch.float16, 1.0),
+    (1, 2, 1, 256, 200, False, 0, torch.bfloat16, 1.0),
+    (1, 4, 4, 700, 420, True, 0, torch.bfloat16, 1.0),          # keys = kept tokens, top-left aligned (truncated) causal mask
+    (1, 2, 2, 640, 640, True, 128, torch.bfloat16, 6.0),         # sharp logits: the lazy rescale of O fires
+    (1, 3, 3, 2048, 2048, True, 128, torch.bfloat16, 1.0),
+    (1, 2, 2, 77, 77, True, 15, torch.float16, 1.0),
+]
+
+
+@pytest.mark.parametrize("B,H,Hkv,Sq,Skv,causal,P,dtype,qscale", CASES)
+def test_flash_prefill_matches_fp32_reference(ops, B, H, Hkv, Sq, Skv, causal, P, dtype, qscale):
+    g = torch.Generator(device="cuda").manual_seed(Sq * 7 + Skv)
+    D = 128
+    q = (torch.randn(B, H, Sq, D, generator=g, device="cuda") * qscale).to(dtype)
+    k = torch.randn(B, Hkv, Skv, D, generator=g, device="cuda").to(dtype)
+    v = torch.randn(B, Hkv, Skv, D, generator=g, device="cuda").to(dtype)
+    scale = 1.0 / math.sqrt(D)
+    out, lse, hs = ops.flash_prefill(q, k, v, scale, causal=causal, prompt_len=P)
+    want, want_lse, want_hs = reference(q, k, v, scale, causal, P)
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    # output: a half-precision tensor; P is rounded to the input dtype before the second product -> a few eps
+    torch.testing.assert_close(out.float(), want, rtol=4 * eps, atol=4 * eps)
+    torch.testing.assert_close(lse, want_lse, rtol=0, atol=2e-3)          # |lse| ~ 10: ~2e-4 relative
+    if P > 0:
+        torch.testing.assert_close(hs, want_hs, rtol=2e-3, atol=1e-6)     # ex2.approx + fp32 sums
+
+
+def test_flash_prefill_strided_inputs_and_bshd_output(ops):
+    """Inputs as the transposed view of [B,S,H,D] projections (what the model hook holds), output written as [B,S,H,D]."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, S, D = 2, 4, 333, 128
+    q = torch.randn(B, S, H, D, generator=g, device="cuda").to(torch.bfloat16).transpose(1, 2)
+    k = torch.randn(B, S, H, D, generator=g, device="cuda").to(torch.bfloat16).transpose(1, 2)
+    v = torch.randn(B, S, H, D, generator=g, device="cuda").to(torch.bfloat16).transpose(1, 2)
+    assert not q.is_contiguous()
+    out, lse, hs = ops.flash_prefill(q, k, v, causal=True, prompt_len=66, out_layout="bshd")
+    want, want_lse, want_hs = reference(q, k, v, D ** -0.5, True, 66)
+    assert out.shape == (B, S, H, D) and out.is_contiguous()
+    torch.testing.assert_close(out.float(), want.transpose(1, 2), rtol=2.0 ** -6, atol=2.0 ** -6)
+    torch.testing.assert_close(lse, want_lse, rtol=0, atol=2e-3)
+    torch.testing.assert_close(hs, want_hs, rtol=2e-3, atol=1e-6)
+
+
+def test_flash_prefill_prompt_mass_feeds_the_compressor(ops):
+    """head_sums -> rtkv_mass_from_head_sums == the mass K1a computes from materialised probabilities, within the
+    tolerance the scoring kernel is held to (2e-4 relative in test_qk_scoring_matches_restatement)."""
+    import rtkv
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, S, D = 1, 8, 900, 128
+    q = torch.randn(B, H, S, D, generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, H, S, D, generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, H, S, D, generator=g, device="cuda").to(torch.bfloat16)
+    P = rtkv.RealTimePrefillCompressor.prompt_length(S)
+    _, _, hs = ops.flash_prefill(q, k, v, causal=True, prompt_len=P)
+    mass = torch.empty(B, S, dtype=torch.float32, device="cuda")
+    ops.check(ops.lib.rtkv_mass_from_head_sums(ops._ptr(hs), B, H, S, ops._ptr(mass), ops._stream()))
+    logits = (q.float() @ k.float().transpose(-1, -2)) / math.sqrt(D)
+    logits = logits + torch.full((S, S), float("-inf"), device="cuda").triu(1)
+    A = torch.softmax(logits, -1)[..., :P].contiguous()
+    want = ops.prompt_mass(A, prompt_len=P)
+    torch.testing.assert_close(mass, want, rtol=1e-3, atol=1e-6)
+
+
+def test_flash_prefill_rejects_unsupported(ops):
+    q = torch.randn(1, 2, 64, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.flash_prefill(q, q, q)
+    q = torch.randn(1, 2, 64, 128, device="cuda", dtype=torch.float32)
+    with pytest.raises((RuntimeError, TypeError)):
+        ops.flash_prefill(q, q, q)
