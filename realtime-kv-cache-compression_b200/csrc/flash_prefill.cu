@@ -15,9 +15,12 @@
 //               two S buffers so that S_{t+1} is computed while softmax works on S_t), then O += P_t V_t with P from
 //               shared memory (K-major, written by the softmax warps in the 128-byte swizzle) and V as an MN-major
 //               operand straight from the TMA tile (no transpose anywhere)
-//   warps 2..5  softmax: a thread owns one query row (TMEM lane), tcgen05.ld of the 128 logits, running max with LAZY
-//               rescaling (the accumulator in TMEM is only rescaled when the row max grows by more than 2^8, which keeps
-//               P <= 256 and makes the TMEM read-modify-write of O rare), exp2, row sum, bf16 P tile to shared memory
+//   warps 2..9  softmax, two warpgroups: warpgroup g owns key columns [64g, 64g+64) of the tile for all 128 query rows
+//               (a thread = one row x 64 columns; the two halves of a row exchange only their partial row max, through
+//               shared memory, once per tile; partial row sums are added at the very end).  tcgen05.ld of the logits,
+//               running max with LAZY rescaling (the accumulator in TMEM is only rescaled when the row max grows by more
+//               than 2^8, which keeps P <= 256 and makes the TMEM read-modify-write of O rare), exp2, bf16 P half-tile to
+//               shared memory (double buffered, so softmax of tile t+1 runs while the tensor pipe does P_t V_t)
 // Numerics: logits and row sums in fp32, P rounded to the input dtype for the second MMA (flash-attention practice);
 // O accumulates in fp32 in TMEM; LSE = ln2 * (m + log2(l)).
 #include "umma.cuh"
@@ -27,8 +30,9 @@ namespace rtkv {
 constexpr int kFT = 128;                         // tile: 128 query rows x 128 keys, head_dim 128
 constexpr int kFTileBytes = kFT * 128 * 2;       // 32 KiB: one Q / K / V / P tile (bf16 or f16)
 constexpr int kFHalf = kFTileBytes / 2;          // the two 64-column (128-byte) halves of a tile
-constexpr int kFThreads = 64 + 128;              // TMA warp, MMA warp, 4 softmax warps
-constexpr size_t kFSmem = 1024 + 6 * (size_t)kFTileBytes + 256;   // Q, K[2], V[2], P + barriers
+constexpr int kFThreads = 64 + 256;              // TMA warp, MMA warp, 8 softmax warps (two warpgroups)
+// Q, K[2], V[2], P[2] + barriers + row exchange + alignment slack: 232448 bytes = the 227 KB a CTA can have
+constexpr size_t kFSmem = 768 + 7 * (size_t)kFTileBytes + 256 + 4 * kFT * sizeof(float);
 
 struct FlashParams {
     void *out;                 // [B,H,Sq,128] elements of the input dtype, strides below (in elements)
@@ -54,13 +58,16 @@ __global__ void __launch_bounds__(kFThreads, 1)
 flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, FlashParams p)
 {
-    extern __shared__ unsigned char fp_smem_raw[];
+    extern __shared__ __align__(1024) unsigned char fp_smem_raw[];
+    // 128-byte swizzle needs 1024-byte aligned tiles; the declared alignment makes the round-up a no-op, the 768 spare bytes
+    // cover a base that is only 256-byte aligned
     unsigned char *smem = (unsigned char *)(((uintptr_t)fp_smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_q = smem, *smem_k = smem + kFTileBytes, *smem_v = smem + 3 * kFTileBytes, *smem_p = smem + 5 * kFTileBytes;
-    uint64_t *bars = (uint64_t *)(smem + 6 * (size_t)kFTileBytes);
+    uint64_t *bars = (uint64_t *)(smem + 7 * (size_t)kFTileBytes);
     uint64_t *qfull = bars, *kfull = bars + 1, *kempty = bars + 3, *vfull = bars + 5, *vempty = bars + 7;
-    uint64_t *sfull = bars + 9, *sfree = bars + 11, *pfull = bars + 13, *pvdone = bars + 14;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 16);
+    uint64_t *sfull = bars + 9, *sfree = bars + 11, *pfull = bars + 13, *pvdone = bars + 15;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 17);
+    float *xch = (float *)((unsigned char *)bars + 256);          // [2 parities][2 warpgroups][128 rows] partial row max / sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_qt = (p.Sq + kFT - 1) / kFT;
@@ -75,9 +82,9 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&kfull[s]), 1); mbar_init(smem_u32(&kempty[s]), 1);
             mbar_init(smem_u32(&vfull[s]), 1); mbar_init(smem_u32(&vempty[s]), 1);
-            mbar_init(smem_u32(&sfull[s]), 1); mbar_init(smem_u32(&sfree[s]), 4);
+            mbar_init(smem_u32(&sfull[s]), 1); mbar_init(smem_u32(&sfree[s]), 8);
+            mbar_init(smem_u32(&pfull[s]), 8); mbar_init(smem_u32(&pvdone[s]), 1);
         }
-        mbar_init(smem_u32(pfull), 4); mbar_init(smem_u32(pvdone), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // 512 TMEM columns: S0 [0,128), S1 [128,256), O [256,384)
@@ -118,7 +125,7 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t qbase = smem_u32(smem_q), pbase = smem_u32(smem_p);
+            const uint32_t qbase = smem_u32(smem_q);
             auto issue_qk = [&](int t) {
                 const int s = t & 1;
                 mbar_wait(smem_u32(&kfull[s]), (uint32_t)((t >> 1) & 1));
@@ -141,10 +148,11 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) issue_qk(t + 1);                                      // overlaps softmax of tile t
                 const int s = t & 1;
-                mbar_wait(smem_u32(pfull), (uint32_t)(t & 1));                       // P_t in shared memory, O rescaled
+                mbar_wait(smem_u32(&pfull[s]), (uint32_t)((t >> 1) & 1));            // P_t in shared memory, O rescaled
                 mbar_wait(smem_u32(&vfull[s]), (uint32_t)((t >> 1) & 1));
                 tc_fence_after();
                 const uint32_t vbase = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                const uint32_t pbase = smem_u32(smem_p + (size_t)s * kFTileBytes);
                 const uint32_t ocol = tmem_base + 2 * kFT;
 #pragma unroll
                 for (int kq = 0; kq < 2; ++kq)          // keys 0..63 / 64..127: the two halves of the P tile
@@ -156,33 +164,34 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                  (uint32_t)((t | kq | kk) != 0));
                     }
                 umma_commit(smem_u32(&vempty[s]));
-                umma_commit(smem_u32(pvdone));
+                umma_commit(smem_u32(&pvdone[s]));
             }
         }
     } else {
-        // ===== softmax + epilogue: thread = query row =====
+        // ===== softmax + epilogue: thread = one query row x 64 key columns (warpgroup g = column half g) =====
         const int quad = warp & 3;
+        const int g = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const int i = qt * kFT + row;                          // query index
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;
+        float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;   // l, mass_acc: this thread's column half only
         for (int t = 0; t < T; ++t) {
             const int s = t & 1;
             mbar_wait(smem_u32(&sfull[s]), (uint32_t)((t >> 1) & 1));
             tc_fence_after();
-            uint32_t raw[4][32];
+            uint32_t raw[2][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32_issue(lane_base + (uint32_t)(s * kFT + 32 * c), raw[c]);
+            for (int c = 0; c < 2; ++c) tmem_ld32_issue(lane_base + (uint32_t)(s * kFT + 64 * g + 32 * c), raw[c]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sfree[s]));
             // scaled logits (log2 domain), masks only where a tile needs them
-            const int j0 = t * kFT;
-            const bool need_mask = (p.causal && j0 + kFT - 1 > qt * kFT) || (j0 + kFT > p.Skv);
+            const int j0 = t * kFT + 64 * g;
+            const bool need_mask = (p.causal && t * kFT + kFT - 1 > qt * kFT) || (t * kFT + kFT > p.Skv);
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     float x = __uint_as_float(raw[c][e]) * p.scale_log2;
@@ -193,6 +202,11 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     raw[c][e] = __float_as_uint(x);
                     mx = fmaxf(mx, x);
                 }
+            // the other half of the row: one float through shared memory, one named barrier per tile
+            float *xm = xch + (size_t)(t & 1) * 2 * kFT;
+            xm[g * kFT + row] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(mx, xm[(g ^ 1) * kFT + row]);
             // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
             float alpha = 1.0f;
             bool rescale = false;
@@ -201,28 +215,28 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 alpha = rescale ? ex2_approx(m_used - mx) : 0.0f;
                 m_used = mx;
             }
-            if (t > 0) {                                         // PV_{t-1} has retired: P tile free, O stable
-                mbar_wait(smem_u32(pvdone), (uint32_t)((t - 1) & 1));
+            if (__any_sync(0xffffffffu, rescale)) {              // warp-uniform: tcgen05.ld/st are warp-wide; rare
+                mbar_wait(smem_u32(&pvdone[(t - 1) & 1]), (uint32_t)(((t - 1) >> 1) & 1));   // P_{t-1} V_{t-1} has retired: O stable
                 tc_fence_after();
-            }
-            if (__any_sync(0xffffffffu, rescale)) {              // warp-uniform: tcgen05.ld/st are warp-wide
                 const float a = rescale ? alpha : 1.0f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t o[32];
-                    tmem_ld32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+                    tmem_ld32(lane_base + (uint32_t)(2 * kFT + 64 * g + 32 * c), o);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * a);
-                    tmem_st32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+                    tmem_st32(lane_base + (uint32_t)(2 * kFT + 64 * g + 32 * c), o);
                 }
                 tmem_st_wait();
             }
             if (rescale) { l *= alpha; mass_acc *= alpha; }
-            // p = 2^(x - m), row sum, prompt-column share, bf16/f16 P tile (K-major, 128-byte swizzle) to shared memory
+            // P buffer (t & 1) is free once P_{t-2} V_{t-2} has retired
+            mbar_wait(smem_u32(&pvdone[s]), (uint32_t)(((t >> 1) & 1) ^ 1));
+            // p = 2^(x - m), row sum, prompt-column share, bf16/f16 P half-tile (K-major, 128-byte swizzle) to shared memory
             float rs = 0.0f, ps = 0.0f;
-            unsigned char *prow = smem_p + (size_t)row * 128;
+            unsigned char *prow = smem_p + (size_t)s * kFTileBytes + (size_t)g * kFHalf + (size_t)row * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
@@ -230,17 +244,15 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     const float p1 = ex2_approx(__uint_as_float(raw[c][e + 1]) - m_used);
                     rs += p0 + p1;
                     if (t == 0) {
-                        const int j = 32 * c + e;
+                        const int j = 64 * g + 32 * c + e;
                         ps += (j < p.P ? p0 : 0.0f) + (j + 1 < p.P ? p1 : 0.0f);
                     }
                     pk[e >> 1] = pack2(p0, p1, p.is_bf16);
                 }
-                // columns 32c..32c+31 = 64 bytes = four 16-byte chunks of half (c >> 1)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(prow + (size_t)(c >> 1) * kFHalf + chunk * 16) =
-                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) {                    // four 16-byte chunks, XOR-swizzled by the row
+                    const int chunk = (c * 4 + q) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
             l += rs;
@@ -248,18 +260,26 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(pfull));
+            if (lane == 0) mbar_arrive(smem_u32(&pfull[s]));
         }
-        // ---- epilogue: O / l, LSE, prompt mass ----
-        mbar_wait(smem_u32(pvdone), (uint32_t)((T - 1) & 1));
+        // ---- epilogue: total row sum over the two halves, O / l, LSE, prompt mass ----
+        float *xl = xch + (size_t)(T & 1) * 2 * kFT;             // the slot the last tile did NOT use
+        xl[g * kFT + row] = l;
+        float *xp = xch + (size_t)((T & 1) ^ 1) * 2 * kFT;
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // everybody is past the last tile's max exchange
+        xp[g * kFT + row] = mass_acc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += xl[(g ^ 1) * kFT + row];
+        mass_acc += xp[(g ^ 1) * kFT + row];
+        mbar_wait(smem_u32(&pvdone[(T - 1) & 1]), (uint32_t)(((T - 1) >> 1) & 1));
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const bool live = i < p.Sq;
         unsigned char *orow = (unsigned char *)p.out + ((size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)i * p.o_ss) * 2;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld32(lane_base + (uint32_t)(2 * kFT + 32 * c), o);
+            tmem_ld32(lane_base + (uint32_t)(2 * kFT + 64 * g + 32 * c), o);
             if (live) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -267,11 +287,11 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         w[e] = pack2(__uint_as_float(o[8 * q + 2 * e]) * inv_l, __uint_as_float(o[8 * q + 2 * e + 1]) * inv_l, p.is_bf16);
-                    *reinterpret_cast<uint4 *>(orow + (size_t)(32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4 *>(orow + (size_t)(64 * g + 32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
-        if (live) {
+        if (live && g == 0) {
             const size_t at = ((size_t)b * p.H + h) * p.Sq + i;
             if (p.lse) p.lse[at] = (m_used + log2f(l)) * 0.6931471805599453f;
             if (p.head_sums) p.head_sums[at] = mass_acc * inv_l;
