@@ -380,6 +380,13 @@ RTKV_API int rtkv_debug_shard_variant(int variant);
 /* Testing aid: cap the persistent grid of the staged statistics kernel (0 = one CTA per SM), so that several emulated
  * ranks can be co-resident on one GPU for rtkv_shard_stats_combine. */
 RTKV_API int rtkv_debug_shard_grid(int max_ctas);
+/* Test harness: rtkv_shard_stats_combine for ALL `world` ranks in ONE cooperative launch on one GPU (blockIdx.y = rank;
+ * kernels that wait for one another must not be separate launches on one device).  [host] arrays of `world` device
+ * pointers; params_scratch: >= 4096 bytes of device memory.  Same kernel body as the per-rank entry. */
+RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a_dtype, int B, int H_local, int S, int64_t sb,
+                      int64_t sh, int64_t si, int P, int group_size, const void *const *K, const void *const *V, int kv_dtype,
+                      int n_local, const uint64_t *xbuf_ptrs, int world, uint32_t *const *state, int H, float *const *mass,
+                      float *const *minmax, void *params_scratch, void *stream);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);

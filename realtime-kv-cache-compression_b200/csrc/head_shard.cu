@@ -104,12 +104,12 @@ __device__ __forceinline__ void combine_token(const char *xlocal, unsigned parit
 // them before thread 0's ticket, and the LAST CTA fences once more (acquire of the other CTAs' tickets + release of
 // everything they ordered before them) and then writes the flags with plain system-scope stores.  One fence per
 // thread plus one in the last CTA: a chain of st.release.sys (a system fence each, ~2.3 us apiece) measured 25 us.
-__device__ __forceinline__ void publish_epoch(const ShardParams &p, unsigned parity, unsigned epoch)
+__device__ __forceinline__ void publish_epoch(const ShardParams &p, unsigned parity, unsigned epoch, unsigned n_ctas)
 {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+        if (atomicAdd(&p.state[1], 1u) == n_ctas - 1) {
             p.state[1] = 0u;
             __threadfence_system();
 #pragma unroll
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kShardWarps * 32) shard_stats_generic_kernel(S
         }
     }
     // ---- publish: every record of this rank is out before the flag ----
-    publish_epoch(p, parity, epoch);
+    publish_epoch(p, parity, epoch, gridDim.x);
 }
 
 // ---- staged path: bulk async copies (TMA engine, cp.async.bulk) into a ring of shared-memory stages ----
@@ -273,7 +273,7 @@ __device__ __forceinline__ float ord2f_u(unsigned o)
 // whatever its size (measured: per-row 512-byte copies ran at 2.5 TB/s).  16 consumer warps share the block's
 // 3*rb (row, task) items: K min/max, V min/max (one REDUX each) or the prompt-mass partials of a row.
 template <int DT>
-__global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(ShardParams p, StagedCfg c)
+__device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, const StagedCfg &c, const int cta, const int n_ctas)
 {
     constexpr int EPV = Vec16<DT>::kElems;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
             const uint64_t pol_kv = p.kv_keep ? l2_policy_evict_last() : l2_policy_evict_first();
             const uint64_t pol_a = l2_policy_evict_first();
             int64_t k = 0;
-            for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
+            for (int64_t blk = cta; blk < n_blocks; blk += n_ctas, ++k) {
                 const int st = (int)(k % c.stages);
                 mbar_wait(empty0 + 8 * st, (uint32_t)(((k / c.stages) & 1) ^ 1));
                 const int b = (int)(blk / bpb);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
         // ---- consumers ----
         const int a_vecs = c.a_bytes / 16;                     // float4 per head row (P/4)
         int64_t k = 0;
-        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++k) {
+        for (int64_t blk = cta; blk < n_blocks; blk += n_ctas, ++k) {
             const int st = (int)(k % c.stages);
             const int b = (int)(blk / bpb);
             const int i0 = (int)(blk - (int64_t)b * bpb) * c.rb;
@@ -419,12 +419,12 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
 #pragma unroll
                 for (int sdst = 0; sdst < 8; ++sdst)
                     if (lane == sdst) base = p.xbuf[sdst];
-                st_sys_u32((unsigned *)(base + 256) + ((size_t)parity * 8 + p.rank) * kMaxShardCtas + blockIdx.x, epoch);
+                st_sys_u32((unsigned *)(base + 256) + ((size_t)parity * 8 + p.rank) * kMaxShardCtas + cta, epoch);
                 unsigned long long mine = 0;
 #pragma unroll
                 for (int sdst = 0; sdst < 8; ++sdst)
                     if (p.rank == sdst) mine = p.xbuf[sdst];
-                const unsigned *flag = (const unsigned *)(mine + 256) + ((size_t)parity * 8 + lane) * kMaxShardCtas + blockIdx.x;
+                const unsigned *flag = (const unsigned *)(mine + 256) + ((size_t)parity * 8 + lane) * kMaxShardCtas + cta;
                 const long long t0 = clock64();
                 while (ld_sys_u32(flag) != epoch) {
                     if (clock64() - t0 > 40000000000LL) { atomicExch(&p.state[2], 1u); break; }     // ~20 s: flag it, never trap
@@ -437,9 +437,9 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
             for (int sdst = 0; sdst < 8; ++sdst)
                 if (p.rank == sdst) mine = p.xbuf[sdst];
             const int per_blk = c.rb;
-            const int64_t my_blocks = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int64_t my_blocks = cta < n_blocks ? (n_blocks - cta + n_ctas - 1) / n_ctas : 0;
             for (int64_t idx = threadIdx.x; idx < my_blocks * per_blk; idx += kStagedConsumers * 32) {
-                const int64_t blk = blockIdx.x + (idx / per_blk) * gridDim.x;
+                const int64_t blk = cta + (idx / per_blk) * n_ctas;
                 const int r = (int)(idx % per_blk);
                 const int b = (int)(blk / bpb);
                 const int i = (int)(blk - (int64_t)b * bpb) * c.rb + r;
@@ -450,14 +450,30 @@ __global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(S
     }
     if (p.mass) {       // only the epoch counter is left to advance (local; the flags were point-to-point)
         __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(&p.state[1], 1u) == gridDim.x - 1) {
+        if (threadIdx.x == 0 && atomicAdd(&p.state[1], 1u) == n_ctas - 1) {
             p.state[1] = 0u;
             __threadfence();
             ((volatile unsigned *)p.state)[0] = epoch;
         }
         return;
     }
-    publish_epoch(p, parity, epoch);
+    publish_epoch(p, parity, epoch, (unsigned)n_ctas);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_kernel(ShardParams p, StagedCfg c)
+{
+    shard_stats_staged_body<DT>(p, c, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Test harness for the one-kernel exchange on a single GPU: ALL ranks in ONE cooperative launch (blockIdx.y = rank), so
+// that the CTAs that wait for each other's flags are guaranteed to be co-resident (separate launches that wait on one
+// another are not: they may never run at the same time).  Same body, same code path as the per-rank kernel.
+template <int DT>
+__global__ void __launch_bounds__(kStagedThreads, 1) shard_stats_staged_allranks_kernel(const ShardParams *ps, StagedCfg c)
+{
+    const ShardParams p = ps[blockIdx.y];
+    shard_stats_staged_body<DT>(p, c, (int)blockIdx.x, (int)gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, unsigned *state, int64_t rows, int world,
@@ -513,10 +529,13 @@ extern "C" int rtkv_debug_shard_grid(int max_ctas)
     return RTKV_OK;
 }
 
+// capture: when not NULL the call fills *capture_p / *capture_c with what it WOULD launch (staged kernel only) and launches
+// nothing - the all-ranks test harness collects one parameter block per rank this way.
 static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh, int64_t si,
                             int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
                             const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, int H_total, float *mass,
-                            float *minmax, void *stream)
+                            float *minmax, void *stream, ShardParams *capture_p = nullptr, StagedCfg *capture_c = nullptr,
+                            int *capture_grid = nullptr, size_t *capture_smem = nullptr)
 {
     RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state, "rtkv_shard_stats: null pointer");
     RTKV_CHECK_ARG(a_dtype == RTKV_F32, "rtkv_shard_stats: head sharding needs float32 probabilities "
@@ -568,6 +587,7 @@ static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int 
         int grid = (int)(n_blocks < sms ? n_blocks : sms);
         if (g_shard_grid_cap > 0 && grid > g_shard_grid_cap) grid = g_shard_grid_cap;
         if (mass && grid > kMaxShardCtas) grid = kMaxShardCtas;
+        if (capture_p) { *capture_p = p; *capture_c = c; *capture_grid = grid; *capture_smem = smem; return RTKV_OK; }
         void (*kern)(ShardParams, StagedCfg) = shard_stats_staged_kernel<RTKV_BF16>;
         if (kv_dtype == RTKV_F32) kern = shard_stats_staged_kernel<RTKV_F32>;
         else if (kv_dtype == RTKV_F16) kern = shard_stats_staged_kernel<RTKV_F16>;
@@ -609,6 +629,42 @@ extern "C" int rtkv_shard_stats_combine(const void *A, int a_dtype, int B, int H
     RTKV_CHECK_ARG((uintptr_t)minmax % 16 == 0, "rtkv_shard_stats_combine: minmax must be 16-byte aligned");
     return shard_stats_impl(A, a_dtype, B, H_local, S, sb, sh, si, P, group_size, K, V, kv_dtype, n_local, xbuf_ptrs, rank, world,
                             state, H, mass, minmax, stream);
+}
+
+extern "C" int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a_dtype, int B, int H_local, int S, int64_t sb,
+                                                       int64_t sh, int64_t si, int P, int group_size, const void *const *K,
+                                                       const void *const *V, int kv_dtype, int n_local, const uint64_t *xbuf_ptrs,
+                                                       int world, uint32_t *const *state, int H, float *const *mass,
+                                                       float *const *minmax, void *params_scratch, void *stream)
+{
+    RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state && mass && minmax && params_scratch, "rtkv_debug_shard_stats_combine_allranks: null pointer");
+    RTKV_CHECK_ARG(world >= 1 && world <= 8, "rtkv_debug_shard_stats_combine_allranks: bad world");
+    ShardParams ps[8];
+    StagedCfg c;
+    int grid = 0;
+    size_t smem = 0;
+    int dev = 0, sms = 0;
+    RTKV_CUDA(cudaGetDevice(&dev));
+    RTKV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int saved_cap = g_shard_grid_cap;
+    g_shard_grid_cap = sms / world > 0 ? sms / world : 1;       // all ranks' CTAs must be co-resident: one CTA per SM
+    int rc = RTKV_OK;
+    for (int r = 0; r < world && !rc; ++r)
+        rc = shard_stats_impl(A[r], a_dtype, B, H_local, S, sb, sh, si, P, group_size, K[r], V[r], kv_dtype, n_local, xbuf_ptrs, r,
+                              world, state[r], H, mass[r], minmax[r], stream, &ps[r], &c, &grid, &smem);
+    g_shard_grid_cap = saved_cap;
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RTKV_CUDA(cudaMemcpyAsync(params_scratch, ps, sizeof(ShardParams) * world, cudaMemcpyHostToDevice, st));
+    RTKV_CUDA(cudaStreamSynchronize(st));                          // ps lives on this stack frame
+    const ShardParams *dps = (const ShardParams *)params_scratch;
+    void *args[2] = {(void *)&dps, (void *)&c};
+    const void *kern = (const void *)shard_stats_staged_allranks_kernel<RTKV_BF16>;
+    if (kv_dtype == RTKV_F32) kern = (const void *)shard_stats_staged_allranks_kernel<RTKV_F32>;
+    else if (kv_dtype == RTKV_F16) kern = (const void *)shard_stats_staged_allranks_kernel<RTKV_F16>;
+    RTKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedHeader + 200 * 1024));
+    RTKV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid, world), dim3(kStagedThreads), args, smem, st));
+    return RTKV_OK;
 }
 
 extern "C" int rtkv_shard_combine(const void *xbuf_local, uint32_t *state, int B, int S, int H, int world,

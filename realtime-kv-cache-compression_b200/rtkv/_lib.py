@@ -138,6 +138,11 @@ PROTOTYPES = {
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_grid": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_shard_stats_combine_allranks": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                               ctypes.c_int, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
+                                                               ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int,
+                                                               ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.POINTER(c_vp),
+                                                               ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp]),
     "rtkv_debug_qk_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "rtkv_ctx_destroy": (ctypes.c_int, [c_vp]),

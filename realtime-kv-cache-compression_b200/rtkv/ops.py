@@ -446,6 +446,26 @@ def shard_stats_combine(attn_local, key_local, value_local, prompt_len, group_si
     return mass, minmax
 
 
+def shard_stats_combine_allranks(attn_slices, key_slices, value_slices, prompt_len, group_size, xbuf_ptrs, states, num_heads,
+                                 masses, minmaxes):
+    """Test harness (one GPU): rtkv_shard_stats_combine of ALL ranks in one cooperative launch (lists of per-rank tensors)."""
+    require_cuda()
+    R = len(attn_slices)
+    A0 = attn_slices[0]
+    B, Hl, S, W = A0.shape
+    for t in list(attn_slices) + list(key_slices) + list(value_slices):
+        assert t.is_contiguous()
+    arr = lambda ts: (ctypes.c_void_p * R)(*[t.data_ptr() for t in ts])
+    ptrs = (ctypes.c_uint64 * R)(*[int(p) for p in xbuf_ptrs])
+    scratch_p = torch.empty(4096, dtype=torch.uint8, device=A0.device)
+    with torch.cuda.device(A0.device):
+        check(lib.rtkv_debug_shard_stats_combine_allranks(arr(attn_slices), dtype_code(A0), B, Hl, S, A0.stride(0), A0.stride(1),
+                                                          A0.stride(2), int(prompt_len), int(group_size), arr(key_slices),
+                                                          arr(value_slices), dtype_code(key_slices[0]), key_slices[0].shape[2],
+                                                          ptrs, R, arr(states), int(num_heads), arr(masses), arr(minmaxes),
+                                                          _ptr(scratch_p), _stream()))
+
+
 @_device_guard
 def shard_combine(xbuf_local, state, batch, seq_len, num_heads, world, mass=None, minmax=None):
     """Consumer half: wait for every rank's records, reduce them in rank order -> mass [B,S] f32 and the whole-row

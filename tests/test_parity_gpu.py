@@ -562,6 +562,36 @@ def _fused_exchange_case(rtkv, ops, rd, kvdt, R, H, D, S, B, bits):
             assert bool((ok[b, c:] == 7.0).all()) and bool((ov[b, c:] == 7.0).all())
 
 
+@pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("R,H,D,S,B", [(8, 32, 128, 2100, 1), (4, 32, 128, 777, 2), (2, 16, 128, 1500, 1)])
+def test_head_sharded_one_kernel_exchange_all_ranks_cooperative(rt, kvdt, R, H, D, S, B):
+    """rtkv_shard_stats_combine (statistics + peer stores + per-CTA flags + reduction in ONE kernel, the default of real
+    multi-GPU runs) with all R ranks inside ONE cooperative launch on this GPU (blockIdx.y = rank): mass and whole-row
+    min/max equal the single-GPU values on every rank, over several layers (epoch parity)."""
+    rtkv, ops = rt
+    from rtkv import dist as rd
+    HD = H * D
+    K, V, A, P = synth_layer(B, H, S, HD, seed=R + S)
+    K, V = K.to(kvdt), V.to(kvdt)
+    hl, wl = H // R, HD // R
+    Ks = [K[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    Vs = [V[..., r * wl:(r + 1) * wl].contiguous() for r in range(R)]
+    As = [A[:, r * hl:(r + 1) * hl].contiguous() for r in range(R)]
+    xch = rd.LocalExchange(B, S, R, K.device)
+    views = [xch.view(r) for r in range(R)]
+    want_mass = ops.prompt_mass(A, prompt_len=P)
+    want_mm = torch.stack([K.float().amin(-1), K.float().amax(-1), V.float().amin(-1), V.float().amax(-1)], dim=-1)
+    for layer in range(5):
+        for v in views:
+            v.mass.fill_(-1.0); v.minmax.fill_(-1.0)
+        ops.shard_stats_combine_allranks(As, Ks, Vs, P, H // 8, xch.ptrs, [v.state for v in views], H,
+                                         [v.mass for v in views], [v.minmax for v in views])
+        torch.cuda.synchronize()
+        for r in range(R):
+            assert int(views[r].state[2]) == 0, "a CTA gave up waiting for its peers"
+            assert torch.equal(views[r].mass, want_mass) and torch.equal(views[r].minmax, want_mm), (layer, r)
+
+
 def test_head_sharded_fused_exchange_propagates_nan_rows(rt):
     """torch.min/max propagate NaN: a NaN anywhere in a row (on any rank) makes that row's scale NaN on every rank."""
     rtkv, ops = rt
