@@ -44,16 +44,58 @@ struct FlashParams {
     uint32_t idesc_qk, idesc_pv;
 };
 
-__device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16)
+template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b)
 {
-    if (is_bf16) {
+    if constexpr (BF16) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t *>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
     }
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
 }
 
+// One thread's 64 logits of a tile -> p = 2^(s*scale - m), row sum, P half-row (input dtype, K-major, 128-byte swizzle) in
+// shared memory.  SLOW: the tile needs masking (diagonal / key tail) or is the first tile (prompt-column sum); every
+// other tile runs the branch-free body: FFMA + MUFU.EX2 + FADD per element and one pack per pair.
+template <bool BF16, bool SLOW>
+__device__ __forceinline__ void exp_store(const uint32_t (&raw)[2][32], float scale_log2, float m_used, uint32_t prow, int row,
+                                          int j_base, int i, int Skv, int causal, int P, bool first, float &rs, float &ps)
+{
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+            float p0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e]), scale_log2, -m_used));
+            float p1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e + 1]), scale_log2, -m_used));
+            if constexpr (SLOW) {
+                const int j = j_base + 32 * c + e;
+                if (j >= Skv || (causal && j > i)) p0 = 0.0f;
+                if (j + 1 >= Skv || (causal && j + 1 > i)) p1 = 0.0f;
+                if (first) ps += (j < P ? p0 : 0.0f) + (j + 1 < P ? p1 : 0.0f);
+            }
+            rs += p0 + p1;
+            pk[e >> 1] = pack2<BF16>(p0, p1);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)                              // four 16-byte chunks, XOR-swizzled by the row
+            sts_v4(prow + (uint32_t)((((c * 4 + q) ^ (row & 7))) * 16), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(kFThreads, 1)
 flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, FlashParams p)
@@ -175,6 +217,7 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int i = qt * kFT + row;                          // query index
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;   // l, mass_acc: this thread's column half only
+        const uint32_t xch_u32 = smem_u32(xch);
         for (int t = 0; t < T; ++t) {
             const int s = t & 1;
             mbar_wait(smem_u32(&sfull[s]), (uint32_t)((t >> 1) & 1));
@@ -186,27 +229,30 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sfree[s]));
-            // scaled logits (log2 domain), masks only where a tile needs them
+            // row max of this thread's 64 logits (raw units; masked entries only where a tile needs masking)
             const int j0 = t * kFT + 64 * g;
             const bool need_mask = (p.causal && t * kFT + kFT - 1 > qt * kFT) || (t * kFT + kFT > p.Skv);
             float mx = -INFINITY;
+            if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    float x = __uint_as_float(raw[c][e]) * p.scale_log2;
-                    if (need_mask) {
+                    for (int e = 0; e < 32; ++e) {
                         const int j = j0 + 32 * c + e;
-                        if (j >= p.Skv || (p.causal && j > i)) x = -INFINITY;
+                        const bool dead = j >= p.Skv || (p.causal && j > i);
+                        mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(raw[c][e]));
                     }
-                    raw[c][e] = __float_as_uint(x);
-                    mx = fmaxf(mx, x);
-                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(raw[c][e]));
+            }
             // the other half of the row: one float through shared memory, one named barrier per tile
-            float *xm = xch + (size_t)(t & 1) * 2 * kFT;
-            xm[g * kFT + row] = mx;
+            const uint32_t xm = xch_u32 + (uint32_t)((t & 1) * 2 * kFT * 4);
+            sts_f32(xm + (uint32_t)((g * kFT + row) * 4), mx);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            mx = fmaxf(mx, xm[(g ^ 1) * kFT + row]);
+            mx = fmaxf(mx, lds_f32(xm + (uint32_t)(((g ^ 1) * kFT + row) * 4))) * p.scale_log2;   // log2 domain from here
             // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
             float alpha = 1.0f;
             bool rescale = false;
@@ -232,29 +278,13 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             if (rescale) { l *= alpha; mass_acc *= alpha; }
             // P buffer (t & 1) is free once P_{t-2} V_{t-2} has retired
             mbar_wait(smem_u32(&pvdone[s]), (uint32_t)(((t >> 1) & 1) ^ 1));
-            // p = 2^(x - m), row sum, prompt-column share, bf16/f16 P half-tile (K-major, 128-byte swizzle) to shared memory
+            // p = 2^(s*scale - m), row sum, prompt-column share, P half-tile to shared memory
             float rs = 0.0f, ps = 0.0f;
-            unsigned char *prow = smem_p + (size_t)s * kFTileBytes + (size_t)g * kFHalf + (size_t)row * 128;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const float p0 = ex2_approx(__uint_as_float(raw[c][e]) - m_used);
-                    const float p1 = ex2_approx(__uint_as_float(raw[c][e + 1]) - m_used);
-                    rs += p0 + p1;
-                    if (t == 0) {
-                        const int j = 64 * g + 32 * c + e;
-                        ps += (j < p.P ? p0 : 0.0f) + (j + 1 < p.P ? p1 : 0.0f);
-                    }
-                    pk[e >> 1] = pack2(p0, p1, p.is_bf16);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {                    // four 16-byte chunks, XOR-swizzled by the row
-                    const int chunk = (c * 4 + q) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                }
-            }
+            const uint32_t prow = smem_u32(smem_p) + (uint32_t)(s * kFTileBytes + g * kFHalf + row * 128);
+            if (need_mask || t == 0)
+                exp_store<BF16, true>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
+            else
+                exp_store<BF16, false>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
             l += rs;
             if (t == 0) mass_acc = ps;
             fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
@@ -286,7 +316,7 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        w[e] = pack2(__uint_as_float(o[8 * q + 2 * e]) * inv_l, __uint_as_float(o[8 * q + 2 * e + 1]) * inv_l, p.is_bf16);
+                        w[e] = pack2<BF16>(__uint_as_float(o[8 * q + 2 * e]) * inv_l, __uint_as_float(o[8 * q + 2 * e + 1]) * inv_l);
                     *reinterpret_cast<uint4 *>(orow + (size_t)(64 * g + 32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
@@ -342,6 +372,7 @@ extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, i
         return RTKV_EUNSUPPORTED;
     }
     RTKV_CHECK_ARG(B > 0 && H > 0 && Hkv > 0 && H % Hkv == 0 && Sq > 0 && Skv > 0, "rtkv_flash_prefill: bad shape");
+    RTKV_CHECK_ARG(sm_scale > 0.0f, "rtkv_flash_prefill: sm_scale must be positive");
     RTKV_CHECK_ARG(P >= 0 && P <= kFT, "rtkv_flash_prefill: prompt length must be <= 128 (got %d)", P);
     RTKV_CHECK_ARG(!head_sums || P > 0, "rtkv_flash_prefill: head_sums needs P > 0");
     for (int k = 0; k < 3; ++k) {
@@ -366,8 +397,13 @@ extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, i
     const int n_qt = (Sq + kFT - 1) / kFT;
     const long long ctas = (long long)n_qt * H * B;
     RTKV_CHECK_ARG(ctas < (1ll << 31), "rtkv_flash_prefill: too many tiles");
-    RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
-    flash_prefill_kernel<<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    if (dtype == RTKV_BF16) {
+        RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+        flash_prefill_kernel<true><<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    } else {
+        RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+        flash_prefill_kernel<false><<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    }
     RTKV_LAUNCH_CHECK("flash_prefill_kernel");
     return RTKV_OK;
 }
