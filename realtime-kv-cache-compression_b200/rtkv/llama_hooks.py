@@ -3,9 +3,9 @@ transformers release in this image (5.x: `position_embeddings`, `past_key_values
 returns `(output, weights)`).
 
 Scope: the *hook* — where the compressor is called, what it is fed,
-how its result is used — not a new attention kernel.  The attention math around the hook
-is the reference's eager formulation in plain torch (SURVEY §8f lists fused replacements as
-"next").  What is kept from the reference:
+how its result is used.  The default branch keeps the reference's eager attention formulation in
+plain torch around the hook; the fused branch (below) replaces it with librtkv's own attention
+kernel.  What is kept from the reference:
   * `set_compressor` chain model -> decoder layer -> attention            (:44-46,183-184,264-268)
   * compression only in eval mode and for q_len > 1 (prefill)             (:102)
   * K/V handed over as [B, S, H_kv*D] contiguous, attention as [B,H,S,S]  (:105-117)
@@ -14,11 +14,14 @@ is the reference's eager formulation in plain torch (SURVEY §8f lists fused rep
   * any exception inside the block prints and falls back to the uncompressed result (:144-149)
   * `outputs.compression_info`, `get_compression_stats`, `reset_compression_state`   (:310-339)
 
-Extension (SURVEY.md §8f rank 1, off by default): `set_compressor(c, fused_scoring=True)` replaces the materialised
-`softmax(QK^T)` of the prefill by a flash attention that also returns the row log-sum-exp (torch's SDPA flash /
-efficient kernels: library code) and takes the prompt-attention mass from librtkv's tcgen05 kernel
-(`ops.prompt_mass_qk`: Q, K_prompt, LSE -> mass), so no [B,H,S,S] tensor exists and the hook works at 32k tokens.
-Needs bf16/fp16 activations, head_dim 128 and a causal mask; `attn_weights` is then returned as None.
+Extension (SURVEY.md §8f rank 1 and 2, off by default): `set_compressor(c, fused_scoring=True)` replaces the materialised
+`softmax(QK^T)` of the prefill by librtkv's own tcgen05 + TMA attention kernel (`ops.flash_prefill`, csrc/flash_prefill.cu):
+one launch returns the attention output, the row log-sum-exp and the prompt-attention mass per head (the by-product of the
+first key tile that token_importance.py:41-45 takes from the materialised probabilities), so no [B,H,S,S] tensor exists
+and the hook works at 32k tokens.  The attention over the kept tokens (:125-142) is the same kernel with kv_len = S'
+(top-left aligned causal mask == the reference's mask truncated to its first S' columns).  No library attention kernel is
+involved.  Needs bf16/fp16 activations, head_dim 128 and a causal mask (None, or an additive mask that is verified to be
+purely causal; any other mask - e.g. padding - takes the eager branch, as does output_attentions=True).
 """
 import logging
 import math
@@ -38,20 +41,29 @@ except Exception:  # pragma: no cover
 log = logging.getLogger(__name__)
 
 
-def _flash_with_lse(q, k, v, scale):
-    """Causal attention output [B,H,S,D] and natural-log row LSE [B,H,S] (float32) from torch's fused SDPA kernels."""
-    errors = []
-    try:
-        r = torch.ops.aten._scaled_dot_product_flash_attention(q, k, v, 0.0, True, False, scale=scale)
-        return r[0], r[1].float()
-    except Exception as e:  # backend not built for this device / shape
-        errors.append(e)
-    try:
-        r = torch.ops.aten._scaled_dot_product_efficient_attention(q, k, v, None, True, 0.0, True, scale=scale)
-        return r[0], r[1][..., : q.shape[2]].float()
-    except Exception as e:
-        errors.append(e)
-    raise RuntimeError(f"no fused attention kernel with LSE output is available: {errors}")
+def _is_causal_mask(mask, q_len, kv_len, cache={}):
+    """True if `mask` is None or an additive [B,1,Sq,Skv] mask that is exactly causal (0 on and below the diagonal, a large
+    negative number above it).  The same mask object is handed to every layer: the verdict is cached per tensor."""
+    if mask is None:
+        return True
+    key = (mask.data_ptr(), tuple(mask.shape), mask._version)
+    if cache.get("key") == key:
+        return cache["ok"]
+    ok = mask.dim() == 4 and mask.shape[-2] == q_len and mask.shape[-1] >= kv_len and q_len == kv_len
+    if ok:
+        m = mask[..., :q_len, :kv_len]
+        rows = max(1, (1 << 24) // max(1, kv_len))                       # bounded temporaries for long sequences
+        j = torch.arange(kv_len, device=mask.device)[None, :]
+        for r0 in range(0, q_len, rows):
+            r1 = min(q_len, r0 + rows)
+            i = torch.arange(r0, r1, device=mask.device)[:, None]
+            blk = m[..., r0:r1, :]
+            if not (bool((blk.masked_select((j <= i).expand_as(blk)) == 0).all())
+                    and bool((blk.masked_select((j > i).expand_as(blk)) <= -1e4).all())):
+                ok = False
+                break
+    cache["key"], cache["ok"] = key, ok
+    return ok
 
 
 def _store_compressed(cache, layer_idx, keys, values):
@@ -80,17 +92,18 @@ class CompressedLlamaAttention(LlamaAttention):
         self.fused_scoring = bool(fused_scoring)
 
     def _forward_fused(self, hidden_states, query_states, key_states, value_states, input_ids):
-        """Prefill without the S x S matrix: flash attention (+LSE) -> tcgen05 prompt mass -> compress ->
-        attention over the kept tokens (top-left aligned causal mask == the reference's truncated mask)."""
+        """Prefill without the S x S matrix, every attention product on librtkv's tcgen05 kernel:
+        flash_prefill (output + LSE + per-head prompt mass) -> compress -> flash_prefill over the kept tokens."""
         from . import ops
         bsz, _, q_len, _ = query_states.shape
-        groups = self.num_heads // self.num_key_value_heads
         scale = 1.0 / math.sqrt(self.head_dim)
-        k_full, v_full = repeat_kv(key_states, groups), repeat_kv(value_states, groups)
-        attn_output, lse = _flash_with_lse(query_states, k_full, v_full, scale)
+        P = self.compressor.prompt_length(q_len)
+        attn_output, _lse, head_sums = ops.flash_prefill(query_states, key_states, value_states, scale, causal=True,
+                                                         prompt_len=P, out_layout="bshd")
         try:
-            P = self.compressor.prompt_length(q_len)
-            mass = ops.prompt_mass_qk(query_states, k_full[:, :, :P], lse, scale, causal=True)
+            mass = torch.empty(bsz, q_len, dtype=torch.float32, device=hidden_states.device)
+            ops.check(ops.lib.rtkv_mass_from_head_sums(ops._ptr(head_sums), bsz, self.num_heads, q_len, ops._ptr(mass),
+                                                       ops._stream()))
             k_flat = key_states.transpose(1, 2).contiguous().view(bsz, q_len, -1)
             v_flat = value_states.transpose(1, 2).contiguous().view(bsz, q_len, -1)
             ids = input_ids if input_ids is not None else torch.zeros((bsz, q_len), device=hidden_states.device,
@@ -100,12 +113,12 @@ class CompressedLlamaAttention(LlamaAttention):
             s_kept = ck.shape[1]
             ck = ck.view(bsz, s_kept, self.num_key_value_heads, self.head_dim).transpose(1, 2)
             cv = cv.view(bsz, s_kept, self.num_key_value_heads, self.head_dim).transpose(1, 2)
-            if s_kept != q_len:
-                attn_output = nn.functional.scaled_dot_product_attention(
-                    query_states, repeat_kv(ck, groups), repeat_kv(cv, groups), is_causal=True, scale=scale)
-            else:
-                attn_output = nn.functional.scaled_dot_product_attention(
-                    query_states, k_full, repeat_kv(cv, groups), is_causal=True, scale=scale)
+            if s_kept != q_len:     # attention over the kept tokens, mask truncated to its first S' columns (:125-140)
+                attn_output, _, _ = ops.flash_prefill(query_states, ck, cv, scale, causal=True, want_lse=False,
+                                                      out_layout="bshd")
+            else:                   # original keys, fake-quantised values (:141-142: attn_weights @ V_quant)
+                attn_output, _, _ = ops.flash_prefill(query_states, key_states, cv, scale, causal=True, want_lse=False,
+                                                      out_layout="bshd")
             return attn_output, (ck, cv)
         except Exception as e:  # same downgrade as the reference
             print(f"Compression failed at layer {self.layer_idx}: {e}")
@@ -126,12 +139,12 @@ class CompressedLlamaAttention(LlamaAttention):
 
         if (self.fused_scoring and self.compressor is not None and not self.training and q_len > 1
                 and hidden_states.is_cuda and query_states.dtype in (torch.bfloat16, torch.float16)
-                and self.head_dim == 128 and key_states.shape[2] == q_len):
+                and self.head_dim == 128 and key_states.shape[2] == q_len and not kwargs.get("output_attentions", False)
+                and _is_causal_mask(attention_mask, q_len, key_states.shape[2])):
             attn_output, kept = self._forward_fused(hidden_states, query_states, key_states, value_states, input_ids)
             if kept is not None and past_key_values is not None:
                 _store_compressed(past_key_values, self.layer_idx, kept[0], kept[1])
-            attn_output = attn_output.transpose(1, 2).contiguous().reshape(bsz, q_len, -1)
-            return self.o_proj(attn_output), None
+            return self.o_proj(attn_output.reshape(bsz, q_len, -1)), None     # the kernel wrote [B,S,H,D]: no transpose
 
         groups = self.num_heads // self.num_key_value_heads
         k_full, v_full = repeat_kv(key_states, groups), repeat_kv(value_states, groups)

@@ -1195,8 +1195,8 @@ def test_precomputed_prompt_mass_input(rt):
 
 
 def test_llama_hook_fused_scoring_no_attention_matrix(rt):
-    """the hook with flash attention (+LSE) and the tcgen05 prompt-mass kernel instead of a
-    materialised softmax(QK^T).  Same weights as the eager hook: same kept counts, (nearly) the same layer-0
+    """the hook with librtkv's tcgen05 prefill attention (output + LSE + fused prompt mass, and the
+    attention over the kept tokens) instead of a materialised softmax(QK^T).  Same weights as the eager hook: same kept counts, (nearly) the same layer-0
     selection, close logits; attention weights are not returned."""
     rtkv, ops = rt
     from rtkv.llama_hooks import CompressedLlamaForCausalLM
@@ -1226,6 +1226,38 @@ def test_llama_hook_fused_scoring_no_attention_matrix(rt):
     overlap = float((m_e & m_f).sum()) / float(m_e.sum())
     assert overlap > 0.8, overlap          # the eager bf16 path rounds the mass to bf16 like the reference does
     assert o_f.past_key_values.layers[2].keys.shape[2] == 256
+
+
+def test_llama_hook_fused_scoring_needs_a_causal_mask(rt):
+    """The fused branch only runs for a None / purely causal mask; a padding mask (or output_attentions=True) takes the
+    eager branch, which returns the attention weights."""
+    rtkv, ops = rt
+    from rtkv.llama_hooks import CompressedLlamaForCausalLM, _is_causal_mask
+    from transformers import LlamaConfig
+    torch.manual_seed(3)
+    hf = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                     num_key_value_heads=2, vocab_size=97, max_position_embeddings=512)
+    model = CompressedLlamaForCausalLM(hf).cuda().to(torch.bfloat16).eval()
+    cfg = rtkv.CompressionConfig(num_hidden_layers=2, num_attention_heads=2, hidden_size=256, high_precision_bits=8,
+                                 medium_precision_bits=8, low_precision_bits=8)
+    model.set_compressor(rtkv.RealTimePrefillCompressor(cfg), fused_scoring=True)
+    attn = model.model.layers[0].self_attn
+    B, S = 2, 200
+    x = torch.randn(B, S, 256, device="cuda", dtype=torch.bfloat16)
+    pos = torch.arange(S, device="cuda")[None].expand(B, -1)
+    pe = model.model.rotary_emb(x, pos)
+    neg = torch.finfo(torch.bfloat16).min
+    causal = torch.full((S, S), neg, device="cuda", dtype=torch.bfloat16).triu(1)[None, None].expand(B, 1, S, S).contiguous()
+    padded = causal.clone()
+    padded[1, :, :, :7] = neg                       # left padding of the second sequence
+    assert _is_causal_mask(None, S, S) and _is_causal_mask(causal, S, S) and not _is_causal_mask(padded, S, S)
+    with torch.no_grad():
+        _, w_none = attn(x, position_embeddings=pe, attention_mask=None)
+        _, w_causal = attn(x, position_embeddings=pe, attention_mask=causal)
+        _, w_padded = attn(x, position_embeddings=pe, attention_mask=padded)
+        _, w_asked = attn(x, position_embeddings=pe, attention_mask=causal, output_attentions=True)
+    assert w_none is None and w_causal is None               # fused branch: no probabilities exist
+    assert w_padded is not None and w_padded.shape == (B, 2, S, S) and w_asked is not None
 
 
 def test_llama_hook_fused_scoring_32k_tokens(rt):
