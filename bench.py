@@ -149,7 +149,7 @@ def llama_prefill_inputs(n_layers, hidden, heads, inter, S, B, P, seed, device, 
                 lse[:, :, r0:r1] = torch.logsumexp(lb, dim=-1)
                 del lb
         if want_qk:
-            qk = (qb.contiguous(), kb[:, :, :P].contiguous(), lse)
+            qk = (qb.contiguous(), kb[:, :, :P].contiguous(), lse, kb.contiguous(), v.to(torch.bfloat16).contiguous())
         if keep_layers is None or l in keep_layers:
             if head_slice is None:
                 out.append((l, k.transpose(1, 2).reshape(B, S, hidden).contiguous(),
@@ -458,7 +458,7 @@ def measure_device_path(args, rtkv, ops, layers, cfg, bits, dev, timer, S, B, P,
 def measure_k1b(ops, qk, timer, steps, S, heads, P, D=128):
     """The fused Q.K_prompt^T scoring kernel (K1b: tcgen05 + TMA), the only dense contraction of the path: its HBM
     floor is streaming Q once; tensor-pipe utilisation comes from the ncu capture in profiles/."""
-    q, kp, lse = qk
+    q, kp, lse = qk[:3]
     B = q.shape[0]
     scale = 1.0 / math.sqrt(D)
     fn = lambda: ops.prompt_mass_qk_partials(q, kp, lse, scale, causal=True)
@@ -472,6 +472,26 @@ def measure_k1b(ops, qk, timer, steps, S, heads, P, D=128):
             "tflops": flops / (ms * 1e-3) / 1e12, "tflops_frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / tf_peak,
             "note": "one layer's Q [B,H,S,128] bf16 + LSE streamed once, P=128 prompt keys resident; replaces K1a's read of "
                     "the materialised probability slice (2x the bytes) when the caller has Q/K/LSE instead of S x S probabilities"}
+
+
+def measure_flash(ops, qk, timer, steps, S, heads, P, D=128):
+    """rtkv_flash_prefill: the hand-written tcgen05 + TMA prefill attention that produces the path's score input (attention
+    output + LSE + per-head prompt mass in one launch).  Tensor-core bound: causal FLOPs / time against the
+    measured cuBLAS bf16 peak."""
+    q, _, lse_ref, k, v = qk
+    B = q.shape[0]
+    scale = 1.0 / math.sqrt(D)
+    fn = lambda: ops.flash_prefill(q, k, v, scale, causal=True, prompt_len=P)
+    ms = timer.run(fn, 2, max(3, min(steps, 5)))
+    out, lse, hs = fn()
+    flops = 4.0 * B * heads * S * S * D / 2.0
+    _, tf_peak, src = measured_peaks()
+    return {"kernel": "flash_prefill_kernel (tcgen05.mma + TMA, bf16, causal, LSE + fused prompt mass)", "ms_per_launch": ms,
+            "bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+            "frac": flops / (ms * 1e-3) / 1e12 / tf_peak, "peak_source": src,
+            "lse_max_abs_diff_vs_torch_fp32": float((lse - lse_ref).abs().max()),
+            "note": "one layer's causal attention [B,H,S,128] x [B,H,S,128]; FLOPs = 4*B*H*S^2*D/2; replaces the library "
+                    "attention + separate scoring kernel of the model hook"}
 
 
 # ----------------------------------------------------------------------------- head-sharded mode
@@ -732,6 +752,10 @@ def main():
                 line["k1b_scoring"] = measure_k1b(ops, qk, timer, args.steps, S, heads, P)
             except Exception as e:  # pragma: no cover
                 line["k1b_scoring"] = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                line["flash_prefill"] = measure_flash(ops, qk, timer, args.steps, S, heads, P)
+            except Exception as e:  # pragma: no cover
+                line["flash_prefill"] = {"error": f"{type(e).__name__}: {e}"}
     del qk
 
     # ------------------------------------------------------------------ e2e: public API, host buffers
