@@ -388,6 +388,10 @@ RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a
                       int n_local, const uint64_t *xbuf_ptrs, int world, uint32_t *const *state, int H, float *const *mass,
                       float *const *minmax, void *params_scratch, void *stream);
 
+/* Testing aid: bf16 rows of rtkv_quant_gather*: 1 (default) packed two-elements-per-instruction path for rows inside its
+ * guard, 0 element-wise code only.  Same results (per device: call with the device current). */
+RTKV_API int rtkv_debug_bf16_packed(int on);
+
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);
 

@@ -275,6 +275,61 @@ template <int DT> struct RowQuant {
     }
 };
 
+// ---- bf16 rows: packed (two elements per instruction) fast path -------------------------------------------------
+// torch computes every bf16 op in fp32 and rounds the result to bf16.  For +, -, * of two bf16 numbers that equals the
+// correctly rounded bf16 operation (double rounding through a format with p' >= 2p + 2 bits is innocuous: 24 >= 2*8 + 2),
+// which is what the hardware's packed HADD2 / HMUL2 .BF16 compute.  The division x/scale needs no exact fp32 quotient
+// either: with 8-bit significands X, S the quotient X/S is never closer than 2^-18 (relative) to a midpoint of the bf16
+// grid and never on one (2^9*X = (2j+1)*S is impossible for S < 2^8), while x * RN(1/scale) is within 2^-22 of x/scale,
+// so rounding that product to bf16 gives RN_bf16(RN_f32(x/scale)) (tools/bf16_divcheck.c: exhaustive over all
+// significand pairs and signs).  round-half-even of 0 <= t < 128 is (t + 128) - 128 in bf16 (ulp 1 in [128,256));
+// t >= 128 is already an integer.  t >= +0 as in RowQuant, so the clamp is one packed min.
+// Row guard (uniform per row): non-constant finite row, scale in [2^-30, 2^30], |min|, |max| zero or in [2^-30, 2^60]:
+// every intermediate that reaches the result is then zero or a normal number, whatever the denormal mode of the packed
+// units.  All other rows keep the element-wise code.  6.5 instructions per element instead of ~20.
+struct Bf16RowPacked {
+    float rcp;
+    __nv_bfloat162 zp2, scale2, qmax2, c128;
+    bool ok;
+    __device__ __forceinline__ void init(float mn, float mx, float scale, float zp, float qmax_r)
+    {
+        const float amn = fabsf(mn), amx = fabsf(mx);
+        ok = (mx != mn) && scale >= 0x1p-30f && scale <= 0x1p30f && (amn == 0.0f || (amn >= 0x1p-30f && amn <= 0x1p60f)) &&
+             (amx == 0.0f || (amx >= 0x1p-30f && amx <= 0x1p60f));
+        rcp = __frcp_rn(scale);
+        zp2 = __float2bfloat162_rn(zp);          // zp, scale, qmax_r are bf16 values already: exact
+        scale2 = __float2bfloat162_rn(scale);
+        qmax2 = __float2bfloat162_rn(qmax_r);
+        c128 = __float2bfloat162_rn(128.0f);
+    }
+    __device__ __forceinline__ uint32_t apply(uint32_t w) const
+    {
+        const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+        __nv_bfloat162 t = __floats2bfloat162_rn(__fmul_rn(lo, rcp), __fmul_rn(hi, rcp));     // rnd(x / scale)
+        t = __hadd2(t, zp2);                                                                // rnd(. + zp)
+        const __nv_bfloat162 r0 = __hsub2(__hadd2(t, c128), c128);                          // rint for t < 128
+        const uint32_t big = __hge2_mask(t, c128);                                          // t >= 128: already integral
+        const uint32_t tb = *reinterpret_cast<const uint32_t *>(&t), rb = *reinterpret_cast<const uint32_t *>(&r0);
+        uint32_t qb = (tb & big) | (rb & ~big);
+        __nv_bfloat162 q = __hmin2(*reinterpret_cast<__nv_bfloat162 *>(&qb), qmax2);        // clamp (lower bound holds)
+        const __nv_bfloat162 y = __hmul2(__hsub2(q, zp2), scale2);                          // rnd(rnd(q - zp) * scale)
+        return *reinterpret_cast<const uint32_t *>(&y);
+    }
+    __device__ __forceinline__ uint4 apply(uint4 v) const { return make_uint4(apply(v.x), apply(v.y), apply(v.z), apply(v.w)); }
+};
+
+// packed min / max of a 16-byte vector of bf16 with NaN propagation (torch.min/max propagate NaN)
+__device__ __forceinline__ void bf16x8_minmax(uint4 v, __nv_bfloat162 &mn2, __nv_bfloat162 &mx2)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[k]);
+        mn2 = __hmin2_nan(mn2, h);
+        mx2 = __hmax2_nan(mx2, h);
+    }
+}
+
 // ---- programmatic dependent launch (PDL) -------------------------------------------------
 // Every hot kernel starts with pdl_wait() (the previous kernel of the stream has completed and its
 // memory is visible) followed by pdl_trigger() (the next kernel may be scheduled as soon as all CTAs

@@ -17,6 +17,8 @@
 
 namespace rtkv {
 
+__device__ int g_bf16_packed = 1;     // rtkv_debug_bf16_packed(): 0 = element-wise bf16 code only (A/B testing)
+
 // NV = 16-byte vectors per thread (n <= NV * kQT * elems_per_vec, n % elems_per_vec == 0)
 template <int DT, int NV>
 __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
@@ -53,13 +55,23 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
     }
     float mn = INFINITY, mx = -INFINITY;
     int nan = 0;
+    if constexpr (DT == RTKV_BF16) {            // packed min/max, NaN propagating: one instruction per element
+        __nv_bfloat162 mn2 = __float2bfloat162_rn(INFINITY), mx2 = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        if (threadIdx.x + k * kQT < nvec) {
-            float f[EPV];
-            Vec16<DT>::unpack(raw[k], f);
+        for (int k = 0; k < NV; ++k)
+            if (threadIdx.x + k * kQT < nvec) bf16x8_minmax(raw[k], mn2, mx2);
+        const float a = __low2float(mn2), c = __high2float(mn2), d = __low2float(mx2), e = __high2float(mx2);
+        nan = (a != a) | (c != c) | (d != d) | (e != e);
+        mn = fminf(a, c); mx = fmaxf(d, e);
+    } else {
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+        for (int k = 0; k < NV; ++k) {
+            if (threadIdx.x + k * kQT < nvec) {
+                float f[EPV];
+                Vec16<DT>::unpack(raw[k], f);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) { nan |= (f[e] != f[e]); mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+            }
         }
     }
     if (p.ext_minmax) {         // row min/max reduced over all ranks' head shards
@@ -70,6 +82,18 @@ __global__ void __launch_bounds__(kQT) quant_gather_vec_kernel(QGParams p)
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
     RowQuant<DT> rq;
     rq.init(mn, mx, bits);
+    if constexpr (DT == RTKV_BF16) {
+        Bf16RowPacked pq;
+        pq.init(mn, mx, rq.scale, rq.zp, rq.qmax_r);
+        if (pq.ok && g_bf16_packed) {           // uniform over the CTA (row-level)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const int v = threadIdx.x + k * kQT;
+                if (v < nvec) stg_stream(dst + v, pq.apply(raw[k]));
+            }
+            return;
+        }
+    }
     if (rq.fast) {                              // uniform over the CTA (row-level)
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -273,6 +297,15 @@ __global__ void __launch_bounds__(kQT) quant_gather_flat_kernel(QGParams p, int 
     const int bits = pick_bits(p, p.labels[(int64_t)b * p.S + tok]);
     RowQuant<DT> rq;
     rq.init(mn, mx, bits);
+    if constexpr (DT == RTKV_BF16) {
+        Bf16RowPacked pq;
+        pq.init(mn, mx, rq.scale, rq.zp, rq.qmax_r);
+        if (pq.ok && g_bf16_packed) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) stg_stream(dst + l + k * tpr, pq.apply(raw[k]));
+            return;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         float f[EPV];
@@ -627,6 +660,13 @@ __global__ void __launch_bounds__(kQT) unpack_dequant_kernel(QGParams p, int64_t
 } // namespace rtkv
 
 using namespace rtkv;
+
+extern "C" int rtkv_debug_bf16_packed(int on)
+{
+    const int v = on ? 1 : 0;
+    RTKV_CUDA(cudaMemcpyToSymbol(g_bf16_packed, &v, sizeof(int)));
+    return RTKV_OK;
+}
 
 extern "C" int rtkv_quant_gather(const void *X0, const void *X1, int dtype, int B, int S, int n,
                                  const int32_t *sel_idx, const rtkv_row_stats *row_stats,
