@@ -426,6 +426,37 @@ def test_fake_quant_bit_widths(rt, dt, bits):
     assert_same(y, w, dt)
 
 
+@pytest.mark.parametrize("n", [512, 4096, 5120])
+def test_bf16_packed_fast_path_equals_elementwise_code(rt, n):
+    """bf16 rows: the packed two-elements-per-instruction path (Bf16RowPacked: HADD2/HMUL2.BF16, reciprocal multiply,
+    (t+128)-128 rounding) against the element-wise code on the same rows - both are compared with the oracle by the fuzz
+    and stress tests in their default setting; this pins them to each other, including rows at the guard's edges."""
+    _, ops = rt
+    rng = np.random.default_rng(n)
+    R = 600
+    x = rng.standard_normal((1, R, n)).astype(np.float32)
+    x[0, :, :] *= np.exp2(rng.integers(-34, 34, size=(R, 1))).astype(np.float32)       # scales around the guard [2^-30, 2^30]
+    x[0, 1] = np.abs(x[0, 1])                      # min == +x
+    x[0, 2, 0] = 0.0                                # a zero minimum candidate
+    x[0, 3] = np.floor(x[0, 3] * 8) / 8
+    x[0, 4, :] = 0.375                              # constant row
+    x[0, 5, :n // 2] = 0.0                          # min == 0 exactly
+    x[0, 5] = np.abs(x[0, 5])
+    xt = torch.from_numpy(x).to(torch.bfloat16).cuda()
+    labels = torch.from_numpy(rng.integers(0, 3, (1, R)).astype(np.uint8)).cuda()
+    for bits in ((2, 4, 8), (4, 8, 16), (3, 5, 7)):
+        ops.lib.rtkv_debug_bf16_packed(1)
+        y1, _ = ops.quant_gather(xt, None, None, labels, bits, R)
+        ops.lib.rtkv_debug_bf16_packed(0)
+        try:
+            y0, _ = ops.quant_gather(xt, None, None, labels, bits, R)
+        finally:
+            ops.lib.rtkv_debug_bf16_packed(1)
+        assert torch.equal(y1.view(torch.int16), y0.view(torch.int16)), bits
+        want, _, _ = oracle.fake_quant_rows(oracle.from_torch(xt.cpu())[0], oracle.BF16, labels.cpu().numpy(), bits)
+        assert_same(y1, want, oracle.BF16)
+
+
 def test_fp16_sixteen_bits_raises_like_the_reference(rt):
     """torch.clamp(x, 0, 65535) on fp16 raises in the reference (dynamic_quantization.py:121)."""
     rtkv, ops = rt

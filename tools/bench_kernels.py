@@ -108,6 +108,11 @@ if only is None or "k3" in only:
         okh, ovh = torch.empty_like(Kh[0]), torch.empty_like(Kh[0])
         t = graph_time(lambda i: ops.quant_gather(Kh[i], Vh[i], None, labels, (2, 4, 8), S, out0=okh, out1=ovh), len(Kh))
         res[f"k3_{tag}_us"] = t; res[f"k3_{tag}_frac"] = 2 * kv_bytes / t / 1e3 / PEAK
+        if tag == "bf16":      # A/B: element-wise bf16 code (the round-1 kernel)
+            ops.lib.rtkv_debug_bf16_packed(0)
+            t = graph_time(lambda i: ops.quant_gather(Kh[i], Vh[i], None, labels, (2, 4, 8), S, out0=okh, out1=ovh), len(Kh))
+            res["k3_bf16_elementwise_us"] = t; res["k3_bf16_elementwise_frac"] = 2 * kv_bytes / t / 1e3 / PEAK
+            ops.lib.rtkv_debug_bf16_packed(1)
         del Kh, Vh
 
 if only is None or "k3ex" in only:
