@@ -392,6 +392,11 @@ RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a
  * guard, 0 element-wise code only.  Same results (per device: call with the device current). */
 RTKV_API int rtkv_debug_bf16_packed(int on);
 
+/* Testing aid: rtkv_flash_prefill kernel: 0 (default) one query tile per CTA with P in shared memory, 1 two query tiles per
+ * CTA with P in tensor memory (A operand of the second product from TMEM; measured slower).  Same results up to fp32
+ * summation order. */
+RTKV_API int rtkv_debug_flash_variant(int variant);
+
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);
 

@@ -337,6 +337,284 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
 }
 
+// ---- ping-pong variant (rtkv_debug_flash_variant(1); measured SLOWER than the kernel above: 577 vs 934 TFLOP/s at 32k) ----
+// The single-tile kernel above leaves the tensor pipe idle while its softmax warps walk through their latency chain
+// (TMEM load -> max -> exp -> P store): tensor pipe 38 % active.  The limiter turned out to be that latency chain per
+// thread, not the hand-off to the tensor pipe: with one thread per row and all 128 columns the chain doubles and the
+// ping-pong cannot hide it with one warp per (tile, scheduler).  Kept as the tested starting point for the FA4-style
+// design (it proves the TMEM-resident P operand and the TS form of tcgen05.mma).  Here a CTA owns TWO query tiles (A, B: 256 rows) of one
+// head; each has its own softmax warpgroup (a thread = one row x all 128 key columns: no exchange between threads at
+// all), its own S and O accumulators in TMEM (4 x 128 columns = all 512), and the tensor pipe alternates between them:
+// while warpgroup A runs softmax on S_A(t), the MMA thread issues P_B(t-1) V, Q_B K(t)^T, ...  P is written back to TMEM
+// over the first 64 columns of its S (two bf16/f16 per 32-bit column) and used as the A operand of the second product
+// straight from there (tcgen05.mma with A in tensor memory): no shared memory for P, which is what makes room for the
+// second Q tile.  K/V tiles are shared by both query tiles (half the L2 -> shared-memory traffic per FLOP).
+constexpr int kPPThreads = 64 + 256;
+constexpr size_t kPPSmem = 768 + 6 * (size_t)kFTileBytes + 256;          // Q_A, Q_B, K[2], V[2] + barriers
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPPThreads, 1)
+flash_prefill_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                        const __grid_constant__ CUtensorMap map_v, FlashParams p)
+{
+    extern __shared__ __align__(1024) unsigned char fp_smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)fp_smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_q = smem, *smem_k = smem + 2 * kFTileBytes, *smem_v = smem + 4 * kFTileBytes;
+    uint64_t *bars = (uint64_t *)(smem + 6 * (size_t)kFTileBytes);
+    uint64_t *qfull = bars, *kfull = bars + 1, *kempty = bars + 3, *vfull = bars + 5, *vempty = bars + 7;
+    uint64_t *sfull = bars + 9, *pfull = bars + 11, *pvdone = bars + 13;       // [2]: query tile A, B
+    uint32_t *tmem_slot = (uint32_t *)(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_qp = (p.Sq + 2 * kFT - 1) / (2 * kFT);
+    const int qp = n_qp - 1 - (int)(blockIdx.x % n_qp);          // heaviest (last) query pairs first
+    const int h = (int)((blockIdx.x / n_qp) % p.H), b = (int)(blockIdx.x / ((size_t)n_qp * p.H));
+    const int hk = h / (p.H / p.Hkv);
+    const int kv_tiles = (p.Skv + kFT - 1) / kFT;
+    int TX[2];                                                   // key tiles each query tile sees
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const int qt = 2 * qp + x;
+        TX[x] = qt * kFT < p.Sq ? ((p.causal && qt + 1 < kv_tiles) ? qt + 1 : kv_tiles) : 0;
+    }
+    const int T = TX[0] > TX[1] ? TX[0] : TX[1];
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(qfull), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&kfull[s]), 1); mbar_init(smem_u32(&kempty[s]), 1);
+            mbar_init(smem_u32(&vfull[s]), 1); mbar_init(smem_u32(&vempty[s]), 1);
+            mbar_init(smem_u32(&sfull[s]), 1); mbar_init(smem_u32(&pfull[s]), 4); mbar_init(smem_u32(&pvdone[s]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // all 512 TMEM columns: S_A [0,128), S_B [128,256), O_A [256,384), O_B [384,512); P_x = first 64 columns of S_x
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t qf = smem_u32(qfull);
+            mbar_expect_tx(qf, 2 * kFTileBytes);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const uint32_t qd = smem_u32(smem_q + (size_t)x * kFTileBytes);
+                tma_load_4d(qd, &map_q, 0, (2 * qp + x) * kFT, h, b, qf);
+                tma_load_4d(qd + kFHalf, &map_q, 64, (2 * qp + x) * kFT, h, b, qf);
+            }
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                const uint32_t par = (uint32_t)(((t >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&kempty[s]), par);
+                const uint32_t kf = smem_u32(&kfull[s]);
+                mbar_expect_tx(kf, kFTileBytes);
+                const uint32_t kd = smem_u32(smem_k + (size_t)s * kFTileBytes);
+                tma_load_4d(kd, &map_k, 0, t * kFT, hk, b, kf);
+                tma_load_4d(kd + kFHalf, &map_k, 64, t * kFT, hk, b, kf);
+                mbar_wait(smem_u32(&vempty[s]), par);
+                const uint32_t vf = smem_u32(&vfull[s]);
+                mbar_expect_tx(vf, kFTileBytes);
+                const uint32_t vd = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                tma_load_4d(vd, &map_v, 0, t * kFT, hk, b, vf);
+                tma_load_4d(vd + kFHalf, &map_v, 64, t * kFT, hk, b, vf);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread).  The tensor pipe executes in issue order, so Q_x K(t+1)^T (which overwrites S_x, hence
+        // P_x) may be issued right behind P_x(t) V(t) without any barrier in between. =====
+        if (lane == 0) {
+            auto issue_qk = [&](int x, int t) {
+                const uint32_t qbase = smem_u32(smem_q + (size_t)x * kFTileBytes);
+                const uint32_t kbase = smem_u32(smem_k + (size_t)(t & 1) * kFTileBytes);
+                const uint32_t dcol = tmem_base + (uint32_t)(x * kFT);
+#pragma unroll
+                for (int kq = 0; kq < 2; ++kq)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t off = (uint32_t)(kq * kFHalf + kk * 32);
+                        umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc_qk, (uint32_t)((kq | kk) != 0));
+                    }
+                umma_commit(smem_u32(&sfull[x]));
+            };
+            auto issue_pv = [&](int x, int t) {
+                const uint32_t vbase = smem_u32(smem_v + (size_t)(t & 1) * kFTileBytes);
+                const uint32_t pcol = tmem_base + (uint32_t)(x * kFT);              // P_x: 64 columns, 8 per 16 keys
+                const uint32_t ocol = tmem_base + (uint32_t)(2 * kFT + x * kFT);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {                                   // 16 keys per MMA
+                    const uint32_t voff = (uint32_t)(ks * 16 * 128);               // 16 key rows of 128 B in each head-dim half
+                    umma_f16_ts(ocol, pcol + (uint32_t)(ks * 8), umma_desc_sw128_mn(vbase + voff, kFHalf), p.idesc_pv,
+                                (uint32_t)((t | ks) != 0));
+                }
+                umma_commit(smem_u32(&pvdone[x]));
+            };
+            mbar_wait(smem_u32(qfull), 0);
+            mbar_wait(smem_u32(&kfull[0]), 0);
+            tc_fence_after();
+            if (TX[0] > 0) issue_qk(0, 0);
+            if (TX[1] > 0) issue_qk(1, 0);
+            umma_commit(smem_u32(&kempty[0]));
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                bool k_next_ready = false, v_ready = false;
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    if (t < TX[x]) {
+                        mbar_wait(smem_u32(&pfull[x]), (uint32_t)(t & 1));           // P_x(t) is in TMEM, O_x rescaled
+                        if (!v_ready) { mbar_wait(smem_u32(&vfull[s]), (uint32_t)((t >> 1) & 1)); v_ready = true; }
+                        tc_fence_after();
+                        issue_pv(x, t);
+                    }
+                    if (t + 1 < TX[x]) {
+                        if (!k_next_ready) { mbar_wait(smem_u32(&kfull[(t + 1) & 1]), (uint32_t)(((t + 1) >> 1) & 1)); k_next_ready = true; }
+                        tc_fence_after();
+                        issue_qk(x, t + 1);
+                    }
+                }
+                umma_commit(smem_u32(&vempty[s]));
+                if (t + 1 < T) umma_commit(smem_u32(&kempty[(t + 1) & 1]));
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: warpgroup x = query tile x; thread = one query row, all 128 key columns of a tile =====
+        const int quad = warp & 3;
+        const int x = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;
+        const int qrow0 = (2 * qp + x) * kFT;
+        const int i = qrow0 + row;                             // query index
+        const int Tx = TX[x];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t s_col = lane_base + (uint32_t)(x * kFT), o_col = lane_base + (uint32_t)(2 * kFT + x * kFT);
+        float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;
+        for (int t = 0; t < Tx; ++t) {
+            mbar_wait(smem_u32(&sfull[x]), (uint32_t)(t & 1));
+            tc_fence_after();
+            uint32_t raw[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32_issue(s_col + (uint32_t)(32 * c), raw[c]);
+            tmem_ld_wait();
+            const int j0 = t * kFT;
+            const bool need_mask = (p.causal && j0 + kFT - 1 > qrow0) || (j0 + kFT > p.Skv);
+            float mx = -INFINITY;
+            if (need_mask) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int j = j0 + 32 * c + e;
+                        const bool dead = j >= p.Skv || (p.causal && j > i);
+                        mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(raw[c][e]));
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(raw[c][e]));
+            }
+            mx *= p.scale_log2;                                  // log2 domain from here
+            float alpha = 1.0f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f) {                            // lazy rescale (see the single-tile kernel)
+                rescale = m_used != -INFINITY;
+                alpha = rescale ? ex2_approx(m_used - mx) : 0.0f;
+                m_used = mx;
+            }
+            if (__any_sync(0xffffffffu, rescale)) {
+                mbar_wait(smem_u32(&pvdone[x]), (uint32_t)((t - 1) & 1));          // P_x(t-1) V(t-1) has retired: O_x stable
+                tc_fence_after();
+                const float a = rescale ? alpha : 1.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(o_col + (uint32_t)(32 * c), o);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * a);
+                    tmem_st32(o_col + (uint32_t)(32 * c), o);
+                }
+                tmem_st_wait();
+            }
+            if (rescale) { l *= alpha; mass_acc *= alpha; }
+            // p = 2^(s*scale - m) -> packed pairs written over the first 64 columns of S_x
+            float rs = 0.0f, ps = 0.0f;
+            const bool slow = need_mask || t == 0;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int c = 2 * c2 + (u >> 4), e = 2 * (u & 15);
+                    float p0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e]), p.scale_log2, -m_used));
+                    float p1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e + 1]), p.scale_log2, -m_used));
+                    if (slow) {
+                        const int j = j0 + 32 * c + e;
+                        if (j >= p.Skv || (p.causal && j > i)) p0 = 0.0f;
+                        if (j + 1 >= p.Skv || (p.causal && j + 1 > i)) p1 = 0.0f;
+                        if (t == 0) ps += (j < p.P ? p0 : 0.0f) + (j + 1 < p.P ? p1 : 0.0f);
+                    }
+                    rs += p0 + p1;
+                    pk[u] = pack2<BF16>(p0, p1);
+                }
+                tmem_st32(s_col + (uint32_t)(32 * c2), pk);
+            }
+            tmem_st_wait();
+            l += rs;
+            if (t == 0) mass_acc = ps;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&pfull[x]));
+        }
+        if (Tx > 0) {
+            mbar_wait(smem_u32(&pvdone[x]), (uint32_t)((Tx - 1) & 1));
+            tc_fence_after();
+            const float inv_l = 1.0f / l;
+            const bool live = i < p.Sq;
+            unsigned char *orow = (unsigned char *)p.out + ((size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)i * p.o_ss) * 2;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t o[32];
+                tmem_ld32(o_col + (uint32_t)(32 * c), o);
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack2<BF16>(__uint_as_float(o[8 * q + 2 * e]) * inv_l, __uint_as_float(o[8 * q + 2 * e + 1]) * inv_l);
+                        *reinterpret_cast<uint4 *>(orow + (size_t)(32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            if (live) {
+                const size_t at = ((size_t)b * p.H + h) * p.Sq + i;
+                if (p.lse) p.lse[at] = (m_used + log2f(l)) * 0.6931471805599453f;
+                if (p.head_sums) p.head_sums[at] = mass_acc * inv_l;
+            }
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // [B,H,S,128] view with unit stride in the last dim -> 4-D tensor map {128, S, H, B}, box {64, 128, 1, 1}, 128-byte swizzle
 static int encode_bhsd_map(CUtensorMap *map, const void *base, int dtype, int B, int H, int S, int64_t sb, int64_t sh, int64_t ss)
 {
@@ -356,6 +634,14 @@ static int encode_bhsd_map(CUtensorMap *map, const void *base, int dtype, int B,
 } // namespace rtkv
 
 using namespace rtkv;
+
+static int g_flash_variant = 0;     // 0: one query tile per CTA, P in shared memory (default, faster); 1: two query tiles per CTA, P in TMEM
+extern "C" int rtkv_debug_flash_variant(int variant)
+{
+    RTKV_CHECK_ARG(variant == 0 || variant == 1, "rtkv_debug_flash_variant: 0 or 1");
+    g_flash_variant = variant;
+    return RTKV_OK;
+}
 
 extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, int dtype, int B, int H, int Hkv, int Sq, int Skv, int D,
                                   const int64_t *q_strides, const int64_t *k_strides, const int64_t *v_strides,
@@ -394,6 +680,20 @@ extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, i
     const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
     p.idesc_qk = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kFT >> 3) << 17) | ((uint32_t)(kFT >> 4) << 24);
     p.idesc_pv = p.idesc_qk | (1u << 16);                       // B operand (V) is MN-major
+    if (g_flash_variant == 1) {          // two query tiles per CTA, P in tensor memory
+        const int n_qp = (Sq + 2 * kFT - 1) / (2 * kFT);
+        const long long ctas2 = (long long)n_qp * H * B;
+        RTKV_CHECK_ARG(ctas2 < (1ll << 31), "rtkv_flash_prefill: too many tiles");
+        if (dtype == RTKV_BF16) {
+            RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPPSmem));
+            flash_prefill_pp_kernel<true><<<dim3((unsigned)ctas2), kPPThreads, kPPSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+        } else {
+            RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPPSmem));
+            flash_prefill_pp_kernel<false><<<dim3((unsigned)ctas2), kPPThreads, kPPSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+        }
+        RTKV_LAUNCH_CHECK("flash_prefill_pp_kernel");
+        return RTKV_OK;
+    }
     const int n_qt = (Sq + kFT - 1) / kFT;
     const long long ctas = (long long)n_qt * H * B;
     RTKV_CHECK_ARG(ctas < (1ll << 31), "rtkv_flash_prefill: too many tiles");

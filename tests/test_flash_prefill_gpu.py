@@ -50,8 +50,17 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["one-tile-P-in-smem", "two-tiles-P-in-TMEM"])
+def variant(request, ops):
+    """Both kernels behind rtkv_flash_prefill: 0 = one query tile per CTA, P in shared memory (default), 1 = two query tiles per
+    CTA, P in tensor memory."""
+    ops.lib.rtkv_debug_flash_variant(request.param)
+    yield request.param
+    ops.lib.rtkv_debug_flash_variant(0)
+
+
 @pytest.mark.parametrize("B,H,Hkv,Sq,Skv,causal,P,dtype,qscale", CASES)
-def test_flash_prefill_matches_fp32_reference(ops, B, H, Hkv, Sq, Skv, causal, P, dtype, qscale):
+def test_flash_prefill_matches_fp32_reference(ops, variant, B, H, Hkv, Sq, Skv, causal, P, dtype, qscale):
     g = torch.Generator(device="cuda").manual_seed(Sq * 7 + Skv)
     D = 128
     q = (torch.randn(B, H, Sq, D, generator=g, device="cuda") * qscale).to(dtype)
@@ -68,7 +77,7 @@ def test_flash_prefill_matches_fp32_reference(ops, B, H, Hkv, Sq, Skv, causal, P
         torch.testing.assert_close(hs, want_hs, rtol=2e-3, atol=1e-6)     # ex2.approx + fp32 sums
 
 
-def test_flash_prefill_strided_inputs_and_bshd_output(ops):
+def test_flash_prefill_strided_inputs_and_bshd_output(ops, variant):
     """Inputs as the transposed view of [B,S,H,D] projections (what the model hook holds), output written as [B,S,H,D]."""
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, S, D = 2, 4, 333, 128
@@ -84,7 +93,7 @@ def test_flash_prefill_strided_inputs_and_bshd_output(ops):
     torch.testing.assert_close(hs, want_hs, rtol=2e-3, atol=1e-6)
 
 
-def test_flash_prefill_prompt_mass_feeds_the_compressor(ops):
+def test_flash_prefill_prompt_mass_feeds_the_compressor(ops, variant):
     """head_sums -> rtkv_mass_from_head_sums == the mass K1a computes from materialised probabilities, within the
     tolerance the scoring kernel is held to (2e-4 relative in test_qk_scoring_matches_restatement)."""
     import rtkv
