@@ -575,7 +575,82 @@ def bench_head_sharded(args, rtkv, ops, layers, cfg, config, dev, rank, world, L
                          "p2p": "NCCL all-gather of the mass partials + row min/max mailboxes inside the quantise kernel"}[mode],
             "exchange_error": xerr,
             "exchange_bytes_per_layer_per_rank": {"sent": B * S * 32 * (world - 1) if mode == "fused" else None}}
+    if not args.no_e2e:
+        line["e2e"] = e2e_head_sharded(args, sharded, layers, dev, world, L, S, B, w, dist)
     return line, run, graph
+
+
+def e2e_head_sharded(args, sharded, layers, dev, world, L, S, B, w, dist):
+    """End to end for the head-sharded job: every rank's K, V and attention slices start in pinned HOST memory and its slice of
+    the compressed K/V ends there.  Per layer: H2D of the three input slices (copy stream, one layer ahead), the sharded layer
+    through the public call HeadShardedCompressor.compress_layer_kv_cache (it synchronises once: S' is a shape), D2H of the
+    [B,S',w] results (download stream).  All N ranks run it together (the exchange is per layer); max over ranks."""
+    n_host = max(1, min(L, 8))
+    host_in = []
+    for j in range(n_host):
+        l, K, V, A = layers[j * L // n_host]
+        hk, hv, ha = (torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (K, V, A))
+        hk.copy_(K, non_blocking=True); hv.copy_(V, non_blocking=True); ha.copy_(A, non_blocking=True)
+        host_in.append((hk, hv, ha))
+    torch.cuda.synchronize()
+    _, K0, V0, A0 = layers[0]
+    dbuf = [(torch.empty_like(K0), torch.empty_like(V0), torch.empty_like(A0)) for _ in range(2)]
+    hout = [(torch.empty(B, S, w, dtype=K0.dtype, pin_memory=True), torch.empty(B, S, w, dtype=K0.dtype, pin_memory=True))
+            for _ in range(2)]
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]          # device input buffers consumed by the layer
+    ev_down = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(j):
+        hk, hv, ha = host_in[j * n_host // L]
+        dk, dv, da = dbuf[j & 1]
+        with torch.cuda.stream(up):
+            up.wait_event(ev_free[j & 1])
+            da.copy_(ha, non_blocking=True); dk.copy_(hk, non_blocking=True); dv.copy_(hv, non_blocking=True)
+            ev_up[j & 1].record(up)
+
+    def step():
+        d2h = 0
+        for e in ev_free + ev_down:
+            e.record(main)
+        upload(0)
+        for j, (l, _, _, _) in enumerate(layers):
+            if j + 1 < L:
+                upload(j + 1)
+            main.wait_event(ev_up[j & 1])
+            dk, dv, da = dbuf[j & 1]
+            k_sel, v_sel, sel = sharded.compress_layer_kv_cache(dk, dv, da, l)
+            ev_free[j & 1].record(main)
+            ok, ov = hout[j & 1]
+            with torch.cuda.stream(down):
+                down.wait_stream(main)
+                down.wait_event(ev_down[j & 1])
+                ms = k_sel.shape[1]
+                ok[:, :ms].copy_(k_sel, non_blocking=True); ov[:, :ms].copy_(v_sel, non_blocking=True)
+                ev_down[j & 1].record(down)
+            k_sel.record_stream(down); v_sel.record_stream(down)
+            d2h += 2 * k_sel.numel() * k_sel.element_size()
+        torch.cuda.synchronize()
+        return d2h
+
+    step()
+    dist.barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d2h = step()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = L * sum(x.numel() * x.element_size() for x in host_in[0])
+    return {"value": B * S / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "per_rank_h2d_bytes_per_step": h2d,
+            "host_input_sets": n_host,
+            "api": "HeadShardedCompressor.compress_layer_kv_cache per rank on slices that start in pinned host memory and end there "
+                   "(H2D one layer ahead on a copy stream, D2H on a download stream); bytes are the totals over all ranks"}
 
 
 # ----------------------------------------------------------------------------- main
