@@ -28,8 +28,8 @@ constexpr int kTileM = 128;      // query rows per CTA
 constexpr int kTileN = 128;      // prompt keys (P <= 128)
 constexpr int kHeadDim = 128;    // K of the GEMM
 constexpr int kKBlock = 64;      // elements per 128-byte swizzle atom row
-constexpr int kStages = 6;       // Q-tile ring (192 KiB in flight per SM)
-constexpr int kKBufs = 1;        // K_prompt tile buffers (1: reloaded at item boundaries after the item's MMAs retire)
+constexpr int kStages = 5;       // Q-tile ring (160 KiB in flight per SM)
+constexpr int kKBufs = 2;        // K_prompt tile buffers: the next work item's tile loads while this item's MMAs run
 constexpr int kOperandBytes = kTileM * kHeadDim * 2;          // 32 KiB: one Q (or K) tile
 constexpr int kQkThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps
 // smem: 2 K tiles (double buffered across work items) + kStages Q tiles + barriers + row-sum exchange
@@ -182,8 +182,36 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kTileN);
                 float rs = 0.0f;
                 uint32_t v0[32], v1[32];
-                if (p.dbg < 2 || p.dbg == 3) {
-                    // software pipeline: the TMEM load of the next 32 columns is in flight during the exp math
+                if (p.dbg == 0 && unmasked) {
+                    // the common tile: every row sees all 128 prompt keys -> FFMA + MUFU.EX2 + FADD per element, nothing else
+                    // (four partial sums break the serial FADD chain); TMEM loads one chunk ahead of the math.  ncu on the
+                    // round-1 loop showed the per-element mask select executed on every tile: this path took 77.6 -> 65 us at C3.
+                    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+                    tmem_ld32_issue(tbase, v0);
+#pragma unroll
+                    for (int cc = 0; cc < kTileN; cc += 64) {
+                        tmem_ld_wait();
+                        tmem_ld32_issue(tbase + cc + 32, v1);
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            r0 += ex2_approx(__fmaf_rn(__uint_as_float(v0[e]), p.scale_log2, -l2));
+                            r1 += ex2_approx(__fmaf_rn(__uint_as_float(v0[e + 1]), p.scale_log2, -l2));
+                            r2 += ex2_approx(__fmaf_rn(__uint_as_float(v0[e + 2]), p.scale_log2, -l2));
+                            r3 += ex2_approx(__fmaf_rn(__uint_as_float(v0[e + 3]), p.scale_log2, -l2));
+                        }
+                        tmem_ld_wait();
+                        if (cc + 64 < kTileN) tmem_ld32_issue(tbase + cc + 64, v0);
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            r0 += ex2_approx(__fmaf_rn(__uint_as_float(v1[e]), p.scale_log2, -l2));
+                            r1 += ex2_approx(__fmaf_rn(__uint_as_float(v1[e + 1]), p.scale_log2, -l2));
+                            r2 += ex2_approx(__fmaf_rn(__uint_as_float(v1[e + 2]), p.scale_log2, -l2));
+                            r3 += ex2_approx(__fmaf_rn(__uint_as_float(v1[e + 3]), p.scale_log2, -l2));
+                        }
+                    }
+                    rs = (r0 + r1) + (r2 + r3);
+                } else if (p.dbg < 2 || p.dbg == 3) {
+                    // masked tiles (the first query tile under a causal mask, P < 128) and the bisecting modes
                     tmem_ld32_issue(tbase, v0);
 #pragma unroll
                     for (int cc = 0; cc < kTileN; cc += 64) {
@@ -281,9 +309,18 @@ extern "C" int rtkv_prompt_mass_qk(const void *Q, const void *Kp, const float *l
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     // Query tiles per work item: as many as possible (each item loads its head's K_prompt tile once)
     // while keeping at least ~1.5 items per SM for balance.
+    // Query tiles per work item (each item loads its head's K_prompt tile once): the power of two that minimises the busiest
+    // SM's tile count, an item switch charged as half a tile (round 1 required >= 1.5 items per SM, which left 256 items of 32
+    // tiles on 148 SMs at 32k tokens: the busiest SM did 64 tiles against an average of 55).
     const int tiles = (S + kTileM - 1) / kTileM;
     int T = 1;
-    while (T * 2 <= tiles && (long long)((tiles + 2 * T - 1) / (2 * T)) * H * B * 2 >= 3LL * sm_count) T *= 2;
+    double best = 1e30;
+    for (int t = 1; t <= tiles; t *= 2) {
+        const long long items = (long long)((tiles + t - 1) / t) * H * B;
+        const long long per_sm = (items + sm_count - 1) / sm_count;
+        const double cost = (double)per_sm * (t + 0.5);
+        if (cost < best) { best = cost; T = t; }
+    }
     p.tiles_per_item = T;
     p.dbg = g_qk_dbg;
     const long long n_items = (long long)((tiles + T - 1) / T) * H * B;
