@@ -235,6 +235,17 @@ RTKV_API int rtkv_shard_stats_combine(const void *A, int a_dtype, int B, int H_l
                       int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
                       const uint64_t *xbuf_ptrs /*[host]*/, int rank, int world, uint32_t *state, int H,
                       float *mass, float *minmax, void *stream);
+/* Same, and additionally reduces the mass RANGE of every batch row into mass_range [B][4] u32 = (min, max of the selection
+ * kernel's descending sort key over the row's mass, NaN flag, pad), which must hold (0xffffffff, 0, 0, 0) on entry.
+ * rtkv_score_select_ranged consumes it (skipping its own pass over the mass and one cross-CTA step) and resets it. */
+RTKV_API int rtkv_shard_stats_combine_ranged(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh,
+                      int64_t si, int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
+                      const uint64_t *xbuf_ptrs /*[host]*/, int rank, int world, uint32_t *state, int H,
+                      float *mass, float *minmax, uint32_t *mass_range, void *stream);
+RTKV_API int rtkv_score_select_ranged(const float *mass, uint32_t *mass_range, float *scores, uint8_t *labels, uint8_t *mask,
+                      int32_t *sel_idx, rtkv_row_stats *row_stats, rtkv_layer_stats *layer_stats,
+                      const void *scratch, size_t scratch_bytes, int B, int S,
+                      const rtkv_layer_params *params /*[host]*/, int flags, void *stream);
 RTKV_API int rtkv_quant_gather_token_minmax(const void *X0, const void *X1, int dtype, int B, int S, int n,
                       const int32_t *sel_idx, const rtkv_row_stats *row_stats,
                       const uint8_t *labels, const int32_t *bits /*[host]*/, int out_rows, int zero_pad,
@@ -386,7 +397,7 @@ RTKV_API int rtkv_debug_shard_grid(int max_ctas);
 RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a_dtype, int B, int H_local, int S, int64_t sb,
                       int64_t sh, int64_t si, int P, int group_size, const void *const *K, const void *const *V, int kv_dtype,
                       int n_local, const uint64_t *xbuf_ptrs, int world, uint32_t *const *state, int H, float *const *mass,
-                      float *const *minmax, void *params_scratch, void *stream);
+                      float *const *minmax, uint32_t *const *mass_range /*NULL or [world]*/, void *params_scratch, void *stream);
 
 /* Testing aid: bf16 rows of rtkv_quant_gather*: 1 (default) packed two-elements-per-instruction path for rows inside its
  * guard, 0 element-wise code only.  Same results (per device: call with the device current). */

@@ -43,6 +43,7 @@ struct ShardParams {
     // fused combine (rtkv_shard_stats_combine): this rank's outputs, NULL = publish only
     float *mass, *minmax;
     float fH;
+    unsigned *mass_range;             // optional [B][4] (min key, max key, NaN flag, pad): see rtkv_score_select_ranged
 };
 
 __device__ __forceinline__ void st_sys_v4(void *p, float a, float b, float c, float d)
@@ -72,7 +73,18 @@ __device__ __forceinline__ size_t record_offset(unsigned parity, int world, int 
 }
 
 // mass and whole-row min/max of one token from the R records of epoch `parity` in this rank's exchange buffer
-__device__ __forceinline__ void combine_token(const char *xlocal, unsigned parity, int world, int gpr, int rec_vecs, int64_t rows,
+// == score_key_desc of score_select.cuh (torch.argsort(descending) order: NaN first, -0 == +0): the mass range handed
+// to the selection kernel is expressed in its key domain
+__device__ __forceinline__ unsigned mass_key_desc(float s)
+{
+    if (s != s) return 0u;
+    unsigned u = __float_as_uint(s);
+    if (u == 0x80000000u) u = 0u;
+    const unsigned asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~asc;
+}
+
+__device__ __forceinline__ float combine_token(const char *xlocal, unsigned parity, int world, int gpr, int rec_vecs, int64_t rows,
                                               int64_t t, float fH, float *__restrict__ mass, float *__restrict__ minmax)
 {
     float tot = 0.0f;
@@ -94,9 +106,11 @@ __device__ __forceinline__ void combine_token(const char *xlocal, unsigned parit
         kmn = fminf(kmn, m.x); kmx = fmaxf(kmx, m.y); vmn = fminf(vmn, m.z); vmx = fmaxf(vmx, m.w);
     }
     const float qnan = __int_as_float(0x7fc00000);
-    mass[t] = __fdiv_rn(tot, fH);
+    const float m = __fdiv_rn(tot, fH);
+    mass[t] = m;
     float4 o = make_float4(knan ? qnan : kmn, knan ? qnan : kmx, vnan ? qnan : vmn, vnan ? qnan : vmx);
     *reinterpret_cast<float4 *>(minmax + 4 * t) = o;
+    return m;
 }
 
 // End of a statistics kernel: every record of this rank must be visible at every peer before the epoch flag is.
@@ -438,13 +452,43 @@ __device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, co
                 if (p.rank == sdst) mine = p.xbuf[sdst];
             const int per_blk = c.rb;
             const int64_t my_blocks = cta < n_blocks ? (n_blocks - cta + n_ctas - 1) / n_ctas : 0;
+            unsigned rk_min = 0xffffffffu, rk_max = 0u, rk_nan = 0u;       // this thread's share of the row's mass range
+            int rk_b = -1;
             for (int64_t idx = threadIdx.x; idx < my_blocks * per_blk; idx += kStagedConsumers * 32) {
                 const int64_t blk = cta + (idx / per_blk) * n_ctas;
                 const int r = (int)(idx % per_blk);
                 const int b = (int)(blk / bpb);
                 const int i = (int)(blk - (int64_t)b * bpb) * c.rb + r;
-                if (i < p.S)
-                    combine_token((const char *)mine, parity, p.world, p.ng, p.rec_vecs, rows, (int64_t)b * p.S + i, p.fH, p.mass, p.minmax);
+                if (i < p.S) {
+                    const float m = combine_token((const char *)mine, parity, p.world, p.ng, p.rec_vecs, rows, (int64_t)b * p.S + i, p.fH,
+                                                  p.mass, p.minmax);
+                    if (p.mass_range) {
+                        if (b != rk_b && rk_b >= 0) {                  // batch row changed: flush (rare)
+                            atomicMin(p.mass_range + 4 * rk_b, rk_min); atomicMax(p.mass_range + 4 * rk_b + 1, rk_max);
+                            if (rk_nan) atomicOr(p.mass_range + 4 * rk_b + 2, 1u);
+                            rk_min = 0xffffffffu; rk_max = 0u; rk_nan = 0u;
+                        }
+                        rk_b = b;
+                        const unsigned k = mass_key_desc(m);
+                        rk_min = k < rk_min ? k : rk_min; rk_max = k > rk_max ? k : rk_max; rk_nan |= (m != m);
+                    }
+                }
+            }
+            if (p.mass_range) {
+                // one REDUX per value when the whole warp worked on the same batch row (always, for B = 1), else per thread
+                const int b0 = __shfl_sync(0xffffffffu, rk_b, 0);
+                if (__all_sync(0xffffffffu, rk_b == b0 || rk_b < 0)) {
+                    const unsigned wmin = __reduce_min_sync(0xffffffffu, rk_min), wmax = __reduce_max_sync(0xffffffffu, rk_max);
+                    const unsigned wnan = __reduce_or_sync(0xffffffffu, rk_nan);
+                    const int bb = __reduce_max_sync(0xffffffffu, rk_b);
+                    if (lane == 0 && bb >= 0) {
+                        atomicMin(p.mass_range + 4 * bb, wmin); atomicMax(p.mass_range + 4 * bb + 1, wmax);
+                        if (wnan) atomicOr(p.mass_range + 4 * bb + 2, 1u);
+                    }
+                } else if (rk_b >= 0) {
+                    atomicMin(p.mass_range + 4 * rk_b, rk_min); atomicMax(p.mass_range + 4 * rk_b + 1, rk_max);
+                    if (rk_nan) atomicOr(p.mass_range + 4 * rk_b + 2, 1u);
+                }
             }
         }
     }
@@ -535,7 +579,7 @@ static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int 
                             int P, int group_size, const void *K, const void *V, int kv_dtype, int n_local,
                             const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, int H_total, float *mass,
                             float *minmax, void *stream, ShardParams *capture_p = nullptr, StagedCfg *capture_c = nullptr,
-                            int *capture_grid = nullptr, size_t *capture_smem = nullptr)
+                            int *capture_grid = nullptr, size_t *capture_smem = nullptr, uint32_t *mass_range = nullptr)
 {
     RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state, "rtkv_shard_stats: null pointer");
     RTKV_CHECK_ARG(a_dtype == RTKV_F32, "rtkv_shard_stats: head sharding needs float32 probabilities "
@@ -560,7 +604,7 @@ static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int 
     for (int s = 0; s < 8; ++s) p.xbuf[s] = s < world ? xbuf_ptrs[s] : 0ull;
     for (int s = 0; s < world; ++s) RTKV_CHECK_ARG(p.xbuf[s] && p.xbuf[s] % 16 == 0, "rtkv_shard_stats: exchange buffer %d", s);
     p.state = state;
-    p.mass = mass; p.minmax = minmax; p.fH = (float)H_total;
+    p.mass = mass; p.minmax = minmax; p.fH = (float)H_total; p.mass_range = mass_range;
     const bool vec = ((uintptr_t)A % 16 == 0) && (sb * 4) % 16 == 0 && (sh * 4) % 16 == 0 && (si * 4) % 16 == 0;
     const int64_t rows = (int64_t)B * S;
     // staged path: every copy must be a 16-byte multiple at a 16-byte aligned address, P <= 128 columns, and the
@@ -631,11 +675,23 @@ extern "C" int rtkv_shard_stats_combine(const void *A, int a_dtype, int B, int H
                             state, H, mass, minmax, stream);
 }
 
+extern "C" int rtkv_shard_stats_combine_ranged(const void *A, int a_dtype, int B, int H_local, int S, int64_t sb, int64_t sh,
+                                               int64_t si, int P, int group_size, const void *K, const void *V, int kv_dtype,
+                                               int n_local, const uint64_t *xbuf_ptrs, int rank, int world, uint32_t *state, int H,
+                                               float *mass, float *minmax, uint32_t *mass_range, void *stream)
+{
+    RTKV_CHECK_ARG(mass && minmax && mass_range && H > 0, "rtkv_shard_stats_combine_ranged: null output");
+    RTKV_CHECK_ARG((uintptr_t)minmax % 16 == 0, "rtkv_shard_stats_combine_ranged: minmax must be 16-byte aligned");
+    return shard_stats_impl(A, a_dtype, B, H_local, S, sb, sh, si, P, group_size, K, V, kv_dtype, n_local, xbuf_ptrs, rank, world,
+                            state, H, mass, minmax, stream, nullptr, nullptr, nullptr, nullptr, mass_range);
+}
+
 extern "C" int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a_dtype, int B, int H_local, int S, int64_t sb,
                                                        int64_t sh, int64_t si, int P, int group_size, const void *const *K,
                                                        const void *const *V, int kv_dtype, int n_local, const uint64_t *xbuf_ptrs,
                                                        int world, uint32_t *const *state, int H, float *const *mass,
-                                                       float *const *minmax, void *params_scratch, void *stream)
+                                                       float *const *minmax, uint32_t *const *mass_range, void *params_scratch,
+                                                       void *stream)
 {
     RTKV_CHECK_ARG(A && K && V && xbuf_ptrs && state && mass && minmax && params_scratch, "rtkv_debug_shard_stats_combine_allranks: null pointer");
     RTKV_CHECK_ARG(world >= 1 && world <= 8, "rtkv_debug_shard_stats_combine_allranks: bad world");
@@ -651,7 +707,7 @@ extern "C" int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int
     int rc = RTKV_OK;
     for (int r = 0; r < world && !rc; ++r)
         rc = shard_stats_impl(A[r], a_dtype, B, H_local, S, sb, sh, si, P, group_size, K[r], V[r], kv_dtype, n_local, xbuf_ptrs, r,
-                              world, state[r], H, mass[r], minmax[r], stream, &ps[r], &c, &grid, &smem);
+                              world, state[r], H, mass[r], minmax[r], stream, &ps[r], &c, &grid, &smem, mass_range ? mass_range[r] : nullptr);
     g_shard_grid_cap = saved_cap;
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;

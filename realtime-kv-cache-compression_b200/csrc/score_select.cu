@@ -50,7 +50,16 @@ __global__ void __launch_bounds__(kT, 1) score_select_kernel(K2Params p)
     const float *__restrict__ ms = p.mass ? p.mass + (int64_t)b * S : nullptr;
     const float *__restrict__ tab = p.log_tab;
     float mn = 0.0f, den = 0.0f;
-    if (p.flags & RTKV_FROM_MASS) {
+    if ((p.flags & RTKV_FROM_MASS) && p.mass_range) {
+        const volatile unsigned *mr = p.mass_range + 4 * b;
+        const unsigned kmin = mr[0], kmax = mr[1], nan = mr[2];
+        __syncthreads();                                // everybody has read it ...
+        if (threadIdx.x == 0) { unsigned *w = p.mass_range + 4 * b; w[0] = 0xffffffffu; w[1] = 0u; w[2] = 0u; }   // ... reset for the next layer
+        mn = score_of_key(kmax);
+        float mx = score_of_key(kmin);
+        if (nan) mn = mx = __int_as_float(0x7fc00000);
+        den = rnd_dt(__fsub_rn(mx, mn), p.score_dt);
+    } else if (p.flags & RTKV_FROM_MASS) {
         RowAgg a = agg_identity();                      // kmin/kmax hold the mass range as walk keys
         for (int i0 = threadIdx.x; i0 < S; i0 += 4 * kT) {
             float v[4];
@@ -318,10 +327,34 @@ extern "C" int rtkv_scratch_init(void *scratch, size_t bytes, void *stream)
     return RTKV_OK;
 }
 
+static int score_select_impl(const float *mass, uint32_t *mass_range, float *scores, uint8_t *labels, uint8_t *mask,
+                             int32_t *sel_idx, rtkv_row_stats *row_stats,
+                             rtkv_layer_stats *layer_stats, const void *scratch, size_t scratch_bytes,
+                             int B, int S, const rtkv_layer_params *prm, int flags, void *stream);
+
 extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labels, uint8_t *mask,
                                  int32_t *sel_idx, rtkv_row_stats *row_stats,
                                  rtkv_layer_stats *layer_stats, const void *scratch, size_t scratch_bytes,
                                  int B, int S, const rtkv_layer_params *prm, int flags, void *stream)
+{
+    return score_select_impl(mass, nullptr, scores, labels, mask, sel_idx, row_stats, layer_stats, scratch, scratch_bytes, B, S, prm,
+                             flags, stream);
+}
+
+extern "C" int rtkv_score_select_ranged(const float *mass, uint32_t *mass_range, float *scores, uint8_t *labels, uint8_t *mask,
+                                        int32_t *sel_idx, rtkv_row_stats *row_stats,
+                                        rtkv_layer_stats *layer_stats, const void *scratch, size_t scratch_bytes,
+                                        int B, int S, const rtkv_layer_params *prm, int flags, void *stream)
+{
+    RTKV_CHECK_ARG(mass && mass_range && (flags & RTKV_FROM_MASS), "rtkv_score_select_ranged: needs mass, mass_range and RTKV_FROM_MASS");
+    return score_select_impl(mass, mass_range, scores, labels, mask, sel_idx, row_stats, layer_stats, scratch, scratch_bytes, B, S,
+                             prm, flags, stream);
+}
+
+static int score_select_impl(const float *mass, uint32_t *mass_range, float *scores, uint8_t *labels, uint8_t *mask,
+                             int32_t *sel_idx, rtkv_row_stats *row_stats,
+                             rtkv_layer_stats *layer_stats, const void *scratch, size_t scratch_bytes,
+                             int B, int S, const rtkv_layer_params *prm, int flags, void *stream)
 {
     RTKV_CHECK_ARG(prm, "rtkv_score_select: params is null");
     RTKV_CHECK_ARG(B > 0 && S > 0, "rtkv_score_select: bad shape B=%d S=%d", B, S);
@@ -334,7 +367,7 @@ extern "C" int rtkv_score_select(const float *mass, float *scores, uint8_t *labe
         for (int c = 0; c < 3; ++c)
             RTKV_CHECK_ARG(prm->bits[c] >= 1 && prm->bits[c] <= 24, "rtkv_score_select: bits[%d]=%d outside 1..24", c, prm->bits[c]);
     K2Params p;
-    p.mass = mass; p.scores = scores; p.labels = labels; p.mask = mask; p.sel_idx = sel_idx;
+    p.mass = mass; p.mass_range = mass_range; p.scores = scores; p.labels = labels; p.mask = mask; p.sel_idx = sel_idx;
     p.row_stats = row_stats; p.layer_stats = layer_stats;
     p.dbg = g_k2_dbg;
     p.log_tab = nullptr; p.log_tab_len = 0;

@@ -16,6 +16,8 @@ constexpr int kMaxDepth = 8;
 
 struct K2Params {
     const float *mass;
+    unsigned *mass_range;   // optional [B][4]: min / max of score_key_desc over the row's mass, NaN flag, pad - produced by the
+                            // head-sharding exchange kernel; consumed and reset to (0xffffffff, 0, 0) here
     long long *dbg;
     const float *log_tab;   // (float)log((double)(i+1)), i < log_tab_len; NULL: compute in place
     int log_tab_len;

@@ -155,7 +155,15 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
 
     // ---- mass range over the whole row ----
     float mn = 0.0f, den = 0.0f;
-    if (p.flags & RTKV_FROM_MASS) {
+    if ((p.flags & RTKV_FROM_MASS) && p.mass_range) {
+        // the exchange kernel already reduced the row's mass range (rtkv_shard_stats_combine): no pass, no cluster step
+        const volatile unsigned *mr = p.mass_range + 4 * b;
+        const unsigned kmin = mr[0], kmax = mr[1], nan = mr[2];
+        mn = score_of_key(kmax);
+        float mx = score_of_key(kmin);
+        if (nan) mn = mx = __int_as_float(0x7fc00000);
+        den = rnd_dt(__fsub_rn(mx, mn), p.score_dt);
+    } else if (p.flags & RTKV_FROM_MASS) {
         RowAgg a = agg_identity();
         for (int i0 = beg + threadIdx.x; i0 < end; i0 += 4 * kT) {
             float v[4];
@@ -431,6 +439,10 @@ __global__ void __launch_bounds__(kT, 1) score_select_cluster_kernel(K2Params p)
     }
     // no CTA touches another CTA's shared memory after the last all-gather: non-root CTAs may leave
     if (rank != 0) return;
+    if (p.mass_range && threadIdx.x == 0) {       // every CTA read the range before the cluster steps above: reset it for the next layer
+        unsigned *mr = p.mass_range + 4 * b;
+        mr[0] = 0xffffffffu; mr[1] = 0u; mr[2] = 0u;
+    }
     ctick(sm);   // emit done
     if (threadIdx.x == 0 && sm.dbg) sm.dbg[0] = sm.dbg_n;
 

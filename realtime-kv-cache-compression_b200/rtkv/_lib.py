@@ -95,6 +95,12 @@ PROTOTYPES = {
                                                 ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
                                                 c_vp, c_vp, c_vp]),
+    "rtkv_shard_stats_combine_ranged": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64, c_i64, c_i64,
+                                                       ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                                       ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
+                                                       c_vp, c_vp, c_vp, c_vp]),
+    "rtkv_score_select_ranged": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t,
+                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(LayerParams), ctypes.c_int, c_vp]),
     "rtkv_shard_combine": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
                                           c_vp]),
     "rtkv_quant_gather_token_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -144,7 +150,8 @@ PROTOTYPES = {
                                                                ctypes.c_int, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                                                ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int,
                                                                ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.POINTER(c_vp),
-                                                               ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp]),
+                                                               ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp,
+                                                               c_vp]),
     "rtkv_debug_qk_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "rtkv_ctx_destroy": (ctypes.c_int, [c_vp]),

@@ -116,6 +116,7 @@ class ShardExchange:
         self.mass = torch.empty(batch, seq_len, dtype=torch.float32, device=device)
         self.minmax = torch.empty(batch, seq_len, 4, dtype=torch.float32, device=device)
         self.concurrent = True                         # one process per rank: all ranks run the same kernel at the same time
+        self.mass_range = ops.new_mass_range(batch, device)   # reduced by the exchange kernel, consumed + reset by K2
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                       # every buffer is zeroed before anybody writes
 
@@ -172,6 +173,7 @@ class HeadShardedCompressor:
         self.p2p = self.mode == "p2p"
         self.mailbox = None
         self.exchange = exchange
+        self._range_pending = False
 
     def _mailbox(self, batch, rows, device):
         if self.mailbox is None or not self.mailbox.fits(batch, rows):
@@ -216,8 +218,12 @@ class HeadShardedCompressor:
         P, gs = self.compressor.prompt_length(S), self.num_heads // N_GROUPS
         if getattr(x, "concurrent", False) and not getattr(self, "_two_kernels", False):
             try:
-                return ops.shard_stats_combine(attention_local, key_local, value_local, P, gs, x.ptrs, x.rank, x.world,
-                                               x.state, self.num_heads, x.mass, x.minmax)
+                if self._range_pending:          # the previous layer's selection never consumed (and reset) the range
+                    x.mass_range.copy_(ops.new_mass_range(B, key_local.device))
+                mm = ops.shard_stats_combine(attention_local, key_local, value_local, P, gs, x.ptrs, x.rank, x.world,
+                                             x.state, self.num_heads, x.mass, x.minmax, mass_range=x.mass_range)
+                self._range_pending = True
+                return mm
             except RtkvError as e:
                 if e.code != -2:                     # RTKV_EUNSUPPORTED: same verdict on every rank (same shapes)
                     raise
@@ -229,6 +235,9 @@ class HeadShardedCompressor:
         from . import ops
         B, S, _ = key_local.shape
         params, _ = self.compressor.layer_params(layer_idx, S, ops.F32)
+        if self._range_pending:                  # the one-kernel exchange also reduced the row's mass range
+            self._range_pending = False
+            return ops.score_select(params, B, S, key_local.device, mass=mass, mass_range=self.exchange.mass_range)
         return ops.score_select(params, B, S, key_local.device, mass=mass)
 
     def fused_publish(self, key_local, value_local, attention_local):

@@ -282,8 +282,15 @@ class Selection:
         return layer.copy(), rows.copy()
 
 
+def new_mass_range(batch, device):
+    """[B,4] u32 initialised to (0xffffffff, 0, 0, 0): min / max sort key of the mass and NaN flag (rtkv_shard_stats_combine_ranged)."""
+    r = torch.zeros(batch, 4, dtype=torch.int32, device=device)
+    r[:, 0] = -1
+    return r
+
+
 @_device_guard
-def score_select(params, B, S, device, mass=None, scores=None, labels=None, select=True, fallback=True):
+def score_select(params, B, S, device, mass=None, scores=None, labels=None, select=True, fallback=True, mass_range=None):
     """Scores -> labels -> budgeted selection (one launch).
 
     mass given: scores are computed (token_importance.py:134-176); else `scores` is used.
@@ -312,6 +319,11 @@ def score_select(params, B, S, device, mass=None, scores=None, labels=None, sele
     alloc = torch.zeros if B > 1 else torch.empty
     stats = alloc(LAYER_STATS_BYTES + ROW_STATS_BYTES * B, dtype=torch.uint8, device=device)
     scr = scratch(device, S)
+    if mass_range is not None:      # the exchange kernel already reduced the row's mass range: K2 skips that pass (and resets it)
+        check(lib.rtkv_score_select_ranged(_ptr(mass), _ptr(mass_range), _ptr(scores), _ptr(labels), _ptr(mask), _ptr(sel_idx),
+                                           ctypes.c_void_p(stats.data_ptr() + LAYER_STATS_BYTES), _ptr(stats),
+                                           _ptr(scr), scr.numel(), B, S, ctypes.byref(params), flags, _stream()))
+        return Selection(scores, labels, mask, sel_idx, stats, B, S)
     check(lib.rtkv_score_select(_ptr(mass), _ptr(scores), _ptr(labels), _ptr(mask), _ptr(sel_idx),
                                 ctypes.c_void_p(stats.data_ptr() + LAYER_STATS_BYTES), _ptr(stats),
                                 _ptr(scr), scr.numel(), B, S, ctypes.byref(params), flags, _stream()))
@@ -427,7 +439,7 @@ def shard_stats(attn_local, key_local, value_local, prompt_len, group_size, xbuf
 
 @_device_guard
 def shard_stats_combine(attn_local, key_local, value_local, prompt_len, group_size, xbuf_ptrs, rank, world, state, num_heads,
-                        mass, minmax):
+                        mass, minmax, mass_range=None):
     """shard_stats + shard_combine in one kernel (per-CTA peer flags; every rank must run it concurrently):
     fills mass [B,S] and minmax [B,S,4].  Raises RtkvError(RTKV_EUNSUPPORTED) for shapes the staged kernel cannot take."""
     require_cuda()
@@ -438,6 +450,13 @@ def shard_stats_combine(attn_local, key_local, value_local, prompt_len, group_si
     if prompt_len > W:
         raise IndexError(f"prompt_len {prompt_len} exceeds attention width {W}")
     ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in xbuf_ptrs])
+    if mass_range is not None:
+        check(lib.rtkv_shard_stats_combine_ranged(_ptr(attn_local), dtype_code(attn_local), B, Hl, S, attn_local.stride(0),
+                                                  attn_local.stride(1), attn_local.stride(2), int(prompt_len), int(group_size),
+                                                  _ptr(key_local), _ptr(value_local), dtype_code(key_local), key_local.shape[2],
+                                                  ptrs, int(rank), int(world), _ptr(state), int(num_heads), _ptr(mass),
+                                                  _ptr(minmax), _ptr(mass_range), _stream()))
+        return mass, minmax
     check(lib.rtkv_shard_stats_combine(_ptr(attn_local), dtype_code(attn_local), B, Hl, S, attn_local.stride(0),
                                        attn_local.stride(1), attn_local.stride(2), int(prompt_len), int(group_size),
                                        _ptr(key_local), _ptr(value_local), dtype_code(key_local), key_local.shape[2],
@@ -447,7 +466,7 @@ def shard_stats_combine(attn_local, key_local, value_local, prompt_len, group_si
 
 
 def shard_stats_combine_allranks(attn_slices, key_slices, value_slices, prompt_len, group_size, xbuf_ptrs, states, num_heads,
-                                 masses, minmaxes):
+                                 masses, minmaxes, mass_ranges=None):
     """Test harness (one GPU): rtkv_shard_stats_combine of ALL ranks in one cooperative launch (lists of per-rank tensors)."""
     require_cuda()
     R = len(attn_slices)
@@ -463,6 +482,7 @@ def shard_stats_combine_allranks(attn_slices, key_slices, value_slices, prompt_l
                                                           A0.stride(2), int(prompt_len), int(group_size), arr(key_slices),
                                                           arr(value_slices), dtype_code(key_slices[0]), key_slices[0].shape[2],
                                                           ptrs, R, arr(states), int(num_heads), arr(masses), arr(minmaxes),
+                                                          arr(mass_ranges) if mass_ranges is not None else None,
                                                           _ptr(scratch_p), _stream()))
 
 

@@ -612,15 +612,36 @@ def test_head_sharded_one_kernel_exchange_all_ranks_cooperative(rt, kvdt, R, H, 
     views = [xch.view(r) for r in range(R)]
     want_mass = ops.prompt_mass(A, prompt_len=P)
     want_mm = torch.stack([K.float().amin(-1), K.float().amax(-1), V.float().amin(-1), V.float().amax(-1)], dim=-1)
+    ranges = [ops.new_mass_range(B, K.device) for _ in range(R)]
+    cfg = rtkv.CompressionConfig(num_attention_heads=H, hidden_size=HD, high_precision_bits=16, medium_precision_bits=8,
+                                 low_precision_bits=4)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
     for layer in range(5):
         for v in views:
             v.mass.fill_(-1.0); v.minmax.fill_(-1.0)
         ops.shard_stats_combine_allranks(As, Ks, Vs, P, H // 8, xch.ptrs, [v.state for v in views], H,
-                                         [v.mass for v in views], [v.minmax for v in views])
+                                         [v.mass for v in views], [v.minmax for v in views], ranges)
         torch.cuda.synchronize()
+        params, _ = comp.layer_params(layer * 6, S, ops.F32)
+        want_by_mode = {}
+        for mode in (1, 2):                                 # 1: single-CTA selection kernel, 2: cluster kernel
+            ops.lib.rtkv_debug_k2_mode(mode)
+            want_by_mode[mode] = ops.score_select(params, B, S, K.device, mass=want_mass)
+        ops.lib.rtkv_debug_k2_mode(0)
         for r in range(R):
             assert int(views[r].state[2]) == 0, "a CTA gave up waiting for its peers"
             assert torch.equal(views[r].mass, want_mass) and torch.equal(views[r].minmax, want_mm), (layer, r)
+            # the mass range reduced by the exchange kernel lets K2 skip its own pass: same selection, range reset afterwards
+            mode = 1 + (layer + r) % 2                             # alternate the two selection kernels
+            want_sel = want_by_mode[mode]
+            ops.lib.rtkv_debug_k2_mode(mode)
+            try:
+                sel = ops.score_select(params, B, S, K.device, mass=views[r].mass, mass_range=ranges[r])
+            finally:
+                ops.lib.rtkv_debug_k2_mode(0)
+            assert torch.equal(sel.scores, want_sel.scores) and torch.equal(sel.labels, want_sel.labels)
+            assert torch.equal(sel.mask, want_sel.mask) and torch.equal(sel.stats, want_sel.stats)
+            assert ranges[r].cpu().tolist() == [[-1, 0, 0, 0]] * B
 
 
 def test_head_sharded_fused_exchange_propagates_nan_rows(rt):
