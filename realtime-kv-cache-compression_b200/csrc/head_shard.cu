@@ -36,7 +36,7 @@ struct ShardParams {
     int64_t sb, sh, si;
     const void *K, *V;
     int B, S, P, gs, ng, n;           // ng local head groups of gs heads; n = local row width in elements
-    int rank, world, rec_vecs, dbg, kv_keep;   // kv_keep: ask L2 to keep the K/V rows (they fit and are re-read soon)
+    int rank, world, rec_vecs, dbg, kv_keep;   // kv_keep: leading token rows whose K/V slices are asked to stay in L2
     //    // dbg (rtkv_debug_shard_variant): 2 no consumer math, 3 no record stores
     unsigned long long xbuf[8];       // exchange buffer of rank s as mapped into this process
     unsigned *state;                  // local: [0] epoch of the last finished call, [1] CTA ticket, [2] error flag
@@ -49,6 +49,16 @@ struct ShardParams {
 __device__ __forceinline__ void st_sys_v4(void *p, float a, float b, float c, float d)
 {
     asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// release/acquire fence at system scope.  __threadfence_system() compiles to the sequentially consistent MEMBAR.SC.SYS;
+// the record -> flag hand-off only needs acquire/release ordering (RTKV_SHARD_SC_FENCE=1 at build time restores SC).
+__device__ __forceinline__ void fence_sys()
+{
+#ifdef RTKV_SHARD_SC_FENCE
+    __threadfence_system();
+#else
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void st_sys_u32(unsigned *p, unsigned v)
 {
@@ -120,12 +130,12 @@ __device__ __forceinline__ float combine_token(const char *xlocal, unsigned pari
 // thread plus one in the last CTA: a chain of st.release.sys (a system fence each, ~2.3 us apiece) measured 25 us.
 __device__ __forceinline__ void publish_epoch(const ShardParams &p, unsigned parity, unsigned epoch, unsigned n_ctas)
 {
-    __threadfence_system();
+    fence_sys();
     __syncthreads();
     if (threadIdx.x == 0) {
         if (atomicAdd(&p.state[1], 1u) == n_ctas - 1) {
             p.state[1] = 0u;
-            __threadfence_system();
+            fence_sys();
 #pragma unroll
             for (int s = 0; s < 8; ++s)
                 if (s < p.world) st_sys_u32((unsigned *)p.xbuf[s] + parity * 8 + p.rank, epoch);
@@ -313,8 +323,11 @@ __device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, co
     if (warp == kStagedConsumers) {
         // ---- producer ----
         if (lane == 0) {
-            const uint64_t pol_kv = p.kv_keep ? l2_policy_evict_last() : l2_policy_evict_first();
-            const uint64_t pol_a = l2_policy_evict_first();
+            // kv_keep = number of leading token rows (per batch row) whose K/V slices are asked to STAY in L2: the quantise kernel
+            // re-reads the kept rows in ascending order a few tens of microseconds later, so the first rows are the ones worth
+            // keeping; everything else (and all of A, which is never read again) streams through with evict-first
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+            const uint64_t pol_a = pol_stream;
             int64_t k = 0;
             for (int64_t blk = cta; blk < n_blocks; blk += n_ctas, ++k) {
                 const int st = (int)(k % c.stages);
@@ -326,6 +339,7 @@ __device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, co
                 const uint32_t dst = smem_u32(data + (size_t)st * c.stage_bytes);
                 mbar_expect_tx(bar, (uint32_t)nr * (2u * c.kv_bytes + (uint32_t)Hl * c.a_bytes));
                 const size_t row0 = (size_t)b * p.S + i0;
+                const uint64_t pol_kv = i0 < p.kv_keep ? pol_keep : pol_stream;
                 bulk_g2s(dst, (const char *)p.K + row0 * c.kv_bytes, nr * c.kv_bytes, bar, pol_kv);
                 bulk_g2s(dst + c.rb * c.kv_bytes, (const char *)p.V + row0 * c.kv_bytes, nr * c.kv_bytes, bar, pol_kv);
                 const float *a0 = (const float *)p.A + b * p.sb + (int64_t)i0 * p.si;
@@ -426,7 +440,7 @@ __device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, co
             // ---- fused combine: CTA c of every rank handles the same token blocks, so this CTA only needs the records
             // of the peers' CTA c.  Point-to-point: fence my record stores, raise my CTA flag at every rank, wait for the
             // R flags of CTA c here, then reduce my own tokens.  No grid-wide flag, no second kernel.
-            __threadfence_system();
+            fence_sys();
             asm volatile("bar.sync 1, %0;" ::"n"(kStagedConsumers * 32) : "memory");
             if (warp == 0 && lane < p.world) {
                 unsigned long long base = 0;
@@ -443,7 +457,7 @@ __device__ __forceinline__ void shard_stats_staged_body(const ShardParams &p, co
                 while (ld_sys_u32(flag) != epoch) {
                     if (clock64() - t0 > 40000000000LL) { atomicExch(&p.state[2], 1u); break; }     // ~20 s: flag it, never trap
                 }
-                __threadfence_system();
+                fence_sys();
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kStagedConsumers * 32) : "memory");
             unsigned long long mine = 0;
@@ -537,7 +551,7 @@ __global__ void __launch_bounds__(256) shard_combine_kernel(const char *xlocal, 
                 break;
             }
         }
-        __threadfence_system();
+        fence_sys();
     }
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,6 +579,7 @@ extern "C" int64_t rtkv_shard_exchange_bytes(int B, int S, int world)
     return (int64_t)kXHeader + (int64_t)2 * world * B * S * rec_vecs_for(world) * 16;
 }
 
+static int g_shard_l2_keep_mb = 0;     // MB of leading K/V rows kept in L2 by the statistics kernel (0: off)
 static int g_shard_grid_cap = 0;    // testing aid: cap the persistent grid (several emulated ranks co-resident on one GPU)
 extern "C" int rtkv_debug_shard_grid(int max_ctas)
 {
@@ -599,8 +614,15 @@ static int shard_stats_impl(const void *A, int a_dtype, int B, int H_local, int 
     p.A = A; p.sb = sb; p.sh = sh; p.si = si; p.K = K; p.V = V;
     p.B = B; p.S = S; p.P = P; p.gs = group_size; p.ng = kGroups / world; p.n = n_local;
     p.rank = rank; p.world = world; p.rec_vecs = rec_vecs_for(world); p.dbg = g_shard_variant;
-    // keep the local K/V slice in L2 when it fits comfortably (the quantise kernel re-reads the kept rows)
-    p.kv_keep = (2.0 * B * S * n_local * dtype_bytes(kv_dtype) <= 80e6) && !getenv("RTKV_SHARD_NO_L2_KEEP");
+    // rows whose K/V slices are asked to stay in L2 for the quantise kernel (see the producer): RTKV_SHARD_L2_KEEP_MB of K+V
+    // per batch row, default g_shard_l2_keep_mb
+    {
+        int keep_mb = g_shard_l2_keep_mb;
+        if (const char *e = getenv("RTKV_SHARD_L2_KEEP_MB")) keep_mb = atoi(e);
+        const double row_kv_bytes = 2.0 * n_local * dtype_bytes(kv_dtype);
+        const double rows_keep = keep_mb > 0 ? keep_mb * 1048576.0 / (row_kv_bytes * B) : 0.0;
+        p.kv_keep = rows_keep >= S ? S : (int)rows_keep;
+    }
     for (int s = 0; s < 8; ++s) p.xbuf[s] = s < world ? xbuf_ptrs[s] : 0ull;
     for (int s = 0; s < world; ++s) RTKV_CHECK_ARG(p.xbuf[s] && p.xbuf[s] % 16 == 0, "rtkv_shard_stats: exchange buffer %d", s);
     p.state = state;

@@ -34,10 +34,8 @@ byts = As[0].numel() * 4 + 2 * Ks[0].numel() * 4
 print(json.dumps({"R": R, "variant": variant, "rb": os.environ.get("RTKV_SHARD_RB"), "stages": os.environ.get("RTKV_SHARD_STAGES"),
                   "us": round(ts[len(ts) // 2], 1), "GBs": round(byts / ts[len(ts) // 2] / 1e3)}))
 ''' % ROOT
-for R in (8, 4, 2):
+for R in (8, 2):
     for S in (1024, 32768):
-        for variant in (0, 2):
-            env = dict(os.environ, S=str(S))
-            r = subprocess.run([sys.executable, "-c", CHILD, str(R), str(variant)], env=env, capture_output=True, text=True)
-            out = r.stdout.strip() or r.stderr[-300:]
-            print("S=%d %s" % (S, out), flush=True)
+        env = dict(os.environ, S=str(S))
+        r = subprocess.run([sys.executable, "-c", CHILD, str(R), "0"], env=env, capture_output=True, text=True)
+        print("S=%d %s" % (S, r.stdout.strip() or r.stderr[-300:]), flush=True)
