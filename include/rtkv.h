@@ -403,9 +403,10 @@ RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a
  * guard, 0 element-wise code only.  Same results (per device: call with the device current). */
 RTKV_API int rtkv_debug_bf16_packed(int on);
 
-/* Testing aid: rtkv_flash_prefill kernel: 0 (default) one query tile per CTA with P in shared memory, 1 two query tiles per
- * CTA with P in tensor memory (A operand of the second product from TMEM; measured slower).  Same results up to fp32
- * summation order. */
+/* Testing aid: rtkv_flash_prefill kernel: 0 (default) one query tile per CTA, P in shared memory, the two softmax warpgroups
+ * agree on the row max every tile; 1 same layout, independent online softmaxes per key half merged in the epilogue; 2 two
+ * query tiles per CTA with P in tensor memory (A operand of the second product from TMEM).  1 and 2 measured slower.  Same
+ * results up to fp32 summation order. */
 RTKV_API int rtkv_debug_flash_variant(int variant);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */

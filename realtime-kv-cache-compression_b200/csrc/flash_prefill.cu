@@ -33,6 +33,7 @@ constexpr int kFHalf = kFTileBytes / 2;          // the two 64-column (128-byte)
 constexpr int kFThreads = 64 + 256;              // TMA warp, MMA warp, 8 softmax warps (two warpgroups)
 // Q, K[2], V[2], P[2] + barriers + row exchange + alignment slack: 232448 bytes = the 227 KB a CTA can have
 constexpr size_t kFSmem = 768 + 7 * (size_t)kFTileBytes + 256 + 4 * kFT * sizeof(float);
+constexpr size_t kIHSmem = 768 + 7 * (size_t)kFTileBytes + 256;   // the epilogue exchange reuses the P buffers
 
 struct FlashParams {
     void *out;                 // [B,H,Sq,128] elements of the input dtype, strides below (in elements)
@@ -325,6 +326,263 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const size_t at = ((size_t)b * p.H + h) * p.Sq + i;
             if (p.lse) p.lse[at] = (m_used + log2f(l)) * 0.6931471805599453f;
             if (p.head_sums) p.head_sums[at] = mass_acc * inv_l;
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- independent key halves (rtkv_debug_flash_variant(1); measured slightly SLOWER: 855 vs 898 TFLOP/s at 32k) -----------
+// Same CTA layout as flash_prefill_kernel, but the two softmax warpgroups no longer meet once per tile to agree on the row
+// max (that barrier kept all eight warps in lockstep: the MUFU pipe idled while everybody loaded, maxed and stored).  Each
+// warpgroup runs its OWN online softmax over its half of the keys of every tile (own running max, own row sum, own
+// accumulator O_g in TMEM, own P half-tile and barriers), the second product is issued per half (4 MMAs of 16 keys into O_g),
+// and the two partial results are merged once, in the epilogue: O = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1), a_g = 2^(m_g - M).
+// Outcome: the per-tile barrier was not the limiter.  Per tile and scheduler the exponentials alone need 1024 MUFU cycles (64 per
+// warp x 8 cycles x 2 warps) of the ~2470 a tile takes; the other phases (TMEM load, max, pack, stores) do not overlap them
+// because both warps of a scheduler start every tile together.  Kept as a tested variant.
+template <bool BF16>
+__global__ void __launch_bounds__(kFThreads, 1)
+flash_prefill_ih_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, FlashParams p)
+{
+    extern __shared__ __align__(1024) unsigned char fp_smem_raw[];
+    // 128-byte swizzle needs 1024-byte aligned tiles; the declared alignment makes the round-up a no-op, the 768 spare bytes
+    // cover a base that is only 256-byte aligned
+    unsigned char *smem = (unsigned char *)(((uintptr_t)fp_smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_q = smem, *smem_k = smem + kFTileBytes, *smem_v = smem + 3 * kFTileBytes, *smem_p = smem + 5 * kFTileBytes;
+    uint64_t *bars = (uint64_t *)(smem + 7 * (size_t)kFTileBytes);
+    uint64_t *qfull = bars, *kfull = bars + 1, *kempty = bars + 3, *vfull = bars + 5, *vempty = bars + 7;
+    uint64_t *sfull = bars + 9, *sfree = bars + 11, *pfull = bars + 13, *pvdone = bars + 17;   // pfull / pvdone: [half g][buffer s]
+    uint32_t *tmem_slot = (uint32_t *)(bars + 21);
+    float *xch = (float *)((unsigned char *)bars + 256);          // epilogue exchange: [3 values][2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_qt = (p.Sq + kFT - 1) / kFT;
+    const int qt = n_qt - 1 - (int)(blockIdx.x % n_qt);          // heaviest (last) query tiles first
+    const int h = (int)((blockIdx.x / n_qt) % p.H), b = (int)(blockIdx.x / ((size_t)n_qt * p.H));
+    const int hk = h / (p.H / p.Hkv);
+    int T = (p.Skv + kFT - 1) / kFT;                             // key tiles this query tile sees
+    if (p.causal && qt + 1 < T) T = qt + 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(qfull), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&kfull[s]), 1); mbar_init(smem_u32(&kempty[s]), 1);
+            mbar_init(smem_u32(&vfull[s]), 1); mbar_init(smem_u32(&vempty[s]), 1);
+            mbar_init(smem_u32(&sfull[s]), 1); mbar_init(smem_u32(&sfree[s]), 8);
+            for (int g = 0; g < 2; ++g) { mbar_init(smem_u32(&pfull[2 * g + s]), 4); mbar_init(smem_u32(&pvdone[2 * g + s]), 1); }
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // 512 TMEM columns: S0 [0,128), S1 [128,256), O_0 [256,384), O_1 [384,512) (one accumulator per key half)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t qf = smem_u32(qfull);
+            mbar_expect_tx(qf, kFTileBytes);
+            tma_load_4d(smem_u32(smem_q), &map_q, 0, qt * kFT, h, b, qf);
+            tma_load_4d(smem_u32(smem_q) + kFHalf, &map_q, 64, qt * kFT, h, b, qf);
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                const uint32_t par = (uint32_t)(((t >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&kempty[s]), par);
+                const uint32_t kf = smem_u32(&kfull[s]);
+                mbar_expect_tx(kf, kFTileBytes);
+                const uint32_t kd = smem_u32(smem_k + (size_t)s * kFTileBytes);
+                tma_load_4d(kd, &map_k, 0, t * kFT, hk, b, kf);
+                tma_load_4d(kd + kFHalf, &map_k, 64, t * kFT, hk, b, kf);
+                mbar_wait(smem_u32(&vempty[s]), par);
+                const uint32_t vf = smem_u32(&vfull[s]);
+                mbar_expect_tx(vf, kFTileBytes);
+                const uint32_t vd = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                tma_load_4d(vd, &map_v, 0, t * kFT, hk, b, vf);
+                tma_load_4d(vd + kFHalf, &map_v, 64, t * kFT, hk, b, vf);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t qbase = smem_u32(smem_q);
+            auto issue_qk = [&](int t) {
+                const int s = t & 1;
+                mbar_wait(smem_u32(&kfull[s]), (uint32_t)((t >> 1) & 1));
+                mbar_wait(smem_u32(&sfree[s]), (uint32_t)(((t >> 1) & 1) ^ 1));      // softmax has S_{t-2} in registers
+                tc_fence_after();
+                const uint32_t kbase = smem_u32(smem_k + (size_t)s * kFTileBytes);
+                const uint32_t dcol = tmem_base + (uint32_t)(s * kFT);
+#pragma unroll
+                for (int kq = 0; kq < 2; ++kq)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t off = (uint32_t)(kq * kFHalf + kk * 32);       // 16 head-dim elements = 32 B
+                        umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc_qk, (uint32_t)((kq | kk) != 0));
+                    }
+                umma_commit(smem_u32(&kempty[s]));
+                umma_commit(smem_u32(&sfull[s]));
+            };
+            mbar_wait(smem_u32(qfull), 0);
+            issue_qk(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) issue_qk(t + 1);                                      // overlaps softmax of tile t
+                const int s = t & 1;
+                mbar_wait(smem_u32(&vfull[s]), (uint32_t)((t >> 1) & 1));
+                const uint32_t vbase = smem_u32(smem_v + (size_t)s * kFTileBytes);
+                const uint32_t pbase = smem_u32(smem_p + (size_t)s * kFTileBytes);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {           // key half g (keys 64g .. 64g+63 of the tile) has its own accumulator O_g
+                    mbar_wait(smem_u32(&pfull[2 * g + s]), (uint32_t)((t >> 1) & 1));   // P_t half g in shared memory, O_g rescaled
+                    tc_fence_after();
+                    const uint32_t ocol = tmem_base + (uint32_t)(2 * kFT + g * kFT);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {    // 16 keys per MMA
+                        const uint32_t poff = (uint32_t)(g * kFHalf + kk * 32);
+                        const uint32_t voff = (uint32_t)((g * 64 + kk * 16) * 128);
+                        umma_f16(ocol, umma_desc_sw128(pbase + poff), umma_desc_sw128_mn(vbase + voff, kFHalf), p.idesc_pv,
+                                 (uint32_t)((t | kk) != 0));
+                    }
+                    umma_commit(smem_u32(&pvdone[2 * g + s]));
+                }
+                umma_commit(smem_u32(&vempty[s]));
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: thread = one query row x 64 key columns (warpgroup g = column half g) =====
+        const int quad = warp & 3;
+        const int g = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;
+        const int i = qt * kFT + row;                          // query index
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float m_used = -INFINITY, l = 0.0f, mass_acc = 0.0f;   // l, mass_acc: this thread's column half only
+        const uint32_t xch_u32 = smem_u32(xch);
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1;
+            mbar_wait(smem_u32(&sfull[s]), (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            uint32_t raw[2][32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tmem_ld32_issue(lane_base + (uint32_t)(s * kFT + 64 * g + 32 * c), raw[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sfree[s]));
+            // row max of this thread's 64 logits (raw units; masked entries only where a tile needs masking)
+            const int j0 = t * kFT + 64 * g;
+            const bool need_mask = (p.causal && t * kFT + kFT - 1 > qt * kFT) || (t * kFT + kFT > p.Skv);
+            float mx = -INFINITY;
+            if (need_mask) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int j = j0 + 32 * c + e;
+                        const bool dead = j >= p.Skv || (p.causal && j > i);
+                        mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(raw[c][e]));
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(raw[c][e]));
+            }
+            mx *= p.scale_log2;                                  // log2 domain from here; this half's own running max: no exchange
+            // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
+            float alpha = 1.0f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f) {
+                rescale = m_used != -INFINITY;
+                alpha = rescale ? ex2_approx(m_used - mx) : 0.0f;
+                m_used = mx;
+            }
+            if (__any_sync(0xffffffffu, rescale)) {              // warp-uniform: tcgen05.ld/st are warp-wide; rare
+                mbar_wait(smem_u32(&pvdone[2 * g + ((t - 1) & 1)]), (uint32_t)(((t - 1) >> 1) & 1));   // P_{t-1} V_{t-1} (half g) retired
+                tc_fence_after();
+                const float a = rescale ? alpha : 1.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(lane_base + (uint32_t)(2 * kFT + g * kFT + 32 * c), o);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * a);
+                    tmem_st32(lane_base + (uint32_t)(2 * kFT + g * kFT + 32 * c), o);
+                }
+                tmem_st_wait();
+            }
+            if (rescale) { l *= alpha; mass_acc *= alpha; }
+            // P buffer (t & 1) is free once P_{t-2} V_{t-2} has retired
+            mbar_wait(smem_u32(&pvdone[2 * g + s]), (uint32_t)(((t >> 1) & 1) ^ 1));
+            // p = 2^(s*scale - m), row sum, prompt-column share, P half-tile to shared memory
+            float rs = 0.0f, ps = 0.0f;
+            const uint32_t prow = smem_u32(smem_p) + (uint32_t)(s * kFTileBytes + g * kFHalf + row * 128);
+            if (need_mask || t == 0)
+                exp_store<BF16, true>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
+            else
+                exp_store<BF16, false>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
+            l += rs;
+            if (t == 0) mass_acc = ps;
+            fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&pfull[2 * g + s]));
+        }
+        // ---- epilogue: merge the two key halves' online softmaxes (each has its own max, sum and accumulator).  Both second
+        // products of the last tile have retired first, so the P buffers are free: they carry the three floats per (row, half).
+        mbar_wait(smem_u32(&pvdone[0 + ((T - 1) & 1)]), (uint32_t)(((T - 1) >> 1) & 1));
+        mbar_wait(smem_u32(&pvdone[2 + ((T - 1) & 1)]), (uint32_t)(((T - 1) >> 1) & 1));
+        tc_fence_after();
+        float *xe = reinterpret_cast<float *>(smem_p);           // [3 values][2 halves][128 rows]
+        xe[(0 * 2 + g) * kFT + row] = m_used;
+        xe[(1 * 2 + g) * kFT + row] = l;
+        xe[(2 * 2 + g) * kFT + row] = mass_acc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float m_o = xe[(0 * 2 + (g ^ 1)) * kFT + row], l_o = xe[(1 * 2 + (g ^ 1)) * kFT + row], mass_o = xe[(2 * 2 + (g ^ 1)) * kFT + row];
+        const float M = fmaxf(m_used, m_o);
+        const float a_me = ex2_approx(m_used - M), a_ot = ex2_approx(m_o - M);       // 2^(-inf) = 0 for a half that saw no key
+        const float L = a_me * l + a_ot * l_o;
+        const float inv_l = 1.0f / L;
+        const float a0 = (g == 0 ? a_me : a_ot) * inv_l, a1 = (g == 0 ? a_ot : a_me) * inv_l;
+        const bool live = i < p.Sq;
+        unsigned char *orow = (unsigned char *)p.out + ((size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)i * p.o_ss) * 2;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                            // this thread writes output columns [64g, 64g + 64)
+            uint32_t o0[32], o1[32];
+            tmem_ld32_issue(lane_base + (uint32_t)(2 * kFT + 64 * g + 32 * c), o0);
+            tmem_ld32_issue(lane_base + (uint32_t)(3 * kFT + 64 * g + 32 * c), o1);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c0 = 8 * q + 2 * e;
+                        w[e] = pack2<BF16>(__uint_as_float(o0[c0]) * a0 + __uint_as_float(o1[c0]) * a1,
+                                           __uint_as_float(o0[c0 + 1]) * a0 + __uint_as_float(o1[c0 + 1]) * a1);
+                    }
+                    *reinterpret_cast<uint4 *>(orow + (size_t)(64 * g + 32 * c + 8 * q) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        if (live && g == 0) {
+            const size_t at = ((size_t)b * p.H + h) * p.Sq + i;
+            if (p.lse) p.lse[at] = (M + log2f(L)) * 0.6931471805599453f;
+            if (p.head_sums) p.head_sums[at] = (a_me * mass_acc + a_ot * mass_o) * inv_l;
         }
         tc_fence_before();
     }
@@ -635,10 +893,10 @@ static int encode_bhsd_map(CUtensorMap *map, const void *base, int dtype, int B,
 
 using namespace rtkv;
 
-static int g_flash_variant = 0;     // 0: one query tile per CTA, P in shared memory (default, faster); 1: two query tiles per CTA, P in TMEM
+static int g_flash_variant = 0;     // 0: the two softmax warpgroups agree on the row max every tile (default, fastest); 1: independent key halves; 2: two query tiles per CTA, P in TMEM
 extern "C" int rtkv_debug_flash_variant(int variant)
 {
-    RTKV_CHECK_ARG(variant == 0 || variant == 1, "rtkv_debug_flash_variant: 0 or 1");
+    RTKV_CHECK_ARG(variant >= 0 && variant <= 2, "rtkv_debug_flash_variant: 0, 1 or 2");
     g_flash_variant = variant;
     return RTKV_OK;
 }
@@ -680,7 +938,21 @@ extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, i
     const uint32_t fmt = dtype == RTKV_BF16 ? 1u : 0u;
     p.idesc_qk = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kFT >> 3) << 17) | ((uint32_t)(kFT >> 4) << 24);
     p.idesc_pv = p.idesc_qk | (1u << 16);                       // B operand (V) is MN-major
-    if (g_flash_variant == 1) {          // two query tiles per CTA, P in tensor memory
+    if (g_flash_variant == 1) {          // independent key halves
+        const int n_qt0 = (Sq + kFT - 1) / kFT;
+        const long long ctas0 = (long long)n_qt0 * H * B;
+        RTKV_CHECK_ARG(ctas0 < (1ll << 31), "rtkv_flash_prefill: too many tiles");
+        if (dtype == RTKV_BF16) {
+            RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_ih_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIHSmem));
+            flash_prefill_ih_kernel<true><<<dim3((unsigned)ctas0), kFThreads, kIHSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+        } else {
+            RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_ih_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIHSmem));
+            flash_prefill_ih_kernel<false><<<dim3((unsigned)ctas0), kFThreads, kIHSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+        }
+        RTKV_LAUNCH_CHECK("flash_prefill_ih_kernel");
+        return RTKV_OK;
+    }
+    if (g_flash_variant == 2) {          // two query tiles per CTA, P in tensor memory
         const int n_qp = (Sq + 2 * kFT - 1) / (2 * kFT);
         const long long ctas2 = (long long)n_qp * H * B;
         RTKV_CHECK_ARG(ctas2 < (1ll << 31), "rtkv_flash_prefill: too many tiles");

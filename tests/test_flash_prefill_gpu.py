@@ -50,10 +50,11 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=["one-tile-P-in-smem", "two-tiles-P-in-TMEM"])
+@pytest.fixture(params=[0, 1, 2], ids=["halves-exchange-max", "independent-key-halves", "two-tiles-P-in-TMEM"])
 def variant(request, ops):
-    """Both kernels behind rtkv_flash_prefill: 0 = one query tile per CTA, P in shared memory (default), 1 = two query tiles per
-    CTA, P in tensor memory."""
+    """The three kernels behind rtkv_flash_prefill: 0 = one query tile per CTA, the two softmax warpgroups agree on the row max
+    every tile (default), 1 = same layout, independent online softmaxes per key half, 2 = two query tiles per CTA with P in
+    tensor memory."""
     ops.lib.rtkv_debug_flash_variant(request.param)
     yield request.param
     ops.lib.rtkv_debug_flash_variant(0)
