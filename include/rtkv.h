@@ -408,6 +408,9 @@ RTKV_API int rtkv_debug_bf16_packed(int on);
  * query tiles per CTA with P in tensor memory (A operand of the second product from TMEM).  1 and 2 measured slower.  Same
  * results up to fp32 summation order. */
 RTKV_API int rtkv_debug_flash_variant(int variant);
+/* Tuning aid: share of the exponentials of an unmasked tile that the default rtkv_flash_prefill kernel computes with a
+ * degree-4 polynomial on the FMA pipe instead of MUFU.EX2: every `every`-th pair (2, 3, 4) or none (0, the default: measured slower at every share). */
+RTKV_API int rtkv_debug_flash_poly(int every);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);

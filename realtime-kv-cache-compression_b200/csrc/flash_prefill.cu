@@ -67,10 +67,27 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     return v;
 }
 
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4 polynomial for 2^f
+// (max relative error 4.2e-5, far below the bf16/f16 rounding of P and the 2e-3 tolerance of LSE / prompt mass), 2^n by adding
+// n to the exponent field.  The exponentials are as expensive as the tensor work on this machine (16 MUFU results per clock
+// and SM against 8192 tensor FLOP: 1024 cycles each per 128 x 128 tile), so a share of them runs here while the MUFU pipe
+// is busy with the rest (the FlashAttention-4 recipe).
+__device__ __forceinline__ float exp2_fma(float x)
+{
+    x = fmaxf(x, -126.0f);
+    const float xr = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of xr hold round(x)
+    const float f = x - (xr - 12582912.0f);
+    float p = __fmaf_rn(f, 0.009618129f, 0.055504109f);
+    p = __fmaf_rn(p, f, 0.240226507f);
+    p = __fmaf_rn(p, f, 0.693147181f);
+    p = __fmaf_rn(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
 // One thread's 64 logits of a tile -> p = 2^(s*scale - m), row sum, P half-row (input dtype, K-major, 128-byte swizzle) in
 // shared memory.  SLOW: the tile needs masking (diagonal / key tail) or is the first tile (prompt-column sum); every
 // other tile runs the branch-free body: FFMA + MUFU.EX2 + FADD per element and one pack per pair.
-template <bool BF16, bool SLOW>
+template <bool BF16, bool SLOW, int PE>
 __device__ __forceinline__ void exp_store(const uint32_t (&raw)[2][32], float scale_log2, float m_used, uint32_t prow, int row,
                                           int j_base, int i, int Skv, int causal, int P, bool first, float &rs, float &ps)
 {
@@ -79,8 +96,14 @@ __device__ __forceinline__ void exp_store(const uint32_t (&raw)[2][32], float sc
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-            float p0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e]), scale_log2, -m_used));
-            float p1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e + 1]), scale_log2, -m_used));
+            float p0, p1;
+            if (!SLOW && PE > 0 && ((e >> 1) % (PE > 0 ? PE : 1)) == PE - 1) {     // this pair on the FMA pipe
+                p0 = exp2_fma(__fmaf_rn(__uint_as_float(raw[c][e]), scale_log2, -m_used));
+                p1 = exp2_fma(__fmaf_rn(__uint_as_float(raw[c][e + 1]), scale_log2, -m_used));
+            } else {
+                p0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e]), scale_log2, -m_used));
+                p1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e + 1]), scale_log2, -m_used));
+            }
             if constexpr (SLOW) {
                 const int j = j_base + 32 * c + e;
                 if (j >= Skv || (causal && j > i)) p0 = 0.0f;
@@ -96,7 +119,7 @@ __device__ __forceinline__ void exp_store(const uint32_t (&raw)[2][32], float sc
     }
 }
 
-template <bool BF16>
+template <bool BF16, int PE>
 __global__ void __launch_bounds__(kFThreads, 1)
 flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, FlashParams p)
@@ -283,9 +306,9 @@ flash_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             float rs = 0.0f, ps = 0.0f;
             const uint32_t prow = smem_u32(smem_p) + (uint32_t)(s * kFTileBytes + g * kFHalf + row * 128);
             if (need_mask || t == 0)
-                exp_store<BF16, true>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
+                exp_store<BF16, true, PE>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
             else
-                exp_store<BF16, false>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
+                exp_store<BF16, false, PE>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
             l += rs;
             if (t == 0) mass_acc = ps;
             fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
@@ -531,9 +554,9 @@ flash_prefill_ih_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             float rs = 0.0f, ps = 0.0f;
             const uint32_t prow = smem_u32(smem_p) + (uint32_t)(s * kFTileBytes + g * kFHalf + row * 128);
             if (need_mask || t == 0)
-                exp_store<BF16, true>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
+                exp_store<BF16, true, 0>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, t == 0, rs, ps);
             else
-                exp_store<BF16, false>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
+                exp_store<BF16, false, 0>(raw, p.scale_log2, m_used, prow, row, j0, i, p.Skv, p.causal, p.P, false, rs, ps);
             l += rs;
             if (t == 0) mass_acc = ps;
             fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA (async proxy)
@@ -894,6 +917,14 @@ static int encode_bhsd_map(CUtensorMap *map, const void *base, int dtype, int B,
 using namespace rtkv;
 
 static int g_flash_variant = 0;     // 0: the two softmax warpgroups agree on the row max every tile (default, fastest); 1: independent key halves; 2: two query tiles per CTA, P in TMEM
+static int g_flash_poly = 0;        // every g_flash_poly-th pair of exponentials of an unmasked tile on the FMA pipe (0: none)
+extern "C" int rtkv_debug_flash_poly(int every)
+{
+    RTKV_CHECK_ARG(every == 0 || every == 2 || every == 3 || every == 4, "rtkv_debug_flash_poly: 0, 2, 3 or 4");
+    g_flash_poly = every;
+    return RTKV_OK;
+}
+
 extern "C" int rtkv_debug_flash_variant(int variant)
 {
     RTKV_CHECK_ARG(variant >= 0 && variant <= 2, "rtkv_debug_flash_variant: 0, 1 or 2");
@@ -969,13 +1000,16 @@ extern "C" int rtkv_flash_prefill(const void *Q, const void *K, const void *V, i
     const int n_qt = (Sq + kFT - 1) / kFT;
     const long long ctas = (long long)n_qt * H * B;
     RTKV_CHECK_ARG(ctas < (1ll << 31), "rtkv_flash_prefill: too many tiles");
-    if (dtype == RTKV_BF16) {
-        RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
-        flash_prefill_kernel<true><<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
-    } else {
-        RTKV_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
-        flash_prefill_kernel<false><<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, FlashParams) = nullptr;
+    const bool bf = dtype == RTKV_BF16;
+    switch (g_flash_poly) {
+    case 2: kern = bf ? flash_prefill_kernel<true, 2> : flash_prefill_kernel<false, 2>; break;
+    case 3: kern = bf ? flash_prefill_kernel<true, 3> : flash_prefill_kernel<false, 3>; break;
+    case 4: kern = bf ? flash_prefill_kernel<true, 4> : flash_prefill_kernel<false, 4>; break;
+    default: kern = bf ? flash_prefill_kernel<true, 0> : flash_prefill_kernel<false, 0>; break;
     }
+    RTKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+    kern<<<dim3((unsigned)ctas), kFThreads, kFSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
     RTKV_LAUNCH_CHECK("flash_prefill_kernel");
     return RTKV_OK;
 }

@@ -143,6 +143,7 @@ PROTOTYPES = {
     "rtkv_debug_k2_mode": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_flash_variant": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_flash_poly": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_bf16_packed": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_grid": (ctypes.c_int, [ctypes.c_int]),

@@ -114,6 +114,18 @@ def test_flash_prefill_prompt_mass_feeds_the_compressor(ops, variant):
     torch.testing.assert_close(mass, want, rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("every", [2, 3, 4])
+def test_flash_prefill_polynomial_exponentials(ops, every):
+    """rtkv_debug_flash_poly: a share of the exponentials of unmasked tiles on the FMA pipe (Cody-Waite split + degree-4
+    polynomial, relative error < 1e-4 — below the bf16 rounding of P).  Off by default (slower); same tolerances."""
+    ops.lib.rtkv_debug_flash_poly(every)
+    try:
+        test_flash_prefill_matches_fp32_reference(ops, 0, 1, 3, 3, 2048, 2048, True, 128, torch.bfloat16, 1.0)
+        test_flash_prefill_matches_fp32_reference(ops, 0, 1, 2, 2, 1000, 1000, True, 128, torch.float16, 1.0)
+    finally:
+        ops.lib.rtkv_debug_flash_poly(0)
+
+
 def test_flash_prefill_rejects_unsupported(ops):
     q = torch.randn(1, 2, 64, 64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="head_dim"):
