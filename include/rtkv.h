@@ -403,14 +403,30 @@ RTKV_API int rtkv_debug_shard_stats_combine_allranks(const void *const *A, int a
  * guard, 0 element-wise code only.  Same results (per device: call with the device current). */
 RTKV_API int rtkv_debug_bf16_packed(int on);
 
-/* Testing aid: rtkv_flash_prefill kernel: 0 (default) one query tile per CTA, P in shared memory, the two softmax warpgroups
- * agree on the row max every tile; 1 same layout, independent online softmaxes per key half merged in the epilogue; 2 two
- * query tiles per CTA with P in tensor memory (A operand of the second product from TMEM).  1 and 2 measured slower.  Same
- * results up to fp32 summation order. */
+/* Testing aid: which kernel rtkv_flash_prefill launches.  -1 (default): by shape -- 4 from 3072 keys on, else 0.
+ * 0: one query tile per CTA, P in shared memory, both softmax warpgroups on every key tile (column halves), agreeing on the row
+ *    max once per tile;
+ * 1: same layout, independent online softmaxes per key half merged in the epilogue;
+ * 2: two query tiles per CTA with P in tensor memory (A operand of the second product from TMEM);
+ * 3: each softmax warpgroup owns every other key tile with its own accumulator, merged in the epilogue;
+ * 4: alternating key tiles with the running max handed from tile to tile, ONE accumulator, P in tensor memory, three K/V stages,
+ *    separate issuing threads for the two products.
+ * Same results up to fp32 summation order. */
 RTKV_API int rtkv_debug_flash_variant(int variant);
 /* Tuning aid: share of the exponentials of an unmasked tile that the default rtkv_flash_prefill kernel computes with a
  * degree-4 polynomial on the FMA pipe instead of MUFU.EX2: every `every`-th pair (2, 3, 4) or none (0, the default: measured slower at every share). */
 RTKV_API int rtkv_debug_flash_poly(int every);
+/* Tuning aid: `counters` = device buffer of >= 40 int64 (or NULL = off).  While set, bf16 launches of the default kernel run an
+ * instrumented build that leaves the cycles CTA 0 spent in each phase of its tile loop there (tools/profile_flash_phases.py). */
+RTKV_API int rtkv_debug_flash_profile(void *counters);
+/* Tuning aid: cycles by which the odd softmax warpgroup of the alternating-tile kernel (variant 4) starts its first exponentials
+ * late, so that the two warps of a scheduler use the MUFU pipe in turn instead of together.  0 = no offset. */
+RTKV_API int rtkv_debug_flash_skew(int cycles);
+/* Tuning aid: cycles one thread needs to issue (counters[0]) and the tensor pipe to retire (counters[1]) `n` back-to-back
+ * 128x128x16 tcgen05.mma of the shapes rtkv_flash_prefill uses, on `ctas` CTAs at once.  mode 0: A, B in shared memory, K-major;
+ * 1: B MN-major; 2: A in tensor memory, B MN-major; 3: 8 of mode 0 then 8 of mode 2, repeated; 4: mode 0 with N = 256;
+ * 5: mode 0 cycling through four accumulators.  counters: >= 2 int64 (device). */
+RTKV_API int rtkv_debug_mma_rate(int mode, int n, int ctas, void *counters, void *stream);
 
 /* Testing aid: launch the hot kernels with (1, default) or without (0) programmatic dependent launch. */
 RTKV_API int rtkv_debug_pdl(int on);

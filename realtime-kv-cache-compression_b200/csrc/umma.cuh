@@ -61,6 +61,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
+// descriptor of the same layout `byte_off` further on (a multiple of 16 that stays inside shared memory): ONE 32-bit add on the
+// low word.  The issuing thread is the critical resource of a tcgen05 pipeline: rebuilding a descriptor from its address costs
+// four dependent uniform-datapath operations and made a 128x128x16 MMA cost 92-134 cycles to ISSUE against the 64 the tensor
+// pipe needs to execute it (tools/mma_rate.py).  Build descriptors once, advance them with this.
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t d, uint32_t byte_off)
+{
+    const uint32_t lo = (uint32_t)d + (byte_off >> 4);
+    return (d & 0xffffffff00000000ull) | lo;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\t"

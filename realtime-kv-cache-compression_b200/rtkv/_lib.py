@@ -144,6 +144,9 @@ PROTOTYPES = {
     "rtkv_debug_pdl": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_flash_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_flash_poly": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_flash_profile": (ctypes.c_int, [ctypes.c_void_p]),
+    "rtkv_debug_flash_skew": (ctypes.c_int, [ctypes.c_int]),
+    "rtkv_debug_mma_rate": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "rtkv_debug_bf16_packed": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_variant": (ctypes.c_int, [ctypes.c_int]),
     "rtkv_debug_shard_grid": (ctypes.c_int, [ctypes.c_int]),

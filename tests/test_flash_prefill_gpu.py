@@ -50,14 +50,15 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["halves-exchange-max", "independent-key-halves", "two-tiles-P-in-TMEM"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["halves-exchange-max", "independent-key-halves", "two-tiles-P-in-TMEM", "alternating-key-tiles", "alternating-tiles-one-accumulator"])
 def variant(request, ops):
-    """The three kernels behind rtkv_flash_prefill: 0 = one query tile per CTA, the two softmax warpgroups agree on the row max
-    every tile (default), 1 = same layout, independent online softmaxes per key half, 2 = two query tiles per CTA with P in
-    tensor memory."""
+    """The five kernels behind rtkv_flash_prefill: 0 = one query tile per CTA, the two softmax warpgroups agree on the row max
+    every tile, 1 = same layout, independent online softmaxes per key half, 2 = two query tiles per CTA with P in tensor
+    memory, 3 = each softmax warpgroup owns every other key tile (own accumulator, merged in the epilogue), 4 = alternating key
+    tiles with the running max handed from tile to tile, one accumulator, P in tensor memory, three K/V stages."""
     ops.lib.rtkv_debug_flash_variant(request.param)
     yield request.param
-    ops.lib.rtkv_debug_flash_variant(0)
+    ops.lib.rtkv_debug_flash_variant(-1)
 
 
 @pytest.mark.parametrize("B,H,Hkv,Sq,Skv,causal,P,dtype,qscale", CASES)
