@@ -115,19 +115,24 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            int q = 0, it = 0;
+            // Descriptors are built once and advanced by one add per MMA, ring positions are counters: the issuing thread is a
+            // serial resource (rebuilding both descriptors per MMA cost ~90 cycles per issue, umma.cuh / tools/mma_rate.py).
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem_q)), kd0 = umma_desc_sw128(smem_u32(smem_k));
+            const uint32_t idesc = p.idesc;
+            int q = 0, it = 0, s = 0;
+            uint32_t sph = 0;                                      // Q ring position and phase
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int c = item % chunks;
                 const int kb = it % kKBufs;
                 mbar_wait(smem_u32(&kfull[kb]), (it / kKBufs) & 1);      // K_prompt tile of this head landed
-                const uint32_t kbase = smem_u32(smem_k + (size_t)kb * kOperandBytes);
+                const uint64_t kd = umma_desc_advance(kd0, (uint32_t)(kb * kOperandBytes));
                 const int t1 = min(tiles, (c + 1) * T);
                 for (int tile = c * T; tile < t1; ++tile, ++q) {
-                    const int s = q % kStages, a = q & 1;
+                    const int a = q & 1;
                     mbar_wait(smem_u32(&tempty[a]), ((q >> 1) & 1) ^ 1);      // epilogue drained this accumulator
-                    mbar_wait(smem_u32(&qfull[s]), (q / kStages) & 1);       // TMA landed the Q tile
+                    mbar_wait(smem_u32(&qfull[s]), sph);                     // TMA landed the Q tile
                     tc_fence_after();
-                    const uint32_t qbase = smem_u32(smem_q + (size_t)s * kOperandBytes);
+                    const uint64_t qd = umma_desc_advance(qd0, (uint32_t)(s * kOperandBytes));
                     const uint32_t dcol = tmem_base + (uint32_t)(a * kTileN);
                     if (p.dbg < 3) {
 #pragma unroll
@@ -135,12 +140,12 @@ prompt_mass_qk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint32_t off = (uint32_t)(kq * (kOperandBytes / 2) + kk * 32);   // 16 elements = 32 B
-                            umma_f16(dcol, umma_desc_sw128(qbase + off), umma_desc_sw128(kbase + off), p.idesc,
-                                     (uint32_t)((kq | kk) != 0));
+                            umma_f16(dcol, umma_desc_advance(qd, off), umma_desc_advance(kd, off), idesc, (uint32_t)((kq | kk) != 0));
                         }
                     }
                     umma_commit(smem_u32(&qempty[s]));     // Q stage reusable once these MMAs retire
                     umma_commit(smem_u32(&tfull[a]));      // accumulator ready for the epilogue
+                    if (++s == kStages) { s = 0; sph ^= 1u; }
                 }
                 umma_commit(smem_u32(&kempty[kb]));        // every MMA that reads this K tile has retired
             }
