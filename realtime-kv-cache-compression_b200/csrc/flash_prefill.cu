@@ -1298,6 +1298,27 @@ template <bool BF16, bool SLOW, int PE = 0>
 __device__ __forceinline__ void exp_pack(const uint32_t (&raw)[2][32], float scale_log2, float m_used, uint32_t (&pk)[32],
                                          int j_base, int i, int Skv, int causal, int P, bool first, float &rs, float &ps)
 {
+    if constexpr (!SLOW && PE == 0) {
+        // The unmasked tile: four independent partial row sums instead of one serial chain of adds (tools/flash_timeline.py: a
+        // warp with the MUFU pipe to itself needed 1850 cycles per 128-column row, 14 per exponential against the pipe's 8).
+        // ptxas interleaves packs and adds two exponentials behind their MUFU whatever the source order; with both warps of a
+        // scheduler in this phase the pipe is saturated (2300 cycles for 2 x 128 exponentials), alone a warp reaches about half.
+        float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float pv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pv[e] = ex2_approx(__fmaf_rn(__uint_as_float(raw[c][e]), scale_log2, -m_used));
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                r0 += pv[e]; r1 += pv[e + 1]; r2 += pv[e + 2]; r3 += pv[e + 3];
+                pk[16 * c + (e >> 1)] = pack2<BF16>(pv[e], pv[e + 1]);
+                pk[16 * c + (e >> 1) + 1] = pack2<BF16>(pv[e + 2], pv[e + 3]);
+            }
+        }
+        rs += (r0 + r1) + (r2 + r3);
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1542,6 +1563,9 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         for (int t = g; t < T; t += 2) {
             const uint32_t par = (uint32_t)((t >> 1) & 1);
             tick(0);
+            if constexpr (PROF) {
+                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 2] = clock64();
+            }
             mbar_wait(sfull_g, par);
             tc_fence_after();
             tick(1);
@@ -1614,6 +1638,9 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             mbar_wait(pvdone_g, par ^ 1u);                       // P_{t-2} V_{t-2} has retired: P buffer g is free
             tc_fence_after();
             tick(5);
+            if constexpr (PROF) {
+                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3] = clock64();
+            }
             // The hand-off above takes a few hundred cycles and the exponentials over a thousand, so left alone the two
             // warpgroups run their exponentials at the same time (sharing the MUFU pipe) and their loads / maxima at the same
             // time (MUFU idle).  Nothing in the chain forces that: the odd warpgroup starts half a tile late, once, and the
@@ -1636,6 +1663,9 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             if (t == 0) mass_acc = ps;
             if constexpr (PROF) { if (l == 12345.678f) prof_acc[7] += 1; }
             tick(6);
+            if constexpr (PROF) {
+                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 1] = clock64();
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();

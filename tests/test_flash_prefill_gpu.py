@@ -127,6 +127,45 @@ def test_flash_prefill_polynomial_exponentials(ops, every):
         ops.lib.rtkv_debug_flash_poly(0)
 
 
+@pytest.mark.parametrize("variant_id", [0, 4])
+def test_flash_prefill_phase_profiler_leaves_results_alone(ops, variant_id):
+    """rtkv_debug_flash_profile: the instrumented build (cycle counters per phase of CTA 0's tile loop, tools/profile_flash_phases.py)
+    computes the same output as the production build and fills its counters."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q, k, v = (torch.randn(1, 2, 1024, 128, generator=g, device="cuda").to(torch.bfloat16) for _ in range(3))
+    ops.lib.rtkv_debug_flash_variant(variant_id)
+    try:
+        want = ops.flash_prefill(q, k, v, causal=True, prompt_len=128)
+        buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+        ops.lib.rtkv_debug_flash_profile(buf.data_ptr())
+        try:
+            got = ops.flash_prefill(q, k, v, causal=True, prompt_len=128)
+            torch.cuda.synchronize()
+        finally:
+            ops.lib.rtkv_debug_flash_profile(None)
+    finally:
+        ops.lib.rtkv_debug_flash_variant(-1)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    c = buf.cpu()
+    assert int(c[8]) > 0 and int(c[6]) > 0 and int(c[33]) > 0          # tiles, cycles in the exponentials, MMA thread loop
+
+
+def test_tensor_pipe_rate_probe(ops):
+    """rtkv_debug_mma_rate (tools/mma_rate.py): runs, and with precomputed descriptors an MMA is issued no slower than when the
+    descriptors are rebuilt per instruction."""
+    buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+    res = {}
+    for mode in (0, 6):
+        ops.check(ops.lib.rtkv_debug_mma_rate(mode, 512, 4, buf.data_ptr(), None))
+        torch.cuda.synchronize()
+        res[mode] = buf.cpu().tolist()[:2]
+        assert res[mode][0] > 0 and res[mode][1] >= res[mode][0]
+    assert res[6][1] <= res[0][1]
+    with pytest.raises(RuntimeError):
+        ops.check(ops.lib.rtkv_debug_mma_rate(9, 512, 4, buf.data_ptr(), None))
+
+
 def test_flash_prefill_rejects_unsupported(ops):
     q = torch.randn(1, 2, 64, 64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="head_dim"):
