@@ -1387,6 +1387,9 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
     pdl_trigger();
+    // PROF: per-tile cycle stamps (tools/flash_timeline.py) are on when counters[62] != 0; read once, not per stamp
+    bool stamps = false;
+    if constexpr (PROF) stamps = blockIdx.x == 0 && p.prof != nullptr && p.prof[62] != 0;
     // warps 0-3 / 4-7: softmax warpgroups; warps 8-11: Q+K producer, Q K^T issuer, V producer, P V issuer.  2 x 216 + 72 = 504 = 3 x 168
     // registers per lane: what the CTA was given at launch (setmaxnreg trades within that pool; it sits at the top of each role's
     // branch so that ptxas sees which budget the code below it runs under).
@@ -1467,8 +1470,10 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 const int sb = t & 1;
                 mbar_wait(smem_u32(&kfull[ks_]), kph);
                 mtick(0);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 0] = clock64(); }
                 mbar_wait(smem_u32(&sfree[sb]), (uint32_t)(((t >> 1) & 1) ^ 1));     // S_{t-2} is in its owner's registers
                 mtick(1);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 1] = clock64(); }
                 tc_fence_after();
                 const uint64_t kd = umma_desc_advance(kd0, (uint32_t)(ks_ * kFTileBytes));
                 const uint32_t dcol = tmem_base + (uint32_t)(sb * kFT);
@@ -1483,6 +1488,7 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 umma_commit(smem_u32(&sfull[sb]));
                 if (++ks_ == kMCStages) { ks_ = 0; kph ^= 1u; }
                 mtick(2);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 2] = clock64(); }
             }
             if constexpr (PROF) {
                 if (blockIdx.x == 0 && p.prof) {
@@ -1512,8 +1518,10 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 const int sb = t & 1;
                 mbar_wait(smem_u32(&pfull[sb]), (uint32_t)((t >> 1) & 1));           // P_t in tensor memory, O rescaled
                 mtick(0);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 3] = clock64(); }
                 mbar_wait(smem_u32(&vfull[vs_]), vph);
                 mtick(1);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 4] = clock64(); }
                 tc_fence_after();
                 const uint64_t vd = umma_desc_advance(vd0, (uint32_t)(vs_ * kFTileBytes));
                 const uint32_t pcol = tmem_base + (uint32_t)(3 * kFT + sb * 64);     // 8 columns per 16 keys
@@ -1527,6 +1535,7 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 umma_commit(smem_u32(&pvdone[sb]));
                 if (++vs_ == kMCStages) { vs_ = 0; vph ^= 1u; }
                 mtick(2);
+                if constexpr (PROF) { if (stamps && t < 48) p.prof[384 + t * 6 + 5] = clock64(); }
             }
             if constexpr (PROF) {
                 if (blockIdx.x == 0 && p.prof) {
@@ -1564,7 +1573,7 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             const uint32_t par = (uint32_t)((t >> 1) & 1);
             tick(0);
             if constexpr (PROF) {
-                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 2] = clock64();
+                if (stamps && lane == 0 && quad == 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 2] = clock64();
             }
             mbar_wait(sfull_g, par);
             tc_fence_after();
@@ -1639,7 +1648,7 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             tc_fence_after();
             tick(5);
             if constexpr (PROF) {
-                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3] = clock64();
+                if (stamps && lane == 0 && quad == 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3] = clock64();
             }
             // The hand-off above takes a few hundred cycles and the exponentials over a thousand, so left alone the two
             // warpgroups run their exponentials at the same time (sharing the MUFU pipe) and their loads / maxima at the same
@@ -1664,7 +1673,7 @@ flash_prefill_mc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             if constexpr (PROF) { if (l == 12345.678f) prof_acc[7] += 1; }
             tick(6);
             if constexpr (PROF) {
-                if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.prof && p.prof[62] != 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 1] = clock64();
+                if (stamps && lane == 0 && quad == 0 && (t >> 1) < 40) p.prof[64 + g * 128 + (t >> 1) * 3 + 1] = clock64();
             }
             tmem_st_wait();
             tc_fence_before();

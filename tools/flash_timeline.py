@@ -11,7 +11,7 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 skew = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 g = torch.Generator(device="cuda").manual_seed(0)
 q, k, v = (torch.randn(1, 32, S, 128, generator=g, device="cuda").to(torch.bfloat16) for _ in range(3))
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
 buf[62] = 1
 ops.lib.rtkv_debug_flash_variant(4)
 ops.lib.rtkv_debug_flash_skew(skew)
@@ -31,3 +31,8 @@ for j in range(24):
     a = [c[64 + j * 3 + 2] - t0, c[64 + j * 3] - t0, c[64 + j * 3 + 1] - t0]
     b = [c[64 + 128 + j * 3 + 2] - t0, c[64 + 128 + j * 3] - t0, c[64 + 128 + j * 3 + 1] - t0]
     print(f"{j:3d} | {a[0]:7d} {a[1]:7d} {a[2]:7d} ({a[2] - a[1]:5d}) | {b[0]:7d} {b[1]:7d} {b[2]:7d} ({b[2] - b[1]:5d}) | {b[1] - a[1]:6d}")
+
+print("key tile | QK thread: K ready, S buffer free, issued | PV thread: P ready, V ready, issued   (cycles, same origin)")
+for t_ in range(4, 20):
+    r = [c[384 + t_ * 6 + i] - t0 for i in range(6)]
+    print(f"{t_:3d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} | {r[3]:7d} {r[4]:7d} {r[5]:7d}")
