@@ -47,8 +47,18 @@ CASES = [
     ("c2_l12_1684", 4096, 12, (4, 8, 16), 108),
     ("c3_l28_842", 32768, 28, (2, 4, 8), 109),
     ("c3_l20_1684", 32768, 20, (4, 8, 16), 110),
+    # BASELINE configs[3] (C4): Llama-2-13B shapes, 16384 tokens, the four bit settings of the sweep; (L, H, HD) as 6th field
+    ("c4_l35_888", 16384, 35, (8, 8, 8), 111, (40, 40, 5120)),
+    ("c4_l30_444", 16384, 30, (4, 4, 4), 112, (40, 40, 5120)),
+    ("c4_l20_222", 16384, 20, (2, 2, 2), 113, (40, 40, 5120)),
+    ("c4_l14_842", 16384, 14, (2, 4, 8), 114, (40, 40, 5120)),
 ]
 H, HD, L = 32, 4096, 32
+
+
+def model_of(case):
+    """(L, H, HD) of a CASES entry: the 7B shapes unless the entry names its own."""
+    return case[5] if len(case) > 5 else (L, H, HD)
 
 
 def baseline_inputs(S, seed, heads=H, width=HD):
@@ -120,10 +130,15 @@ def main():
     oracle.set_num_threads(os.cpu_count() or 1)
     tally = {"torch": torch.__version__, "cases": {}}
     rng_rows = np.random.default_rng(7)
-    for name, S, layer, bits, seed in CASES:
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None     # e.g. --only c4: these cases, no survey
+    for case in CASES:
+        name, S, layer, bits, seed = case[:5]
+        Lc, Hc, HDc = model_of(case)
+        if only and not name.startswith(only):
+            continue
         t0 = time.time()
-        K, V, A, P = baseline_inputs(S, seed)
-        cfg = CompressionConfig(num_hidden_layers=L, num_attention_heads=H, hidden_size=HD,
+        K, V, A, P = baseline_inputs(S, seed, heads=Hc, width=HDc)
+        cfg = CompressionConfig(num_hidden_layers=Lc, num_attention_heads=Hc, hidden_size=HDc,
                                 high_precision_bits=bits[2], medium_precision_bits=bits[1], low_precision_bits=bits[0])
         comp = RealTimePrefillCompressor(cfg)
         ids = torch.zeros(1, S, dtype=torch.long)
@@ -149,7 +164,7 @@ def main():
         thr_ulps = int(min(ulp_diff(scores.ravel(), np.full(scores.size, t, dtype=np.float32)).min() for t in th))
         kept = int(mask.sum())
         sample = np.sort(rng_rows.choice(k_sel.shape[1], size=min(64, k_sel.shape[1]), replace=False))
-        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=H, HD=HD, L=L, P=P, ratio=ratio,
+        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=Hc, HD=HDc, L=Lc, P=P, ratio=ratio,
                     layer_weight=cfg.layer_weights[layer], alpha=cfg.alpha, beta=cfg.beta, gamma=cfg.gamma,
                     theta_h=cfg.theta_h, theta_m=cfg.theta_m, kept=kept, compressed_shape=list(k_sel.shape),
                     input_crc=dict(K=crc_all(K), V=crc_all(V), A=crc_all(A)),
@@ -166,6 +181,13 @@ def main():
                                     class_boundary_margin_ulps=margins, nearest_label_threshold_ulps=thr_ulps,
                                     reference_seconds=round(t_ref, 2))
         print(name, json.dumps(tally["cases"][name]), flush=True)
+    if only:                                                   # merge into the existing tally, keep its survey
+        path = os.path.join(GOLD, "PINNING_BASELINE.json")
+        old = json.load(open(path))
+        old["cases"].update(tally["cases"])
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1)
+        return
     # ---- flip survey: many seeded layers where the budget BINDS (tally only, no fixtures)
     n_survey = int(sys.argv[sys.argv.index("--survey") + 1]) if "--survey" in sys.argv else 48
     sv = dict(cases=0, selection_flips=0, cases_with_flips=0, label_flips=0, outputs_identical=0, score_max_ulp=0,

@@ -1,6 +1,7 @@
 """Parity at BASELINE sizes against the REAL reference (tests/golden/baseline_*.npz, written by
 oracle/pin_baseline_sizes.py from the unmodified reference): configs[0] [1,2048,4096] layers 0/15/31 with bits 8/4/2
-and 16/8/4, one [1,4096,4096] layer and one [1,32768,4096] layer (the metric's 32k shape) per bit setting.
+and 16/8/4, one [1,4096,4096] layer and one [1,32768,4096] layer (the metric's 32k shape) per bit setting, and configs[3]
+(Llama-2-13B shapes: 40 heads, width 5120, 16384 tokens) with each bit setting of its sweep (8/8/8, 4/4/4, 2/2/2, 8/4/2).
 
 The inputs are regenerated from integer draws with exact elementwise arithmetic (bit-identical on every machine,
 verified by CRC32 against the fixture); the reference's outputs travel as a digest: scores, labels, mask, a CRC32 of
@@ -15,7 +16,7 @@ import torch
 
 import oracle
 from conftest import GOLDEN
-from oracle.pin_baseline_sizes import CASES, H, HD, L, baseline_inputs, crc_all, crc_rows, ulp_diff
+from oracle.pin_baseline_sizes import CASES, baseline_inputs, crc_all, crc_rows, ulp_diff
 
 NAMES = [c[0] for c in CASES]
 
@@ -28,7 +29,7 @@ def load(name):
 
 
 def inputs_for(meta):
-    K, V, A, P = baseline_inputs(meta["S"], meta["seed"])
+    K, V, A, P = baseline_inputs(meta["S"], meta["seed"], heads=meta["H"], width=meta["HD"])
     assert P == meta["P"]
     got = dict(K=crc_all(K), V=crc_all(V), A=crc_all(A))
     assert got == meta["input_crc"], "the regenerated inputs differ from the ones the reference was run on"
@@ -82,7 +83,7 @@ def test_cuda_path_equals_reference_at_baseline_sizes(name, on_host):
         pytest.skip("host-buffer path is covered at 2048/4096 tokens")
     K, V, A, P = inputs_for(m)
     bits = m["bits"]
-    cfg = rtkv.CompressionConfig(num_hidden_layers=L, num_attention_heads=H, hidden_size=HD, high_precision_bits=bits[2],
+    cfg = rtkv.CompressionConfig(num_hidden_layers=m["L"], num_attention_heads=m["H"], hidden_size=m["HD"], high_precision_bits=bits[2],
                                  medium_precision_bits=bits[1], low_precision_bits=bits[0])
     comp = rtkv.RealTimePrefillCompressor(cfg)
     to = (lambda a: torch.from_numpy(a)) if on_host else (lambda a: torch.from_numpy(a).cuda())
