@@ -52,8 +52,23 @@ CASES = [
     ("c4_l30_444", 16384, 30, (4, 4, 4), 112, (40, 40, 5120)),
     ("c4_l20_222", 16384, 20, (2, 2, 2), 113, (40, 40, 5120)),
     ("c4_l14_842", 16384, 14, (2, 4, 8), 114, (40, 40, 5120)),
+    # BASELINE configs[4] (C5): one rank's share of the 64-sequence batch (8 sequences of 4096 tokens, 7B shapes); 16/8/4 on a
+    # later layer so that the rows keep different numbers of tokens and the zero padding to max_selected is exercised; 7th field = B
+    ("c5_b8_l25_1684", 4096, 25, (4, 8, 16), 115, (32, 32, 4096), 8),
 ]
 H, HD, L = 32, 4096, 32
+
+
+def batch_of(case):
+    return case[6] if len(case) > 6 else 1
+
+
+def batched_inputs(S, seed, heads, width, B):
+    """B independent sequences (seed, seed + 1000, ...) stacked along the batch dimension."""
+    if B == 1:
+        return baseline_inputs(S, seed, heads=heads, width=width)
+    parts = [baseline_inputs(S, seed + 1000 * b, heads=heads, width=width) for b in range(B)]
+    return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]), parts[0][3])
 
 
 def model_of(case):
@@ -137,11 +152,12 @@ def main():
         if only and not name.startswith(only):
             continue
         t0 = time.time()
-        K, V, A, P = baseline_inputs(S, seed, heads=Hc, width=HDc)
+        Bc = batch_of(case)
+        K, V, A, P = batched_inputs(S, seed, Hc, HDc, Bc)
         cfg = CompressionConfig(num_hidden_layers=Lc, num_attention_heads=Hc, hidden_size=HDc,
                                 high_precision_bits=bits[2], medium_precision_bits=bits[1], low_precision_bits=bits[0])
         comp = RealTimePrefillCompressor(cfg)
-        ids = torch.zeros(1, S, dtype=torch.long)
+        ids = torch.zeros(Bc, S, dtype=torch.long)
         with stable_argsort():
             k_sel, v_sel, info = comp.compress_layer_kv_cache(torch.from_numpy(K), torch.from_numpy(V), torch.from_numpy(A),
                                                               ids, layer)
@@ -159,12 +175,15 @@ def main():
         lab_flips = int((labels != o["labels"]).sum())
         same_out = bool(sel_flips == 0 and np.array_equal(k_sel, o["k_sel"]) and np.array_equal(v_sel, o["v_sel"]))
         margins = boundary_margins(scores[0], labels[0], mask[0])
+        for b in range(1, Bc):                                  # smallest margin over the batch rows
+            for c, mg in boundary_margins(scores[b], labels[b], mask[b]).items():
+                margins[c] = min(margins.get(c, mg), mg)
         # distance of every score to the nearest label threshold, in ulps (a label flip needs it within the score error)
         th = np.array([np.float32(cfg.theta_h), np.float32(cfg.theta_m)])
         thr_ulps = int(min(ulp_diff(scores.ravel(), np.full(scores.size, t, dtype=np.float32)).min() for t in th))
         kept = int(mask.sum())
         sample = np.sort(rng_rows.choice(k_sel.shape[1], size=min(64, k_sel.shape[1]), replace=False))
-        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=Hc, HD=HDc, L=Lc, P=P, ratio=ratio,
+        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=Hc, HD=HDc, L=Lc, B=Bc, P=P, ratio=ratio,
                     layer_weight=cfg.layer_weights[layer], alpha=cfg.alpha, beta=cfg.beta, gamma=cfg.gamma,
                     theta_h=cfg.theta_h, theta_m=cfg.theta_m, kept=kept, compressed_shape=list(k_sel.shape),
                     input_crc=dict(K=crc_all(K), V=crc_all(V), A=crc_all(A)),

@@ -1,7 +1,8 @@
 """Parity at BASELINE sizes against the REAL reference (tests/golden/baseline_*.npz, written by
 oracle/pin_baseline_sizes.py from the unmodified reference): configs[0] [1,2048,4096] layers 0/15/31 with bits 8/4/2
 and 16/8/4, one [1,4096,4096] layer and one [1,32768,4096] layer (the metric's 32k shape) per bit setting, and configs[3]
-(Llama-2-13B shapes: 40 heads, width 5120, 16384 tokens) with each bit setting of its sweep (8/8/8, 4/4/4, 2/2/2, 8/4/2).
+(Llama-2-13B shapes: 40 heads, width 5120, 16384 tokens) with each bit setting of its sweep (8/8/8, 4/4/4, 2/2/2, 8/4/2), and one
+rank's share of configs[4] (8 sequences of 4096 tokens in one call: rows keep different numbers of tokens, zero padded).
 
 The inputs are regenerated from integer draws with exact elementwise arithmetic (bit-identical on every machine,
 verified by CRC32 against the fixture); the reference's outputs travel as a digest: scores, labels, mask, a CRC32 of
@@ -16,7 +17,7 @@ import torch
 
 import oracle
 from conftest import GOLDEN
-from oracle.pin_baseline_sizes import CASES, baseline_inputs, crc_all, crc_rows, ulp_diff
+from oracle.pin_baseline_sizes import CASES, batched_inputs, crc_all, crc_rows, ulp_diff
 
 NAMES = [c[0] for c in CASES]
 
@@ -29,7 +30,7 @@ def load(name):
 
 
 def inputs_for(meta):
-    K, V, A, P = baseline_inputs(meta["S"], meta["seed"], heads=meta["H"], width=meta["HD"])
+    K, V, A, P = batched_inputs(meta["S"], meta["seed"], meta["H"], meta["HD"], meta.get("B", 1))
     assert P == meta["P"]
     got = dict(K=crc_all(K), V=crc_all(V), A=crc_all(A))
     assert got == meta["input_crc"], "the regenerated inputs differ from the ones the reference was run on"
@@ -87,7 +88,7 @@ def test_cuda_path_equals_reference_at_baseline_sizes(name, on_host):
                                  medium_precision_bits=bits[1], low_precision_bits=bits[0])
     comp = rtkv.RealTimePrefillCompressor(cfg)
     to = (lambda a: torch.from_numpy(a)) if on_host else (lambda a: torch.from_numpy(a).cuda())
-    ids = torch.zeros(1, m["S"], dtype=torch.long)
+    ids = torch.zeros(m.get("B", 1), m["S"], dtype=torch.long)
     k_sel, v_sel, info = comp.compress_layer_kv_cache(to(K), to(V), to(A), ids if on_host else ids.cuda(), m["layer"])
     scores = comp.importance_tracker.layer_scores[m["layer"]].numpy()
     labels = info["quantization_info"]["bit_assignments"]
