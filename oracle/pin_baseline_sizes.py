@@ -55,6 +55,10 @@ CASES = [
     # BASELINE configs[4] (C5): one rank's share of the 64-sequence batch (8 sequences of 4096 tokens, 7B shapes); 16/8/4 on a
     # later layer so that the rows keep different numbers of tokens and the zero padding to max_selected is exercised; 7th field = B
     ("c5_b8_l25_1684", 4096, 25, (4, 8, 16), 115, (32, 32, 4096), 8),
+    # configs[0] shape in the deployment dtypes: K, V and the attention slice rounded to bf16 / f16 (8th field), every reference
+    # operation then runs in that dtype (dynamic_quantization.py:62-126 on half tensors)
+    ("c1_l15_842_bf16", 2048, 15, (2, 4, 8), 116, (32, 32, 4096), 1, "bf16"),
+    ("c1_l31_888_f16", 2048, 31, (8, 8, 8), 117, (32, 32, 4096), 1, "f16"),         # the budget binds: selection + gather in f16
 ]
 H, HD, L = 32, 4096, 32
 
@@ -69,6 +73,20 @@ def batched_inputs(S, seed, heads, width, B):
         return baseline_inputs(S, seed, heads=heads, width=width)
     parts = [baseline_inputs(S, seed + 1000 * b, heads=heads, width=width) for b in range(B)]
     return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]), parts[0][3])
+
+
+def dtype_of(case):
+    return case[7] if len(case) > 7 else "f32"
+
+
+def as_dtype(a, name):
+    """float32 numpy array -> (array in the storage the oracle takes: float32, or uint16 bit patterns; oracle dtype code).
+    Rounding to the half types is torch's (round to nearest even): deterministic, checked by the CRC in the fixture."""
+    import oracle
+    if name == "f32":
+        return a, oracle.F32
+    t = torch.from_numpy(a).to(torch.bfloat16 if name == "bf16" else torch.float16)
+    return oracle.from_torch(t)
 
 
 def model_of(case):
@@ -153,22 +171,24 @@ def main():
             continue
         t0 = time.time()
         Bc = batch_of(case)
+        dname = dtype_of(case)
         K, V, A, P = batched_inputs(S, seed, Hc, HDc, Bc)
+        (K, dt), (V, _), (A, adt) = as_dtype(K, dname), as_dtype(V, dname), as_dtype(A, dname)
         cfg = CompressionConfig(num_hidden_layers=Lc, num_attention_heads=Hc, hidden_size=HDc,
                                 high_precision_bits=bits[2], medium_precision_bits=bits[1], low_precision_bits=bits[0])
         comp = RealTimePrefillCompressor(cfg)
         ids = torch.zeros(Bc, S, dtype=torch.long)
         with stable_argsort():
-            k_sel, v_sel, info = comp.compress_layer_kv_cache(torch.from_numpy(K), torch.from_numpy(V), torch.from_numpy(A),
+            k_sel, v_sel, info = comp.compress_layer_kv_cache(oracle.to_torch(K, dt), oracle.to_torch(V, dt), oracle.to_torch(A, adt),
                                                               ids, layer)
         t_ref = time.time() - t0
         scores = comp.importance_tracker.layer_scores[layer].numpy()
         labels = info["quantization_info"]["bit_assignments"].astype(np.uint8)
         mask = info["propagation_info"]["selection_mask"].numpy().astype(np.uint8)
-        k_sel, v_sel = k_sel.numpy(), v_sel.numpy()
+        k_sel, v_sel = oracle.from_torch(k_sel)[0], oracle.from_torch(v_sel)[0]
         ratio = info["propagation_info"]["propagation_ratio"]
         # ---- oracle on the same inputs
-        o = oracle.compress_layer(K, V, oracle.F32, A, oracle.F32, P, cfg.alpha, cfg.beta, cfg.gamma, cfg.layer_weights[layer],
+        o = oracle.compress_layer(K, V, dt, A, adt, P, cfg.alpha, cfg.beta, cfg.gamma, cfg.layer_weights[layer],
                                   cfg.theta_h, cfg.theta_m, bits, ratio)
         ud = ulp_diff(scores, o["scores"])
         sel_flips = int((mask != o["mask"]).sum())
@@ -183,7 +203,7 @@ def main():
         thr_ulps = int(min(ulp_diff(scores.ravel(), np.full(scores.size, t, dtype=np.float32)).min() for t in th))
         kept = int(mask.sum())
         sample = np.sort(rng_rows.choice(k_sel.shape[1], size=min(64, k_sel.shape[1]), replace=False))
-        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=Hc, HD=HDc, L=Lc, B=Bc, P=P, ratio=ratio,
+        meta = dict(name=name, S=S, layer=layer, bits=list(bits), seed=seed, H=Hc, HD=HDc, L=Lc, B=Bc, dtype=dname, P=P, ratio=ratio,
                     layer_weight=cfg.layer_weights[layer], alpha=cfg.alpha, beta=cfg.beta, gamma=cfg.gamma,
                     theta_h=cfg.theta_h, theta_m=cfg.theta_m, kept=kept, compressed_shape=list(k_sel.shape),
                     input_crc=dict(K=crc_all(K), V=crc_all(V), A=crc_all(A)),

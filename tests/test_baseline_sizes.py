@@ -2,7 +2,8 @@
 oracle/pin_baseline_sizes.py from the unmodified reference): configs[0] [1,2048,4096] layers 0/15/31 with bits 8/4/2
 and 16/8/4, one [1,4096,4096] layer and one [1,32768,4096] layer (the metric's 32k shape) per bit setting, and configs[3]
 (Llama-2-13B shapes: 40 heads, width 5120, 16384 tokens) with each bit setting of its sweep (8/8/8, 4/4/4, 2/2/2, 8/4/2), and one
-rank's share of configs[4] (8 sequences of 4096 tokens in one call: rows keep different numbers of tokens, zero padded).
+rank's share of configs[4] (8 sequences of 4096 tokens in one call: rows keep different numbers of tokens, zero padded), and the
+configs[0] shape with K, V and the attention slice in bf16 and in f16 (every reference operation then runs in that dtype).
 
 The inputs are regenerated from integer draws with exact elementwise arithmetic (bit-identical on every machine,
 verified by CRC32 against the fixture); the reference's outputs travel as a digest: scores, labels, mask, a CRC32 of
@@ -17,7 +18,7 @@ import torch
 
 import oracle
 from conftest import GOLDEN
-from oracle.pin_baseline_sizes import CASES, batched_inputs, crc_all, crc_rows, ulp_diff
+from oracle.pin_baseline_sizes import CASES, as_dtype, batched_inputs, crc_all, crc_rows, ulp_diff
 
 NAMES = [c[0] for c in CASES]
 
@@ -32,9 +33,11 @@ def load(name):
 def inputs_for(meta):
     K, V, A, P = batched_inputs(meta["S"], meta["seed"], meta["H"], meta["HD"], meta.get("B", 1))
     assert P == meta["P"]
+    name = meta.get("dtype", "f32")
+    (K, dt), (V, _), (A, adt) = as_dtype(K, name), as_dtype(V, name), as_dtype(A, name)   # half types: uint16 bit patterns
     got = dict(K=crc_all(K), V=crc_all(V), A=crc_all(A))
     assert got == meta["input_crc"], "the regenerated inputs differ from the ones the reference was run on"
-    return K, V, A, P
+    return K, V, A, P, dt, adt
 
 
 def check_against_digest(g, scores, labels, mask, k_sel, v_sel):
@@ -55,8 +58,8 @@ def test_oracle_equals_reference_at_baseline_sizes(name):
     """CPU: the oracle restatement against the reference digest (this is what pins the oracle at these sizes)."""
     g = load(name)
     m = g["meta"]
-    K, V, A, P = inputs_for(m)
-    o = oracle.compress_layer(K, V, oracle.F32, A, oracle.F32, P, m["alpha"], m["beta"], m["gamma"], m["layer_weight"],
+    K, V, A, P, dt, adt = inputs_for(m)
+    o = oracle.compress_layer(K, V, dt, A, adt, P, m["alpha"], m["beta"], m["gamma"], m["layer_weight"],
                               m["theta_h"], m["theta_m"], tuple(m["bits"]), m["ratio"])
     check_against_digest(g, o["scores"], o["labels"], o["mask"], o["k_sel"], o["v_sel"])
 
@@ -82,18 +85,18 @@ def test_cuda_path_equals_reference_at_baseline_sizes(name, on_host):
     m = g["meta"]
     if on_host and m["S"] > 4096:
         pytest.skip("host-buffer path is covered at 2048/4096 tokens")
-    K, V, A, P = inputs_for(m)
+    K, V, A, P, dt, adt = inputs_for(m)
     bits = m["bits"]
     cfg = rtkv.CompressionConfig(num_hidden_layers=m["L"], num_attention_heads=m["H"], hidden_size=m["HD"], high_precision_bits=bits[2],
                                  medium_precision_bits=bits[1], low_precision_bits=bits[0])
     comp = rtkv.RealTimePrefillCompressor(cfg)
-    to = (lambda a: torch.from_numpy(a)) if on_host else (lambda a: torch.from_numpy(a).cuda())
+    to = (lambda a, d: oracle.to_torch(a, d)) if on_host else (lambda a, d: oracle.to_torch(a, d).cuda())
     ids = torch.zeros(m.get("B", 1), m["S"], dtype=torch.long)
-    k_sel, v_sel, info = comp.compress_layer_kv_cache(to(K), to(V), to(A), ids if on_host else ids.cuda(), m["layer"])
+    k_sel, v_sel, info = comp.compress_layer_kv_cache(to(K, dt), to(V, dt), to(A, adt), ids if on_host else ids.cuda(), m["layer"])
     scores = comp.importance_tracker.layer_scores[m["layer"]].numpy()
     labels = info["quantization_info"]["bit_assignments"]
     mask = info["propagation_info"]["selection_mask"].cpu().numpy()
-    check_against_digest(g, scores, labels, mask, k_sel.cpu().numpy(), v_sel.cpu().numpy())
+    check_against_digest(g, scores, labels, mask, oracle.from_torch(k_sel)[0], oracle.from_torch(v_sel)[0])
     assert info["precision_stats"] == m["precision_stats"]
     for k, v in m["importance_stats"].items():
         assert info["importance_stats"][k] == pytest.approx(v, rel=1e-5, abs=1e-7)
