@@ -43,9 +43,35 @@ def _worker(rank, world, port, q):
         mm = rd.reduce_minmax(torch.from_numpy(mm_local)).numpy()
         want = np.stack([K.min(-1), -K.max(-1), V.min(-1), -V.max(-1)], axis=-1)
         ok2 = np.array_equal(mm, want)
+        # the whole head-sharded layer from the exchanged statistics: scores / labels / selection from the combined mass
+        # (replicated), the rank's column slice quantised with the row-wide min/max, kept rows gathered -> equal, bit for bit, to
+        # the same columns of the unsharded layer (token_importance.py:45 and dynamic_quantization.py:183-184 are the two
+        # couplings across heads; everything else is per column slice)
+        alpha, beta, gamma, w_l, th, tm, bits, ratio = 0.4, 0.3, 0.3, 0.75, 0.7, 0.3, (4, 8, 16), 0.6
+        full = oracle.compress_layer(K, V, oracle.F32, A, oracle.F32, P, alpha, beta, gamma, w_l, th, tm, bits, ratio)
+        mass = oracle.mass_from_partials(gathered, H)
+        scores = oracle.importance_scores(mass, P, alpha, beta, gamma, w_l)
+        labels, _ = oracle.assign_precision(scores, th, tm)
+        mask, counts, _, _, _ = oracle.select_tokens(scores, labels, bits, S * ratio)
+        ok3 = np.array_equal(scores, full["scores"]) and np.array_equal(labels, full["labels"]) and np.array_equal(mask, full["mask"])
+        ok3 = ok3 and int(counts.min()) > 0 and 0 < int(counts.max()) < S       # the budget binds and no fallback is involved
+        levels = (np.float32(2.0) ** np.asarray(bits, np.float32)[labels] - np.float32(1.0)).astype(np.float32)   # [B,S]
+
+        def fake_quant(x, mn, mx):                           # dynamic_quantization.py:62-126, one fp32 rounding per operation
+            flat = mx == mn
+            scale = np.where(flat, np.float32(1.0), (mx - mn) / levels).astype(np.float32)
+            zp = np.where(flat, np.float32(0.0), np.float32(0.0) - mn / scale).astype(np.float32)
+            qv = np.clip(np.rint(x / scale[..., None] + zp[..., None]), np.float32(0.0), levels[..., None]).astype(np.float32)
+            return ((qv - zp[..., None]) * scale[..., None]).astype(np.float32)
+
+        ms = int(counts.max())
+        for x, lo, hi, name in ((kl, mm[..., 0], -mm[..., 1], "k_sel"), (vl, mm[..., 2], -mm[..., 3], "v_sel")):
+            fq = fake_quant(np.ascontiguousarray(x), lo, hi)
+            got = oracle.gather_rows(fq, oracle.F32, mask, ms)
+            ok3 = ok3 and np.array_equal(got, full[name][..., rank * w:(rank + 1) * w])
         # batch sharding covers every row exactly once
         sl = rd.batch_shard(5, rank, world)
-        q.put((rank, bool(ok1), bool(ok2), (sl.start, sl.stop)))
+        q.put((rank, bool(ok1), bool(ok2) and bool(ok3), (sl.start, sl.stop)))
     finally:
         dist.destroy_process_group()
 
