@@ -59,6 +59,7 @@ CASES = [
     # operation then runs in that dtype (dynamic_quantization.py:62-126 on half tensors)
     ("c1_l15_842_bf16", 2048, 15, (2, 4, 8), 116, (32, 32, 4096), 1, "bf16"),
     ("c1_l31_888_f16", 2048, 31, (8, 8, 8), 117, (32, 32, 4096), 1, "f16"),         # the budget binds: selection + gather in f16
+    ("c3_l28_888_bf16", 32768, 28, (8, 8, 8), 118, (32, 32, 4096), 1, "bf16"),      # the metric's 32k shape in the deployment dtype
 ]
 H, HD, L = 32, 4096, 32
 
