@@ -152,6 +152,53 @@ def boundary_margins(scores, labels, mask):
     return out
 
 
+def survey_large(n, oracle, CompressionConfig, RealTimePrefillCompressor, stable_argsort):
+    """Oracle vs reference selection flips where the budget binds at the LONG shapes (16384 and 32768 tokens, 7B widths):
+    tally only (tests/golden/PINNING_BASELINE.json: flip_survey_large), about 20 s of reference time per layer."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    oracle.set_num_threads(os.cpu_count() or 1)
+    sv = dict(cases=0, selection_flips=0, label_flips=0, outputs_identical=0, score_max_ulp=0, tokens=0, kept=0,
+              min_class_boundary_margin_ulps=None, margin_histogram_ulps={"<=2": 0, "3-16": 0, "17-256": 0, ">256": 0}, shapes=[])
+    srng = np.random.default_rng(4242)
+    for t in range(n):
+        S = [16384, 32768][t % 2]
+        bits = [(8, 8, 8), (4, 8, 16), (4, 4, 4), (8, 8, 8)][t % 4]
+        layer = int(srng.integers(9, 32))
+        K, V, A, P = baseline_inputs(S, 9000 + t)
+        cfg = CompressionConfig(num_hidden_layers=L, num_attention_heads=H, hidden_size=HD,
+                                high_precision_bits=bits[2], medium_precision_bits=bits[1], low_precision_bits=bits[0])
+        comp = RealTimePrefillCompressor(cfg)
+        with stable_argsort():
+            k_sel, v_sel, info = comp.compress_layer_kv_cache(torch.from_numpy(K), torch.from_numpy(V), torch.from_numpy(A),
+                                                              torch.zeros(1, S, dtype=torch.long), layer)
+        scores = comp.importance_tracker.layer_scores[layer].numpy()
+        labels = info["quantization_info"]["bit_assignments"].astype(np.uint8)
+        mask = info["propagation_info"]["selection_mask"].numpy().astype(np.uint8)
+        o = oracle.compress_layer(K, V, oracle.F32, A, oracle.F32, P, cfg.alpha, cfg.beta, cfg.gamma, cfg.layer_weights[layer],
+                                  cfg.theta_h, cfg.theta_m, bits, info["propagation_info"]["propagation_ratio"])
+        flips = int((mask != o["mask"]).sum())
+        sv["cases"] += 1
+        sv["selection_flips"] += flips
+        sv["label_flips"] += int((labels != o["labels"]).sum())
+        sv["outputs_identical"] += int(flips == 0 and np.array_equal(k_sel.numpy(), o["k_sel"]) and np.array_equal(v_sel.numpy(), o["v_sel"]))
+        sv["score_max_ulp"] = max(sv["score_max_ulp"], int(ulp_diff(scores, o["scores"]).max()))
+        sv["tokens"] += S
+        sv["kept"] += int(mask.sum())
+        sv["shapes"].append([S, list(bits), layer, int(mask.sum())])
+        for c, m in boundary_margins(scores[0], labels[0], mask[0]).items():
+            cur = sv["min_class_boundary_margin_ulps"]
+            sv["min_class_boundary_margin_ulps"] = m if cur is None else min(cur, m)
+            key = "<=2" if m <= 2 else "3-16" if m <= 16 else "17-256" if m <= 256 else ">256"
+            sv["margin_histogram_ulps"][key] += 1
+        print("survey-large", t, S, bits, layer, "kept", int(mask.sum()), "flips", flips, flush=True)
+    path = os.path.join(GOLD, "PINNING_BASELINE.json")
+    old = json.load(open(path))
+    old["flip_survey_large"] = sv
+    with open(path, "w") as f:
+        json.dump(old, f, indent=1)
+    print(json.dumps(sv, indent=1))
+
+
 def main():
     sys.path.insert(0, ROOT)
     sys.path.insert(0, REF)
@@ -164,6 +211,9 @@ def main():
     oracle.set_num_threads(os.cpu_count() or 1)
     tally = {"torch": torch.__version__, "cases": {}}
     rng_rows = np.random.default_rng(7)
+    if "--survey-large" in sys.argv:                          # flip tally at 16k / 32k tokens only, merged into the JSON
+        survey_large(int(sys.argv[sys.argv.index("--survey-large") + 1]), oracle, CompressionConfig, RealTimePrefillCompressor, stable_argsort)
+        return
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None     # e.g. --only c4: these cases, no survey
     for case in CASES:
         name, S, layer, bits, seed = case[:5]

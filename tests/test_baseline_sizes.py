@@ -72,6 +72,9 @@ def test_flip_survey_is_recorded():
         assert c["oracle_vs_reference"]["selection_flips"] == 0 and c["oracle_vs_reference"]["outputs_identical"]
     sv = t["flip_survey"]
     assert sv["cases"] >= 40 and sv["selection_flips"] == 0 and sv["outputs_identical"] == sv["cases"]
+    lg = t["flip_survey_large"]                                # 16384 / 32768 tokens, budget binding in most
+    assert lg["cases"] >= 12 and lg["selection_flips"] == 0 and lg["label_flips"] == 0 and lg["outputs_identical"] == lg["cases"]
+    assert lg["score_max_ulp"] <= 8 and lg["min_class_boundary_margin_ulps"] > lg["score_max_ulp"]
 
 
 @pytest.mark.gpu
