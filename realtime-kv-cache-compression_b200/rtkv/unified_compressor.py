@@ -88,6 +88,20 @@ class PackedKV:
                                            self.values["qparams"], self._row_bits, self.sel, hkv, sm_scale,
                                            want_lse=want_lse)
 
+    def attend_prefill(self, q, num_kv_heads=None, sm_scale=None, causal=True, want_lse=False):
+        """Prefill attention of q [B,H,Sq,128] (bf16/f16) over this layer's packed rows: the rows are unpacked and dequantised
+        once (rtkv_unpack_dequant_ex, any packing mode), rounded to q's dtype, and attended with rtkv_flash_prefill.  Keys are the
+        S' kept tokens in ascending position order; `causal` is the top-left aligned rule j <= i over kept-row indices, i.e. the
+        reference's attention over K_sel / V_sel with the mask truncated to its first S' columns (modified_llama.py:125-140),
+        zero rows of shorter batch rows included, as there.  Returns out [B,H,Sq,128] (and the row LSE)."""
+        k, v = self.dequantize()
+        B, kept, width = k.shape
+        hkv = num_kv_heads if num_kv_heads is not None else width // 128
+        k4 = k.to(q.dtype).view(B, kept, hkv, width // hkv).transpose(1, 2)
+        v4 = v.to(q.dtype).view(B, kept, hkv, width // hkv).transpose(1, 2)
+        out, lse, _ = ops.flash_prefill(q, k4, v4, sm_scale, causal=causal, prompt_len=0, want_lse=want_lse)
+        return (out, lse) if want_lse else out
+
     def dequantize(self):
         k = ops.unpack_dequant_ex(self.keys, self.dtype, self.seq_len, self.width, self.sel, self.sel.labels, self.bits,
                                   self.options, tensor=0)

@@ -63,6 +63,37 @@ def test_attention_over_packed_rows(rt, bits, B, Hq, S, HD):
         assert float((lse.double() - want_lse).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,Hq,S,HD,Sq", [(1, 8, 2000, 1024, 2000), (2, 4, 600, 512, 333)])
+def test_prefill_attention_over_packed_rows(rt, dtype, B, Hq, S, HD, Sq):
+    """PackedKV.attend_prefill: queries of a prefill against the packed kept rows (unpack + dequantise, then the tcgen05 attention
+    kernel) == fp32 eager attention over dequantize() with the reference's truncated causal mask (modified_llama.py:125-140)."""
+    rtkv, ops = rt
+    from test_parity_gpu import synth_layer
+    K, V, A, P = synth_layer(B, 8, S, HD, seed=S + 3)
+    cfg = rtkv.CompressionConfig(num_hidden_layers=8, num_attention_heads=8, hidden_size=HD, low_precision_bits=4,
+                                 medium_precision_bits=8, high_precision_bits=8)
+    comp = rtkv.RealTimePrefillCompressor(cfg)
+    packed = comp.compress_layer_kv_cache_packed(K, V, A, torch.zeros(B, S, dtype=torch.long, device="cuda"), 6)
+    hkv = HD // 128
+    g = torch.Generator(device="cuda").manual_seed(9)
+    q = torch.randn(B, Hq, Sq, 128, generator=g, device="cuda").to(dtype)
+    out, lse = packed.attend_prefill(q, hkv, want_lse=True)
+    dk, dv = packed.dequantize()
+    kept = dk.shape[1]
+    assert kept == packed.max_selected and kept < S                      # the budget binds: S' < S
+    k4 = dk.to(dtype).float().view(B, kept, hkv, 128).transpose(1, 2).repeat_interleave(Hq // hkv, dim=1)
+    v4 = dv.to(dtype).float().view(B, kept, hkv, 128).transpose(1, 2).repeat_interleave(Hq // hkv, dim=1)
+    logits = (q.float() @ k4.transpose(-1, -2)) * 128 ** -0.5
+    i = torch.arange(Sq, device="cuda")[:, None]
+    j = torch.arange(kept, device="cuda")[None, :]
+    logits = logits.masked_fill(j > i, float("-inf"))
+    want = torch.softmax(logits, -1) @ v4
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    torch.testing.assert_close(out.float(), want, rtol=4 * eps, atol=4 * eps)
+    torch.testing.assert_close(lse, torch.logsumexp(logits, -1), rtol=0, atol=2e-3)
+
+
 def test_rejects_unsupported(rt):
     rtkv, ops = rt
     from test_parity_gpu import synth_layer
