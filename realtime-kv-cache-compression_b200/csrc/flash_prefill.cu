@@ -8,7 +8,12 @@
 //              S' kept (fake-quantised) tokens, with the reference's truncated mask: query i sees kept slots j <= i
 //              -> the same kernel with kv_len = S' < q_len.
 //
-// One CTA = 128 query rows of one (batch row, head); keys/values stream through in tiles of 128:
+// Five kernels sit behind rtkv_flash_prefill (rtkv_debug_flash_variant; DESIGN.md §5 K-flash has the measurements that led from
+// one to the next).  By default the entry launches flash_prefill_kernel (described next) below 3072 keys and
+// flash_prefill_mc_kernel (alternating key tiles, one accumulator, P in tensor memory, three K/V stages, separate issuing
+// threads for the two products; described at its definition) from there on.
+//
+// flash_prefill_kernel: one CTA = 128 query rows of one (batch row, head); keys/values stream through in tiles of 128:
 //   warp 0      TMA producer: Q tile once, K and V tiles through 2-stage rings (4-D tensor maps: any [B,H,S,128]
 //               view with unit stride in the last dim, e.g. the transposed view of a [B,S,H,128] projection)
 //   warp 1      MMA issuer (one thread): S_t = Q K_t^T (tcgen05.mma 128x128x16, both operands K-major, fp32 in TMEM,
